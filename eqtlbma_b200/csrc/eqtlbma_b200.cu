@@ -1,0 +1,1141 @@
+// eqtlbma_b200.cu -- C ABI (include/eqtlbma_b200.h) and host orchestration of the CUDA hot path.
+//
+// Host side: owns the device-resident all-sample-space layouts, replays the reference's
+// MT19937 / gsl_ran_shuffle stream into permutation tables (gene.cpp:617-639,
+// eqtlbma_bf.cpp:847), launches the kernels of pair_kernel.cuh and gathers results.
+// There is no CPU compute fallback anywhere in this file: without a CUDA device every entry
+// point that computes returns an error.
+#include "../../include/eqtlbma_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "pair_kernel.cuh"
+
+using namespace eqb;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+      return 100;                                                                                  \
+    }                                                                                              \
+  } while (0)
+
+namespace {
+
+// ---------------------------------------------------------------- MT19937 + Fisher-Yates replay
+// gsl_rng_mt19937 (2002 seeding), gsl_rng_uniform_int, gsl_ran_shuffle, gsl_ran_flat as documented
+// in SURVEY.md App. A.7; integer-exact.
+struct Mt19937 {
+  uint32_t mt[624];
+  int mti;
+  void seed(uint64_t s_)
+  {
+    uint32_t s = (uint32_t)(s_ & 0xffffffffULL);
+    if (s_ == 0) s = 4357;
+    mt[0] = s;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253U * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    mti = 624;
+  }
+  uint32_t get()
+  {
+    if (mti >= 624) {
+      int kk;
+      for (kk = 0; kk < 624 - 397; ++kk) {
+        const uint32_t y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
+        mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+      }
+      for (; kk < 623; ++kk) {
+        const uint32_t y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU);
+        mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+      }
+      const uint32_t y = (mt[623] & 0x80000000U) | (mt[0] & 0x7fffffffU);
+      mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+      mti = 0;
+    }
+    uint32_t k = mt[mti++];
+    k ^= (k >> 11);
+    k ^= (k << 7) & 0x9d2c5680U;
+    k ^= (k << 15) & 0xefc60000U;
+    k ^= (k >> 18);
+    return k;
+  }
+  uint32_t uniform_int(uint32_t n)
+  {
+    const uint32_t scale = 0xffffffffU / n;
+    uint32_t k;
+    do {
+      k = get() / scale;
+    } while (k >= n);
+    return k;
+  }
+  double uniform() { return get() / 4294967296.0; }
+  template <class T>
+  void shuffle(T *a, int n)
+  {
+    for (int i = n - 1; i > 0; --i) {
+      const uint32_t j = uniform_int((uint32_t)i + 1);
+      const T t = a[i];
+      a[i] = a[j];
+      a[j] = t;
+    }
+  }
+};
+
+// ---------------------------------------------------------------- small kernels
+
+// out[r][i] = map[i] >= 0 ? in[r][map[i]] : fill   (re-index a matrix into the all-sample space)
+__global__ void expand_rows_kernel(const double *__restrict__ in, int n_cols, const int *__restrict__ map,
+                                   const uint8_t *__restrict__ row_ok, double *__restrict__ out, int N, int ldn,
+                                   long long n_rows, double fill, double fill_bad_row)
+{
+  const long long r = blockIdx.x;
+  if (r >= n_rows) return;
+  const bool ok = row_ok ? row_ok[r] != 0 : true;
+  const double *src = in + (size_t)r * n_cols;
+  double *dst = out + (size_t)r * ldn;
+  for (int i = threadIdx.x; i < ldn; i += blockDim.x) {
+    double v = fill;
+    if (i < N) {
+      const int c = map[i];
+      if (!ok)
+        v = fill_bad_row;
+      else if (c >= 0)
+        v = src[c];
+    } else
+      v = (fill != fill) ? fill : 0.0; // padding: NaN for expression rows, 0 otherwise
+    dst[i] = v;
+  }
+}
+
+// Gene::SetCisSnps + Snp::IsInCis (gene.cpp:140-157, snp.cpp:274-297) as two binary searches on the
+// position-sorted SNPs of the gene's chromosome; integer arithmetic with the reference's
+// underflow guard (start < radius => no lower bound).
+__global__ void cis_window_kernel(const int *__restrict__ gene_chr, const long long *__restrict__ gene_start,
+                                  const long long *__restrict__ gene_end, const long long *__restrict__ chr_lo,
+                                  const long long *__restrict__ chr_hi, const long long *__restrict__ snp_pos,
+                                  int anchor, long long radius, long long G, long long *__restrict__ beg,
+                                  long long *__restrict__ end)
+{
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int c = gene_chr[g];
+  long long lo_i = 0, hi_i = 0;
+  if (c >= 0) {
+    lo_i = chr_lo[c];
+    hi_i = chr_hi[c];
+  }
+  if (hi_i <= lo_i) {
+    beg[g] = 0;
+    end[g] = 0;
+    return;
+  }
+  const unsigned long long start = (unsigned long long)gene_start[g], endc = (unsigned long long)gene_end[g];
+  const unsigned long long r = (unsigned long long)radius;
+  const unsigned long long lo_pos = (start >= r) ? start - r : 0ull;
+  const unsigned long long hi_pos = (anchor == EQB_ANCHOR_TSS_TES ? endc : start) + r;
+  long long a = lo_i, b = hi_i; // first index with pos >= lo_pos
+  while (a < b) {
+    const long long mid = (a + b) >> 1;
+    if ((unsigned long long)snp_pos[mid] < lo_pos) a = mid + 1;
+    else b = mid;
+  }
+  const long long first = a;
+  a = first;
+  b = hi_i; // first index with pos > hi_pos
+  while (a < b) {
+    const long long mid = (a + b) >> 1;
+    if ((unsigned long long)snp_pos[mid] <= hi_pos) a = mid + 1;
+    else b = mid;
+  }
+  if (a > first) {
+    beg[g] = first;
+    end[g] = a;
+  } else {
+    beg[g] = 0;
+    end[g] = 0;
+  }
+}
+
+// Exceedance counters of the permutation loops (gene.cpp:431-442, 551-562, 680-706): one thread per
+// (gene[, subgroup]) walks its permuted statistics in order.
+__global__ void perm_count_kernel(const double *__restrict__ stat, const double *__restrict__ truth, long long P,
+                                  long long n_rows, int join, int trick, int tricut, long long *__restrict__ count,
+                                  long long *__restrict__ done, long long *__restrict__ total_eff)
+{
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const double *st = stat + (size_t)r * P;
+  const double tv = truth[r];
+  long long cnt = 1, nd = 0, nan_seen = 0;
+  for (long long p = 0; p < P; ++p) {
+    const double v = st[p];
+    if (isnan(v)) {
+      nan_seen++; // nb_permutations-- in the reference
+      continue;
+    }
+    nd++;
+    if (join ? (v >= tv) : (v <= tv)) cnt++;
+    if (trick != 0 && cnt == 1 + tricut) break;
+  }
+  count[r] = cnt;
+  done[r] = nd;
+  total_eff[r] = P - nan_seen;
+}
+
+struct SubHost {
+  bool set = false;
+  int geno_id = 0, n_exp_cols = 0, Q = 0, n_cov_cols = 0;
+  std::vector<int> all2geno, all2exp, all2cov;
+  std::vector<uint8_t> snp_has, gene_has;
+  double *d_Yraw = nullptr, *d_Craw = nullptr;
+  // finalized
+  int xvar = -1;
+  double *d_Yall = nullptr, *d_Call = nullptr;
+  uint8_t *d_gmask = nullptr, *d_cmask = nullptr, *d_snp_has = nullptr, *d_gene_has = nullptr;
+};
+
+struct GenoHost {
+  double *d_raw = nullptr;
+  int n_cols = 0;
+};
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+} // namespace
+
+struct eqb_ctx {
+  eqb_config cfg;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  bool finalized = false;
+  int ldn = 0, Qmax = 0;
+  std::vector<GenoHost> genos;
+  std::vector<SubHost> subs;
+  std::vector<double> phi2L, oma2L, phi2S, oma2S;
+  std::vector<long long> cb, ce;
+  std::vector<uint8_t> analyzed;
+  std::vector<double *> d_X; // all-sample-space genotype variants
+  DevParams hp;
+  DevParams *d_prm = nullptr;
+  double *d_grids = nullptr;
+  unsigned long long *d_cfg_mask = nullptr;
+  double *d_cfg_weight = nullptr;
+  long long *d_cb = nullptr, *d_ce = nullptr;
+  int *d_err = nullptr;
+  long long n_cfg_all = 0;
+  long long launches = 0;
+  // work buffers (grow-only)
+  DevBuf<int> d_genes, d_slots, d_out_n;
+  DevBuf<long long> d_pair_off, d_count, d_done, d_total;
+  DevBuf<double> d_ss, d_gen, d_cfg, d_w, d_stat, d_true, d_basis_ws, d_table_ws;
+  DevBuf<unsigned short> d_perm;
+  // cached permutation table key
+  uint64_t perm_seed = 0;
+  long long perm_P = -1;
+  int perm_slots = 0;
+};
+
+namespace {
+
+int fail(eqb_ctx *ctx, const std::string &msg)
+{
+  ctx->err = msg;
+  return 1;
+}
+
+long long n_configs_for(const eqb_ctx *ctx)
+{
+  const int S = ctx->cfg.n_subgroups;
+  if (ctx->cfg.analysis != EQB_ANALYSIS_JOIN || ctx->cfg.bfs == EQB_BFS_GEN) return 0;
+  if (ctx->cfg.bfs == EQB_BFS_SIN) return S;
+  return (1LL << S) - 1;
+}
+
+// gsl_combination order: sizes k = 1..S, lexicographic inside (gene_snp_pair.cpp:504-550)
+void enumerate_configs(int S, std::vector<unsigned long long> &masks, std::vector<double> &weights)
+{
+  masks.clear();
+  weights.clear();
+  std::vector<double> choose(S + 1, 1.0);
+  for (int k = 1; k <= S; ++k) {
+    long double r = 1.0L;
+    for (int i = 1; i <= k; ++i) r = r * (long double)(S - k + i) / (long double)i;
+    choose[k] = (double)floorl(r + 0.5L);
+  }
+  std::vector<int> d;
+  for (int k = 1; k <= S; ++k) {
+    d.resize(k);
+    for (int i = 0; i < k; ++i) d[i] = i;
+    while (true) {
+      unsigned long long m = 0;
+      for (int i = 0; i < k; ++i) m |= 1ull << d[i];
+      masks.push_back(m);
+      weights.push_back((1.0 / (double)S) * (1.0 / choose[k]));
+      int i = k - 1;
+      while (i > 0 && d[i] == S - k + i) --i;
+      if (i == 0 && d[i] == S - k) break;
+      ++d[i];
+      for (; i < k - 1; ++i) d[i + 1] = d[i] + 1;
+    }
+  }
+}
+
+template <int NPL>
+cudaError_t launch_pair(eqb_ctx *ctx, const LaunchArgs &la, int grid, size_t smem)
+{
+  cudaError_t e = cudaFuncSetAttribute(pair_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  pair_kernel<NPL><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, la);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+// picks workspaces (shared memory when they fit, else global) and the row-register template
+int run_pair_kernel(eqb_ctx *ctx, LaunchArgs la, long long n_ctas_total, int ppg)
+{
+  const int S = ctx->cfg.n_subgroups;
+  const size_t nb = basis_doubles(S, ctx->Qmax, ctx->ldn, ctx->cfg.qnorm) * sizeof(double);
+  const size_t nt = table_doubles(S, (int)ctx->phi2S.size()) * sizeof(double) * WARPS;
+  const size_t budget = 200 * 1024;
+  bool basis_smem = true, table_smem = true;
+  if (nb + nt > budget) {
+    basis_smem = false;
+    if (nt > budget) table_smem = false;
+  }
+  const size_t smem = (basis_smem ? nb : 0) + (table_smem ? nt : 0);
+  // CTAs per launch: bounded when a global workspace is needed
+  long long max_ctas = (1LL << 30);
+  if (!basis_smem || !table_smem) max_ctas = 148 * 8;
+  const int npl_need = (ctx->ldn + 31) / 32;
+  const long long genes_per_launch_cap = std::max<long long>(1, max_ctas / std::max(1, ppg));
+  // the caller already split by permutation chunks; here split by genes if a workspace bounds the grid
+  const int n_genes = la.n_genes;
+  for (long long g0 = 0; g0 < n_genes; g0 += genes_per_launch_cap) {
+    const long long g1 = std::min<long long>(n_genes, g0 + genes_per_launch_cap);
+    LaunchArgs l2 = la;
+    l2.genes = la.genes + g0;
+    l2.gene_slot = la.gene_slot ? la.gene_slot + g0 : nullptr;
+    l2.pair_off = la.pair_off ? la.pair_off + g0 : nullptr;
+    l2.n_genes = (int)(g1 - g0);
+    const int per = (la.stat_kind == STAT_SEP_PER) ? S : 1;
+    if (la.out_stat)
+      l2.out_stat = la.out_stat + (size_t)g0 * per * (la.perms_per_gene > 0 ? (size_t)la.P_total : 1);
+    const long long grid = (g1 - g0) * std::max(1, ppg);
+    if (!basis_smem) {
+      if (ctx->d_basis_ws.ensure((size_t)grid * nb / sizeof(double)) != cudaSuccess) return fail(ctx, "workspace alloc failed");
+      l2.basis_ws = ctx->d_basis_ws.p;
+    }
+    if (!table_smem) {
+      if (ctx->d_table_ws.ensure((size_t)grid * nt / sizeof(double)) != cudaSuccess) return fail(ctx, "workspace alloc failed");
+      l2.table_ws = ctx->d_table_ws.p;
+    }
+    cudaError_t e;
+    if (npl_need <= 4) e = launch_pair<4>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 8) e = launch_pair<8>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 12) e = launch_pair<12>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 16) e = launch_pair<16>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 24) e = launch_pair<24>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 32) e = launch_pair<32>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 64) e = launch_pair<64>(ctx, l2, (int)grid, smem);
+    else return fail(ctx, "more than 2048 samples are not supported yet");
+    if (e != cudaSuccess) return fail(ctx, std::string("pair_kernel launch: ") + cudaGetErrorString(e));
+  }
+  (void)n_ctas_total;
+  return 0;
+}
+
+int check_device_errors(eqb_ctx *ctx)
+{
+  int h[2] = {0, 0};
+  if (cudaMemcpyAsync(h, ctx->d_err, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    return fail(ctx, std::string("device error: ") + cudaGetErrorString(cudaGetLastError()));
+  if (h[0]) return fail(ctx, "ERROR: missing covariate for a sample kept in the regression (gene_snp_pair.cpp:138-144)");
+  return 0;
+}
+
+// analysed genes of [lo,hi), their pair offsets
+void build_work_list(const eqb_ctx *ctx, long long lo, long long hi, std::vector<int> &genes,
+                     std::vector<long long> &pair_off, long long &n_pairs)
+{
+  genes.clear();
+  pair_off.clear();
+  n_pairs = 0;
+  for (long long g = lo; g < hi; ++g) {
+    if (!ctx->analyzed[g]) continue;
+    genes.push_back((int)g);
+    pair_off.push_back(n_pairs);
+    n_pairs += ctx->ce[g] - ctx->cb[g];
+  }
+}
+
+int stat_kind_for(const eqb_ctx *ctx, const eqb_perm_config *pc)
+{
+  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN) return pc->maxbf ? STAT_JOIN_MAX : STAT_JOIN_AVG;
+  return pc->permsep == 2 ? STAT_SEP_PER : STAT_SEP_ALL;
+}
+
+} // namespace
+
+extern "C" {
+
+int eqb_create(eqb_ctx **out, const eqb_config *cfg)
+{
+  if (!out || !cfg) return 1;
+  *out = nullptr;
+  eqb_ctx *ctx = new eqb_ctx();
+  ctx->cfg = *cfg;
+  *out = ctx; // returned even on failure so that eqb_last_error() can be read
+  if (cfg->abi_version != EQB_ABI_VERSION) return fail(ctx, "ABI version mismatch");
+  if (cfg->n_subgroups < 1 || cfg->n_subgroups > MAXS) return fail(ctx, "1..64 subgroups are supported");
+  if (cfg->n_samples_all < 1 || cfg->n_samples_all > 65535) return fail(ctx, "1..65535 samples are supported");
+  if (cfg->bfs == EQB_BFS_ALL && cfg->analysis == EQB_ANALYSIS_JOIN && cfg->n_subgroups > 20)
+    return fail(ctx, "--bfs all supports at most 20 subgroups");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(ctx, "no CUDA device: the eqtlbma_b200 hot path has no CPU fallback");
+  CK(cudaSetDevice(cfg->device));
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->subs.resize(cfg->n_subgroups);
+  ctx->ldn = ((cfg->n_samples_all + 15) / 16) * 16;
+  CK(cudaMalloc(&ctx->d_err, 2 * sizeof(int)));
+  CK(cudaMemset(ctx->d_err, 0, 2 * sizeof(int)));
+  return 0;
+}
+
+void eqb_destroy(eqb_ctx *ctx)
+{
+  if (!ctx) return;
+  if (ctx->stream) {
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  for (auto &g : ctx->genos)
+    if (g.d_raw) cudaFree(g.d_raw);
+  for (auto &s : ctx->subs) {
+    if (s.d_Yraw) cudaFree(s.d_Yraw);
+    if (s.d_Craw) cudaFree(s.d_Craw);
+    if (s.d_Yall) cudaFree(s.d_Yall);
+    if (s.d_Call) cudaFree(s.d_Call);
+    if (s.d_gmask) cudaFree(s.d_gmask);
+    if (s.d_cmask) cudaFree(s.d_cmask);
+    if (s.d_snp_has) cudaFree(s.d_snp_has);
+    if (s.d_gene_has) cudaFree(s.d_gene_has);
+  }
+  for (auto p : ctx->d_X)
+    if (p) cudaFree(p);
+  if (ctx->d_prm) cudaFree(ctx->d_prm);
+  if (ctx->d_grids) cudaFree(ctx->d_grids);
+  if (ctx->d_cfg_mask) cudaFree(ctx->d_cfg_mask);
+  if (ctx->d_cfg_weight) cudaFree(ctx->d_cfg_weight);
+  if (ctx->d_cb) cudaFree(ctx->d_cb);
+  if (ctx->d_ce) cudaFree(ctx->d_ce);
+  if (ctx->d_err) cudaFree(ctx->d_err);
+  ctx->d_genes.release();
+  ctx->d_slots.release();
+  ctx->d_out_n.release();
+  ctx->d_pair_off.release();
+  ctx->d_count.release();
+  ctx->d_done.release();
+  ctx->d_total.release();
+  ctx->d_ss.release();
+  ctx->d_gen.release();
+  ctx->d_cfg.release();
+  ctx->d_w.release();
+  ctx->d_stat.release();
+  ctx->d_true.release();
+  ctx->d_basis_ws.release();
+  ctx->d_table_ws.release();
+  ctx->d_perm.release();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *eqb_last_error(const eqb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int eqb_set_genotypes(eqb_ctx *ctx, int32_t geno_id, const double *G, int64_t n_snps, int32_t n_cols)
+{
+  if (!ctx->stream) return fail(ctx, "context not usable");
+  if (geno_id < 0 || n_snps != ctx->cfg.n_snps || n_cols < 1) return fail(ctx, "bad genotype matrix");
+  CK(cudaSetDevice(ctx->cfg.device));
+  if ((size_t)geno_id >= ctx->genos.size()) ctx->genos.resize(geno_id + 1);
+  GenoHost &gh = ctx->genos[geno_id];
+  if (gh.d_raw) cudaFree(gh.d_raw);
+  gh.n_cols = n_cols;
+  const size_t bytes = (size_t)n_snps * n_cols * sizeof(double);
+  CK(cudaMalloc(&gh.d_raw, std::max<size_t>(bytes, 8)));
+  CK(cudaMemcpyAsync(gh.d_raw, G, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int eqb_set_subgroup(eqb_ctx *ctx, int32_t s, const eqb_subgroup *sg)
+{
+  if (!ctx->stream) return fail(ctx, "context not usable");
+  if (s < 0 || s >= ctx->cfg.n_subgroups) return fail(ctx, "bad subgroup index");
+  if (sg->n_covariates > MAXQ) return fail(ctx, "at most 31 covariates per subgroup are supported");
+  CK(cudaSetDevice(ctx->cfg.device));
+  SubHost &sb = ctx->subs[s];
+  const int N = ctx->cfg.n_samples_all;
+  const long long M = ctx->cfg.n_snps, G = ctx->cfg.n_genes;
+  sb.set = true;
+  sb.geno_id = sg->geno_id;
+  sb.n_exp_cols = sg->n_exp_cols;
+  sb.Q = sg->n_covariates;
+  sb.n_cov_cols = sg->n_cov_cols;
+  sb.all2geno.assign(sg->all2geno, sg->all2geno + N);
+  sb.all2exp.assign(sg->all2exp, sg->all2exp + N);
+  if (sg->all2cov && sb.Q > 0) sb.all2cov.assign(sg->all2cov, sg->all2cov + N);
+  else sb.all2cov.assign(N, -1);
+  if (sg->snp_has_geno) sb.snp_has.assign(sg->snp_has_geno, sg->snp_has_geno + M);
+  else sb.snp_has.assign(M, 1);
+  if (sg->gene_has_exp) sb.gene_has.assign(sg->gene_has_exp, sg->gene_has_exp + G);
+  else sb.gene_has.assign(G, 1);
+  if (sb.d_Yraw) cudaFree(sb.d_Yraw);
+  if (sb.d_Craw) cudaFree(sb.d_Craw);
+  sb.d_Yraw = sb.d_Craw = nullptr;
+  const size_t yb = (size_t)G * sg->n_exp_cols * sizeof(double);
+  CK(cudaMalloc(&sb.d_Yraw, std::max<size_t>(yb, 8)));
+  CK(cudaMemcpyAsync(sb.d_Yraw, sg->Y, yb, cudaMemcpyHostToDevice, ctx->stream));
+  if (sb.Q > 0) {
+    const size_t cbytes = (size_t)sb.Q * sb.n_cov_cols * sizeof(double);
+    CK(cudaMalloc(&sb.d_Craw, cbytes));
+    CK(cudaMemcpyAsync(sb.d_Craw, sg->C, cbytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return 0;
+}
+
+int eqb_set_grids(eqb_ctx *ctx, const double *phi2L, const double *oma2L, int32_t L, const double *phi2S,
+                  const double *oma2S, int32_t K)
+{
+  ctx->phi2L.assign(phi2L, phi2L + L);
+  ctx->oma2L.assign(oma2L, oma2L + L);
+  ctx->phi2S.assign(phi2S, phi2S + K);
+  ctx->oma2S.assign(oma2S, oma2S + K);
+  return 0;
+}
+
+int eqb_set_cis_windows(eqb_ctx *ctx, const int64_t *begin, const int64_t *end)
+{
+  ctx->cb.assign(begin, begin + ctx->cfg.n_genes);
+  ctx->ce.assign(end, end + ctx->cfg.n_genes);
+  return 0;
+}
+
+int eqb_build_cis_windows(eqb_ctx *ctx, const int32_t *gene_chr, const int64_t *gene_start,
+                          const int64_t *gene_end, const int32_t *snp_chr, const int64_t *snp_pos,
+                          int32_t anchor, int64_t radius, int64_t *begin_out, int64_t *end_out)
+{
+  if (!ctx->stream) return fail(ctx, "context not usable");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const long long G = ctx->cfg.n_genes, M = ctx->cfg.n_snps;
+  // contiguous index range of each chromosome in the SNP order (chromosomes are contiguous there)
+  int nchr = 0;
+  for (long long m = 0; m < M; ++m) nchr = std::max(nchr, snp_chr[m] + 1);
+  for (long long g = 0; g < G; ++g) nchr = std::max(nchr, gene_chr[g] + 1);
+  std::vector<long long> lo(nchr, 0), hi(nchr, 0);
+  std::vector<char> seen(nchr, 0);
+  for (long long m = 0; m < M; ++m) {
+    const int c = snp_chr[m];
+    if (!seen[c]) {
+      seen[c] = 1;
+      lo[c] = m;
+    } else if (hi[c] != m)
+      return fail(ctx, "SNPs of a chromosome must be contiguous and position-sorted");
+    hi[c] = m + 1;
+    if (m > 0 && snp_chr[m - 1] == c && snp_pos[m - 1] > snp_pos[m])
+      return fail(ctx, "SNPs of a chromosome must be contiguous and position-sorted");
+  }
+  int *d_gc = nullptr;
+  long long *d_gs = nullptr, *d_ge = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_pos = nullptr, *d_b = nullptr,
+            *d_e = nullptr;
+  CK(cudaMalloc(&d_gc, std::max<size_t>(G, 1) * sizeof(int)));
+  CK(cudaMalloc(&d_gs, std::max<size_t>(G, 1) * 8));
+  CK(cudaMalloc(&d_ge, std::max<size_t>(G, 1) * 8));
+  CK(cudaMalloc(&d_lo, std::max<size_t>(nchr, 1) * 8));
+  CK(cudaMalloc(&d_hi, std::max<size_t>(nchr, 1) * 8));
+  CK(cudaMalloc(&d_pos, std::max<size_t>(M, 1) * 8));
+  CK(cudaMalloc(&d_b, std::max<size_t>(G, 1) * 8));
+  CK(cudaMalloc(&d_e, std::max<size_t>(G, 1) * 8));
+  CK(cudaMemcpyAsync(d_gc, gene_chr, G * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_gs, gene_start, G * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ge, gene_end, G * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_lo, lo.data(), nchr * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_hi, hi.data(), nchr * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_pos, snp_pos, M * 8, cudaMemcpyHostToDevice, ctx->stream));
+  cis_window_kernel<<<(unsigned)((G + 127) / 128), 128, 0, ctx->stream>>>(d_gc, d_gs, d_ge, d_lo, d_hi, d_pos, anchor,
+                                                                         radius, G, d_b, d_e);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  ctx->cb.resize(G);
+  ctx->ce.resize(G);
+  CK(cudaMemcpyAsync(ctx->cb.data(), d_b, G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->ce.data(), d_e, G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_gc);
+  cudaFree(d_gs);
+  cudaFree(d_ge);
+  cudaFree(d_lo);
+  cudaFree(d_hi);
+  cudaFree(d_pos);
+  cudaFree(d_b);
+  cudaFree(d_e);
+  if (begin_out) std::copy(ctx->cb.begin(), ctx->cb.end(), begin_out);
+  if (end_out) std::copy(ctx->ce.begin(), ctx->ce.end(), end_out);
+  return 0;
+}
+
+int eqb_finalize(eqb_ctx *ctx)
+{
+  if (!ctx->stream) return fail(ctx, "context not usable");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int S = ctx->cfg.n_subgroups, N = ctx->cfg.n_samples_all, ldn = ctx->ldn;
+  const long long M = ctx->cfg.n_snps, G = ctx->cfg.n_genes;
+  if ((long long)ctx->cb.size() != G) return fail(ctx, "cis windows not set");
+  for (int s = 0; s < S; ++s)
+    if (!ctx->subs[s].set) return fail(ctx, "a subgroup was not set");
+  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->phi2L.empty()) return fail(ctx, "grids not set");
+
+  // genotype variants: one all-sample-space copy per distinct (file, sample map)
+  std::map<std::pair<int, std::vector<int> >, int> variants;
+  ctx->Qmax = 0;
+  for (int s = 0; s < S; ++s) {
+    SubHost &sb = ctx->subs[s];
+    ctx->Qmax = std::max(ctx->Qmax, sb.Q);
+    if (sb.geno_id < 0 || (size_t)sb.geno_id >= ctx->genos.size() || !ctx->genos[sb.geno_id].d_raw)
+      return fail(ctx, "subgroup refers to a genotype matrix that was not set");
+    auto key = std::make_pair(sb.geno_id, sb.all2geno);
+    auto it = variants.find(key);
+    if (it == variants.end()) {
+      const int v = (int)ctx->d_X.size();
+      double *dX = nullptr;
+      int *dmap = nullptr;
+      CK(cudaMalloc(&dX, std::max<size_t>((size_t)M * ldn, 1) * sizeof(double)));
+      CK(cudaMalloc(&dmap, N * sizeof(int)));
+      CK(cudaMemcpyAsync(dmap, sb.all2geno.data(), N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      if (M > 0) {
+        expand_rows_kernel<<<(unsigned)M, 128, 0, ctx->stream>>>(ctx->genos[sb.geno_id].d_raw,
+                                                                 ctx->genos[sb.geno_id].n_cols, dmap, nullptr, dX, N,
+                                                                 ldn, M, 0.0, 0.0);
+        ctx->launches++;
+      }
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(dmap);
+      ctx->d_X.push_back(dX);
+      variants[key] = v;
+      sb.xvar = v;
+    } else
+      sb.xvar = it->second;
+  }
+  for (auto &g : ctx->genos) {
+    if (g.d_raw) cudaFree(g.d_raw);
+    g.d_raw = nullptr;
+  }
+  const double qnan = std::numeric_limits<double>::quiet_NaN();
+  for (int s = 0; s < S; ++s) {
+    SubHost &sb = ctx->subs[s];
+    int *dmap = nullptr;
+    CK(cudaMalloc(&dmap, N * sizeof(int)));
+    CK(cudaMalloc(&sb.d_gene_has, std::max<size_t>(G, 1)));
+    CK(cudaMalloc(&sb.d_snp_has, std::max<size_t>(M, 1)));
+    CK(cudaMemcpyAsync(sb.d_gene_has, sb.gene_has.data(), G, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(sb.d_snp_has, sb.snp_has.data(), M, cudaMemcpyHostToDevice, ctx->stream));
+    // expression -> all-sample space, NaN where the sample is absent or the gene is not expressed
+    CK(cudaMalloc(&sb.d_Yall, std::max<size_t>((size_t)G * ldn, 1) * sizeof(double)));
+    CK(cudaMemcpyAsync(dmap, sb.all2exp.data(), N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (G > 0) {
+      expand_rows_kernel<<<(unsigned)G, 128, 0, ctx->stream>>>(sb.d_Yraw, sb.n_exp_cols, dmap, sb.d_gene_has,
+                                                               sb.d_Yall, N, ldn, G, qnan, qnan);
+      ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    // covariates
+    std::vector<uint8_t> gm(ldn, 0), cm(ldn, 0);
+    for (int i = 0; i < N; ++i) {
+      gm[i] = sb.all2geno[i] >= 0;
+      cm[i] = sb.all2cov[i] >= 0;
+    }
+    CK(cudaMalloc(&sb.d_gmask, ldn));
+    CK(cudaMalloc(&sb.d_cmask, ldn));
+    CK(cudaMemcpyAsync(sb.d_gmask, gm.data(), ldn, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(sb.d_cmask, cm.data(), ldn, cudaMemcpyHostToDevice, ctx->stream));
+    if (sb.Q > 0) {
+      CK(cudaMalloc(&sb.d_Call, (size_t)sb.Q * ldn * sizeof(double)));
+      CK(cudaMemcpyAsync(dmap, sb.all2cov.data(), N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      expand_rows_kernel<<<(unsigned)sb.Q, 128, 0, ctx->stream>>>(sb.d_Craw, sb.n_cov_cols, dmap, nullptr, sb.d_Call,
+                                                                  N, ldn, sb.Q, 0.0, 0.0);
+      ctx->launches++;
+      CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dmap);
+    if (sb.d_Yraw) cudaFree(sb.d_Yraw);
+    if (sb.d_Craw) cudaFree(sb.d_Craw);
+    sb.d_Yraw = sb.d_Craw = nullptr;
+  }
+
+  // analysed genes (eqtlbma_bf.cpp:747-762) from per-subgroup prefix counts of genotyped SNPs
+  ctx->analyzed.assign(G, 0);
+  {
+    std::vector<std::vector<int> > cum(S, std::vector<int>(M + 1, 0));
+    for (int s = 0; s < S; ++s)
+      for (long long m = 0; m < M; ++m) cum[s][m + 1] = cum[s][m] + (ctx->subs[s].snp_has[m] ? 1 : 0);
+    for (long long g = 0; g < G; ++g) {
+      bool any = false, all_exp = true;
+      for (int s = 0; s < S; ++s) {
+        if (!ctx->subs[s].gene_has[g]) {
+          all_exp = false;
+          continue;
+        }
+        if (ctx->ce[g] > ctx->cb[g] && cum[s][ctx->ce[g]] - cum[s][ctx->cb[g]] > 0) any = true;
+      }
+      if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model != EQB_ERROR_UVLR && !all_exp) any = false;
+      ctx->analyzed[g] = any ? 1 : 0;
+    }
+  }
+
+  // grids, configurations, windows, parameter block
+  const int L = (int)ctx->phi2L.size(), K = (int)ctx->phi2S.size();
+  std::vector<double> grids;
+  grids.insert(grids.end(), ctx->phi2L.begin(), ctx->phi2L.end());
+  grids.insert(grids.end(), ctx->oma2L.begin(), ctx->oma2L.end());
+  grids.insert(grids.end(), ctx->phi2S.begin(), ctx->phi2S.end());
+  grids.insert(grids.end(), ctx->oma2S.begin(), ctx->oma2S.end());
+  CK(cudaMalloc(&ctx->d_grids, std::max<size_t>(grids.size(), 1) * sizeof(double)));
+  CK(cudaMemcpyAsync(ctx->d_grids, grids.data(), grids.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<unsigned long long> masks;
+  std::vector<double> weights;
+  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.bfs == EQB_BFS_ALL) enumerate_configs(S, masks, weights);
+  ctx->n_cfg_all = (long long)masks.size();
+  CK(cudaMalloc(&ctx->d_cfg_mask, std::max<size_t>(masks.size(), 1) * 8));
+  CK(cudaMalloc(&ctx->d_cfg_weight, std::max<size_t>(masks.size(), 1) * 8));
+  CK(cudaMemcpyAsync(ctx->d_cfg_mask, masks.data(), masks.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_cfg_weight, weights.data(), weights.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMalloc(&ctx->d_cb, std::max<size_t>(G, 1) * 8));
+  CK(cudaMalloc(&ctx->d_ce, std::max<size_t>(G, 1) * 8));
+  CK(cudaMemcpyAsync(ctx->d_cb, ctx->cb.data(), G * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_ce, ctx->ce.data(), G * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  DevParams &hp = ctx->hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.S = S;
+  hp.N = N;
+  hp.ldn = ldn;
+  hp.analysis = ctx->cfg.analysis;
+  hp.bfs = ctx->cfg.bfs;
+  hp.qnorm = ctx->cfg.qnorm;
+  hp.error_model = ctx->cfg.error_model;
+  hp.L = L;
+  hp.K = K;
+  hp.Qmax = ctx->Qmax;
+  hp.fiterr = ctx->cfg.fiterr;
+  hp.M = M;
+  hp.G = G;
+  hp.C = ctx->n_cfg_all;
+  hp.phi2L = ctx->d_grids;
+  hp.oma2L = ctx->d_grids + L;
+  hp.phi2S = ctx->d_grids + 2 * L;
+  hp.oma2S = ctx->d_grids + 2 * L + K;
+  hp.cfg_mask = ctx->d_cfg_mask;
+  hp.cfg_weight = ctx->d_cfg_weight;
+  hp.cis_begin = ctx->d_cb;
+  hp.cis_end = ctx->d_ce;
+  for (int s = 0; s < S; ++s) {
+    const SubHost &sb = ctx->subs[s];
+    hp.sub[s].X = ctx->d_X[sb.xvar];
+    hp.sub[s].Yall = sb.d_Yall;
+    hp.sub[s].Call = sb.d_Call;
+    hp.sub[s].gmask = sb.d_gmask;
+    hp.sub[s].cmask = sb.d_cmask;
+    hp.sub[s].snp_has = sb.d_snp_has;
+    hp.sub[s].gene_has = sb.d_gene_has;
+    hp.sub[s].Q = sb.Q;
+  }
+  CK(cudaMalloc(&ctx->d_prm, sizeof(DevParams)));
+  CK(cudaMemcpyAsync(ctx->d_prm, &hp, sizeof(DevParams), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->finalized = true;
+  return 0;
+}
+
+int64_t eqb_n_configs(const eqb_ctx *ctx) { return n_configs_for(ctx); }
+
+int eqb_pair_offsets(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int64_t *offsets)
+{
+  if (!ctx->finalized) return fail(ctx, "eqb_finalize() not called");
+  if (gene_lo < 0 || gene_hi > ctx->cfg.n_genes || gene_lo > gene_hi) return fail(ctx, "bad gene range");
+  long long acc = 0;
+  for (long long g = gene_lo; g < gene_hi; ++g) {
+    offsets[g - gene_lo] = acc;
+    if (ctx->analyzed[g]) acc += ctx->ce[g] - ctx->cb[g];
+  }
+  offsets[gene_hi - gene_lo] = acc;
+  return 0;
+}
+
+int64_t eqb_launch_count(const eqb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_results *res, bool want_raw,
+                         bool device_only, float *ms)
+{
+  if (!ctx->finalized) return fail(ctx, "eqb_finalize() not called");
+  if (gene_lo < 0 || gene_hi > ctx->cfg.n_genes || gene_lo > gene_hi) return fail(ctx, "bad gene range");
+  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model != EQB_ERROR_UVLR)
+    return fail(ctx, "--error mvlr is not implemented on the device yet");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int S = ctx->cfg.n_subgroups;
+  const bool join = ctx->cfg.analysis == EQB_ANALYSIS_JOIN;
+  const long long C = n_configs_for(ctx);
+  const int L = (int)ctx->phi2L.size(), K = (int)ctx->phi2S.size();
+  if (res && res->gene_analyzed)
+    for (long long g = gene_lo; g < gene_hi; ++g) res->gene_analyzed[g - gene_lo] = ctx->analyzed[g];
+
+  // bytes of device output per pair; genes are processed in chunks that fit the budget
+  const bool o_n = device_only || (res && res->n), o_ss = device_only || (res && res->sstats);
+  const bool o_gen = join && (device_only ? want_raw : (res && res->abf_gen));
+  const bool o_cfg = join && C > 0 && (device_only ? want_raw : (res && res->abf_cfg));
+  const bool o_w = join && (device_only || (res && res->abf_w));
+  const size_t per_pair = (o_n ? S * 4 : 0) + (o_ss ? S * 40 : 0) + (o_gen ? 3 * L * 8 : 0) +
+                          (o_cfg ? (size_t)C * K * 8 : 0) + (o_w ? (5 + C) * 8 : 0);
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = std::max<size_t>(64u << 20, std::min<size_t>(free_b / 2, (size_t)24 << 30));
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ms) {
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, ctx->stream));
+  }
+  long long pair_base = 0;
+  long long g0 = gene_lo;
+  while (g0 < gene_hi) {
+    // grow the chunk gene by gene
+    long long g1 = g0, pairs = 0;
+    while (g1 < gene_hi) {
+      const long long add = ctx->analyzed[g1] ? (ctx->ce[g1] - ctx->cb[g1]) : 0;
+      if (g1 > g0 && (size_t)(pairs + add) * std::max<size_t>(per_pair, 1) > budget) break;
+      pairs += add;
+      ++g1;
+    }
+    std::vector<int> genes;
+    std::vector<long long> pair_off;
+    long long n_pairs = 0;
+    build_work_list(ctx, g0, g1, genes, pair_off, n_pairs);
+    if (!genes.empty()) {
+      CK(ctx->d_genes.ensure(genes.size()));
+      CK(ctx->d_pair_off.ensure(genes.size()));
+      CK(cudaMemcpyAsync(ctx->d_genes.p, genes.data(), genes.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->d_pair_off.p, pair_off.data(), genes.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+      if (o_n) CK(ctx->d_out_n.ensure((size_t)n_pairs * S));
+      if (o_ss) CK(ctx->d_ss.ensure((size_t)n_pairs * S * 5));
+      if (o_gen) CK(ctx->d_gen.ensure((size_t)n_pairs * 3 * L));
+      if (o_cfg) CK(ctx->d_cfg.ensure((size_t)n_pairs * C * K));
+      if (o_w) CK(ctx->d_w.ensure((size_t)n_pairs * (5 + C)));
+      LaunchArgs la;
+      memset(&la, 0, sizeof(la));
+      la.genes = ctx->d_genes.p;
+      la.n_genes = (int)genes.size();
+      la.perms_per_gene = 0;
+      la.which = ctx->cfg.bfs + 1;
+      la.stat_kind = STAT_NONE;
+      la.want_outputs = 1;
+      la.pair_off = ctx->d_pair_off.p;
+      la.out_n = o_n ? ctx->d_out_n.p : nullptr;
+      la.out_ss = o_ss ? ctx->d_ss.p : nullptr;
+      la.out_gen = o_gen ? ctx->d_gen.p : nullptr;
+      la.out_cfg = o_cfg ? ctx->d_cfg.p : nullptr;
+      la.out_w = o_w ? ctx->d_w.p : nullptr;
+      la.err_flag = ctx->d_err;
+      int rc = run_pair_kernel(ctx, la, (long long)genes.size(), 1);
+      if (rc) return rc;
+      if (!device_only) {
+        if (res->n)
+          CK(cudaMemcpyAsync(res->n + pair_base * S, ctx->d_out_n.p, (size_t)n_pairs * S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (res->sstats)
+          CK(cudaMemcpyAsync(res->sstats + pair_base * S * 5, ctx->d_ss.p, (size_t)n_pairs * S * 40, cudaMemcpyDeviceToHost, ctx->stream));
+        if (o_gen)
+          CK(cudaMemcpyAsync(res->abf_gen + pair_base * 3 * L, ctx->d_gen.p, (size_t)n_pairs * 3 * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (o_cfg)
+          CK(cudaMemcpyAsync(res->abf_cfg + pair_base * C * K, ctx->d_cfg.p, (size_t)n_pairs * C * K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (o_w)
+          CK(cudaMemcpyAsync(res->abf_w + pair_base * (5 + C), ctx->d_w.p, (size_t)n_pairs * (5 + C) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream)); // buffers are reused by the next chunk
+      }
+    }
+    pair_base += n_pairs;
+    g0 = g1;
+  }
+  if (ms) {
+    CK(cudaEventRecord(ev1, ctx->stream));
+    CK(cudaEventSynchronize(ev1));
+    CK(cudaEventElapsedTime(ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
+  return check_device_errors(ctx);
+}
+
+int eqb_run(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_results *res)
+{
+  if (!res) return fail(ctx, "null results");
+  return run_true_impl(ctx, gene_lo, gene_hi, res, true, false, nullptr);
+}
+
+int eqb_run_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int32_t want_raw, float *ms)
+{
+  return run_true_impl(ctx, gene_lo, gene_hi, nullptr, want_raw != 0, true, ms);
+}
+
+static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const eqb_perm_config *pc,
+                         eqb_perm_results *res, bool device_only, float *ms)
+{
+  if (!ctx->finalized) return fail(ctx, "eqb_finalize() not called");
+  if (gene_lo < 0 || gene_hi > ctx->cfg.n_genes || gene_lo > gene_hi) return fail(ctx, "bad gene range");
+  if (pc->wrtsize <= 0 || gene_lo % pc->wrtsize != 0) return fail(ctx, "gene_lo must be a multiple of wrtsize");
+  if (pc->nperm <= 0) return fail(ctx, "nperm must be positive");
+  if (pc->trick == 1) return fail(ctx, "--trick 1 is not implemented on the device yet");
+  const bool join = ctx->cfg.analysis == EQB_ANALYSIS_JOIN;
+  if (join && ctx->cfg.error_model != EQB_ERROR_UVLR) return fail(ctx, "--error mvlr is not implemented on the device yet");
+  if (join && (pc->pbf < EQB_PBF_GEN || pc->pbf > EQB_PBF_ALL)) return fail(ctx, "bad --pbf");
+  if (join && pc->pbf > ctx->cfg.bfs + 1) return fail(ctx, "--pbf needs Bayes factors that --bfs does not compute");
+  if (!join && pc->permsep != 1 && pc->permsep != 2) return fail(ctx, "bad --permsep");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int S = ctx->cfg.n_subgroups, N = ctx->cfg.n_samples_all;
+  const long long P = pc->nperm;
+  const int kind = stat_kind_for(ctx, pc);
+  const int per = (kind == STAT_SEP_PER) ? S : 1;
+  const long long n_all = gene_hi - gene_lo;
+  const double qnan = std::numeric_limits<double>::quiet_NaN();
+
+  // work list + slot of each analysed gene inside its write-group (skipped genes consume no RNG)
+  std::vector<int> genes, slots;
+  int max_slot = -1;
+  for (long long g0 = gene_lo; g0 < gene_hi; g0 += pc->wrtsize) {
+    int slot = 0;
+    for (long long g = g0; g < std::min<long long>(g0 + pc->wrtsize, gene_hi); ++g) {
+      if (!ctx->analyzed[g]) continue;
+      genes.push_back((int)g);
+      slots.push_back(slot);
+      max_slot = std::max(max_slot, slot);
+      ++slot;
+    }
+  }
+  const size_t n_items = genes.size();
+  if (res) {
+    for (long long i = 0; i < n_all * per; ++i) {
+      if (res->pval) res->pval[i] = qnan;
+      if (res->nperm_done) res->nperm_done[i] = 0;
+      if (res->count) res->count[i] = 0;
+      if (res->true_stat) res->true_stat[i] = qnan;
+      if (res->median_perm) res->median_perm[i] = qnan;
+    }
+    if (res->perm_stats)
+      for (long long i = 0; i < n_all * per * P; ++i) res->perm_stats[i] = qnan;
+  }
+  if (n_items == 0) {
+    if (ms) *ms = 0.f;
+    return 0;
+  }
+
+  // permutation tables: table[slot][p] = cumulative gsl_ran_shuffle of the identity, the generator
+  // being seeded once per write-group and running on across the genes of the group
+  const int n_slots = max_slot + 1;
+  if (ctx->perm_seed != pc->seed || ctx->perm_P != P || ctx->perm_slots < n_slots) {
+    std::vector<unsigned short> tab((size_t)n_slots * P * N);
+    Mt19937 rng;
+    rng.seed(pc->seed);
+    std::vector<unsigned short> perm(N);
+    for (int sl = 0; sl < n_slots; ++sl) {
+      for (int i = 0; i < N; ++i) perm[i] = (unsigned short)i;
+      for (long long p = 0; p < P; ++p) {
+        rng.shuffle(perm.data(), N);
+        memcpy(&tab[((size_t)sl * P + p) * N], perm.data(), N * sizeof(unsigned short));
+      }
+    }
+    CK(ctx->d_perm.ensure(tab.size()));
+    CK(cudaMemcpyAsync(ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->perm_seed = pc->seed;
+    ctx->perm_P = P;
+    ctx->perm_slots = n_slots;
+  }
+
+  CK(ctx->d_genes.ensure(n_items));
+  CK(ctx->d_slots.ensure(n_items));
+  CK(cudaMemcpyAsync(ctx->d_genes.p, genes.data(), n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_slots.p, slots.data(), n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->d_stat.ensure(n_items * per * (size_t)P));
+  CK(ctx->d_true.ensure(n_items * per));
+  CK(ctx->d_count.ensure(n_items * per));
+  CK(ctx->d_done.ensure(n_items * per));
+  CK(ctx->d_total.ensure(n_items * per));
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ms) {
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, ctx->stream));
+  }
+  LaunchArgs la;
+  memset(&la, 0, sizeof(la));
+  la.genes = ctx->d_genes.p;
+  la.n_genes = (int)n_items;
+  la.gene_slot = ctx->d_slots.p;
+  la.perm_tab = ctx->d_perm.p;
+  la.P_total = P;
+  la.which = join ? pc->pbf : 1;
+  la.stat_kind = kind;
+  la.err_flag = ctx->d_err;
+  // statistic of the true data (identity permutation, the reference's true-data rules)
+  la.perms_per_gene = 0;
+  la.true_rules = 1;
+  la.out_stat = ctx->d_true.p;
+  int rc = run_pair_kernel(ctx, la, (long long)n_items, 1);
+  if (rc) return rc;
+  // permuted statistics, in chunks of permutations
+  la.true_rules = 0;
+  la.out_stat = ctx->d_stat.p;
+  const long long max_grid = 1LL << 22;
+  long long pcnk = std::max<long long>(1, std::min<long long>(P, max_grid / (long long)n_items));
+  for (long long p0 = 0; p0 < P; p0 += pcnk) {
+    la.p0 = p0;
+    la.perms_per_gene = (int)std::min<long long>(pcnk, P - p0);
+    rc = run_pair_kernel(ctx, la, (long long)n_items * la.perms_per_gene, la.perms_per_gene);
+    if (rc) return rc;
+  }
+  const long long n_rows = (long long)n_items * per;
+  perm_count_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>(
+      ctx->d_stat.p, ctx->d_true.p, P, n_rows, join ? 1 : 0, pc->trick, pc->tricut, ctx->d_count.p, ctx->d_done.p,
+      ctx->d_total.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (ms) {
+    CK(cudaEventRecord(ev1, ctx->stream));
+    CK(cudaEventSynchronize(ev1));
+    CK(cudaEventElapsedTime(ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
+  if (device_only) return check_device_errors(ctx);
+
+  // host gather
+  std::vector<long long> h_count(n_rows), h_done(n_rows), h_total(n_rows);
+  std::vector<double> h_true(n_rows), h_stat;
+  CK(cudaMemcpyAsync(h_count.data(), ctx->d_count.p, n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h_done.data(), ctx->d_done.p, n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h_total.data(), ctx->d_total.p, n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h_true.data(), ctx->d_true.p, n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  const bool need_stats = res->perm_stats || (join && res->median_perm);
+  if (need_stats) {
+    h_stat.resize((size_t)n_rows * P);
+    CK(cudaMemcpyAsync(h_stat.data(), ctx->d_stat.p, (size_t)n_rows * P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  rc = check_device_errors(ctx);
+  if (rc) return rc;
+
+  // p-values: Gene::CalcPermutationPvalue (gene.cpp:348-364); rngTrick is seeded like rngPerm and
+  // drawn once per gene (and per subgroup for --permsep 2) in group order, only when needed
+  Mt19937 rngTrick;
+  size_t it = 0;
+  for (long long g0 = gene_lo; g0 < gene_hi; g0 += pc->wrtsize) {
+    size_t it_end = it;
+    while (it_end < n_items && genes[it_end] < std::min<long long>(g0 + pc->wrtsize, gene_hi)) ++it_end;
+    const int n_sub_loops = (kind == STAT_SEP_PER) ? S : 1;
+    for (int sl = 0; sl < n_sub_loops; ++sl) {
+      if (pc->trick != 0) rngTrick.seed(pc->seed);
+      for (size_t i = it; i < it_end; ++i) {
+        const size_t r = i * per + (kind == STAT_SEP_PER ? sl : 0);
+        const long long o = ((long long)genes[i] - gene_lo) * per + (kind == STAT_SEP_PER ? sl : 0);
+        double pv;
+        if (h_done[r] == h_total[r])
+          pv = (double)h_count[r] / (double)(h_total[r] + 1);
+        else {
+          const double a = (1 + pc->tricut) / ((double)(h_done[r] + 2)), b = (1 + pc->tricut) / ((double)(h_done[r] + 1));
+          const double u = rngTrick.uniform();
+          pv = a * (1.0 - u) + b * u;
+        }
+        if (res->pval) res->pval[o] = pv;
+        if (res->nperm_done) res->nperm_done[o] = h_done[r];
+        if (res->count) res->count[o] = h_count[r];
+        if (res->true_stat) res->true_stat[o] = h_true[r];
+        if (need_stats) {
+          const double *st = &h_stat[r * (size_t)P];
+          // statistics actually evaluated: the first ones up to the stopping point
+          std::vector<double> kept;
+          long long nd = 0;
+          for (long long p = 0; p < P && nd < h_done[r]; ++p) {
+            if (res->perm_stats) res->perm_stats[(size_t)o * P + p] = st[p];
+            if (st[p] == st[p]) {
+              kept.push_back(st[p]);
+              ++nd;
+            }
+          }
+          if (join && res->median_perm) {
+            // gene.cpp:713-714 reads one element past the stored statistics (0.0 with glibc here)
+            kept.push_back(0.0);
+            const size_t size = kept.size(), mid = size / 2;
+            std::nth_element(kept.begin(), kept.begin() + mid, kept.end());
+            double med = kept[mid];
+            if (size % 2 == 0) {
+              std::nth_element(kept.begin(), kept.begin() + mid - 1, kept.end());
+              med = (med + kept[mid - 1]) / 2.0;
+            }
+            res->median_perm[o] = med;
+          }
+        }
+      }
+    }
+    it = it_end;
+  }
+  return 0;
+}
+
+int eqb_run_permutations(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const eqb_perm_config *pc,
+                         eqb_perm_results *res)
+{
+  if (!res || !pc) return fail(ctx, "null argument");
+  return run_perm_impl(ctx, gene_lo, gene_hi, pc, res, false, nullptr);
+}
+
+int eqb_run_permutations_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const eqb_perm_config *pc,
+                                     float *ms)
+{
+  if (!pc) return fail(ctx, "null argument");
+  return run_perm_impl(ctx, gene_lo, gene_hi, pc, nullptr, true, ms);
+}
+
+} // extern "C"

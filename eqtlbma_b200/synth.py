@@ -84,11 +84,14 @@ class Dataset:
         Gene::SetCisSnps (gene.cpp:140-157) with integer arithmetic."""
         beg = np.zeros(self.n_genes, dtype=np.int64)
         end = np.zeros(self.n_genes, dtype=np.int64)
+        chr_rng = {}
+        for c in np.unique(self.snp_chr):
+            idx = np.nonzero(self.snp_chr == c)[0]
+            chr_rng[int(c)] = (int(idx[0]), int(idx[-1]) + 1)
         for g in range(self.n_genes):
-            idx = np.nonzero(self.snp_chr == self.gene_chr[g])[0]
-            if idx.size == 0:
+            if int(self.gene_chr[g]) not in chr_rng:
                 continue
-            lo_chr, hi_chr = idx[0], idx[-1] + 1
+            lo_chr, hi_chr = chr_rng[int(self.gene_chr[g])]
             pos = self.snp_pos[lo_chr:hi_chr]
             start, endc = int(self.gene_start[g]), int(self.gene_end[g])
             lo = start - self.radius if start >= self.radius else 0
@@ -173,7 +176,7 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
                  n_cov=0, ragged=False, ragged_min_frac=0.4, absent_gene_frac=0.0, nan_frac=0.0,
                  dosage=False, maf=0.3, gridL=None, gridS=None, radius=None, anchor="TSS",
                  null_frac=0.3, separate_geno_files=False, missing_geno_frac=0.0,
-                 pad_names=False, monomorphic_frac=0.0) -> Dataset:
+                 pad_names=False, monomorphic_frac=0.0, gene_spacing=1000, far_snp=True) -> Dataset:
     """Generate a dataset. One SNP stream per chromosome at uniform spacing; each gene's +-radius
     TSS window holds ~snps_per_gene SNPs; expression y = mu_s + b_s*g + N(0,1) with ES-model
     effects from the first cis SNP of the gene (simul_flutre_et_al.cpp:682-743)."""
@@ -192,7 +195,7 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
     chr_names = sorted(chr_names_unsorted)
 
     # genes: equally spread over chromosomes, spacing 1000 bp, length 200
-    spacing, glen = 1000, 200
+    spacing, glen = gene_spacing, 200
     if radius is None:
         radius = 100  # window 2*radius+1
     snp_step = max(1, (2 * radius + 1) // max(1, snps_per_gene))
@@ -217,8 +220,9 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
             sid += 1
             snps.append((nm("snp", sid), chr_names_unsorted[c], pos))
             pos += snp_step
-        sid += 1
-        snps.append((nm("snp", sid), chr_names_unsorted[c], hi + 50 * radius + 7))
+        if far_snp:
+            sid += 1
+            snps.append((nm("snp", sid), chr_names_unsorted[c], hi + 50 * radius + 7))
     # orderings of the reference loader
     genes.sort(key=lambda t: t[0].encode())
     snps.sort(key=lambda t: (chr_names.index(t[1]), t[2], t[0].encode()))
@@ -264,7 +268,8 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
 
     # effects
     pos_in_sorted = {n: i for i, n in enumerate(samples)}
-    all2geno = np.array([ind_names.index(s) for s in samples], dtype=np.int32)
+    ind_pos = {n: i for i, n in enumerate(ind_names)}
+    all2geno = np.array([ind_pos[s] for s in samples], dtype=np.int32)
     mus = rng.normal(4, 2, size=S)
     cov_names = sorted([f"cov{q + 1}" for q in range(max(0, n_cov - 1))] + (["sex"] if n_cov > 0 else []))
     Cfull = np.zeros((n_cov, n_inds))

@@ -1,0 +1,82 @@
+"""GPU parity tests: the CUDA library, called through its C ABI, against (a) the golden dumps of the
+UNMODIFIED reference and (b) the CPU oracle on the same seeded inputs.
+Tolerances (BASELINE.json north_star): pair sets / sample sizes / exceedance counts bit-exact,
+summary statistics 1e-9 relative, log10 ABFs 1e-8 absolute."""
+import os
+
+import numpy as np
+import pytest
+
+from eqtlbma_b200._capi import Engine as AnyEngine
+from refdump import parse_dump
+from scenarios import SCENARIOS, build_dataset, engine_kwargs, perm_kwargs
+from test_oracle_vs_reference import GOLD, check_against_dump
+
+pytestmark = pytest.mark.gpu
+
+# paths of the reference that the CUDA library does not cover yet (reported as errors by the ABI)
+NOT_YET = {"mvlr_fit0", "mvlr_fit05_cov", "basic_all_trick1"}
+# degenerate rank-deficient designs: documented tie, checked separately
+DEGENERATE = {"monomorphic"}
+
+
+@pytest.mark.parametrize("name", sorted(set(SCENARIOS) - NOT_YET - DEGENERATE))
+def test_cuda_matches_reference_dump(cuda_lib, name):
+    import eqtlbma_b200
+    sc = SCENARIOS[name]
+    ds = build_dataset(sc)
+    dump = parse_dump(os.path.join(GOLD, name + ".dump.gz"))
+    eng = eqtlbma_b200.Engine(ds, **engine_kwargs(sc))
+    res = eng.run()
+    pk = perm_kwargs(sc)
+    perm = eng.run_permutations(**pk) if pk else None
+    check_against_dump(eng, ds, sc, dump, res, perm)
+    assert eng.launch_count() > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("name", sorted(set(SCENARIOS) - NOT_YET))
+def test_cuda_matches_oracle(cuda_lib, oracle_lib, name):
+    import eqtlbma_b200
+    sc = SCENARIOS[name]
+    ds = build_dataset(sc)
+    eng = eqtlbma_b200.Engine(ds, **engine_kwargs(sc))
+    ora = AnyEngine(oracle_lib, "eqo_", ds, **engine_kwargs(sc))
+    a, b = eng.run(), ora.run()
+    assert np.array_equal(a.offsets, b.offsets)
+    assert np.array_equal(a.gene_analyzed, b.gene_analyzed)
+    assert np.array_equal(a.n, b.n)
+    # pve = 1 - rss/tss is compared absolutely (it is exactly 0 up to rounding for null designs)
+    assert np.allclose(a.sstats[..., 0], b.sstats[..., 0], rtol=1e-9, atol=1e-12, equal_nan=True)
+    assert np.allclose(a.sstats[..., 1:], b.sstats[..., 1:], rtol=1e-9, atol=0, equal_nan=True)
+    if sc["analysis"] == "join":
+        assert np.allclose(a.abf_gen, b.abf_gen, rtol=0, atol=1e-8, equal_nan=True)
+        assert np.allclose(a.abf_cfg, b.abf_cfg, rtol=0, atol=1e-8, equal_nan=True)
+        assert np.allclose(a.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
+    pk = perm_kwargs(sc)
+    if pk:
+        pa, pb = eng.run_permutations(**pk), ora.run_permutations(**pk)
+        assert np.array_equal(pa.count, pb.count)
+        assert np.array_equal(pa.nperm_done, pb.nperm_done)
+        assert np.allclose(pa.pval, pb.pval, rtol=1e-12, atol=0, equal_nan=True)
+        tol = dict(rtol=0, atol=1e-8) if sc["analysis"] == "join" else dict(rtol=1e-9, atol=0)
+        assert np.allclose(pa.true_stat, pb.true_stat, equal_nan=True, **tol)
+        assert np.allclose(pa.perm_stats, pb.perm_stats, equal_nan=True, **tol)
+    eng.close()
+    ora.close()
+
+
+def test_cis_windows_match_linear_scan(cuda_lib, oracle_lib):
+    """a1: the device binary search reproduces Gene::SetCisSnps / Snp::IsInCis bit-exactly,
+    including the start < radius underflow guard and both anchors."""
+    import eqtlbma_b200
+    from eqtlbma_b200.synth import make_dataset
+    for anchor, radius in [("TSS", 100), ("TSS+TES", 150), ("TSS", 5000), ("TSS+TES", 1)]:
+        ds = make_dataset(seed=3, n_genes=40, snps_per_gene=5, n_inds=20, n_chr=3, anchor=anchor, radius=radius)
+        ds.radius = radius
+        eng = eqtlbma_b200.Engine(ds, analysis="sep", bfs="gen")
+        ora = AnyEngine(oracle_lib, "eqo_", ds, analysis="sep", bfs="gen")
+        assert np.array_equal(eng.cis_begin, ora.cis_begin)
+        assert np.array_equal(eng.cis_end, ora.cis_end)
+        eng.close()
+        ora.close()
