@@ -60,6 +60,11 @@ class Engine(_Engine):
         f.restype = ctypes.c_int64
         return int(f(self.ctx))
 
+    def fast_gene_count(self) -> int:
+        f = self.lib.eqb_fast_gene_count
+        f.restype = ctypes.c_int64
+        return int(f(self.ctx))
+
     def run_device_only(self, lo=0, hi=None, raw=False) -> float:
         hi = self.ds.n_genes if hi is None else hi
         ms = ctypes.c_float(0)

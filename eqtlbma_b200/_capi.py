@@ -76,6 +76,8 @@ def _ptr(a):
 class Engine:
     """One context of the C ABI (``prefix`` selects eqb_ = CUDA library, eqo_ = CPU oracle)."""
 
+    timing = None  # set to a dict to accumulate host wall time per C entry point (diagnostics)
+
     def __init__(self, lib: C.CDLL, prefix: str, ds, analysis="join", bfs="all", error="uvlr",
                  fiterr=0.5, qnorm=False, device=0, pinned=False):
         self.lib, self.prefix = lib, prefix
@@ -88,7 +90,10 @@ class Engine:
         self.ctx = C.c_void_p()
         self._call("create", C.byref(self.ctx), C.byref(cfg), ctx_first=False)
         for gi, G in enumerate(ds.genos):
-            Gc = np.ascontiguousarray(np.nan_to_num(G, nan=0.0), dtype=np.float64)
+            if getattr(ds, "_clean", False) and G.flags.c_contiguous and G.dtype == np.float64:
+                Gc = G  # already NaN-free and contiguous (e.g. pinned by the caller): no host copy
+            else:
+                Gc = np.ascontiguousarray(np.nan_to_num(G, nan=0.0), dtype=np.float64)
             self._call("set_genotypes", C.c_int32(gi), _ptr(Gc), C.c_int64(Gc.shape[0]), C.c_int32(Gc.shape[1]))
         for s, sg in enumerate(ds.subgroups):
             arrs = dict(all2geno=np.ascontiguousarray(sg.all2geno, dtype=np.int32),
@@ -127,7 +132,13 @@ class Engine:
     def _call(self, name, *args, ctx_first=True):
         f = getattr(self.lib, self.prefix + name)
         f.restype = C.c_int
-        rc = f(self.ctx, *args) if ctx_first else f(*args)
+        if Engine.timing is not None:
+            import time
+            t0 = time.perf_counter()
+            rc = f(self.ctx, *args) if ctx_first else f(*args)
+            Engine.timing[name] = Engine.timing.get(name, 0.0) + time.perf_counter() - t0
+        else:
+            rc = f(self.ctx, *args) if ctx_first else f(*args)
         if rc != 0:
             e = getattr(self.lib, self.prefix + "last_error")
             e.restype = C.c_char_p
@@ -153,20 +164,39 @@ class Engine:
         self._call("pair_offsets", C.c_int64(lo), C.c_int64(hi), _ptr(off))
         return off
 
-    def run(self, lo=0, hi=None, raw=True) -> TrueResults:
+    def alloc_results(self, lo=0, hi=None, raw=True, pinned=False) -> TrueResults:
+        """Host result buffers for run(); pinned (page-locked, via torch) makes the D2H copies DMA."""
         hi = self.ds.n_genes if hi is None else hi
         off = self.pair_offsets(lo, hi)
         P, S, Cn = int(off[-1]), self.S, self.n_configs
         join = self.analysis == "join"
-        n = np.zeros((P, S), dtype=np.int32)
-        ss = np.full((P, S, 5), np.nan)
-        ga = np.zeros(hi - lo, dtype=np.uint8)
-        ag = np.full((P, 3, self.L), np.nan) if join and raw else None
-        ac = np.full((P, Cn, self.K), np.nan) if join and raw else None
-        aw = np.full((P, 5 + Cn), np.nan) if join else None
-        rc = ResultsC(_ptr(n), _ptr(ss), _ptr(ag), _ptr(ac), _ptr(aw), _ptr(ga))
-        self._call("run", C.c_int64(lo), C.c_int64(hi), C.byref(rc))
+
+        def mk(shape, dtype, fill):
+            if pinned:
+                import torch
+                t = torch.empty(shape, dtype={np.float64: torch.float64, np.int32: torch.int32,
+                                              np.uint8: torch.uint8}[dtype]).pin_memory()
+                self._keep.append(t)
+                a = t.numpy()
+                a[...] = fill
+                return a
+            return np.full(shape, fill, dtype=dtype)
+
+        n = mk((P, S), np.int32, 0)
+        ss = mk((P, S, 5), np.float64, np.nan)
+        ga = mk((hi - lo,), np.uint8, 0)
+        ag = mk((P, 3, self.L), np.float64, np.nan) if join and raw else None
+        ac = mk((P, Cn, self.K), np.float64, np.nan) if join and raw else None
+        aw = mk((P, 5 + Cn), np.float64, np.nan) if join else None
         return TrueResults(off, ga, n, ss, ag, ac, aw)
+
+    def run(self, lo=0, hi=None, raw=True, out: TrueResults | None = None) -> TrueResults:
+        hi = self.ds.n_genes if hi is None else hi
+        r = out if out is not None else self.alloc_results(lo, hi, raw)
+        rc = ResultsC(_ptr(r.n), _ptr(r.sstats), _ptr(r.abf_gen), _ptr(r.abf_cfg), _ptr(r.abf_w),
+                      _ptr(r.gene_analyzed))
+        self._call("run", C.c_int64(lo), C.c_int64(hi), C.byref(rc))
+        return r
 
     def perm_config(self, nperm, seed, trick=0, tricut=10, permsep=0, pbf="none", maxbf=False, wrtsize=10):
         return PermConfigC(int(nperm), int(seed) & 0xFFFFFFFFFFFFFFFF, trick, tricut, permsep, PBF[pbf],

@@ -21,7 +21,7 @@ __device__ __forceinline__ double lgam_corr(double z)
 }
 
 // ln[Gamma(a+b) / (Gamma(a) Gamma(b))] without cancelling three large lgamma values
-__device__ inline double ln_inv_beta(double a, double b)
+__device__ __noinline__ double ln_inv_beta(double a, double b)
 {
   if (a < b) {
     const double t = a;
@@ -37,7 +37,7 @@ __device__ inline double ln_inv_beta(double a, double b)
 }
 
 // continued fraction of the incomplete beta function, modified Lentz
-__device__ inline double beta_cf(double a, double b, double x)
+__device__ __noinline__ double beta_cf(double a, double b, double x)
 {
   const double tiny = 1e-300, eps = 1e-16;
   const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
@@ -92,7 +92,7 @@ __device__ inline void beta_inc_pair(double a, double b, double x, double y, dou
 }
 
 // two-sided Student tail Pr(|T_nu| > |t|) and its complement
-__device__ inline void tdist_tails(double t, double nu, double &tail, double &central)
+__device__ __noinline__ void tdist_tails(double t, double nu, double &tail, double &central)
 {
   const double t2 = t * t;
   if (t2 == 0.0) {
@@ -139,7 +139,7 @@ __device__ inline double fdist_Q(double x, double nu1, double nu2)
 }
 
 // gsl_cdf_ugaussian_Pinv: lower-tail standard normal quantile
-__device__ inline double ugaussian_Pinv(double P)
+__device__ __noinline__ double ugaussian_Pinv(double P)
 {
   if (isnan(P)) return nan("");
   if (P <= 0.0) return (P == 0.0) ? -INFINITY : nan("");

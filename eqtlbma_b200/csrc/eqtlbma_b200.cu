@@ -18,7 +18,7 @@
 #include <string>
 #include <vector>
 
-#include "pair_kernel.cuh"
+#include "fast_kernels.cuh"
 
 using namespace eqb;
 
@@ -199,6 +199,7 @@ struct SubHost {
   std::vector<int> all2geno, all2exp, all2cov;
   std::vector<uint8_t> snp_has, gene_has;
   double *d_Yraw = nullptr, *d_Craw = nullptr;
+  std::vector<double> covkey; // covariates in all-sample space (host copy, for duplicate detection)
   // finalized
   int xvar = -1;
   double *d_Yall = nullptr, *d_Call = nullptr;
@@ -260,6 +261,18 @@ struct eqb_ctx {
   DevBuf<long long> d_pair_off, d_count, d_done, d_total;
   DevBuf<double> d_ss, d_gen, d_cfg, d_w, d_stat, d_true, d_basis_ws, d_table_ws;
   DevBuf<unsigned short> d_perm;
+  // fast path (gene-independent masks): K1 outputs
+  FastParams hfp;
+  FastParams *d_fp = nullptr;
+  std::vector<double *> d_Bs, d_Ytil, d_ystat, d_xstat;
+  std::vector<uint8_t *> d_emask;
+  std::vector<uint8_t> gene_fast;
+  DevBuf<int> d_genes2;
+  DevBuf<long long> d_pair_off2, d_fast_base;
+  GridTab gt;              // unique phi2 values of the consistent-configuration rows
+  double *d_gt_d = nullptr; // uphi[UL] | omaL[3L]
+  int *d_gt_i = nullptr;    // idxL[3L] | dup_of[S]
+  double **d_prep_ptrs = nullptr;
   // cached permutation table key
   uint64_t perm_seed = 0;
   long long perm_P = -1;
@@ -406,6 +419,171 @@ int stat_kind_for(const eqb_ctx *ctx, const eqb_perm_config *pc)
   return pc->permsep == 2 ? STAT_SEP_PER : STAT_SEP_ALL;
 }
 
+
+// K1b + K1c launches (residual phenotypes, residual genotype sums of squares); re-run by the
+// device-only benchmark entry so that the projection is inside the timed region.
+int launch_prep_yx(eqb_ctx *ctx)
+{
+  const int S = ctx->cfg.n_subgroups, ldn = ctx->ldn;
+  const long long M = ctx->cfg.n_snps, G = ctx->cfg.n_genes;
+  double **d_ptrs = ctx->d_prep_ptrs;
+  if (!d_ptrs) return 0;
+  if (G > 0) {
+    prep_y_kernel<<<(unsigned)((G * S + WARPS - 1) / WARPS), THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp,
+                                                                                      d_ptrs + S, d_ptrs + 2 * S);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  if (M > 0) {
+    const unsigned grid = (unsigned)((M + WARPS - 1) / WARPS);
+    const int npl = (ldn + 31) / 32;
+    const int *dup = ctx->d_gt_i + 3 * (int)ctx->phi2L.size();
+    double **xp = d_ptrs + 3 * S;
+    if (npl <= 4) prep_x_kernel<4><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup);
+    else if (npl <= 8) prep_x_kernel<8><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup);
+    else if (npl <= 12) prep_x_kernel<12><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup);
+    else if (npl <= 16) prep_x_kernel<16><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup);
+    else if (npl <= 32) prep_x_kernel<32><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup);
+    else prep_x_kernel<64><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// K1: per-subgroup basis, residual phenotypes and residual genotype sums of squares for the
+// gene-independent masks; decides which genes can take the fast path.
+int prepare_fast_path(eqb_ctx *ctx)
+{
+  const int S = ctx->cfg.n_subgroups, N = ctx->cfg.n_samples_all, ldn = ctx->ldn;
+  const long long M = ctx->cfg.n_snps, G = ctx->cfg.n_genes;
+  ctx->gene_fast.assign(G, 0);
+  ctx->d_Bs.assign(S, nullptr);
+  ctx->d_Ytil.assign(S, nullptr);
+  ctx->d_ystat.assign(S, nullptr);
+  ctx->d_xstat.assign(S, nullptr);
+  ctx->d_emask.assign(S, nullptr);
+  if (ctx->ldn > 32 * 64) return 0; // general path only
+  for (int s = 0; s < S; ++s) {
+    const SubHost &sb = ctx->subs[s];
+    CK(cudaMalloc(&ctx->d_Bs[s], (size_t)(sb.Q + 1) * ldn * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_Ytil[s], std::max<size_t>((size_t)G * ldn, 1) * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_ystat[s], std::max<size_t>((size_t)G * 4, 1) * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_xstat[s], std::max<size_t>((size_t)M * 3, 1) * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_emask[s], ldn));
+    std::vector<uint8_t> em(ldn, 0);
+    for (int i = 0; i < N; ++i) em[i] = sb.all2exp[i] >= 0;
+    CK(cudaMemcpyAsync(ctx->d_emask[s], em.data(), ldn, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  // device arrays of pointers
+  double **d_ptrs = nullptr;
+  uint8_t **d_eptr = nullptr;
+  int *d_ints = nullptr;
+  CK(cudaMalloc(&d_ptrs, (size_t)4 * S * sizeof(double *)));
+  CK(cudaMalloc(&d_eptr, (size_t)S * sizeof(uint8_t *)));
+  CK(cudaMalloc(&d_ints, (size_t)3 * S * sizeof(int)));
+  std::vector<double *> hp(4 * S);
+  for (int s = 0; s < S; ++s) {
+    hp[s] = ctx->d_Bs[s];
+    hp[S + s] = ctx->d_Ytil[s];
+    hp[2 * S + s] = ctx->d_ystat[s];
+    hp[3 * S + s] = ctx->d_xstat[s];
+  }
+  CK(cudaMemcpyAsync(d_ptrs, hp.data(), hp.size() * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_eptr, ctx->d_emask.data(), S * sizeof(uint8_t *), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->d_prep_ptrs = d_ptrs;
+  // unique phi2 table of the gen / gen-fix / gen-maxh rows + duplicate-subgroup map
+  {
+    const int L = (int)ctx->phi2L.size();
+    std::vector<double> uphi, omaL(3 * L);
+    std::vector<int> idxL(3 * L + S);
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < L; ++k) {
+        const double ph = ctx->phi2L[k], om = ctx->oma2L[k];
+        const double phi2 = (r == 0) ? ph : ((r == 1) ? 0.0 : ph + om);
+        const double oma2 = (r == 0) ? om : ((r == 1) ? ph + om : 0.0);
+        int u = -1;
+        for (size_t i = 0; i < uphi.size(); ++i)
+          if (uphi[i] == phi2) u = (int)i;
+        if (u < 0) {
+          u = (int)uphi.size();
+          uphi.push_back(phi2);
+        }
+        idxL[r * L + k] = u;
+        omaL[r * L + k] = oma2;
+      }
+    // dup_of[s]: an earlier subgroup with the same genotype variant, individuals and covariates
+    for (int s = 0; s < S; ++s) {
+      int dup = -1;
+      for (int t = 0; t < s && dup < 0; ++t) {
+        const SubHost &a = ctx->subs[s], &b = ctx->subs[t];
+        if (a.xvar != b.xvar || a.Q != b.Q || a.all2exp.size() != b.all2exp.size()) continue;
+        bool same = true;
+        for (int i = 0; i < N && same; ++i)
+          same = ((a.all2exp[i] >= 0) == (b.all2exp[i] >= 0)) && ((a.all2geno[i] >= 0) == (b.all2geno[i] >= 0));
+        if (same && a.Q > 0) same = (a.covkey == b.covkey);
+        if (same) dup = t;
+      }
+      idxL[3 * L + s] = dup;
+    }
+    std::vector<double> gd(uphi);
+    gd.insert(gd.end(), omaL.begin(), omaL.end());
+    CK(cudaMalloc(&ctx->d_gt_d, std::max<size_t>(gd.size(), 1) * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_gt_i, std::max<size_t>(idxL.size(), 1) * sizeof(int)));
+    CK(cudaMemcpyAsync(ctx->d_gt_d, gd.data(), gd.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_gt_i, idxL.data(), idxL.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->gt.uphi = ctx->d_gt_d;
+    ctx->gt.omaL = ctx->d_gt_d + uphi.size();
+    ctx->gt.idxL = ctx->d_gt_i;
+    ctx->gt.UL = (int)uphi.size();
+  }
+  prep_basis_kernel<<<S, 32, 0, ctx->stream>>>(ctx->d_prm, d_ptrs, d_eptr, d_ints, d_ints + S,
+                                              (unsigned int *)(d_ints + 2 * S), ctx->d_err);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  std::vector<int> hi(3 * S);
+  CK(cudaMemcpyAsync(hi.data(), d_ints, hi.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memset(&ctx->hfp, 0, sizeof(ctx->hfp));
+  for (int s = 0; s < S; ++s) {
+    FastSub &fs = ctx->hfp.sub[s];
+    fs.Bs = ctx->d_Bs[s];
+    fs.Ytil = ctx->d_Ytil[s];
+    fs.ystat = ctx->d_ystat[s];
+    fs.xstat = ctx->d_xstat[s];
+    fs.n = hi[s];
+    fs.rankz = hi[S + s];
+    fs.colvalid = (unsigned int)hi[2 * S + s];
+  }
+  CK(cudaMalloc(&ctx->d_fp, sizeof(FastParams)));
+  CK(cudaMemcpyAsync(ctx->d_fp, &ctx->hfp, sizeof(FastParams), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    int rc2 = launch_prep_yx(ctx);
+    if (rc2) return rc2;
+  }
+  // which genes are generic in every subgroup where they are expressed
+  std::vector<double> ystat((size_t)G * 4);
+  int herr[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(herr, ctx->d_err, sizeof(herr), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint8_t> ok(G, 1);
+  for (int s = 0; s < S; ++s) {
+    CK(cudaMemcpyAsync(ystat.data(), ctx->d_ystat[s], ystat.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (long long g = 0; g < G; ++g)
+      if (ystat[(size_t)g * 4 + 3] == 0.0) ok[g] = 0;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  // a generic mask that keeps an individual without covariates is fatal in the reference only when
+  // such a regression is actually run: let the general path find and report it
+  if (herr[2]) std::fill(ok.begin(), ok.end(), 0);
+  ctx->gene_fast = ok;
+  cudaFree(d_eptr);
+  cudaFree(d_ints);
+  return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -429,8 +607,8 @@ int eqb_create(eqb_ctx **out, const eqb_config *cfg)
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->subs.resize(cfg->n_subgroups);
   ctx->ldn = ((cfg->n_samples_all + 15) / 16) * 16;
-  CK(cudaMalloc(&ctx->d_err, 2 * sizeof(int)));
-  CK(cudaMemset(ctx->d_err, 0, 2 * sizeof(int)));
+  CK(cudaMalloc(&ctx->d_err, 4 * sizeof(int)));
+  CK(cudaMemset(ctx->d_err, 0, 4 * sizeof(int)));
   return 0;
 }
 
@@ -455,6 +633,18 @@ void eqb_destroy(eqb_ctx *ctx)
   }
   for (auto p : ctx->d_X)
     if (p) cudaFree(p);
+  for (auto p : ctx->d_Bs) if (p) cudaFree(p);
+  for (auto p : ctx->d_Ytil) if (p) cudaFree(p);
+  for (auto p : ctx->d_ystat) if (p) cudaFree(p);
+  for (auto p : ctx->d_xstat) if (p) cudaFree(p);
+  for (auto p : ctx->d_emask) if (p) cudaFree(p);
+  if (ctx->d_fp) cudaFree(ctx->d_fp);
+  if (ctx->d_gt_d) cudaFree(ctx->d_gt_d);
+  if (ctx->d_gt_i) cudaFree(ctx->d_gt_i);
+  if (ctx->d_prep_ptrs) cudaFree(ctx->d_prep_ptrs);
+  ctx->d_genes2.release();
+  ctx->d_pair_off2.release();
+  ctx->d_fast_base.release();
   if (ctx->d_prm) cudaFree(ctx->d_prm);
   if (ctx->d_grids) cudaFree(ctx->d_grids);
   if (ctx->d_cfg_mask) cudaFree(ctx->d_cfg_mask);
@@ -527,7 +717,12 @@ int eqb_set_subgroup(eqb_ctx *ctx, int32_t s, const eqb_subgroup *sg)
   const size_t yb = (size_t)G * sg->n_exp_cols * sizeof(double);
   CK(cudaMalloc(&sb.d_Yraw, std::max<size_t>(yb, 8)));
   CK(cudaMemcpyAsync(sb.d_Yraw, sg->Y, yb, cudaMemcpyHostToDevice, ctx->stream));
+  sb.covkey.clear();
   if (sb.Q > 0) {
+    sb.covkey.assign((size_t)sb.Q * N, 0.0);
+    for (int q = 0; q < sb.Q; ++q)
+      for (int i = 0; i < N; ++i)
+        if (sb.all2cov[i] >= 0) sb.covkey[(size_t)q * N + i] = sg->C[(size_t)q * sb.n_cov_cols + sb.all2cov[i]];
     const size_t cbytes = (size_t)sb.Q * sb.n_cov_cols * sizeof(double);
     CK(cudaMalloc(&sb.d_Craw, cbytes));
     CK(cudaMemcpyAsync(sb.d_Craw, sg->C, cbytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -786,6 +981,8 @@ int eqb_finalize(eqb_ctx *ctx)
   CK(cudaMalloc(&ctx->d_prm, sizeof(DevParams)));
   CK(cudaMemcpyAsync(ctx->d_prm, &hp, sizeof(DevParams), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  int rc = prepare_fast_path(ctx);
+  if (rc) return rc;
   ctx->finalized = true;
   return 0;
 }
@@ -807,9 +1004,18 @@ int eqb_pair_offsets(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int64_t *of
 
 int64_t eqb_launch_count(const eqb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int64_t eqb_fast_gene_count(const eqb_ctx *ctx)
+{
+  long long n = 0;
+  if (ctx)
+    for (size_t g = 0; g < ctx->gene_fast.size(); ++g) n += (ctx->gene_fast[g] && ctx->analyzed[g]) ? 1 : 0;
+  return n;
+}
+
 static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_results *res, bool want_raw,
                          bool device_only, float *ms)
 {
+  const bool prep_in_timed_region = true; // K1 (projection) belongs to the measured hot path
   if (!ctx->finalized) return fail(ctx, "eqb_finalize() not called");
   if (gene_lo < 0 || gene_hi > ctx->cfg.n_genes || gene_lo > gene_hi) return fail(ctx, "bad gene range");
   if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model != EQB_ERROR_UVLR)
@@ -826,9 +1032,8 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
   const bool o_n = device_only || (res && res->n), o_ss = device_only || (res && res->sstats);
   const bool o_gen = join && (device_only ? want_raw : (res && res->abf_gen));
   const bool o_cfg = join && C > 0 && (device_only ? want_raw : (res && res->abf_cfg));
-  const bool o_w = join && (device_only || (res && res->abf_w));
   const size_t per_pair = (o_n ? S * 4 : 0) + (o_ss ? S * 40 : 0) + (o_gen ? 3 * L * 8 : 0) +
-                          (o_cfg ? (size_t)C * K * 8 : 0) + (o_w ? (5 + C) * 8 : 0);
+                          (o_cfg ? (size_t)C * K * 8 : 0) + (join ? (5 + C) * 8 : 0);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t budget = std::max<size_t>(64u << 20, std::min<size_t>(free_b / 2, (size_t)24 << 30));
@@ -855,32 +1060,86 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
     long long n_pairs = 0;
     build_work_list(ctx, g0, g1, genes, pair_off, n_pairs);
     if (!genes.empty()) {
-      CK(ctx->d_genes.ensure(genes.size()));
-      CK(ctx->d_pair_off.ensure(genes.size()));
-      CK(cudaMemcpyAsync(ctx->d_genes.p, genes.data(), genes.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(ctx->d_pair_off.p, pair_off.data(), genes.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+      // fast path (gene-independent masks) vs general path
+      std::vector<int> gf, gs;
+      std::vector<long long> pf, ps;
+      for (size_t i = 0; i < genes.size(); ++i) {
+        if (ctx->gene_fast[genes[i]]) {
+          gf.push_back(genes[i]);
+          pf.push_back(pair_off[i]);
+        } else {
+          gs.push_back(genes[i]);
+          ps.push_back(pair_off[i]);
+        }
+      }
       if (o_n) CK(ctx->d_out_n.ensure((size_t)n_pairs * S));
       if (o_ss) CK(ctx->d_ss.ensure((size_t)n_pairs * S * 5));
       if (o_gen) CK(ctx->d_gen.ensure((size_t)n_pairs * 3 * L));
       if (o_cfg) CK(ctx->d_cfg.ensure((size_t)n_pairs * C * K));
-      if (o_w) CK(ctx->d_w.ensure((size_t)n_pairs * (5 + C)));
-      LaunchArgs la;
-      memset(&la, 0, sizeof(la));
-      la.genes = ctx->d_genes.p;
-      la.n_genes = (int)genes.size();
-      la.perms_per_gene = 0;
-      la.which = ctx->cfg.bfs + 1;
-      la.stat_kind = STAT_NONE;
-      la.want_outputs = 1;
-      la.pair_off = ctx->d_pair_off.p;
-      la.out_n = o_n ? ctx->d_out_n.p : nullptr;
-      la.out_ss = o_ss ? ctx->d_ss.p : nullptr;
-      la.out_gen = o_gen ? ctx->d_gen.p : nullptr;
-      la.out_cfg = o_cfg ? ctx->d_cfg.p : nullptr;
-      la.out_w = o_w ? ctx->d_w.p : nullptr;
-      la.err_flag = ctx->d_err;
-      int rc = run_pair_kernel(ctx, la, (long long)genes.size(), 1);
-      if (rc) return rc;
+      if (join) CK(ctx->d_w.ensure((size_t)n_pairs * (5 + C)));
+      if (!gs.empty()) {
+        CK(ctx->d_genes.ensure(gs.size()));
+        CK(ctx->d_pair_off.ensure(gs.size()));
+        CK(cudaMemcpyAsync(ctx->d_genes.p, gs.data(), gs.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_pair_off.p, ps.data(), gs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        LaunchArgs la;
+        memset(&la, 0, sizeof(la));
+        la.genes = ctx->d_genes.p;
+        la.n_genes = (int)gs.size();
+        la.perms_per_gene = 0;
+        la.which = ctx->cfg.bfs + 1;
+        la.stat_kind = STAT_NONE;
+        la.want_outputs = 1;
+        la.pair_off = ctx->d_pair_off.p;
+        la.out_n = o_n ? ctx->d_out_n.p : nullptr;
+        la.out_ss = o_ss ? ctx->d_ss.p : nullptr;
+        la.out_gen = o_gen ? ctx->d_gen.p : nullptr;
+        la.out_cfg = o_cfg ? ctx->d_cfg.p : nullptr;
+        la.out_w = join ? ctx->d_w.p : nullptr;
+        la.err_flag = ctx->d_err;
+        int rc = run_pair_kernel(ctx, la, (long long)gs.size(), 1);
+        if (rc) return rc;
+      }
+      if (!gf.empty()) {
+        CK(ctx->d_genes2.ensure(gf.size()));
+        CK(ctx->d_pair_off2.ensure(gf.size()));
+        CK(cudaMemcpyAsync(ctx->d_genes2.p, gf.data(), gf.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_pair_off2.p, pf.data(), gf.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<long long> fbase(gf.size());
+        long long nfp = 0;
+        for (size_t i = 0; i < gf.size(); ++i) {
+          fbase[i] = nfp;
+          nfp += ctx->ce[gf[i]] - ctx->cb[gf[i]];
+        }
+        CK(ctx->d_fast_base.ensure(gf.size()));
+        CK(cudaMemcpyAsync(ctx->d_fast_base.p, fbase.data(), gf.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        FastArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.genes = ctx->d_genes2.p;
+        fa.n_genes = (int)gf.size();
+        fa.which = ctx->cfg.bfs + 1;
+        fa.n_pairs = nfp;
+        fa.fast_base = ctx->d_fast_base.p;
+        fa.pair_off = ctx->d_pair_off2.p;
+        fa.out_n = o_n ? ctx->d_out_n.p : nullptr;
+        fa.out_ss = o_ss ? ctx->d_ss.p : nullptr;
+        fa.out_gen = o_gen ? ctx->d_gen.p : nullptr;
+        fa.out_cfg = o_cfg ? ctx->d_cfg.p : nullptr;
+        fa.out_w = join ? ctx->d_w.p : nullptr;
+        int T = 64;
+        while (T > 4 && fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which) > 72 * 1024) T /= 2;
+        fa.T = T;
+        const size_t smem = fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which);
+        if (smem > 200 * 1024) return fail(ctx, "configuration table does not fit in shared memory");
+        CK(cudaFuncSetAttribute(fast_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (device_only && prep_in_timed_region) {
+          int rcp = launch_prep_yx(ctx);
+          if (rcp) return rcp;
+        }
+        fast_pair_kernel<<<(unsigned)((nfp + T - 1) / T), THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt);
+        ctx->launches++;
+        CK(cudaGetLastError());
+      }
       if (!device_only) {
         if (res->n)
           CK(cudaMemcpyAsync(res->n + pair_base * S, ctx->d_out_n.p, (size_t)n_pairs * S * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -890,7 +1149,7 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           CK(cudaMemcpyAsync(res->abf_gen + pair_base * 3 * L, ctx->d_gen.p, (size_t)n_pairs * 3 * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
         if (o_cfg)
           CK(cudaMemcpyAsync(res->abf_cfg + pair_base * C * K, ctx->d_cfg.p, (size_t)n_pairs * C * K * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (o_w)
+        if (res->abf_w && join)
           CK(cudaMemcpyAsync(res->abf_w + pair_base * (5 + C), ctx->d_w.p, (size_t)n_pairs * (5 + C) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream)); // buffers are reused by the next chunk
       }

@@ -213,7 +213,7 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
         gs = [g for g in genes if g[1] == chr_names_unsorted[c]]
         if not gs:
             continue
-        lo = min(g[2] for g in gs) - radius
+        lo = max(1, min(g[2] for g in gs) - radius)
         hi = max(g[2] for g in gs) + radius
         pos = lo + snp_step // 2
         while pos <= hi:

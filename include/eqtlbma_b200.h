@@ -157,6 +157,9 @@ int eqb_run_permutations(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
 int eqb_run_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int32_t want_raw, float *ms);
 int eqb_run_permutations_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi,
                                      const eqb_perm_config *pc, float *ms);
+/* Number of genes whose (gene, subgroup) row sets are gene-independent (K1 outputs reusable: the
+ * split projection / contraction path); the others take the general fused kernel. Diagnostic. */
+int64_t eqb_fast_gene_count(const eqb_ctx *ctx);
 /* Number of kernel launches issued by this context so far. */
 int64_t eqb_launch_count(const eqb_ctx *ctx);
 
