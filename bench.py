@@ -75,6 +75,10 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)  # never let nvidia-smi run into the next timed region
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             try:
@@ -151,13 +155,18 @@ def run_ours(args, rank, world, local_rank):
     # ---- device-resident throughput ("value")
     eng = eqtlbma_b200.Engine(ds, **kw)
     pairs = int(eng.pair_offsets()[-1])
-    for _ in range(args.warmup):
-        eng.run_device_only(raw=True)
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_w = time.perf_counter()
+    n_w = 0
+    # at least --warmup untimed steps, and at least ~1.5 s of load so that clocks settle and the
+    # nvidia-smi sampler sees the device under load
+    while n_w < args.warmup or time.perf_counter() - t_w < 1.5:
+        eng.run_device_only(raw=True)
+        n_w += 1
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
     l0 = eng.launch_count()
     ms_list = [eng.run_device_only(raw=True) for _ in range(args.steps)]
     torch.cuda.synchronize()

@@ -30,7 +30,13 @@ struct FastSub {
   int n, rankz;        // kept individuals, rank of [1, covariates]
   unsigned int colvalid;
   int pad;
+  const double *tz;    // [TZ_NI][TZ_NC] Chebyshev coefficients of r(w) = -z(w)/w (see build_tz_kernel), or nullptr
+  double tz_nu;        // degrees of freedom the table was built for
+  double tz_wmax;      // the table is valid for w < tz_wmax
 };
+
+constexpr int TZ_NI = 39; // unit intervals of w in [0, 39)
+constexpr int TZ_NC = 11; // Chebyshev coefficients per interval (degree 10)
 
 struct FastParams {
   FastSub sub[MAXS];
@@ -201,7 +207,8 @@ __global__ void __launch_bounds__(THREADS) prep_y_kernel(const DevParams *__rest
 // matrix, the mask and the covariates (dup_of[s] >= 0) reuse the result of the earlier subgroup.
 template <int NPL>
 __global__ void __launch_bounds__(THREADS) prep_x_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
-                                                         double *const *xstat_all, const int *__restrict__ dup_of)
+                                                         double *const *xstat_all, const int *__restrict__ dup_of,
+                                                         const int fixup_only)
 {
   const DevParams &prm = *prm_;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,7 +227,13 @@ __global__ void __launch_bounds__(THREADS) prep_x_kernel(const DevParams *__rest
       }
       continue;
     }
-    if (dup_of[s] >= 0 && prm.sub[dup_of[s]].snp_has[m]) {
+    if (fixup_only) {
+      if (dup_of[s] >= 0) continue; // aliases the output of an identical earlier subgroup
+      // second pass after the DMMA projection: only the entries whose Gram-form residual lost
+      // accuracy (x nearly inside span([1, covariates])) are recomputed with explicit CGS2
+      const double xx0 = xs[0], xr0 = xs[1];
+      if (!(xr0 > 0.0 && xx0 < 1e-2 * xr0)) continue;
+    } else if (dup_of[s] >= 0 && prm.sub[dup_of[s]].snp_has[m]) {
       // same genotype row, same individuals, same covariates: identical residual
       if (lane == 0) {
         const double *src = xstat_all[dup_of[s]] + (size_t)m * 3;
@@ -288,7 +301,168 @@ __global__ void __launch_bounds__(THREADS) prep_x_kernel(const DevParams *__rest
   }
 }
 
+// ---------------------------------------------------------------- K1c on the FP64 tensor cores
+// H = X * Bcat (projections on every basis column) and R2 = (X o X) * Mcat (masked sums of squares)
+// with mma.sync m8n8k4 f64 (DMMA; tcgen05 has no f64 kind).  One warp = 8 SNP rows; the k index is
+// permuted so that lane (row g, k-slot kk) streams the contiguous quarter kk of its genotype row
+// straight from global memory (16-byte loads), Bcat / Mcat sit in shared memory with a row stride
+// = 1 mod 16 doubles (conflict-free fragment loads).  Gram form: xx = R2 - sum_k H_k^2.
+struct PrepCols {
+  int n_sub;            // subgroups of this chunk
+  int sub[16];          // their indexes
+  int col0[16];         // first basis column of each
+  int ncol[16];         // number of basis columns (Q+1)
+  int mcol[16];         // mask column of each
+  double sqrt_n[16];
+};
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+template <int NT, int NM>
+__global__ void __launch_bounds__(THREADS) prep_x_dmma_kernel(const DevParams *__restrict__ prm_, const double *__restrict__ X,
+                                                              const double *__restrict__ Bcat, const double *__restrict__ Mcat,
+                                                              const PrepCols pc, double *const *xstat_all)
+{
+  const DevParams &prm = *prm_;
+  extern __shared__ double psm[];
+  const int ldn = prm.ldn, ldn4 = ldn >> 2, strideB = ldn + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, kk = lane & 3;
+  double *Bsm = psm;                                  // [NT*8][strideB]
+  double *Msm = Bsm + (size_t)NT * 8 * strideB;       // [NM*8][strideB]
+  double *Hsm = Msm + (size_t)NM * 8 * strideB;       // [WARPS][8][(NT+NM)*8]
+  for (int idx = threadIdx.x; idx < NT * 8 * ldn; idx += THREADS) {
+    const int c = idx / ldn, i = idx % ldn;
+    Bsm[(size_t)c * strideB + i] = Bcat[idx];
+  }
+  for (int idx = threadIdx.x; idx < NM * 8 * ldn; idx += THREADS) {
+    const int c = idx / ldn, i = idx % ldn;
+    Msm[(size_t)c * strideB + i] = Mcat[idx];
+  }
+  __syncthreads();
+  const long long m0 = ((long long)blockIdx.x * WARPS + warp) * 8;
+  if (m0 >= prm.M) return;
+  const long long mrow = min(m0 + g, prm.M - 1);
+  const double *xrow = X + (size_t)mrow * ldn + (size_t)kk * ldn4;
+  const double *brow = Bsm + (size_t)g * strideB + (size_t)kk * ldn4;
+  const double *mrowp = Msm + (size_t)g * strideB + (size_t)kk * ldn4;
+  double c[NT][2], c2[NM][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) c[nt][0] = c[nt][1] = 0.0;
+#pragma unroll
+  for (int nm = 0; nm < NM; ++nm) c2[nm][0] = c2[nm][1] = 0.0;
+#pragma unroll 2
+  for (int t = 0; t < ldn4; t += 2) {
+    const double2 a = *reinterpret_cast<const double2 *>(xrow + t);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      dmma_m8n8k4(c[nt][0], c[nt][1], a.x, brow[(size_t)nt * 8 * strideB + t]);
+      dmma_m8n8k4(c[nt][0], c[nt][1], a.y, brow[(size_t)nt * 8 * strideB + t + 1]);
+    }
+    const double ax2 = a.x * a.x, ay2 = a.y * a.y;
+#pragma unroll
+    for (int nm = 0; nm < NM; ++nm) {
+      dmma_m8n8k4(c2[nm][0], c2[nm][1], ax2, mrowp[(size_t)nm * 8 * strideB + t]);
+      dmma_m8n8k4(c2[nm][0], c2[nm][1], ay2, mrowp[(size_t)nm * 8 * strideB + t + 1]);
+    }
+  }
+  // epilogue through shared memory: per (row, subgroup) xx = R2 - sum H^2, xraw2 = R2, xsum = sqrt(n) H_0
+  const int W = (NT + NM) * 8;
+  double *Hw = Hsm + (size_t)warp * 8 * W;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    Hw[g * W + nt * 8 + 2 * kk] = c[nt][0];
+    Hw[g * W + nt * 8 + 2 * kk + 1] = c[nt][1];
+  }
+#pragma unroll
+  for (int nm = 0; nm < NM; ++nm) {
+    Hw[g * W + NT * 8 + nm * 8 + 2 * kk] = c2[nm][0];
+    Hw[g * W + NT * 8 + nm * 8 + 2 * kk + 1] = c2[nm][1];
+  }
+  __syncwarp();
+  for (int it = lane; it < 8 * pc.n_sub; it += 32) {
+    const int r = it / pc.n_sub, si = it % pc.n_sub;
+    const long long m = m0 + r;
+    if (m >= prm.M) continue;
+    const int s = pc.sub[si];
+    double *xs = xstat_all[s] + (size_t)m * 3;
+    if (!prm.sub[s].snp_has[m]) {
+      xs[0] = 0.0;
+      xs[1] = 0.0;
+      xs[2] = 0.0;
+      continue;
+    }
+    const double *h = Hw + r * W + pc.col0[si];
+    double hh = 0.0;
+    for (int k = 0; k < pc.ncol[si]; ++k) hh += h[k] * h[k];
+    const double r2 = Hw[r * W + NT * 8 + pc.mcol[si]];
+    xs[0] = r2 - hh;
+    xs[1] = r2;
+    xs[2] = pc.sqrt_n[si] * h[0];
+  }
+}
+
 // ---------------------------------------------------------------- K2 + K3
+// ---------------------------------------------------------------- Student-t -> normal score table
+// The standardisation maps |t| (nu degrees of freedom) to z = Phi^-1(T_nu(-|t|))
+// (gene_snp_pair.cpp:273-274).  In the variable w = sqrt(nu log1p(t^2/nu)) the ratio r(w) = -z/w is
+// a smooth function close to 1; it is tabulated per subgroup (nu is shared by every pair of the
+// subgroup on this path) as piecewise Chebyshev series fitted to the exact evaluation
+// (tdist_P + ugaussian_Pinv), |error| ~ 1e-13, so that the per-pair cost is one short Clenshaw
+// recurrence instead of a data-dependent continued fraction.  p-value = 2 Phi(z) = erfc(|z|/sqrt 2).
+__global__ void __launch_bounds__(TZ_NI * 16) build_tz_kernel(const double *__restrict__ nus, double *const *tz_all,
+                                                              double *__restrict__ wmax_out)
+{
+  __shared__ double f[TZ_NI][16];
+  __shared__ int bad[TZ_NI];
+  const int s = blockIdx.x, iv = threadIdx.x / 16, k = threadIdx.x % 16;
+  const double nu = nus[s];
+  if (k == 0) bad[iv] = 0;
+  __syncthreads();
+  if (k < TZ_NC && nu > 0.0) {
+    const double x = cospi((k + 0.5) / TZ_NC);
+    const double w = iv + 0.5 + 0.5 * x;
+    const double a = sqrt(nu * expm1(w * w / nu));
+    const double z = ugaussian_Pinv(tdist_P(-a, nu));
+    const double r = -z / w;
+    f[iv][k] = r;
+    if (!(fabs(r) < 1e300)) atomicExch(&bad[iv], 1);
+  }
+  __syncthreads();
+  if (k < TZ_NC && nu > 0.0) {
+    double c = 0.0;
+    for (int j = 0; j < TZ_NC; ++j) c += f[iv][j] * cospi(k * (j + 0.5) / TZ_NC);
+    c *= 2.0 / TZ_NC;
+    if (k == 0) c *= 0.5;
+    tz_all[s][iv * TZ_NC + k] = c;
+  }
+  if (threadIdx.x == 0) {
+    int first_bad = TZ_NI;
+    for (int i = TZ_NI - 1; i >= 0; --i)
+      if (bad[i]) first_bad = i;
+    wmax_out[s] = (nu > 0.0) ? (double)first_bad : 0.0;
+  }
+}
+
+__device__ __forceinline__ double tz_eval(const double *__restrict__ tz, double w)
+{
+  const int iv = (int)w;
+  const double x = 2.0 * (w - iv) - 1.0;
+  const double *c = tz + iv * TZ_NC;
+  double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+  for (int j = TZ_NC - 1; j >= 1; --j) {
+    const double t = 2.0 * x * b1 - b2 + c[j];
+    b2 = b1;
+    b1 = t;
+  }
+  return x * b1 - b2 + c[0];
+}
+
 // per-thread standardisation + summary statistics of one (pair, subgroup)
 struct PairStat {
   double pve, sigmahat, betahat, se, pval; // outputs of utils::FitSingleGeneWithSingleSnp
@@ -296,7 +470,8 @@ struct PairStat {
 };
 
 __device__ __noinline__ void stats_from_dots(double xy, double xx, double xraw2, double xsum, double yy, double tss,
-                                             double ybar, int n, int Q, int rankz, PairStat &o)
+                                             double ybar, int n, int Q, int rankz, const double *__restrict__ tz,
+                                             double tz_nu, double tz_wmax, PairStat &o)
 {
   const double qn = nan("");
   o.pve = o.sigmahat = o.betahat = o.se = o.pval = qn;
@@ -335,21 +510,34 @@ __device__ __noinline__ void stats_from_dots(double xy, double xx, double xraw2,
       return; // documented unsupported degenerate design (NaN)
   }
   const double tt = o.betahat / o.se;
-  double central;
-  if (!isnan(tt)) {
-    tdist_tails(fabs(tt), (double)(n - rank), tail, central);
-    o.pval = (fabs(tt) > 0.0) ? tail : 1.0; // 2 * gsl_cdf_tdist_Q(|t|, n - rank)
-  }
-  // standardisation
   double bhat = o.betahat / o.sigmahat, sebhat = o.se / o.sigmahat, t = bhat / sebhat;
-  if (isnan(t)) return;
   const double nu = (double)n - 2.0 - Q;
-  double P;
-  if (nu == (double)(n - rank) && !isnan(tail))
-    P = (t == 0.0) ? 0.5 : 0.5 * tail; // gsl_cdf_tdist_P(-|t|, nu) shares the tail
-  else
-    P = tdist_P(-fabs(t), nu);
-  t = ugaussian_Pinv(P);
+  bool done = false;
+  if (tz != nullptr && !isnan(tt) && !isnan(t) && nu == (double)(n - rank) && nu == tz_nu) {
+    // tabulated map |t| -> z (same degrees of freedom for the p-value and the standardisation)
+    const double a = fabs(t);
+    const double w = sqrt(nu * log1p(a * a / nu));
+    if (w < tz_wmax) {
+      const double z = (w > 0.0) ? -w * tz_eval(tz, w) : 0.0;
+      o.pval = (fabs(tt) > 0.0) ? erfc(-z * 0.70710678118654752440) : 1.0;
+      t = z;
+      done = true;
+    }
+  }
+  if (!done) {
+    double central;
+    if (!isnan(tt)) {
+      tdist_tails(fabs(tt), (double)(n - rank), tail, central);
+      o.pval = (fabs(tt) > 0.0) ? tail : 1.0; // 2 * gsl_cdf_tdist_Q(|t|, n - rank)
+    }
+    if (isnan(t)) return;
+    double P;
+    if (nu == (double)(n - rank) && !isnan(tail))
+      P = (t == 0.0) ? 0.5 : 0.5 * tail; // gsl_cdf_tdist_P(-|t|, nu) shares the tail
+    else
+      P = tdist_P(-fabs(t), nu);
+    t = ugaussian_Pinv(P);
+  }
   if (fabs(t) > 1e-8) {
     const double sg2 = fabs(o.betahat) / (fabs(t) * sebhat);
     bhat = o.betahat / sg2;
@@ -421,8 +609,7 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
   double *xy = fsm;                                          // [T][S]
   double *st = xy + (size_t)T * S;                           // [T][3][S]
   double *agg = st + (size_t)T * 3 * S;                      // [T][UL][3]
-  double *vals = agg + (size_t)T * UL * 3;                   // [T][vals_per_pair]
-  double *wrow = vals + (size_t)T * vals_per_pair;           // [T][3+S] weighted small rows
+  double *wrow = agg + (size_t)T * UL * 3;                   // [T][3+S] weighted small rows
   double *tab = wrow + (size_t)T * (3 + S);                  // [T][K][S][3] (which == 3)
   unsigned long long *hasm = (unsigned long long *)(tab + ((fa.which == 3) ? (size_t)T * K * S * 3 : 0)); // [T]
   long long *s_pair = (long long *)(hasm + T);               // [T] output pair index
@@ -459,11 +646,14 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
       for (int a = 1; a < sn; ++a) same = same && (prm.sub[s0 + a].X == prm.sub[s0].X);
       if (same) {
         const double *Xm = prm.sub[s0].X + (size_t)m * ldn;
+        const double *yp[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) yp[a] = fp_->sub[s0 + min(a, sn - 1)].Ytil + grow;
         for (int i = lane; i < ldn; i += 32) {
           const double x = Xm[i];
 #pragma unroll
           for (int a = 0; a < 8; ++a)
-            if (a < sn) acc[a] += x * fp_->sub[s0 + a].Ytil[grow + i];
+            if (a < sn) acc[a] += x * yp[a][i];
         }
       } else {
         for (int a = 0; a < sn; ++a) {
@@ -501,7 +691,8 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
     ps.b = ps.v = ps.t = nan("");
     if (have) {
       const double *xs = fs.xstat + (size_t)m * 3;
-      stats_from_dots(xy[(size_t)j * S + s], xs[0], xs[1], xs[2], ys[0], ys[1], ys[2], fs.n, sb.Q, fs.rankz, ps);
+      stats_from_dots(xy[(size_t)j * S + s], xs[0], xs[1], xs[2], ys[0], ys[1], ys[2], fs.n, sb.Q, fs.rankz, fs.tz, fs.tz_nu,
+                      fs.tz_wmax, ps);
       atomicOr(&hasm[j], 1ull << s);
     }
     st[((size_t)j * 3 + 0) * S + s] = ps.b;
@@ -564,7 +755,7 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
     if (e < 3 * L) {
       const double *a = agg + ((size_t)j * UL + gt.idxL[e]) * 3;
       v = abf_from_sums(a[0], a[1], a[2], gt.omaL[e]);
-      if (fa.out_gen) fa.out_gen[pair * 3 * L + e] = v;
+      fa.out_gen[pair * 3 * L + e] = v; // staged in global memory (L1/L2 resident), re-read in phase C2
     } else {
       const int e2 = e - 3 * L, c = e2 / K, k = e2 % K;
       const double *stj = st + (size_t)j * 3 * S;
@@ -574,16 +765,15 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
         term_entry(stj[c], stj[S + c], stj[2 * S + c], prm.phi2S[k], d, bd, sg);
         v = abf_from_sums(d, bd, sg, prm.oma2S[k]);
       }
-      if (fa.out_cfg) fa.out_cfg[(pair * C + c) * K + k] = v;
+      fa.out_cfg[(pair * C + c) * K + k] = v;
     }
-    vals[(size_t)j * vals_per_pair + e] = v;
   }
   __syncthreads();
   // ---------------- phase C2: log10_weighted_sum of each staged row (utils_math.cpp:100-131)
   for (int it = threadIdx.x; it < tn * nrow_small; it += THREADS) {
     const int j = it / nrow_small, r = it % nrow_small;
     const int nk = (r < 3) ? L : K;
-    const double *v = vals + (size_t)j * vals_per_pair + ((r < 3) ? r * L : 3 * L + (r - 3) * K);
+    const double *v = (r < 3) ? fa.out_gen + (s_pair[j] * 3 + r) * L : fa.out_cfg + (s_pair[j] * C + (r - 3)) * K;
     Lse a;
     a.init();
     for (int k = 0; k < nk; ++k) a.add(v[k], 1.0 / (double)nk, k == 0);
@@ -660,8 +850,8 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
 // shared-memory bytes of fast_pair_kernel for a tile of T pairs
 __host__ __device__ inline size_t fast_smem_bytes(int T, int S, int L, int K, int UL, int which)
 {
-  size_t d = (size_t)T * S + (size_t)T * 3 * S + (size_t)T * UL * 3 +
-             (size_t)T * (3 * L + (which == 2 ? S * K : 0)) + (size_t)T * (3 + S);
+  size_t d = (size_t)T * S + (size_t)T * 3 * S + (size_t)T * UL * 3 + (size_t)T * (3 + S);
+  (void)L;
   if (which == 3) d += (size_t)T * K * S * 3;
   return d * 8 + (size_t)T * (8 + 8 + 8 + 4) + 16;
 }
