@@ -318,7 +318,7 @@ struct PrepCols {
 
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
 {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
@@ -355,9 +355,29 @@ __global__ void __launch_bounds__(THREADS) prep_x_dmma_kernel(const DevParams *_
   for (int nt = 0; nt < NT; ++nt) c[nt][0] = c[nt][1] = 0.0;
 #pragma unroll
   for (int nm = 0; nm < NM; ++nm) c2[nm][0] = c2[nm][1] = 0.0;
-#pragma unroll 2
-  for (int t = 0; t < ldn4; t += 2) {
-    const double2 a = *reinterpret_cast<const double2 *>(xrow + t);
+  // software-pipelined main loop: 4 independent 16-byte genotype loads in flight per lane
+  int t = 0;
+  for (; t + 8 <= ldn4; t += 8) {
+    double2 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = __ldcs(reinterpret_cast<const double2 *>(xrow + t + 2 * u));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        dmma_m8n8k4(c[nt][0], c[nt][1], a[u].x, brow[(size_t)nt * 8 * strideB + t + 2 * u]);
+        dmma_m8n8k4(c[nt][0], c[nt][1], a[u].y, brow[(size_t)nt * 8 * strideB + t + 2 * u + 1]);
+      }
+      const double ax2 = a[u].x * a[u].x, ay2 = a[u].y * a[u].y;
+#pragma unroll
+      for (int nm = 0; nm < NM; ++nm) {
+        dmma_m8n8k4(c2[nm][0], c2[nm][1], ax2, mrowp[(size_t)nm * 8 * strideB + t + 2 * u]);
+        dmma_m8n8k4(c2[nm][0], c2[nm][1], ay2, mrowp[(size_t)nm * 8 * strideB + t + 2 * u + 1]);
+      }
+    }
+  }
+  for (; t < ldn4; t += 2) {
+    const double2 a = __ldcs(reinterpret_cast<const double2 *>(xrow + t));
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       dmma_m8n8k4(c[nt][0], c[nt][1], a.x, brow[(size_t)nt * 8 * strideB + t]);
@@ -570,9 +590,9 @@ __device__ __forceinline__ double abf_from_sums(double den, double num, double s
   const double V = (den != 0.0) ? 1.0 / den : INFINITY;
   if (bbar != 0.0 && V < INFINITY) {
     const double T2 = bbar * bbar / V;
-    if (T2 == 0.0) return sing;
-    const double z = 1.0 + oma2 * den;
-    return sing + (-0.5 * log1p(oma2 * den) + 0.5 * num * num * oma2 / z) / LN10;
+    if (T2 == 0.0 || oma2 == 0.0) return sing; // (a zero numerator would take the slow division path)
+    const double od = oma2 * den;
+    return sing + (-0.5 * log1p(od) + 0.5 * num * num * oma2 / (1.0 + od)) / LN10;
   }
   return 0.0;
 }
@@ -589,7 +609,7 @@ __device__ __forceinline__ void term_entry(double b, double v, double t, double 
     const double inv = 1.0 / (v + phi2);
     d = inv;
     bd = b * inv;
-    sg = (-0.5 * log1p(phi2 / v) + 0.5 * t * t * phi2 * inv) / LN10;
+    sg = (phi2 == 0.0) ? 0.0 : (-0.5 * log1p(phi2 / v) + 0.5 * t * t * phi2 * inv) / LN10;
   }
 }
 
