@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "fast_kernels.cuh"
+#include "mvlr_kernel.cuh"
 
 using namespace eqb;
 
@@ -212,13 +213,14 @@ __global__ void cis_window_kernel(const int *__restrict__ gene_chr, const long l
 // (gene[, subgroup]) walks its permuted statistics in order.
 __global__ void perm_count_kernel(const double *__restrict__ stat, const double *__restrict__ truth, long long P,
                                   long long n_rows, int join, int trick, int tricut, long long *__restrict__ count,
-                                  long long *__restrict__ done, long long *__restrict__ total_eff)
+                                  long long *__restrict__ done, long long *__restrict__ total_eff,
+                                  long long *__restrict__ consumed)
 {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const double *st = stat + (size_t)r * P;
   const double tv = truth[r];
-  long long cnt = 1, nd = 0, nan_seen = 0;
+  long long cnt = 1, nd = 0, nan_seen = 0, used = P;
   for (long long p = 0; p < P; ++p) {
     const double v = st[p];
     if (isnan(v)) {
@@ -227,11 +229,15 @@ __global__ void perm_count_kernel(const double *__restrict__ stat, const double 
     }
     nd++;
     if (join ? (v >= tv) : (v <= tv)) cnt++;
-    if (trick != 0 && cnt == 1 + tricut) break;
+    if (trick != 0 && cnt == 1 + tricut) {
+      used = p + 1; // --trick 1 leaves the loop here: p+1 shuffles of the generator were consumed
+      break;
+    }
   }
   count[r] = cnt;
   done[r] = nd;
   total_eff[r] = P - nan_seen;
+  consumed[r] = used;
 }
 
 struct SubHost {
@@ -299,8 +305,8 @@ struct eqb_ctx {
   long long launches = 0;
   // work buffers (grow-only)
   DevBuf<int> d_genes, d_slots, d_out_n;
-  DevBuf<long long> d_pair_off, d_count, d_done, d_total;
-  DevBuf<double> d_ss, d_gen, d_cfg, d_w, d_stat, d_true, d_basis_ws, d_table_ws;
+  DevBuf<long long> d_pair_off, d_count, d_done, d_total, d_consumed;
+  DevBuf<double> d_ss, d_gen, d_cfg, d_w, d_stat, d_stat2, d_true, d_basis_ws, d_table_ws;
   DevBuf<unsigned short> d_perm;
   // fast path (gene-independent masks): K1 outputs
   FastParams hfp;
@@ -321,6 +327,7 @@ struct eqb_ctx {
   uint64_t perm_seed = 0;
   long long perm_P = -1;
   int perm_slots = 0;
+  int perm_N = 0;
 };
 
 namespace {
@@ -378,9 +385,39 @@ cudaError_t launch_pair(eqb_ctx *ctx, const LaunchArgs &la, int grid, size_t sme
   return cudaGetLastError();
 }
 
+template <int NPL>
+cudaError_t launch_mvlr(eqb_ctx *ctx, const LaunchArgs &la, int grid, size_t smem)
+{
+  cudaError_t e = cudaFuncSetAttribute(mvlr_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  mvlr_kernel<NPL><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, la);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+int run_mvlr_kernel(eqb_ctx *ctx, const LaunchArgs &la, int ppg)
+{
+  const int S = ctx->cfg.n_subgroups;
+  if (S > MV_MAXS) return fail(ctx, "--error mvlr supports at most 16 subgroups on the device");
+  const size_t smem = mvlr_smem_doubles(S, ctx->Qmax, ctx->ldn) * sizeof(double);
+  if (smem > 200 * 1024) return fail(ctx, "--error mvlr: too many samples x subgroups for shared memory");
+  const long long grid = (long long)la.n_genes * std::max(1, ppg);
+  const int npl_need = (ctx->ldn + 31) / 32;
+  cudaError_t e;
+  if (npl_need <= 4) e = launch_mvlr<4>(ctx, la, (int)grid, smem);
+  else if (npl_need <= 8) e = launch_mvlr<8>(ctx, la, (int)grid, smem);
+  else if (npl_need <= 16) e = launch_mvlr<16>(ctx, la, (int)grid, smem);
+  else if (npl_need <= 32) e = launch_mvlr<32>(ctx, la, (int)grid, smem);
+  else if (npl_need <= 64) e = launch_mvlr<64>(ctx, la, (int)grid, smem);
+  else return fail(ctx, "more than 2048 samples are not supported yet");
+  if (e != cudaSuccess) return fail(ctx, std::string("mvlr_kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 // picks workspaces (shared memory when they fit, else global) and the row-register template
 int run_pair_kernel(eqb_ctx *ctx, LaunchArgs la, long long n_ctas_total, int ppg)
 {
+  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model == EQB_ERROR_MVLR) return run_mvlr_kernel(ctx, la, ppg);
   const int S = ctx->cfg.n_subgroups;
   const size_t nb = basis_doubles(S, ctx->Qmax, ctx->ldn, ctx->cfg.qnorm) * sizeof(double);
   const size_t nt = table_doubles(S, (int)ctx->phi2S.size()) * sizeof(double) * WARPS;
@@ -434,11 +471,12 @@ int run_pair_kernel(eqb_ctx *ctx, LaunchArgs la, long long n_ctas_total, int ppg
 
 int check_device_errors(eqb_ctx *ctx)
 {
-  int h[2] = {0, 0};
+  int h[4] = {0, 0, 0, 0};
   if (cudaMemcpyAsync(h, ctx->d_err, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
       cudaStreamSynchronize(ctx->stream) != cudaSuccess)
     return fail(ctx, std::string("device error: ") + cudaGetErrorString(cudaGetLastError()));
   if (h[0]) return fail(ctx, "ERROR: missing covariate for a sample kept in the regression (gene_snp_pair.cpp:138-144)");
+  if (h[3]) return fail(ctx, "ERROR: --error mvlr requires the same individuals in every subgroup");
   return 0;
 }
 
@@ -584,6 +622,7 @@ int prepare_fast_path(eqb_ctx *ctx)
   ctx->d_xstat.assign(S, nullptr);
   ctx->d_emask.assign(S, nullptr);
   if (ctx->ldn > 32 * 64) return 0; // general path only
+  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model == EQB_ERROR_MVLR) return 0; // MVLR kernel only
   for (int s = 0; s < S; ++s) {
     const SubHost &sb = ctx->subs[s];
     CK(dmalloc(&ctx->d_Bs[s], (size_t)(sb.Q + 1) * ldn * sizeof(double)));
@@ -818,6 +857,8 @@ void eqb_destroy(eqb_ctx *ctx)
   ctx->d_count.release();
   ctx->d_done.release();
   ctx->d_total.release();
+  ctx->d_consumed.release();
+  ctx->d_stat2.release();
   ctx->d_ss.release();
   ctx->d_gen.release();
   ctx->d_cfg.release();
@@ -1185,8 +1226,6 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
   const bool prep_in_timed_region = true; // K1 (projection) belongs to the measured hot path
   if (!ctx->finalized) return fail(ctx, "eqb_finalize() not called");
   if (gene_lo < 0 || gene_hi > ctx->cfg.n_genes || gene_lo > gene_hi) return fail(ctx, "bad gene range");
-  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model != EQB_ERROR_UVLR)
-    return fail(ctx, "--error mvlr is not implemented on the device yet");
   CK(cudaSetDevice(ctx->cfg.device));
   const int S = ctx->cfg.n_subgroups;
   const bool join = ctx->cfg.analysis == EQB_ANALYSIS_JOIN;
@@ -1345,6 +1384,55 @@ int eqb_run_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int32_t 
   return run_true_impl(ctx, gene_lo, gene_hi, nullptr, want_raw != 0, true, ms);
 }
 
+// device evaluation of a set of (gene, permutation table) items: statistic of the true data, the P
+// permuted statistics, and the exceedance counters
+static int eval_perm_items(eqb_ctx *ctx, const std::vector<int> &genes, const std::vector<int> &tab_idx,
+                           const eqb_perm_config *pc, int kind, size_t row0)
+{
+  const int S = ctx->cfg.n_subgroups;
+  const bool join = ctx->cfg.analysis == EQB_ANALYSIS_JOIN;
+  const long long P = pc->nperm;
+  const int per = (kind == STAT_SEP_PER) ? S : 1;
+  const size_t n_items = genes.size();
+  if (n_items == 0) return 0;
+  CK(ctx->d_genes.ensure(n_items));
+  CK(ctx->d_slots.ensure(n_items));
+  CK(cudaMemcpyAsync(ctx->d_genes.p, genes.data(), n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_slots.p, tab_idx.data(), n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  LaunchArgs la;
+  memset(&la, 0, sizeof(la));
+  la.genes = ctx->d_genes.p;
+  la.n_genes = (int)n_items;
+  la.gene_slot = ctx->d_slots.p;
+  la.perm_tab = ctx->d_perm.p;
+  la.P_total = P;
+  la.which = join ? pc->pbf : 1;
+  la.stat_kind = kind;
+  la.err_flag = ctx->d_err;
+  la.perms_per_gene = 0;
+  la.true_rules = 1; // statistic of the true data: identity permutation, the reference's true-data rules
+  la.out_stat = ctx->d_true.p + row0 * 1;
+  int rc = run_pair_kernel(ctx, la, (long long)n_items, 1);
+  if (rc) return rc;
+  la.true_rules = 0;
+  la.out_stat = ctx->d_stat.p + row0 * (size_t)P;
+  const long long max_grid = 1LL << 22;
+  const long long pcnk = std::max<long long>(1, std::min<long long>(P, max_grid / (long long)n_items));
+  for (long long p0 = 0; p0 < P; p0 += pcnk) {
+    la.p0 = p0;
+    la.perms_per_gene = (int)std::min<long long>(pcnk, P - p0);
+    rc = run_pair_kernel(ctx, la, (long long)n_items * la.perms_per_gene, la.perms_per_gene);
+    if (rc) return rc;
+  }
+  const long long n_rows = (long long)n_items * per;
+  perm_count_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>(
+      ctx->d_stat.p + row0 * (size_t)P, ctx->d_true.p + row0, P, n_rows, join ? 1 : 0, pc->trick, pc->tricut,
+      ctx->d_count.p + row0, ctx->d_done.p + row0, ctx->d_total.p + row0, ctx->d_consumed.p + row0);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const eqb_perm_config *pc,
                          eqb_perm_results *res, bool device_only, float *ms)
 {
@@ -1353,9 +1441,7 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
   if (gene_lo < 0 || gene_hi > ctx->cfg.n_genes || gene_lo > gene_hi) return fail(ctx, "bad gene range");
   if (pc->wrtsize <= 0 || gene_lo % pc->wrtsize != 0) return fail(ctx, "gene_lo must be a multiple of wrtsize");
   if (pc->nperm <= 0) return fail(ctx, "nperm must be positive");
-  if (pc->trick == 1) return fail(ctx, "--trick 1 is not implemented on the device yet");
   const bool join = ctx->cfg.analysis == EQB_ANALYSIS_JOIN;
-  if (join && ctx->cfg.error_model != EQB_ERROR_UVLR) return fail(ctx, "--error mvlr is not implemented on the device yet");
   if (join && (pc->pbf < EQB_PBF_GEN || pc->pbf > EQB_PBF_ALL)) return fail(ctx, "bad --pbf");
   if (join && pc->pbf > ctx->cfg.bfs + 1) return fail(ctx, "--pbf needs Bayes factors that --bfs does not compute");
   if (!join && pc->permsep != 1 && pc->permsep != 2) return fail(ctx, "bad --permsep");
@@ -1368,14 +1454,15 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
   const double qnan = std::numeric_limits<double>::quiet_NaN();
 
   // work list + slot of each analysed gene inside its write-group (skipped genes consume no RNG)
-  std::vector<int> genes, slots;
-  int max_slot = -1;
-  for (long long g0 = gene_lo; g0 < gene_hi; g0 += pc->wrtsize) {
+  std::vector<int> genes, slots, group_of;
+  int max_slot = -1, n_groups = 0;
+  for (long long g0 = gene_lo; g0 < gene_hi; g0 += pc->wrtsize, ++n_groups) {
     int slot = 0;
     for (long long g = g0; g < std::min<long long>(g0 + pc->wrtsize, gene_hi); ++g) {
       if (!ctx->analyzed[g]) continue;
       genes.push_back((int)g);
       slots.push_back(slot);
+      group_of.push_back(n_groups);
       max_slot = std::max(max_slot, slot);
       ++slot;
     }
@@ -1396,39 +1483,13 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
     if (ms) *ms = 0.f;
     return 0;
   }
-
-  // permutation tables: table[slot][p] = cumulative gsl_ran_shuffle of the identity, the generator
-  // being seeded once per write-group and running on across the genes of the group
-  const int n_slots = max_slot + 1;
-  if (ctx->perm_seed != pc->seed || ctx->perm_P != P || ctx->perm_slots < n_slots) {
-    std::vector<unsigned short> tab((size_t)n_slots * P * N);
-    Mt19937 rng;
-    rng.seed(pc->seed);
-    std::vector<unsigned short> perm(N);
-    for (int sl = 0; sl < n_slots; ++sl) {
-      for (int i = 0; i < N; ++i) perm[i] = (unsigned short)i;
-      for (long long p = 0; p < P; ++p) {
-        rng.shuffle(perm.data(), N);
-        memcpy(&tab[((size_t)sl * P + p) * N], perm.data(), N * sizeof(unsigned short));
-      }
-    }
-    CK(ctx->d_perm.ensure(tab.size()));
-    CK(cudaMemcpyAsync(ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->perm_seed = pc->seed;
-    ctx->perm_P = P;
-    ctx->perm_slots = n_slots;
-  }
-
-  CK(ctx->d_genes.ensure(n_items));
-  CK(ctx->d_slots.ensure(n_items));
-  CK(cudaMemcpyAsync(ctx->d_genes.p, genes.data(), n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_slots.p, slots.data(), n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CK(ctx->d_stat.ensure(n_items * per * (size_t)P));
-  CK(ctx->d_true.ensure(n_items * per));
-  CK(ctx->d_count.ensure(n_items * per));
-  CK(ctx->d_done.ensure(n_items * per));
-  CK(ctx->d_total.ensure(n_items * per));
+  const long long n_rows = (long long)n_items * per;
+  CK(ctx->d_stat.ensure((size_t)n_rows * (size_t)P));
+  CK(ctx->d_true.ensure(n_rows));
+  CK(ctx->d_count.ensure(n_rows));
+  CK(ctx->d_done.ensure(n_rows));
+  CK(ctx->d_total.ensure(n_rows));
+  CK(ctx->d_consumed.ensure(n_rows));
 
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ms) {
@@ -1436,39 +1497,135 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
     CK(cudaEventCreate(&ev1));
     CK(cudaEventRecord(ev0, ctx->stream));
   }
-  LaunchArgs la;
-  memset(&la, 0, sizeof(la));
-  la.genes = ctx->d_genes.p;
-  la.n_genes = (int)n_items;
-  la.gene_slot = ctx->d_slots.p;
-  la.perm_tab = ctx->d_perm.p;
-  la.P_total = P;
-  la.which = join ? pc->pbf : 1;
-  la.stat_kind = kind;
-  la.err_flag = ctx->d_err;
-  // statistic of the true data (identity permutation, the reference's true-data rules)
-  la.perms_per_gene = 0;
-  la.true_rules = 1;
-  la.out_stat = ctx->d_true.p;
-  int rc = run_pair_kernel(ctx, la, (long long)n_items, 1);
-  if (rc) return rc;
-  // permuted statistics, in chunks of permutations
-  la.true_rules = 0;
-  la.out_stat = ctx->d_stat.p;
-  const long long max_grid = 1LL << 22;
-  long long pcnk = std::max<long long>(1, std::min<long long>(P, max_grid / (long long)n_items));
-  for (long long p0 = 0; p0 < P; p0 += pcnk) {
-    la.p0 = p0;
-    la.perms_per_gene = (int)std::min<long long>(pcnk, P - p0);
-    rc = run_pair_kernel(ctx, la, (long long)n_items * la.perms_per_gene, la.perms_per_gene);
+  const int n_slots = max_slot + 1;
+  if (pc->trick != 1 || kind == STAT_SEP_PER) {
+    if (pc->trick == 1) return fail(ctx, "--trick 1 with --permsep 2 is not implemented on the device yet");
+    // --trick 0|2: every gene consumes exactly P shuffles, so the k-th analysed gene of any
+    // write-group sees table[k][p] = cumulative gsl_ran_shuffle of the identity, the generator being
+    // seeded once per write-group and running on across its genes (eqtlbma_bf.cpp:847, gene.cpp:617-639)
+    if (ctx->perm_seed != pc->seed || ctx->perm_P != P || ctx->perm_slots < n_slots || ctx->perm_N != N) {
+      std::vector<unsigned short> tab((size_t)n_slots * P * N);
+      Mt19937 rng;
+      rng.seed(pc->seed);
+      std::vector<unsigned short> perm(N);
+      for (int sl = 0; sl < n_slots; ++sl) {
+        for (int i = 0; i < N; ++i) perm[i] = (unsigned short)i;
+        for (long long p = 0; p < P; ++p) {
+          rng.shuffle(perm.data(), N);
+          memcpy(&tab[((size_t)sl * P + p) * N], perm.data(), N * sizeof(unsigned short));
+        }
+      }
+      CK(ctx->d_perm.ensure(tab.size()));
+      CK(cudaMemcpyAsync(ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      ctx->perm_seed = pc->seed;
+      ctx->perm_P = P;
+      ctx->perm_slots = n_slots;
+      ctx->perm_N = N;
+    }
+    int rc = eval_perm_items(ctx, genes, slots, pc, kind, 0);
     if (rc) return rc;
+  } else {
+    // --trick 1: a gene stops at its (1+tricut)-th exceedance, so the generator position at which the
+    // next gene of the write-group starts depends on the data.  Write-groups are
+    // independent (each re-seeds): rounds over the slot index, per-gene tables built from the master
+    // stream of Fisher-Yates swap targets at the offset where the previous gene of the group stopped.
+    ctx->perm_P = -1; // the cached --trick 0|2 tables are overwritten
+    Mt19937 rng;
+    rng.seed(pc->seed);
+    std::vector<std::vector<unsigned short> > swaps; // swaps[q][i] = target j of position i in the q-th shuffle
+    auto need_swaps = [&](size_t upto) {
+      while (swaps.size() < upto) {
+        std::vector<unsigned short> sw(N, 0);
+        for (int i = N - 1; i > 0; --i) sw[i] = (unsigned short)rng.uniform_int((uint32_t)i + 1);
+        swaps.push_back(sw);
+      }
+    };
+    std::vector<long long> group_off(n_groups, 0);
+    std::vector<long long> h_consumed;
+    for (int k = 0; k < n_slots; ++k) {
+      std::vector<int> it_idx;
+      for (size_t i = 0; i < n_items; ++i)
+        if (slots[i] == k) it_idx.push_back((int)i);
+      // process the round in sub-batches of distinct offsets to bound the table memory
+      size_t pos = 0;
+      while (pos < it_idx.size()) {
+        std::map<long long, int> off2tab;
+        std::vector<int> bg, bt;
+        std::vector<int> bidx;
+        const size_t max_tabs = std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)P * N * 2));
+        while (pos < it_idx.size()) {
+          const int i = it_idx[pos];
+          const long long o = group_off[group_of[i]];
+          if (off2tab.find(o) == off2tab.end()) {
+            if (off2tab.size() >= max_tabs) break;
+            const int t = (int)off2tab.size();
+            off2tab[o] = t;
+          }
+          bg.push_back(genes[i]);
+          bt.push_back(off2tab[o]);
+          bidx.push_back(i);
+          ++pos;
+        }
+        std::vector<unsigned short> tab(off2tab.size() * (size_t)P * N);
+        std::vector<unsigned short> perm(N);
+        for (auto &kv : off2tab) {
+          need_swaps((size_t)(kv.first + P));
+          for (int i = 0; i < N; ++i) perm[i] = (unsigned short)i;
+          for (long long p = 0; p < P; ++p) {
+            const std::vector<unsigned short> &sw = swaps[(size_t)(kv.first + p)];
+            for (int i = N - 1; i > 0; --i) std::swap(perm[i], perm[sw[i]]);
+            memcpy(&tab[((size_t)kv.second * P + p) * N], perm.data(), N * sizeof(unsigned short));
+          }
+        }
+        CK(ctx->d_perm.ensure(tab.size()));
+        CK(cudaMemcpyAsync(ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        // rows of this sub-batch are contiguous in a scratch region, then scattered to their items
+        CK(ctx->d_stat2.ensure(bg.size() * (size_t)P));
+        std::swap(ctx->d_stat.p, ctx->d_stat2.p);
+        std::swap(ctx->d_stat.cap, ctx->d_stat2.cap);
+        // evaluate into scratch rows [0, bg.size())
+        DevBuf<double> keep_true;
+        DevBuf<long long> kc, kd, kt, ku;
+        std::swap(keep_true.p, ctx->d_true.p); std::swap(keep_true.cap, ctx->d_true.cap);
+        std::swap(kc.p, ctx->d_count.p); std::swap(kc.cap, ctx->d_count.cap);
+        std::swap(kd.p, ctx->d_done.p); std::swap(kd.cap, ctx->d_done.cap);
+        std::swap(kt.p, ctx->d_total.p); std::swap(kt.cap, ctx->d_total.cap);
+        std::swap(ku.p, ctx->d_consumed.p); std::swap(ku.cap, ctx->d_consumed.cap);
+        CK(ctx->d_true.ensure(bg.size()));
+        CK(ctx->d_count.ensure(bg.size()));
+        CK(ctx->d_done.ensure(bg.size()));
+        CK(ctx->d_total.ensure(bg.size()));
+        CK(ctx->d_consumed.ensure(bg.size()));
+        int rc = eval_perm_items(ctx, bg, bt, pc, kind, 0);
+        if (rc) return rc;
+        // scatter to the final rows
+        for (size_t b = 0; b < bg.size(); ++b) {
+          const size_t r = (size_t)bidx[b];
+          CK(cudaMemcpyAsync(ctx->d_stat2.p + r * (size_t)P, ctx->d_stat.p + b * (size_t)P, (size_t)P * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+          CK(cudaMemcpyAsync(keep_true.p + r, ctx->d_true.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+          CK(cudaMemcpyAsync(kc.p + r, ctx->d_count.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+          CK(cudaMemcpyAsync(kd.p + r, ctx->d_done.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+          CK(cudaMemcpyAsync(kt.p + r, ctx->d_total.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+          CK(cudaMemcpyAsync(ku.p + r, ctx->d_consumed.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        h_consumed.resize(bg.size());
+        CK(cudaMemcpyAsync(h_consumed.data(), ctx->d_consumed.p, bg.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (size_t b = 0; b < bg.size(); ++b) group_off[group_of[bidx[b]]] += h_consumed[b];
+        // restore the full-size buffers
+        ctx->d_true.release(); ctx->d_count.release(); ctx->d_done.release(); ctx->d_total.release(); ctx->d_consumed.release();
+        std::swap(keep_true.p, ctx->d_true.p); std::swap(keep_true.cap, ctx->d_true.cap);
+        std::swap(kc.p, ctx->d_count.p); std::swap(kc.cap, ctx->d_count.cap);
+        std::swap(kd.p, ctx->d_done.p); std::swap(kd.cap, ctx->d_done.cap);
+        std::swap(kt.p, ctx->d_total.p); std::swap(kt.cap, ctx->d_total.cap);
+        std::swap(ku.p, ctx->d_consumed.p); std::swap(ku.cap, ctx->d_consumed.cap);
+        std::swap(ctx->d_stat.p, ctx->d_stat2.p);
+        std::swap(ctx->d_stat.cap, ctx->d_stat2.cap);
+      }
+    }
   }
-  const long long n_rows = (long long)n_items * per;
-  perm_count_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, ctx->stream>>>(
-      ctx->d_stat.p, ctx->d_true.p, P, n_rows, join ? 1 : 0, pc->trick, pc->tricut, ctx->d_count.p, ctx->d_done.p,
-      ctx->d_total.p);
-  ctx->launches++;
-  CK(cudaGetLastError());
   if (ms) {
     CK(cudaEventRecord(ev1, ctx->stream));
     CK(cudaEventSynchronize(ev1));
@@ -1491,7 +1648,7 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
     CK(cudaMemcpyAsync(h_stat.data(), ctx->d_stat.p, (size_t)n_rows * P * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
   CK(cudaStreamSynchronize(ctx->stream));
-  rc = check_device_errors(ctx);
+  int rc = check_device_errors(ctx);
   if (rc) return rc;
 
   // p-values: Gene::CalcPermutationPvalue (gene.cpp:348-364); rngTrick is seeded like rngPerm and
@@ -1521,8 +1678,7 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
         if (res->true_stat) res->true_stat[o] = h_true[r];
         if (need_stats) {
           const double *st = &h_stat[r * (size_t)P];
-          // statistics actually evaluated: the first ones up to the stopping point
-          std::vector<double> kept;
+          std::vector<double> kept; // statistics actually evaluated: the first ones up to the stopping point
           long long nd = 0;
           for (long long p = 0; p < P && nd < h_done[r]; ++p) {
             if (res->perm_stats) res->perm_stats[(size_t)o * P + p] = st[p];

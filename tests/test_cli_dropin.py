@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "eqtlbma_b200", "eqtlbma_bf")
-NOT_YET = {"mvlr_fit0", "mvlr_fit05_cov", "basic_all_trick1"}
+NOT_YET = set()
 DEGENERATE = {"monomorphic"}
 
 

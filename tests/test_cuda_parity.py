@@ -15,7 +15,7 @@ from test_oracle_vs_reference import GOLD, check_against_dump
 pytestmark = pytest.mark.gpu
 
 # paths of the reference that the CUDA library does not cover yet (reported as errors by the ABI)
-NOT_YET = {"mvlr_fit0", "mvlr_fit05_cov", "basic_all_trick1"}
+NOT_YET = set()
 # degenerate rank-deficient designs: documented tie, checked separately
 DEGENERATE = {"monomorphic"}
 
