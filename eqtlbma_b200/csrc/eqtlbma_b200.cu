@@ -1209,6 +1209,31 @@ int eqb_pair_offsets(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int64_t *of
   return 0;
 }
 
+int eqb_partition_by_cost(const int64_t *cost, int64_t n_genes, int64_t wrtsize, int32_t n_shards, int64_t *shard_begin)
+{
+  if (!cost || !shard_begin || n_genes < 0 || wrtsize < 1 || n_shards < 1) return 1;
+  const int64_t n_groups = (n_genes + wrtsize - 1) / wrtsize;
+  std::vector<double> gcost(n_groups, 0.0);
+  double total = 0.0;
+  for (int64_t g = 0; g < n_genes; ++g) {
+    gcost[g / wrtsize] += (double)cost[g];
+    total += (double)cost[g];
+  }
+  // greedy prefix split: shard k ends at the first group boundary where the running cost reaches
+  // (k+1)/n_shards of the total (ties resolved towards the closer boundary)
+  shard_begin[0] = 0;
+  int64_t grp = 0;
+  double run = 0.0;
+  for (int32_t k = 1; k < n_shards; ++k) {
+    const double target = total * (double)k / (double)n_shards;
+    while (grp < n_groups && run + gcost[grp] <= target) run += gcost[grp++];
+    if (grp < n_groups && (target - run) > (run + gcost[grp] - target)) run += gcost[grp++];
+    shard_begin[k] = std::min<int64_t>(grp * wrtsize, n_genes);
+  }
+  shard_begin[n_shards] = n_genes;
+  return 0;
+}
+
 int64_t eqb_launch_count(const eqb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int64_t eqb_fast_gene_count(const eqb_ctx *ctx)

@@ -141,6 +141,7 @@ struct Options {
       bfs = "gen", error = "uvlr", pbf = "none", snp;
   vector<string> sbgrp;
   int device = 0;
+  int shard_k = 0, shard_n = 1; // --shard k/N (extension): this process handles the k-th of N gene shards
 };
 
 void help(char **argv)
@@ -154,7 +155,10 @@ void help(char **argv)
        << "      --geno --scoord --exp --gcoord --anchor --cis --out --outss --outw --lik --analys" << endl
        << "      --qnorm --maf --covar --gridL --gridS --bfs --error --fiterr --nperm --seed --trick" << endl
        << "      --tricut --permsep --pbf --maxbf --thread --snp --sbgrp --wrtsize" << endl
-       << "      --device\tCUDA device ordinal (extension)" << endl;
+       << "      --device\tCUDA device ordinal (extension)" << endl
+       << "      --shard\tk/N: handle the k-th of N contiguous, cost-balanced gene shards (extension;\n"
+       << "\t\tone process per GPU, outputs concatenate in shard order like the batches of\n"
+       << "\t\teqtlbma_bf_parallel.bash)" << endl;
 }
 
 void die_usage(int argc, char **argv, const string &msg)
@@ -187,6 +191,7 @@ void parse_cmdline(int argc, char **argv, Options &o)
       {"maxbf", no_argument, 0, 0},           {"thread", required_argument, 0, 0},
       {"snp", required_argument, 0, 0},       {"sbgrp", required_argument, 0, 0},
       {"wrtsize", required_argument, 0, 0},   {"device", required_argument, 0, 0},
+      {"shard", required_argument, 0, 0},
       {0, 0, 0, 0}};
   while (true) {
     int idx = 0;
@@ -242,6 +247,10 @@ void parse_cmdline(int argc, char **argv, Options &o)
     else if (n == "sbgrp") split(optarg, "+", o.sbgrp);
     else if (n == "wrtsize") o.wrtsize = atoi(optarg);
     else if (n == "device") o.device = atoi(optarg);
+    else if (n == "shard") {
+      if (sscanf(optarg, "%d/%d", &o.shard_k, &o.shard_n) != 2 || o.shard_n < 1 || o.shard_k < 0 || o.shard_k >= o.shard_n)
+        die_usage(argc, argv, "--shard should be k/N with 0 <= k < N");
+    }
   }
   // validation: same conditions and messages as eqtlbma_bf.cpp:463-692
   if (!o.inss.empty()) die_usage(argc, argv, "--inss is not supported by the B200 front-end (out of scope)");
@@ -1037,12 +1046,22 @@ int main(int argc, char **argv)
   const size_t per_pair = (size_t)S * 44 + (join ? ((size_t)3 * L + (size_t)C * K + 5 + C) * 8 : 0);
   const size_t budget = (size_t)1 << 30;
   size_t nbAnalyzedGenes = 0, nbAnalyzedPairs = 0;
-  int64_t g0 = 0;
-  while (g0 < G) {
+  int64_t g0 = 0, g_end = G;
+  if (o.shard_n > 1) { // gene sharding over GPUs: contiguous cost-balanced ranges of whole write-groups
+    vector<int64_t> cost(G), sb(o.shard_n + 1);
+    for (int64_t g = 0; g < G; ++g) cost[g] = (ce[g] - cb[g]) * (int64_t)(1 + o.nb_permutations);
+    if (eqb_partition_by_cost(cost.data(), G, o.wrtsize, o.shard_n, sb.data()) != 0) {
+      cerr << "ERROR: eqb_partition_by_cost failed" << endl;
+      exit(EXIT_FAILURE);
+    }
+    g0 = sb[o.shard_k];
+    g_end = sb[o.shard_k + 1];
+  }
+  while (g0 < g_end) {
     int64_t g1 = g0;
     size_t pairs_est = 0;
-    while (g1 < G) {
-      int64_t gn = min<int64_t>(G, g1 + o.wrtsize);
+    while (g1 < g_end) {
+      int64_t gn = min<int64_t>(g_end, g1 + o.wrtsize);
       size_t add = 0;
       for (int64_t g = g1; g < gn; ++g) add += (size_t)(ce[g] - cb[g]);
       if (g1 > g0 && (pairs_est + add) * per_pair > budget) break;

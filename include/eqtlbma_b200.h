@@ -157,6 +157,15 @@ int eqb_run_permutations(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
 int eqb_run_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int32_t want_raw, float *ms);
 int eqb_run_permutations_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi,
                                      const eqb_perm_config *pc, float *ms);
+/* Multi-GPU sharding (replaces scripts/eqtlbma_bf_parallel.bash:248-262, one OS process per gene batch):
+ * genes are independent, so the G genes are cut into n_shards CONTIGUOUS ranges of whole write-groups
+ * (the generator is re-seeded per write-group, eqtlbma_bf.cpp:847, so a group never straddles two
+ * GPUs and results do not depend on the GPU count), balanced on the caller's per-gene cost (e.g.
+ * cis SNPs x (1 + nperm)).  Pure host function, no context, no device: shard k owns genes
+ * [shard_begin[k], shard_begin[k+1]); concatenating the shards' outputs in shard order restores the
+ * reference's gene order (the final host gather). */
+int eqb_partition_by_cost(const int64_t *cost_per_gene, int64_t n_genes, int64_t wrtsize, int32_t n_shards,
+                          int64_t *shard_begin /* n_shards + 1 */);
 /* Number of genes whose (gene, subgroup) row sets are gene-independent (K1 outputs reusable: the
  * split projection / contraction path); the others take the general fused kernel. Diagnostic. */
 int64_t eqb_fast_gene_count(const eqb_ctx *ctx);
