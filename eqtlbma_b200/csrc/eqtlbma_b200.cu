@@ -20,6 +20,7 @@
 
 #include "fast_kernels.cuh"
 #include "mvlr_kernel.cuh"
+#include "perm_kernel.cuh"
 
 using namespace eqb;
 
@@ -1409,6 +1410,24 @@ int eqb_run_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int32_t 
   return run_true_impl(ctx, gene_lo, gene_hi, nullptr, want_raw != 0, true, ms);
 }
 
+// K4 on the tensor cores when the shape allows it, else the general fused kernel
+static int run_perm_or_pair_kernel(eqb_ctx *ctx, const LaunchArgs &la, long long n_ctas, int ppg)
+{
+  const int S = ctx->cfg.n_subgroups;
+  const bool mvlr = ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model == EQB_ERROR_MVLR;
+  const size_t smem = perm_smem_doubles(S, ctx->Qmax, ctx->ldn, (int)ctx->phi2S.size(), (int)ctx->phi2L.size(), ctx->gt.UL) * sizeof(double);
+  const bool ok = !mvlr && ctx->d_fp != nullptr && ctx->ldn <= 512 && smem <= 220 * 1024 &&
+                  (!ctx->cfg.qnorm || ctx->Qmax >= 2) && !getenv("EQB_NO_PERM_DMMA");
+  if (!ok) return run_pair_kernel(ctx, la, n_ctas, ppg);
+  cudaError_t e = cudaFuncSetAttribute(perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel attribute: ") + cudaGetErrorString(e));
+  perm_kernel<<<(unsigned)((long long)la.n_genes * std::max(1, ppg)), THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, la, ctx->gt);
+  ctx->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 // device evaluation of a set of (gene, permutation table) items: statistic of the true data, the P
 // permuted statistics, and the exceedance counters
 static int eval_perm_items(eqb_ctx *ctx, const std::vector<int> &genes, const std::vector<int> &tab_idx,
@@ -1437,7 +1456,7 @@ static int eval_perm_items(eqb_ctx *ctx, const std::vector<int> &genes, const st
   la.perms_per_gene = 0;
   la.true_rules = 1; // statistic of the true data: identity permutation, the reference's true-data rules
   la.out_stat = ctx->d_true.p + row0 * 1;
-  int rc = run_pair_kernel(ctx, la, (long long)n_items, 1);
+  int rc = run_perm_or_pair_kernel(ctx, la, (long long)n_items, 1);
   if (rc) return rc;
   la.true_rules = 0;
   la.out_stat = ctx->d_stat.p + row0 * (size_t)P;
@@ -1446,7 +1465,7 @@ static int eval_perm_items(eqb_ctx *ctx, const std::vector<int> &genes, const st
   for (long long p0 = 0; p0 < P; p0 += pcnk) {
     la.p0 = p0;
     la.perms_per_gene = (int)std::min<long long>(pcnk, P - p0);
-    rc = run_pair_kernel(ctx, la, (long long)n_items * la.perms_per_gene, la.perms_per_gene);
+    rc = run_perm_or_pair_kernel(ctx, la, (long long)n_items * la.perms_per_gene, la.perms_per_gene);
     if (rc) return rc;
   }
   const long long n_rows = (long long)n_items * per;
