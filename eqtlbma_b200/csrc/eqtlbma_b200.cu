@@ -319,6 +319,7 @@ struct eqb_ctx {
   DevBuf<int> d_genes2;
   DevBuf<long long> d_pair_off2, d_fast_base;
   DevBuf<double> d_bcat;
+  DevBuf<unsigned long long> d_fix; // [0] = count, then (snp << 8 | subgroup) entries needing the explicit K1c pass
   GridTab gt;              // unique phi2 values of the consistent-configuration rows
   double *d_gt_d = nullptr; // uphi[UL] | omaL[3L]
   int *d_gt_i = nullptr;    // idxL[3L] | dup_of[S]
@@ -512,7 +513,7 @@ cudaError_t launch_dmma(eqb_ctx *ctx, const double *X, const double *Bcat, const
   cudaError_t e = cudaFuncSetAttribute(prep_x_dmma_kernel<NT, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((M + 8 * WARPS - 1) / (8 * WARPS));
-  prep_x_dmma_kernel<NT, NM><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, X, Bcat, Mcat, pc, xp);
+  prep_x_dmma_kernel<NT, NM><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, X, Bcat, Mcat, pc, xp, ctx->d_fix.p, (int)ctx->d_fix.cap);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -525,6 +526,8 @@ int launch_prep_x(eqb_ctx *ctx)
   const long long M = ctx->cfg.n_snps;
   double **xp = ctx->d_prep_ptrs + 3 * S;
   const int *dup = ctx->d_gt_i + 3 * (int)ctx->phi2L.size();
+  CK(ctx->d_fix.ensure(1 << 16));
+  CK(cudaMemsetAsync(ctx->d_fix.p, 0, sizeof(unsigned long long), ctx->stream));
   // chunks of subgroups sharing a genotype variant, <= 8 basis tiles and <= 8 mask tiles, <= 16 subgroups
   std::vector<char> done(S, 0);
   for (int s0 = 0; s0 < S; ++s0) {
@@ -575,15 +578,17 @@ int launch_prep_x(eqb_ctx *ctx)
     else e = launch_dmma<8, 2>(ctx, X, Bcat, Mcat, pc, xp);
     if (e != cudaSuccess) return fail(ctx, std::string("prep_x_dmma launch: ") + cudaGetErrorString(e));
   }
-  // fix-up pass
-  const unsigned grid = (unsigned)((M + WARPS - 1) / WARPS);
+  // fix-up pass over the queued entries (a small persistent grid; the list is normally empty)
+  const unsigned grid = 148 * 2;
   const int npl = (ldn + 31) / 32;
-  if (npl <= 4) prep_x_kernel<4><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1);
-  else if (npl <= 8) prep_x_kernel<8><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1);
-  else if (npl <= 12) prep_x_kernel<12><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1);
-  else if (npl <= 16) prep_x_kernel<16><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1);
-  else if (npl <= 32) prep_x_kernel<32><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1);
-  else prep_x_kernel<64><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1);
+  const unsigned long long *fl = ctx->d_fix.p;
+  const int fc = (int)ctx->d_fix.cap;
+  if (npl <= 4) prep_x_kernel<4><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
+  else if (npl <= 8) prep_x_kernel<8><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
+  else if (npl <= 12) prep_x_kernel<12><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
+  else if (npl <= 16) prep_x_kernel<16><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
+  else if (npl <= 32) prep_x_kernel<32><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
+  else prep_x_kernel<64><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -844,6 +849,7 @@ void eqb_destroy(eqb_ctx *ctx)
   ctx->d_pair_off2.release();
   ctx->d_fast_base.release();
   ctx->d_bcat.release();
+  ctx->d_fix.release();
   if (ctx->d_prm) dfree(ctx->d_prm);
   if (ctx->d_grids) dfree(ctx->d_grids);
   if (ctx->d_cfg_mask) dfree(ctx->d_cfg_mask);

@@ -179,14 +179,28 @@ __global__ void __launch_bounds__(THREADS) prep_y_kernel(const DevParams *__rest
     }
   tss = warp_sum(tss);
   const int Q = sb.Q;
+  // projection on the (orthonormal) basis: blocks of 4 independent dot products, two passes (CGS2)
   for (int pass = 0; pass < 2; ++pass)
-    for (int j = 0; j <= Q; ++j) {
-      if (!((fs.colvalid >> j) & 1u)) continue;
-      const double *qj = q + (size_t)j * ldn;
-      double h = 0.0;
-      for (int i = lane; i < ldn; i += 32) h += qj[i] * yt[i];
-      h = warp_sum(h);
-      for (int i = lane; i < ldn; i += 32) yt[i] -= h * qj[i];
+    for (int k0 = 0; k0 <= Q; k0 += 4) {
+      double h[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = lane; i < ldn; i += 32) {
+        const double y = yt[i];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (k0 + a <= Q) h[a] += q[(size_t)(k0 + a) * ldn + i] * y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) h[a] += __shfl_xor_sync(0xffffffffu, h[a], o);
+      }
+      for (int i = lane; i < ldn; i += 32) {
+        double y = yt[i];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          if (k0 + a <= Q && ((fs.colvalid >> (k0 + a)) & 1u)) y -= h[a] * q[(size_t)(k0 + a) * ldn + i];
+        yt[i] = y;
+      }
       __syncwarp();
     }
   double yy = 0.0;
@@ -208,14 +222,21 @@ __global__ void __launch_bounds__(THREADS) prep_y_kernel(const DevParams *__rest
 template <int NPL>
 __global__ void __launch_bounds__(THREADS) prep_x_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
                                                          double *const *xstat_all, const int *__restrict__ dup_of,
-                                                         const int fixup_only)
+                                                         const int fixup_only, const unsigned long long *__restrict__ fix_list,
+                                                         int fix_cap)
 {
   const DevParams &prm = *prm_;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long m = (long long)blockIdx.x * WARPS + warp;
-  if (m >= prm.M) return;
   const int S = prm.S, ldn = prm.ldn;
+  // fix-up mode: grid-stride walk over the entries queued by the DMMA pass (fix_list[0] = count; if the
+  // list overflowed, every SNP is re-checked)
+  const bool listed = fixup_only && fix_list != nullptr && fix_list[0] + 1 < (unsigned long long)fix_cap;
+  const long long n_items = listed ? (long long)fix_list[0] : prm.M;
+  for (long long item = (long long)blockIdx.x * WARPS + warp; item < n_items; item += (long long)gridDim.x * WARPS) {
+  const long long m = listed ? (long long)(fix_list[item + 1] >> 8) : item;
+  const int s_only = listed ? (int)(fix_list[item + 1] & 0xffull) : -1;
   for (int s = 0; s < S; ++s) {
+    if (s_only >= 0 && s != s_only) continue;
     const SubDev &sb = prm.sub[s];
     const FastSub &fs = fp_->sub[s];
     double *xs = xstat_all[s] + (size_t)m * 3;
@@ -299,6 +320,7 @@ __global__ void __launch_bounds__(THREADS) prep_x_kernel(const DevParams *__rest
       xs[2] = xsum;
     }
   }
+  }
 }
 
 // ---------------------------------------------------------------- K1c on the FP64 tensor cores
@@ -326,7 +348,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 template <int NT, int NM>
 __global__ void __launch_bounds__(THREADS) prep_x_dmma_kernel(const DevParams *__restrict__ prm_, const double *__restrict__ X,
                                                               const double *__restrict__ Bcat, const double *__restrict__ Mcat,
-                                                              const PrepCols pc, double *const *xstat_all)
+                                                              const PrepCols pc, double *const *xstat_all,
+                                                              unsigned long long *__restrict__ fix_list, int fix_cap)
 {
   const DevParams &prm = *prm_;
   extern __shared__ double psm[];
@@ -423,6 +446,11 @@ __global__ void __launch_bounds__(THREADS) prep_x_dmma_kernel(const DevParams *_
     xs[0] = r2 - hh;
     xs[1] = r2;
     xs[2] = pc.sqrt_n[si] * h[0];
+    if (r2 > 0.0 && (r2 - hh) < 1e-2 * r2) {
+      // Gram-form residual lost accuracy (x nearly inside span([1, covariates])): queue for the explicit pass
+      const unsigned long long slot = atomicAdd(fix_list, 1ull);
+      if (slot + 1 < (unsigned long long)fix_cap) fix_list[slot + 1] = ((unsigned long long)m << 8) | (unsigned long long)s;
+    }
   }
 }
 
@@ -683,16 +711,12 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
         }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int a = 0; a < 8; ++a) {
+        if (a < sn) { // sn is warp-uniform
 #pragma unroll
-        for (int a = 0; a < 8; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
-      }
-      if (lane < sn) {
-        double r = acc[0];
-#pragma unroll
-        for (int a = 1; a < 8; ++a)
-          if (lane == a) r = acc[a];
-        xy[(size_t)j * S + s0 + lane] = r;
+          for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+          if (lane == a) xy[(size_t)j * S + s0 + a] = acc[a];
+        }
       }
     }
   }
@@ -840,6 +864,19 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
     }
     return;
   }
+  if (fa.which == 2) {
+    // singletons only: one thread per pair walks its S+1 terms (CalcBMAlite, gene_snp_pair.cpp:552-570)
+    for (int j = threadIdx.x; j < tn; j += THREADS) {
+      Lse lite;
+      lite.init();
+      for (int c = 0; c < S; ++c) lite.add(wrow[(size_t)j * (3 + S) + 3 + c], 0.5 / (double)S, c == 0);
+      lite.add(wrow[(size_t)j * (3 + S) + 0], 0.5, false);
+      double *o = fa.out_w + s_pair[j] * (5 + C);
+      o[3] = lite.result();
+      o[4] = nan("");
+    }
+    return;
+  }
   for (int j = warp; j < tn; j += WARPS) {
     const long long pair = s_pair[j];
     const double *wcfg = fa.out_w + pair * (5 + C) + 5;
@@ -847,18 +884,15 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
     lite.init();
     bma.init();
     for (long long c = lane; c < C; c += 32) {
-      const double wc = (fa.which == 2) ? wrow[(size_t)j * (3 + S) + 3 + c] : wcfg[c];
+      const double wc = wcfg[c];
       if (c < S) lite.add(wc, 0.5 / (double)S, c == 0);
-      if (fa.which == 3) bma.add(wc, prm.cfg_weight[c], c == 0);
+      bma.add(wc, prm.cfg_weight[c], c == 0);
     }
     lite = warp_merge(lite);
     lite.add(wrow[(size_t)j * (3 + S) + 0], 0.5, false);
     const double w_gensin = lite.result();
-    double w_all = nan("");
-    if (fa.which == 3) {
-      bma = warp_merge(bma);
-      w_all = bma.result();
-    }
+    bma = warp_merge(bma);
+    const double w_all = bma.result();
     if (lane == 0) {
       double *o = fa.out_w + pair * (5 + C);
       o[3] = w_gensin;

@@ -1,0 +1,73 @@
+"""Size-independent properties of the CUDA path at bench-scale shapes (GPU):
+ * the split K1/K2+K3 fast path and the general fused kernel are two independent implementations of
+   the same statistics: they must agree on every pair of a large workload;
+ * results do not depend on how genes are sharded (gene ranges processed separately = all at once);
+ * permutation statistics are invariant to the chunking of the permutation dimension and the DMMA
+   permutation kernel agrees with the general kernel (exceedance counts identical)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ds(**kw):
+    from eqtlbma_b200.synth import make_dataset
+    base = dict(seed=77, n_subgroups=3, n_inds=300, n_genes=400, snps_per_gene=50, n_cov=11, dosage=True,
+                radius=100, gene_spacing=201, far_snp=False, n_chr=4)
+    base.update(kw)
+    return make_dataset(**base)
+
+
+def test_fast_path_equals_general_path_at_scale(cuda_lib):
+    import eqtlbma_b200
+    ds = _ds()
+    eng = eqtlbma_b200.Engine(ds, analysis="join", bfs="sin")
+    assert eng.fast_gene_count() == ds.n_genes
+    a = eng.run()
+    # same data with ONE NaN per gene in the last subgroup: every gene leaves the fast path; the
+    # other subgroups' statistics must be unchanged
+    ds2 = _ds()
+    for g in range(ds2.n_genes):
+        ds2.subgroups[2].Y[g, g % 300] = np.nan
+    eng2 = eqtlbma_b200.Engine(ds2, analysis="join", bfs="sin")
+    assert eng2.fast_gene_count() == 0
+    b = eng2.run()
+    assert np.array_equal(a.n[:, :2], b.n[:, :2])
+    assert np.allclose(a.sstats[:, :2, 1:], b.sstats[:, :2, 1:], rtol=1e-9, atol=0, equal_nan=True)
+    assert np.allclose(a.sstats[:, :2, 0], b.sstats[:, :2, 0], rtol=1e-9, atol=1e-12, equal_nan=True)
+    # singleton ABFs of the untouched subgroups (configs 0 and 1) agree to the 1e-8 budget
+    assert np.allclose(a.abf_cfg[:, :2], b.abf_cfg[:, :2], rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(a.abf_w[:, 5:7], b.abf_w[:, 5:7], rtol=0, atol=1e-8, equal_nan=True)
+
+
+def test_results_independent_of_gene_sharding(cuda_lib):
+    import eqtlbma_b200
+    from eqtlbma_b200.shard import gene_costs, partition
+    ds = _ds(n_genes=203, n_subgroups=4, n_cov=2, ragged=True)
+    eng = eqtlbma_b200.Engine(ds, analysis="join", bfs="all")
+    full = eng.run()
+    pfull = eng.run_permutations(40, 1859, pbf="all", wrtsize=10)
+    sb = partition(cuda_lib, gene_costs(eng.cis_begin, eng.cis_end, 40), 10, 3)
+    parts = [eng.run(int(sb[k]), int(sb[k + 1])) for k in range(3)]
+    pparts = [eng.run_permutations(40, 1859, lo=int(sb[k]), hi=int(sb[k + 1]), pbf="all", wrtsize=10) for k in range(3)]
+    assert np.array_equal(np.concatenate([p.n for p in parts]), full.n)
+    assert np.array_equal(np.concatenate([p.abf_w for p in parts]), full.abf_w, equal_nan=True)
+    assert np.array_equal(np.concatenate([p.count for p in pparts]), pfull.count)
+    assert np.array_equal(np.concatenate([p.perm_stats for p in pparts]), pfull.perm_stats, equal_nan=True)
+
+
+def test_dmma_permutation_kernel_equals_general_kernel(cuda_lib):
+    import eqtlbma_b200
+    ds = _ds(n_genes=60, n_subgroups=5, n_inds=200, n_cov=3, ragged=True, snps_per_gene=30)
+    eng = eqtlbma_b200.Engine(ds, analysis="join", bfs="sin")
+    a = eng.run_permutations(64, 7, pbf="gen-sin", wrtsize=7)
+    os.environ["EQB_NO_PERM_DMMA"] = "1"
+    try:
+        b = eng.run_permutations(64, 7, pbf="gen-sin", wrtsize=7)
+    finally:
+        del os.environ["EQB_NO_PERM_DMMA"]
+    assert np.array_equal(a.count, b.count)
+    assert np.allclose(a.perm_stats, b.perm_stats, rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(a.true_stat, b.true_stat, rtol=0, atol=1e-8, equal_nan=True)
