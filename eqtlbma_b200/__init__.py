@@ -60,6 +60,11 @@ class Engine(_Engine):
         f.restype = ctypes.c_int64
         return int(f(self.ctx))
 
+    def last_pair_kernel_ms(self) -> float:
+        f = self.lib.eqb_last_pair_kernel_ms
+        f.restype = ctypes.c_float
+        return float(f(self.ctx))
+
     def fast_gene_count(self) -> int:
         f = self.lib.eqb_fast_gene_count
         f.restype = ctypes.c_int64

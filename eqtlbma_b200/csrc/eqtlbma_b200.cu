@@ -325,6 +325,7 @@ struct eqb_ctx {
   int *d_gt_i = nullptr;    // idxL[3L] | dup_of[S]
   double **d_prep_ptrs = nullptr;
   double *d_tz = nullptr;
+  float last_pair_ms = 0.f;
   // cached permutation table key
   uint64_t perm_seed = 0;
   long long perm_P = -1;
@@ -1179,6 +1180,11 @@ int eqb_finalize(eqb_ctx *ctx)
   hp.oma2S = ctx->d_grids + 2 * L + K;
   hp.cfg_mask = ctx->d_cfg_mask;
   hp.cfg_weight = ctx->d_cfg_weight;
+  for (int k = 1; k <= S && k <= MAXS; ++k) {
+    long double r = 1.0L;
+    for (int i = 1; i <= k; ++i) r = r * (long double)(S - k + i) / (long double)i;
+    hp.size_weight[k] = (1.0 / (double)S) * (1.0 / (double)floorl(r + 0.5L));
+  }
   hp.cis_begin = ctx->d_cb;
   hp.cis_end = ctx->d_ce;
   for (int s = 0; s < S; ++s) {
@@ -1240,6 +1246,8 @@ int eqb_partition_by_cost(const int64_t *cost, int64_t n_genes, int64_t wrtsize,
   shard_begin[n_shards] = n_genes;
   return 0;
 }
+
+float eqb_last_pair_kernel_ms(const eqb_ctx *ctx) { return ctx ? ctx->last_pair_ms : 0.f; }
 
 int64_t eqb_launch_count(const eqb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
@@ -1374,7 +1382,20 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           int rcp = launch_prep_yx(ctx);
           if (rcp) return rcp;
         }
+        cudaEvent_t k0 = nullptr, k1 = nullptr;
+        if (device_only) {
+          CK(cudaEventCreate(&k0));
+          CK(cudaEventCreate(&k1));
+          CK(cudaEventRecord(k0, ctx->stream));
+        }
         fast_pair_kernel<<<(unsigned)((nfp + T - 1) / T), THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt);
+        if (device_only) {
+          CK(cudaEventRecord(k1, ctx->stream));
+          CK(cudaEventSynchronize(k1));
+          CK(cudaEventElapsedTime(&ctx->last_pair_ms, k0, k1));
+          cudaEventDestroy(k0);
+          cudaEventDestroy(k1);
+        }
         ctx->launches++;
         CK(cudaGetLastError());
       }

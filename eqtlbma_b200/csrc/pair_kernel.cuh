@@ -49,6 +49,7 @@ struct DevParams {
   const double *phi2L, *oma2L, *phi2S, *oma2S;
   const unsigned long long *cfg_mask; // [C] subgroup bitmask of each configuration, reference order
   const double *cfg_weight;           // [C] (1/S)(1/choose(S,|config|)), gene_snp_pair.cpp:590-592
+  double size_weight[MAXS + 1];       // the same weight as a function of the configuration size
   const long long *cis_begin, *cis_end;
   SubDev sub[MAXS];
 };

@@ -24,10 +24,14 @@ __host__ __device__ inline int perm_lds(int ldn) { return ldn + 1; }
 // rows of the shared B matrix: S*(Qmax+2) data rows, then 8 zero rows of padding (partial tiles read them)
 __host__ __device__ inline int perm_brows(int S, int Qmax) { return S * (Qmax + 2) + 8; }
 // per-warp scratch (doubles): H[8][W], st[8][3][S], tab[K][S][3], flags[8], agg[8][UL][3], vals[8][L], wc[8][S], wg[8], has[8]
+// ... + mitm[K][2^SA][3] (all-configuration sums of the low SA subgroups, S <= 10 and K <= 12 only)
+__host__ __device__ inline int perm_mitm_sa(int S, int K) { return (S <= 10 && K <= 12 && S > 5) ? S - 5 : (S <= 5 && K <= 12 ? 0 : -1); }
 __host__ __device__ inline size_t perm_warp_doubles(int S, int Qmax, int K, int L, int UL)
 {
   const size_t W = (size_t)(((S * (Qmax + 2) + 7) / 8) * 8 + ((S + 7) / 8) * 8);
-  return 8 * W + 8 * 3 * S + 3 * K * S + 8 + (size_t)8 * UL * 3 + (size_t)8 * L + (size_t)8 * S + 8 + 8;
+  const int sa = perm_mitm_sa(S, K);
+  return 8 * W + 8 * 3 * S + 3 * K * S + 8 + (size_t)8 * UL * 3 + (size_t)8 * L + (size_t)8 * S + 8 + 8 +
+         (sa >= 0 ? (size_t)3 * K * (1u << sa) : 0);
 }
 __host__ __device__ inline size_t perm_smem_doubles(int S, int Qmax, int ldn, int K, int L, int UL)
 {
@@ -121,6 +125,7 @@ __global__ void __launch_bounds__(THREADS) perm_kernel(const DevParams *__restri
   double *wcw = valw + 8 * L;                                          // [8][S]
   double *wgw = wcw + 8 * S;                                           // [8]
   unsigned long long *hasw = (unsigned long long *)(wgw + 8);          // [8]
+  double *mitm = (double *)(hasw + 8);                                 // [K][2^SA][3]
 
   if (threadIdx.x < MAXS) w_sep_nan[threadIdx.x] = 0;
   // zero the padding rows
@@ -521,45 +526,127 @@ __global__ void __launch_bounds__(THREADS) perm_kernel(const DevParams *__restri
       }
       __syncwarp();
     } else if (la.which == 3) {
-      // 4e: all configurations, warp per SNP (lanes over configurations)
+      // 4e: all 2^S-1 configurations, warp per SNP.  Fast form (S <= 10): meet in the middle -- lane b owns
+      // the subset b of the high min(5,S) subgroups (its per-grid-point sums live in registers), the 2^SA
+      // subsets of the low subgroups come from a shared table -- and the BMA sum is accumulated in the
+      // linear domain against the bound M = sum_s t_s^2/2 - 350 >= every exponent - 359:
+      //   10^abf = exp(A) (1 + oma2 den)^-1/2 exp(num^2 oma2 / (2 (1 + oma2 den)))   (no log, no division)
+      const int SA = perm_mitm_sa(S, K);
       for (int j = 0; j < tn; ++j) {
         const double *st = stw + j * 3 * S;
         const unsigned long long has_mask = hasw[j];
+        bool fast_ok = SA >= 0;
+        double Mref = 0.0;
+        for (int s = 0; s < S; ++s)
+          if ((has_mask >> s) & 1ull) {
+            const double t = st[2 * S + s];
+            if (isnan(t) || isnan(st[s]) || isnan(st[S + s]) || isinf(st[s])) fast_ok = false;
+            else if (fabs(t) >= 1e-8) Mref += 0.5 * t * t;
+          }
+        Mref -= 350.0;
+        // per-(grid point, subgroup) terms {1/(v+phi2), b/(v+phi2), ln of the single-subgroup ABF}
         for (int e = lane; e < K * S; e += 32) {
           const int k = e / S, s = e % S;
           double *te = tab + (size_t)e * 3;
-          if ((has_mask >> s) & 1ull)
+          te[0] = 0.0;
+          te[1] = 0.0;
+          te[2] = 0.0;
+          if ((has_mask >> s) & 1ull) {
             term_entry(st[s], st[S + s], st[2 * S + s], prm.phi2S[k], te[0], te[1], te[2]);
-          else {
-            te[0] = 0.0;
-            te[1] = 0.0;
-            te[2] = 0.0;
+            if (fast_ok) te[2] *= LN10;
           }
         }
         __syncwarp();
-        Lse bma;
-        bma.init();
-        for (long long c = lane; c < C; c += 32) {
-          const unsigned long long mask = prm.cfg_mask[c] & has_mask;
-          Lse b;
-          b.init();
-          for (int k = 0; k < K; ++k) {
-            const double *tk = tab + (size_t)k * S * 3;
-            double den = 0.0, num = 0.0, sing = 0.0;
-            unsigned long long mm = mask;
-            while (mm) {
-              const int s = __ffsll((long long)mm) - 1;
-              mm &= mm - 1;
-              den += tk[3 * s];
-              num += tk[3 * s + 1];
-              sing += tk[3 * s + 2];
-            }
-            b.add(abf_from_sums(den, num, sing, prm.oma2S[k]), 1.0 / (double)K, k == 0);
+        double res = nan("");
+        bool done = false;
+        if (fast_ok) {
+          const int SB = S - SA;
+          const int nA = 1 << SA;
+          for (int e = lane; e < K * nA; e += 32) { // sums over the subsets of the low subgroups
+            const int k = e / nA, a = e % nA;
+            double d = 0.0, n_ = 0.0, A = 0.0;
+            for (int s = 0; s < SA; ++s)
+              if ((a >> s) & 1) {
+                const double *te = tab + ((size_t)k * S + s) * 3;
+                d += te[0];
+                n_ += te[1];
+                A += te[2];
+              }
+            double *m3 = mitm + (size_t)e * 3;
+            m3[0] = d;
+            m3[1] = n_;
+            m3[2] = A;
           }
-          bma.add(b.result(), prm.cfg_weight[c], c == 0); // CalcBMA (gene_snp_pair.cpp:572-602)
+          __syncwarp();
+          double acc = 0.0;
+          if (lane < (1 << SB)) {
+            double hd[12], hn[12], hA[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+              hd[k] = hn[k] = hA[k] = 0.0;
+              if (k < K)
+                for (int s = 0; s < SB; ++s)
+                  if ((lane >> s) & 1) {
+                    const double *te = tab + ((size_t)k * S + SA + s) * 3;
+                    hd[k] += te[0];
+                    hn[k] += te[1];
+                    hA[k] += te[2];
+                  }
+            }
+            const int pb = __popc(lane);
+            for (int a = 0; a < nA; ++a) {
+              if (a == 0 && lane == 0) continue; // the empty configuration is not part of the model
+              const double w = prm.size_weight[pb + __popc(a)];
+              double part = 0.0;
+#pragma unroll
+              for (int k = 0; k < 12; ++k)
+                if (k < K) {
+                  const double *m3 = mitm + ((size_t)k * nA + a) * 3;
+                  const double den = hd[k] + m3[0], num = hn[k] + m3[1], A = hA[k] + m3[2];
+                  const double om = prm.oma2S[k];
+                  const double r = rsqrt(1.0 + om * den);
+                  part += r * exp(A + 0.5 * num * num * om * r * r - Mref);
+                }
+              acc += w * part;
+            }
+          }
+          acc = warp_sum(acc);
+          if (acc > 0.0 && acc < INFINITY) {
+            res = (Mref + log(acc / (double)K)) / LN10;
+            if (fabs(res) <= DBL_EPSILON) res = 0.0;
+            done = true;
+          } else {
+            // out of the representable window (or NaN): redo this SNP in the log domain
+            for (int e = lane; e < K * S; e += 32) tab[(size_t)e * 3 + 2] /= LN10;
+            __syncwarp();
+          }
         }
-        bma = warp_merge(bma);
-        if (lane == 0) wgw[j] = bma.result();
+        if (!done) {
+          Lse bma;
+          bma.init();
+          for (long long c = lane; c < C; c += 32) {
+            const unsigned long long mask = prm.cfg_mask[c] & has_mask;
+            Lse b;
+            b.init();
+            for (int k = 0; k < K; ++k) {
+              const double *tk = tab + (size_t)k * S * 3;
+              double den = 0.0, num = 0.0, sing = 0.0;
+              unsigned long long mm = mask;
+              while (mm) {
+                const int s = __ffsll((long long)mm) - 1;
+                mm &= mm - 1;
+                den += tk[3 * s];
+                num += tk[3 * s + 1];
+                sing += tk[3 * s + 2];
+              }
+              b.add(abf_from_sums(den, num, sing, prm.oma2S[k]), 1.0 / (double)K, k == 0);
+            }
+            bma.add(b.result(), prm.cfg_weight[c], c == 0); // CalcBMA (gene_snp_pair.cpp:572-602)
+          }
+          bma = warp_merge(bma);
+          res = bma.result();
+        }
+        if (lane == 0) wgw[j] = res;
         __syncwarp();
       }
     }

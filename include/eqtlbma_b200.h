@@ -169,6 +169,9 @@ int eqb_partition_by_cost(const int64_t *cost_per_gene, int64_t n_genes, int64_t
 /* Number of genes whose (gene, subgroup) row sets are gene-independent (K1 outputs reusable: the
  * split projection / contraction path); the others take the general fused kernel. Diagnostic. */
 int64_t eqb_fast_gene_count(const eqb_ctx *ctx);
+/* Duration (ms, CUDA events on the library's stream) of the last K2+K3 launch (fast_pair_kernel) issued by
+ * eqb_run_device_only: the dominant kernel of the non-permuted pass, for roofline accounting. */
+float eqb_last_pair_kernel_ms(const eqb_ctx *ctx);
 /* Number of kernel launches issued by this context so far. */
 int64_t eqb_launch_count(const eqb_ctx *ctx);
 

@@ -71,3 +71,27 @@ def test_dmma_permutation_kernel_equals_general_kernel(cuda_lib):
     assert np.array_equal(a.count, b.count)
     assert np.allclose(a.perm_stats, b.perm_stats, rtol=0, atol=1e-8, equal_nan=True)
     assert np.allclose(a.true_stat, b.true_stat, rtol=0, atol=1e-8, equal_nan=True)
+
+
+def test_gtex_shape_slice_matches_oracle(cuda_lib, oracle_lib):
+    """c3/c4 shape at reduced counts: 9 ragged subgroups, --bfs all (511 configurations), permutations
+    with --pbf all and --pbf gen-sin, against the CPU oracle."""
+    import eqtlbma_b200
+    from eqtlbma_b200._capi import Engine as AnyEngine
+    from eqtlbma_b200.synth import make_dataset, make_grid
+    ds = make_dataset(seed=99, n_subgroups=9, n_inds=150, n_genes=8, snps_per_gene=6, ragged=True,
+                      ragged_min_frac=0.34, gridL=make_grid("general")[:10], n_chr=2)
+    eng = eqtlbma_b200.Engine(ds, analysis="join", bfs="all")
+    ora = AnyEngine(oracle_lib, "eqo_", ds, analysis="join", bfs="all")
+    a, b = eng.run(), ora.run()
+    assert eng.n_configs == 511
+    assert np.array_equal(a.n, b.n)
+    assert np.allclose(a.sstats[..., 1:], b.sstats[..., 1:], rtol=1e-9, atol=0, equal_nan=True)
+    assert np.allclose(a.abf_gen, b.abf_gen, rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(a.abf_cfg, b.abf_cfg, rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(a.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
+    for pbf in ("all", "gen-sin"):
+        pa = eng.run_permutations(25, 1859, pbf=pbf, wrtsize=3)
+        pb = ora.run_permutations(25, 1859, pbf=pbf, wrtsize=3)
+        assert np.array_equal(pa.count, pb.count)
+        assert np.allclose(pa.perm_stats, pb.perm_stats, rtol=0, atol=1e-8, equal_nan=True)
