@@ -1442,13 +1442,31 @@ static int run_perm_or_pair_kernel(eqb_ctx *ctx, const LaunchArgs &la, long long
 {
   const int S = ctx->cfg.n_subgroups;
   const bool mvlr = ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model == EQB_ERROR_MVLR;
-  const size_t smem = perm_smem_doubles(S, ctx->Qmax, ctx->ldn, (int)ctx->phi2S.size(), (int)ctx->phi2L.size(), ctx->gt.UL) * sizeof(double);
-  const bool ok = !mvlr && ctx->d_fp != nullptr && ctx->ldn <= 512 && smem <= 220 * 1024 &&
+  const int K = (int)ctx->phi2S.size(), L = (int)ctx->phi2L.size();
+  // dynamic shared memory available = opt-in maximum of the device minus the kernel's static shared memory
+  int optin = 0;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->cfg.device);
+  cudaFuncAttributes fa16, fa8;
+  cudaFuncGetAttributes(&fa16, perm_kernel<16>);
+  cudaFuncGetAttributes(&fa8, perm_kernel<8>);
+  const size_t lim16 = (size_t)std::max(0, optin - (int)fa16.sharedSizeBytes - 1024);
+  const size_t lim = (size_t)std::max(0, optin - (int)fa8.sharedSizeBytes - 1024);
+  const size_t smem16 = perm_smem_doubles(S, ctx->Qmax, ctx->ldn, K, L, ctx->gt.UL, la.which, 16) * sizeof(double);
+  const size_t smem8 = perm_smem_doubles(S, ctx->Qmax, ctx->ldn, K, L, ctx->gt.UL, la.which, 8) * sizeof(double);
+  const bool ok = !mvlr && ctx->d_fp != nullptr && ctx->ldn <= 512 && smem8 <= lim &&
                   (!ctx->cfg.qnorm || ctx->Qmax >= 2) && !getenv("EQB_NO_PERM_DMMA");
   if (!ok) return run_pair_kernel(ctx, la, n_ctas, ppg);
-  cudaError_t e = cudaFuncSetAttribute(perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel attribute: ") + cudaGetErrorString(e));
-  perm_kernel<<<(unsigned)((long long)la.n_genes * std::max(1, ppg)), THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, la, ctx->gt);
+  const unsigned grid = (unsigned)((long long)la.n_genes * std::max(1, ppg));
+  cudaError_t e;
+  if (smem16 <= lim16) { // 16 warps share the CTA's B matrix: twice the latency hiding
+    e = cudaFuncSetAttribute(perm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+    if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel attribute: ") + cudaGetErrorString(e));
+    perm_kernel<16><<<grid, 16 * 32, smem16, ctx->stream>>>(ctx->d_prm, ctx->d_fp, la, ctx->gt);
+  } else {
+    e = cudaFuncSetAttribute(perm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
+    if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel attribute: ") + cudaGetErrorString(e));
+    perm_kernel<8><<<grid, 8 * 32, smem8, ctx->stream>>>(ctx->d_prm, ctx->d_fp, la, ctx->gt);
+  }
   ctx->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel launch: ") + cudaGetErrorString(e));

@@ -24,21 +24,27 @@ __host__ __device__ inline int perm_lds(int ldn) { return ldn + 1; }
 // rows of the shared B matrix: S*(Qmax+2) data rows, then 8 zero rows of padding (partial tiles read them)
 __host__ __device__ inline int perm_brows(int S, int Qmax) { return S * (Qmax + 2) + 8; }
 // per-warp scratch (doubles): H[8][W], st[8][3][S], tab[K][S][3], flags[8], agg[8][UL][3], vals[8][L], wc[8][S], wg[8], has[8]
-// ... + mitm[K][2^SA][3] (all-configuration sums of the low SA subgroups, S <= 10 and K <= 12 only)
+// per-warp scratch (doubles): [H[8][W] aliased with agg[8][UL][3]], st[8][3][S], flags[8], vals[8][L], wc[8][S],
+// wg[8], has[8]; for --pbf all also tab[K][S][3] and mitm[K][2^SA][3] (sums over the low SA subgroups; S <= 10, K <= 12)
 __host__ __device__ inline int perm_mitm_sa(int S, int K) { return (S <= 10 && K <= 12 && S > 5) ? S - 5 : (S <= 5 && K <= 12 ? 0 : -1); }
-__host__ __device__ inline size_t perm_warp_doubles(int S, int Qmax, int K, int L, int UL)
+__host__ __device__ inline size_t perm_u1_doubles(int S, int Qmax, int UL)
 {
   const size_t W = (size_t)(((S * (Qmax + 2) + 7) / 8) * 8 + ((S + 7) / 8) * 8);
-  const int sa = perm_mitm_sa(S, K);
-  return 8 * W + 8 * 3 * S + 3 * K * S + 8 + (size_t)8 * UL * 3 + (size_t)8 * L + (size_t)8 * S + 8 + 8 +
-         (sa >= 0 ? (size_t)3 * K * (1u << sa) : 0);
+  const size_t a = 8 * W, b = (size_t)8 * UL * 3;
+  return a > b ? a : b;
 }
-__host__ __device__ inline size_t perm_smem_doubles(int S, int Qmax, int ldn, int K, int L, int UL)
+__host__ __device__ inline size_t perm_warp_doubles(int S, int Qmax, int K, int L, int UL, int which)
 {
-  return (size_t)perm_brows(S, Qmax) * perm_lds(ldn) + (size_t)WARPS * perm_warp_doubles(S, Qmax, K, L, UL);
+  const int sa = perm_mitm_sa(S, K);
+  size_t d = perm_u1_doubles(S, Qmax, UL) + 8 * 3 * S + 8 + (size_t)8 * L + (size_t)8 * S + 8 + 8;
+  if (which == 3) d += (size_t)3 * K * S + (sa >= 0 ? (size_t)3 * K * (1u << sa) : 0);
+  return d;
+}
+__host__ __device__ inline size_t perm_smem_doubles(int S, int Qmax, int ldn, int K, int L, int UL, int which, int pw)
+{
+  return (size_t)perm_brows(S, Qmax) * perm_lds(ldn) + (size_t)pw * perm_warp_doubles(S, Qmax, K, L, UL, which);
 }
 
-// H[8][ncol8*8] += X[rows m0..m0+7][:] * B[row_begin .. row_begin + ncol8*8)[:]'   (optionally with X squared)
 // column c of the block is B row min(c * rstride, zero_row): rstride = 1 for the data rows, = Qmax+2 to pick
 // the intercept row of every subgroup (the mask operand of the sums of squares, scaled by 1/sqrt(n))
 __device__ __forceinline__ void dmma_block(const double *__restrict__ xrow, const double *__restrict__ Bsm, int lds,
@@ -88,18 +94,20 @@ __device__ __forceinline__ void dmma_block(const double *__restrict__ xrow, cons
   }
 }
 
-__global__ void __launch_bounds__(THREADS) perm_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
+template <int PW>
+__global__ void __launch_bounds__(PW * 32) perm_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
                                                        const LaunchArgs la, const GridTab gt)
 {
+  constexpr int PTHREADS = PW * 32;
   const DevParams &prm = *prm_;
   extern __shared__ double dyn_smem[];
   __shared__ int s_n[MAXS];
   __shared__ int s_rankz[MAXS];
   __shared__ unsigned int s_colvalid[MAXS];
   __shared__ double s_yy[MAXS], s_tss[MAXS], s_ybar[MAXS];
-  __shared__ double w_part[WARPS][2];
-  __shared__ int w_flag[WARPS][3];
-  __shared__ double w_sep[WARPS][MAXS];
+  __shared__ double w_part[PW][2];
+  __shared__ int w_flag[PW][3];
+  __shared__ double w_sep[PW][MAXS];
   __shared__ int w_sep_nan[MAXS];
 
   const int S = prm.S, N = prm.N, ldn = prm.ldn, Qmax = prm.Qmax, L = prm.L, K = prm.K;
@@ -116,23 +124,23 @@ __global__ void __launch_bounds__(THREADS) perm_kernel(const DevParams *__restri
   double *Bsm = dyn_smem;                                  // [perm_brows][lds]
   double *wbase = Bsm + (size_t)perm_brows(S, Qmax) * lds; // per-warp scratch
   const int UL = gt.UL;
-  double *Hw = wbase + (size_t)warp * perm_warp_doubles(S, Qmax, K, L, UL);
-  double *stw = Hw + 8 * W;      // [8][3][S] standardised statistics of the tile's SNPs
-  double *tab = stw + 8 * 3 * S; // [K][S][3]
-  unsigned long long *flagw = (unsigned long long *)(tab + 3 * K * S); // [8] subgroups needing the explicit path
-  double *agg = (double *)(flagw + 8);                                 // [8][UL][3]
-  double *valw = agg + 8 * UL * 3;                                     // [8][L]
-  double *wcw = valw + 8 * L;                                          // [8][S]
-  double *wgw = wcw + 8 * S;                                           // [8]
-  unsigned long long *hasw = (unsigned long long *)(wgw + 8);          // [8]
-  double *mitm = (double *)(hasw + 8);                                 // [K][2^SA][3]
+  double *Hw = wbase + (size_t)warp * perm_warp_doubles(S, Qmax, K, L, UL, la.which);
+  double *agg = Hw;                                    // [8][UL][3], aliases H (dead after phase 3 in join mode)
+  double *stw = Hw + perm_u1_doubles(S, Qmax, UL);     // [8][3][S] standardised statistics of the tile's SNPs
+  unsigned long long *flagw = (unsigned long long *)(stw + 8 * 3 * S); // [8] subgroups needing the explicit path
+  double *valw = (double *)(flagw + 8);                // [8][L]
+  double *wcw = valw + 8 * L;                          // [8][S]
+  double *wgw = wcw + 8 * S;                           // [8]
+  unsigned long long *hasw = (unsigned long long *)(wgw + 8); // [8]
+  double *tab = (double *)(hasw + 8);                  // [K][S][3]   (--pbf all only)
+  double *mitm = tab + 3 * K * S;                      // [K][2^SA][3] (--pbf all only)
 
   if (threadIdx.x < MAXS) w_sep_nan[threadIdx.x] = 0;
   // zero the padding rows
-  for (int i = threadIdx.x; i < 8 * lds; i += THREADS) Bsm[(size_t)nrowB * lds + i] = 0.0;
+  for (int i = threadIdx.x; i < 8 * lds; i += PTHREADS) Bsm[(size_t)nrowB * lds + i] = 0.0;
 
   // ------------------------------------------------------------------ phase 1
-  for (int s = warp; s < S; s += WARPS) {
+  for (int s = warp; s < S; s += PW) {
     const SubDev &sb = prm.sub[s];
     double *q = Bsm + (size_t)s * R * lds;
     double *yt = q + (size_t)(Qmax + 1) * lds;
@@ -289,7 +297,7 @@ __global__ void __launch_bounds__(THREADS) perm_kernel(const DevParams *__restri
     for (int s = lane; s < S; s += 32) w_sep[warp][s] = INFINITY;
   __syncwarp();
 
-  for (long long m0 = mbeg + (long long)warp * 8; m0 < mend; m0 += (long long)WARPS * 8) {
+  for (long long m0 = mbeg + (long long)warp * 8; m0 < mend; m0 += (long long)PW * 8) {
     const int tn = (int)min((long long)8, mend - m0);
     const long long mrow = min(m0 + g8, mend - 1);
     // ---- phase 2: DMMA contraction of the tile against every B row and mask row
@@ -684,9 +692,9 @@ __global__ void __launch_bounds__(THREADS) perm_kernel(const DevParams *__restri
   }
   __syncthreads();
   if (la.stat_kind == STAT_SEP_PER) {
-    for (int s = threadIdx.x; s < S; s += THREADS) {
+    for (int s = threadIdx.x; s < S; s += PTHREADS) {
       double v = INFINITY;
-      for (int w = 0; w < WARPS; ++w) v = fmin(v, w_sep[w][s]);
+      for (int w = 0; w < PW; ++w) v = fmin(v, w_sep[w][s]);
       if (la.true_rules) {
         if (!(v < 1.0)) v = 1.0;
       } else if (w_sep_nan[s])
@@ -701,19 +709,19 @@ __global__ void __launch_bounds__(THREADS) perm_kernel(const DevParams *__restri
     const long long Mg = mend - mbeg;
     bool fn = false;
     int nn = 0;
-    for (int w = 0; w < WARPS; ++w) {
+    for (int w = 0; w < PW; ++w) {
       fn = fn || w_flag[w][0];
       nn += w_flag[w][2];
     }
     double res;
     if (la.stat_kind == STAT_JOIN_MAX) {
       double v = -INFINITY;
-      for (int w = 0; w < WARPS; ++w) v = fmax(v, w_part[w][0]);
+      for (int w = 0; w < PW; ++w) v = fmax(v, w_part[w][0]);
       res = (fn && !la.true_rules) ? nan("") : v;
     } else if (la.stat_kind == STAT_JOIN_AVG) {
       Lse t;
       t.init();
-      for (int w = 0; w < WARPS; ++w) {
+      for (int w = 0; w < PW; ++w) {
         Lse o;
         o.m = w_part[w][0];
         o.acc = w_part[w][1];
@@ -730,7 +738,7 @@ __global__ void __launch_bounds__(THREADS) perm_kernel(const DevParams *__restri
       }
     } else {
       double v = 1.0;
-      for (int w = 0; w < WARPS; ++w) v = fmin(v, w_part[w][0]);
+      for (int w = 0; w < PW; ++w) v = fmin(v, w_part[w][0]);
       res = v;
     }
     out[0] = res;
