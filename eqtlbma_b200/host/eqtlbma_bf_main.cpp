@@ -25,6 +25,7 @@
 #include <sstream>
 #include <string>
 #include <sys/time.h>
+#include <thread>
 #include <vector>
 
 #include "../../include/eqtlbma_b200.h"
@@ -129,6 +130,86 @@ void gz_write(const string &path, const char *mode, const string &txt)
     off += chunk;
   }
   gzclose(f);
+}
+
+// One gzip member from a text chunk (in memory).  Concatenated members are a valid gzip file -- it is
+// also what the reference produces by re-opening its outputs in "ab" mode for every write-group
+// (eqtlbma_bf.cpp:1121-1125).
+void deflate_member(const string &txt, vector<unsigned char> &out)
+{
+  out.clear();
+  if (txt.empty()) return;
+  z_stream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
+    cerr << "ERROR: deflateInit2 failed" << endl;
+    exit(EXIT_FAILURE);
+  }
+  out.resize(deflateBound(&zs, txt.size()) + 64);
+  zs.next_in = (Bytef *)txt.data();
+  zs.avail_in = (uInt)txt.size();
+  zs.next_out = out.data();
+  zs.avail_out = (uInt)out.size();
+  if (deflate(&zs, Z_FINISH) != Z_STREAM_END) {
+    cerr << "ERROR: deflate failed" << endl;
+    exit(EXIT_FAILURE);
+  }
+  out.resize(zs.total_out);
+  deflateEnd(&zs);
+}
+
+// Output encoder: the genes [g0, g1) of a batch are cut into `nthreads` contiguous slices;
+// every slice is formatted and deflated by its own thread, the members are appended in gene order.
+// fmt(ga, gb, txt) must append the text of genes [ga, gb) to txt.
+template <class F>
+void parallel_emit(const string &path, int nthreads, int64_t g0, int64_t g1, const vector<int64_t> &weight_prefix, F fmt)
+{
+  nthreads = max(1, nthreads);
+  // slice boundaries balanced on the number of pairs (weight_prefix[g - g0] = pairs before gene g)
+  vector<int64_t> cut(nthreads + 1, g1);
+  cut[0] = g0;
+  const int64_t total = weight_prefix[g1 - g0];
+  for (int t = 1; t < nthreads; ++t) {
+    const int64_t target = total * t / nthreads;
+    int64_t g = cut[t - 1];
+    while (g < g1 && weight_prefix[g - g0] < target) ++g;
+    cut[t] = g;
+  }
+  vector<vector<unsigned char> > members(nthreads);
+  vector<thread> pool;
+  auto work = [&](int t) {
+    // chunks of at most ~256 MB of text per member (zlib's 32-bit counters)
+    string txt;
+    fmt(cut[t], cut[t + 1], txt);
+    if (txt.size() < ((size_t)1 << 31))
+      deflate_member(txt, members[t]);
+    else {
+      size_t off = 0;
+      vector<unsigned char> part;
+      while (off < txt.size()) {
+        size_t len = min<size_t>((size_t)1 << 28, txt.size() - off);
+        const size_t nl = txt.rfind('\n', off + len - 1);
+        if (nl != string::npos && nl >= off) len = nl + 1 - off;
+        deflate_member(txt.substr(off, len), part);
+        members[t].insert(members[t].end(), part.begin(), part.end());
+        off += len;
+      }
+    }
+  };
+  for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+  FILE *f = fopen(path.c_str(), "ab");
+  if (f == NULL) {
+    cerr << "ERROR: can't open file " << path << " with mode ab" << endl;
+    exit(EXIT_FAILURE);
+  }
+  for (int t = 0; t < nthreads; ++t)
+    if (!members[t].empty() && fwrite(members[t].data(), 1, members[t].size(), f) != members[t].size()) {
+      cerr << "ERROR: can't write to file " << path << endl;
+      exit(EXIT_FAILURE);
+    }
+  fclose(f);
 }
 
 // ------------------------------------------------------------------ options (eqtlbma_bf.cpp:1586-1597)
@@ -1118,83 +1199,92 @@ int main(int argc, char **argv)
     }
 
     // ---- serialisation (writeRes*, eqtlbma_bf.cpp:919-1399)
+    // --thread is repurposed for the output encoder (formatting + deflate), SURVEY 8b
+    const int nthr = o.nb_threads;
     if (write_ss) {
       for (int s = 0; s < S; ++s) {
-        string txt;
-        for (int64_t g = g0; g < g1; ++g) {
-          if (!analyzed[g - g0]) continue;
-          for (int64_t j = 0; j < ce[g] - cb[g]; ++j) {
-            const int64_t p = off[g - g0] + j;
-            if (n[p * S + s] <= 0) continue;
-            const SnpRec *sr = snps[cb[g] + j];
-            txt += genes[g]->name;
-            txt += sep;
-            txt += sr->name;
-            txt += sep;
-            put_sci(txt, sr->maf.find(d.subgroups[s])->second);
-            txt += sep;
-            txt += to_string(n[p * S + s]);
-            for (int k = 0; k < 5; ++k) {
+        parallel_emit(o.out + "_sumstats_" + d.subgroups[s] + ".txt.gz", nthr, g0, g1, off,
+                      [&](int64_t ga, int64_t gb, string &txt) {
+          for (int64_t g = ga; g < gb; ++g) {
+            if (!analyzed[g - g0]) continue;
+            for (int64_t j = 0; j < ce[g] - cb[g]; ++j) {
+              const int64_t p = off[g - g0] + j;
+              if (n[p * S + s] <= 0) continue;
+              const SnpRec *sr = snps[cb[g] + j];
+              txt += genes[g]->name;
               txt += sep;
-              put_sci(txt, ss[(p * S + s) * 5 + k]);
+              txt += sr->name;
+              txt += sep;
+              put_sci(txt, sr->maf.find(d.subgroups[s])->second);
+              txt += sep;
+              txt += to_string(n[p * S + s]);
+              for (int k = 0; k < 5; ++k) {
+                txt += sep;
+                put_sci(txt, ss[(p * S + s) * 5 + k]);
+              }
+              txt += "\n";
             }
-            txt += "\n";
           }
-        }
-        gz_write(o.out + "_sumstats_" + d.subgroups[s] + ".txt.gz", "ab", txt);
+        });
       }
     }
     if (join) {
-      string raw, avg;
-      for (int64_t g = g0; g < g1; ++g) {
-        if (!analyzed[g - g0]) continue;
-        for (int64_t j = 0; j < ce[g] - cb[g]; ++j) {
-          const int64_t p = off[g - g0] + j;
-          const string &gn = genes[g]->name, &sn = snps[cb[g] + j]->name;
-          static const char *rows[3] = {"gen", "gen-fix", "gen-maxh"};
-          for (int r = 0; r < 3; ++r) {
-            raw += gn + sep + sn + sep + rows[r];
-            for (int k = 0; k < L; ++k) {
-              raw += sep;
-              put_sci(raw, agen[(p * 3 + r) * L + k]);
-            }
-            raw += "\n";
-          }
-          for (int64_t c = 0; c < C; ++c) {
-            raw += gn + sep + sn + sep + cnames[c];
-            for (int k = 0; k < L; ++k) { // padded / truncated to |gridL| columns (eqtlbma_bf.cpp:1207-1212)
-              raw += sep;
-              put_sci(raw, k < K ? acfg[(p * C + c) * K + k] : kNaN);
-            }
-            raw += "\n";
-          }
-          if (o.outw) {
-            int nsub = 0;
-            for (int s = 0; s < S; ++s) nsub += n[p * S + s] > 0 ? 1 : 0;
-            avg += gn + sep + sn + sep + to_string(nsub);
-            const double *w = &aw[p * (5 + C)];
-            for (int k = 0; k < 3; ++k) {
-              avg += sep;
-              put_sci(avg, w[k]);
-            }
-            if (o.bfs != "gen") {
-              avg += sep;
-              put_sci(avg, w[3]);
-            }
-            if (o.bfs == "all") {
-              avg += sep;
-              put_sci(avg, w[4]);
+      static const char *rows[3] = {"gen", "gen-fix", "gen-maxh"};
+      parallel_emit(o.out + "_l10abfs_raw.txt.gz", nthr, g0, g1, off, [&](int64_t ga, int64_t gb, string &raw) {
+        for (int64_t g = ga; g < gb; ++g) {
+          if (!analyzed[g - g0]) continue;
+          for (int64_t j = 0; j < ce[g] - cb[g]; ++j) {
+            const int64_t p = off[g - g0] + j;
+            const string &gn = genes[g]->name, &sn = snps[cb[g] + j]->name;
+            for (int r = 0; r < 3; ++r) {
+              raw += gn + sep + sn + sep + rows[r];
+              for (int k = 0; k < L; ++k) {
+                raw += sep;
+                put_sci(raw, agen[(p * 3 + r) * L + k]);
+              }
+              raw += "\n";
             }
             for (int64_t c = 0; c < C; ++c) {
-              avg += sep;
-              put_sci(avg, w[5 + c]);
+              raw += gn + sep + sn + sep + cnames[c];
+              for (int k = 0; k < L; ++k) { // padded / truncated to |gridL| columns (eqtlbma_bf.cpp:1207-1212)
+                raw += sep;
+                put_sci(raw, k < K ? acfg[(p * C + c) * K + k] : kNaN);
+              }
+              raw += "\n";
             }
-            avg += "\n";
           }
         }
-      }
-      gz_write(o.out + "_l10abfs_raw.txt.gz", "ab", raw);
-      if (o.outw) gz_write(o.out + "_l10abfs_avg-grids.txt.gz", "ab", avg);
+      });
+      if (o.outw)
+        parallel_emit(o.out + "_l10abfs_avg-grids.txt.gz", nthr, g0, g1, off, [&](int64_t ga, int64_t gb, string &avg) {
+          for (int64_t g = ga; g < gb; ++g) {
+            if (!analyzed[g - g0]) continue;
+            for (int64_t j = 0; j < ce[g] - cb[g]; ++j) {
+              const int64_t p = off[g - g0] + j;
+              int nsub = 0;
+              for (int s = 0; s < S; ++s) nsub += n[p * S + s] > 0 ? 1 : 0;
+              avg += genes[g]->name + sep + snps[cb[g] + j]->name + sep + to_string(nsub);
+              const double *w = &aw[p * (5 + C)];
+              for (int k = 0; k < 3; ++k) {
+                avg += sep;
+                put_sci(avg, w[k]);
+              }
+              if (o.bfs != "gen") {
+                avg += sep;
+                put_sci(avg, w[3]);
+              }
+              if (o.bfs == "all") {
+                avg += sep;
+                put_sci(avg, w[4]);
+              }
+              for (int64_t c = 0; c < C; ++c) {
+                avg += sep;
+                put_sci(avg, w[5 + c]);
+              }
+              avg += "\n";
+            }
+          }
+        });
     }
     if (o.nb_permutations > 0 && (join || o.perm_sep != 0)) {
       for (int s = 0; s < per; ++s) {

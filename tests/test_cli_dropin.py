@@ -36,6 +36,16 @@ def cells_match(a, b):
 
 @pytest.mark.parametrize("name", sorted(set(SCENARIOS) - NOT_YET - DEGENERATE))
 def test_cli_outputs_match_reference_text(tmp_path, name):
+    _run_and_compare(tmp_path, name, threads=1)
+
+
+@pytest.mark.parametrize("name", ["ragged5", "covariates", "sep_permsep2_trick2"])
+def test_cli_parallel_encoder_is_byte_identical_after_gunzip(tmp_path, name):
+    """--thread N drives the multi-threaded output encoder (one gzip member per thread slice)."""
+    _run_and_compare(tmp_path, name, threads=4)
+
+
+def _run_and_compare(tmp_path, name, threads):
     if not os.path.exists(EXE):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "eqtlbma_b200", "host")])
     sc = SCENARIOS[name]
@@ -43,7 +53,7 @@ def test_cli_outputs_match_reference_text(tmp_path, name):
     d = str(tmp_path / "in")
     ds.write_files(d)
     out = str(tmp_path / "obs")
-    cmd = [EXE] + ds.ref_args(d, out) + ref_flags(sc) + ["-v", "0"]
+    cmd = [EXE] + ds.ref_args(d, out) + ref_flags(sc) + ["-v", "0", "--thread", str(threads)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     gold = json.loads(gzip.open(os.path.join(GOLD, name + ".text.json.gz"), "rt").read())
