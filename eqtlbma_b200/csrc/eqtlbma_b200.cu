@@ -1373,7 +1373,10 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         fa.out_cfg = (join && C > 0) ? ctx->d_cfg.p : nullptr;
         fa.out_w = join ? ctx->d_w.p : nullptr;
         int T = 64;
-        while (T > 4 && fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which) > 72 * 1024) T /= 2;
+        if (const char *e = getenv("EQB_FAST_T")) T = std::max(4, atoi(e)); // tuning knob (power of two)
+        size_t tile_budget = 72 * 1024;
+        if (const char *e = getenv("EQB_FAST_SMEM_KB")) tile_budget = (size_t)std::max(8, atoi(e)) * 1024;
+        while (T > 4 && ((T & (T - 1)) || fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which) > tile_budget)) T /= 2;
         fa.T = T;
         const size_t smem = fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which);
         if (smem > 200 * 1024) return fail(ctx, "configuration table does not fit in shared memory");

@@ -611,16 +611,16 @@ struct GridTab {
 
 // ES-model log10 ABF from the sums over the active subgroups (CalcLog10AbfUvlr, gene_snp_pair.cpp:332-355)
 // lbar = 0.5 log10(V) - 0.5 log10(V+oma2) + 0.5 T2 oma2/(V+oma2)/ln10 with V = 1/den, T2 = num^2/den,
-// rewritten as -0.5 log10(1 + oma2 den) + 0.5 num^2 oma2 / (1 + oma2 den) / ln10
+// rewritten as -0.5 log10(1 + oma2 den) + 0.5 num^2 oma2 / (1 + oma2 den) / ln10.
+// The reference's guards "bbar != 0 && V < +Inf" and "T2 != 0" are the exact-zero cases num == 0 / den == 0
+// (every contributing term has |t| >= 1e-8, so neither quotient can underflow), tested without the divisions.
+#define EQB_INV_LN10 0.43429448190325182765
 __device__ __forceinline__ double abf_from_sums(double den, double num, double sing, double oma2)
 {
-  const double bbar = (den != 0.0) ? num / den : 0.0;
-  const double V = (den != 0.0) ? 1.0 / den : INFINITY;
-  if (bbar != 0.0 && V < INFINITY) {
-    const double T2 = bbar * bbar / V;
-    if (T2 == 0.0 || oma2 == 0.0) return sing; // (a zero numerator would take the slow division path)
-    const double od = oma2 * den;
-    return sing + (-0.5 * log1p(od) + 0.5 * num * num * oma2 / (1.0 + od)) / LN10;
+  if (num != 0.0 && den != 0.0 && den == den) { // (a NaN denominator fails the reference's "V < +Inf")
+    if (oma2 == 0.0) return sing; // (a zero numerator would take the slow division path)
+    const double z = 1.0 + oma2 * den; // log(1 + x) has an ABSOLUTE error of ~1e-16 here: no log1p needed
+    return sing + (-0.5 * log(z) + 0.5 * num * num * oma2 / z) * EQB_INV_LN10;
   }
   return 0.0;
 }
@@ -637,28 +637,69 @@ __device__ __forceinline__ void term_entry(double b, double v, double t, double 
     const double inv = 1.0 / (v + phi2);
     d = inv;
     bd = b * inv;
-    sg = (phi2 == 0.0) ? 0.0 : (-0.5 * log1p(phi2 / v) + 0.5 * t * t * phi2 * inv) / LN10;
+    // -0.5 log10(1 + phi2/v) = 0.5 log10(v / (v + phi2)) = 0.5 log10(v * inv)
+    sg = (phi2 == 0.0) ? 0.0 : (0.5 * log(v * inv) + 0.5 * t * t * phi2 * inv) * EQB_INV_LN10;
   }
 }
 
-__global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__restrict__ prm_,
+// phase A helper: SN contractions of one genotype row against the SN residualised expression rows of the gene
+// (one warp; 16-byte loads -- rows are ldn*8 bytes apart with ldn a multiple of 16)
+template <int SN>
+__device__ __forceinline__ void contract_shared_x(const double *__restrict__ Xm, const FastSub *__restrict__ fsub, size_t grow,
+                                                  int ldn, int lane, double *__restrict__ out)
+{
+  const double2 *x2 = reinterpret_cast<const double2 *>(Xm);
+  const double2 *y2[SN];
+#pragma unroll
+  for (int a = 0; a < SN; ++a) y2[a] = reinterpret_cast<const double2 *>(fsub[a].Ytil + grow);
+  double acc[SN];
+#pragma unroll
+  for (int a = 0; a < SN; ++a) acc[a] = 0.0;
+  const int h = ldn >> 1;
+#pragma unroll(SN <= 4 ? 2 : 1)
+  for (int i = lane; i < h; i += 32) {
+    const double2 x = x2[i];
+#pragma unroll
+    for (int a = 0; a < SN; ++a) {
+      const double2 y = y2[a][i];
+      acc[a] += x.x * y.x;
+      acc[a] += x.y * y.y;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < SN; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+    if (lane == a) out[a] = acc[a];
+  }
+}
+
+// Tile of T pairs (T a power of two) per CTA, phase-synchronous.  Work items of the ABF phases are numbered
+// (value, pair) with the PAIR index fastest, so that a warp evaluates ONE grid point / configuration for 32 pairs:
+// the data-independent branches (oma2 == 0 of the gen-fix row, phi2 == 0 of the gen-maxh row, consistent vs
+// singleton value) are warp-uniform.  Values are staged in shared memory ([value][T+1], conflict-free both ways),
+// reduced there, and written to the output rows with coalesced stores.
+__global__ void __launch_bounds__(THREADS, 3) fast_pair_kernel(const DevParams *__restrict__ prm_,
                                                             const FastParams *__restrict__ fp_, const FastArgs fa,
                                                             const GridTab gt)
 {
   const DevParams &prm = *prm_;
   extern __shared__ double fsm[];
   const int S = prm.S, ldn = prm.ldn, L = prm.L, K = prm.K, T = fa.T, UL = gt.UL;
+  const int lgT = 31 - __clz(T), T1 = T + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long C = (fa.which == 1) ? 0 : ((fa.which == 2) ? S : prm.C);
   const bool join = prm.analysis == 1;
   const int nrow_small = 3 + ((fa.which == 2) ? S : 0); // rows whose values are staged in shared memory
   const int vals_per_pair = 3 * L + ((fa.which == 2) ? S * K : 0);
+  const int sst = (3 * S) | 1, sag = (3 * UL) | 1; // odd strides: conflict-free when the pair index varies across lanes
   // shared memory carve-up
   double *xy = fsm;                                          // [T][S]
-  double *st = xy + (size_t)T * S;                           // [T][3][S]
-  double *agg = st + (size_t)T * 3 * S;                      // [T][UL][3]
-  double *wrow = agg + (size_t)T * UL * 3;                   // [T][3+S] weighted small rows
-  double *tab = wrow + (size_t)T * (3 + S);                  // [T][K][S][3] (which == 3)
+  double *st = xy + (size_t)T * S;                           // [T][sst]  b, v, t per subgroup
+  double *agg = st + (size_t)T * sst;                        // [T][sag]  den, num, sing per unique phi2
+  double *wrow = agg + (size_t)T * sag;                      // [T][3+S] weighted small rows
+  double *vs = wrow + (size_t)T * (3 + S);                   // [vals_per_pair][T+1] staged values
+  double *tab = vs + (size_t)vals_per_pair * T1;             // [T][K][S][3] (which == 3)
   unsigned long long *hasm = (unsigned long long *)(tab + ((fa.which == 3) ? (size_t)T * K * S * 3 : 0)); // [T]
   long long *s_pair = (long long *)(hasm + T);               // [T] output pair index
   long long *s_m = s_pair + T;                               // [T] SNP index
@@ -684,39 +725,28 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
   }
   __syncthreads();
   // ---------------- phase A: contraction x . ytil_s (one warp per pair)
-  for (int j = warp; j < tn; j += WARPS) {
-    const long long m = s_m[j];
-    const size_t grow = (size_t)s_gene[j] * ldn;
-    for (int s0 = 0; s0 < S; s0 += 8) {
-      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const int sn = min(8, S - s0);
-      bool same = true;
-      for (int a = 1; a < sn; ++a) same = same && (prm.sub[s0 + a].X == prm.sub[s0].X);
+  for (int s0 = 0; s0 < S; s0 += 8) {
+    const int sn = min(8, S - s0);
+    bool same = true;
+    for (int a = 1; a < sn; ++a) same = same && (prm.sub[s0 + a].X == prm.sub[s0].X);
+    const FastSub *fsub = fp_->sub + s0;
+    for (int j = warp; j < tn; j += WARPS) {
+      const size_t xoff = (size_t)s_m[j] * ldn, grow = (size_t)s_gene[j] * ldn;
+      double *out = xy + (size_t)j * S + s0;
       if (same) {
-        const double *Xm = prm.sub[s0].X + (size_t)m * ldn;
-        const double *yp[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) yp[a] = fp_->sub[s0 + min(a, sn - 1)].Ytil + grow;
-        for (int i = lane; i < ldn; i += 32) {
-          const double x = Xm[i];
-#pragma unroll
-          for (int a = 0; a < 8; ++a)
-            if (a < sn) acc[a] += x * yp[a][i];
+        const double *Xm = prm.sub[s0].X + xoff;
+        switch (sn) {
+        case 1: contract_shared_x<1>(Xm, fsub, grow, ldn, lane, out); break;
+        case 2: contract_shared_x<2>(Xm, fsub, grow, ldn, lane, out); break;
+        case 3: contract_shared_x<3>(Xm, fsub, grow, ldn, lane, out); break;
+        case 4: contract_shared_x<4>(Xm, fsub, grow, ldn, lane, out); break;
+        case 5: contract_shared_x<5>(Xm, fsub, grow, ldn, lane, out); break;
+        case 6: contract_shared_x<6>(Xm, fsub, grow, ldn, lane, out); break;
+        case 7: contract_shared_x<7>(Xm, fsub, grow, ldn, lane, out); break;
+        default: contract_shared_x<8>(Xm, fsub, grow, ldn, lane, out); break;
         }
       } else {
-        for (int a = 0; a < sn; ++a) {
-          const double *Xa = prm.sub[s0 + a].X + (size_t)m * ldn;
-          const double *Ya = fp_->sub[s0 + a].Ytil + grow;
-          for (int i = lane; i < ldn; i += 32) acc[a] += Xa[i] * Ya[i];
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        if (a < sn) { // sn is warp-uniform
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
-          if (lane == a) xy[(size_t)j * S + s0 + a] = acc[a];
-        }
+        for (int a = 0; a < sn; ++a) contract_shared_x<1>(prm.sub[s0 + a].X + xoff, fsub + a, grow, ldn, lane, out + a);
       }
     }
   }
@@ -739,9 +769,9 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
                       fs.tz_wmax, ps);
       atomicOr(&hasm[j], 1ull << s);
     }
-    st[((size_t)j * 3 + 0) * S + s] = ps.b;
-    st[((size_t)j * 3 + 1) * S + s] = ps.v;
-    st[((size_t)j * 3 + 2) * S + s] = ps.t;
+    st[(size_t)j * sst + s] = ps.b;
+    st[(size_t)j * sst + S + s] = ps.v;
+    st[(size_t)j * sst + 2 * S + s] = ps.t;
     const long long pair = s_pair[j];
     if (fa.out_n) fa.out_n[pair * S + s] = have ? fs.n : 0;
     if (fa.out_ss) {
@@ -756,9 +786,10 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
   __syncthreads();
   if (!join) return;
   // ---------------- phase C0: sums over the subgroups with results, per unique phi2 (consistent configuration)
-  for (int it = threadIdx.x; it < tn * UL; it += THREADS) {
-    const int j = it / UL, u = it % UL;
-    const double *stj = st + (size_t)j * 3 * S;
+  for (int it = threadIdx.x; it < (UL << lgT); it += THREADS) {
+    const int u = it >> lgT, j = it & (T - 1);
+    if (j >= tn) continue;
+    const double *stj = st + (size_t)j * sst;
     unsigned long long mask = hasm[j];
     const double phi2 = gt.uphi[u];
     double den = 0.0, num = 0.0, sing = 0.0;
@@ -771,7 +802,7 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
       num += bd;
       sing += sg;
     }
-    double *a = agg + ((size_t)j * UL + u) * 3;
+    double *a = agg + (size_t)j * sag + 3 * u;
     a[0] = den;
     a[1] = num;
     a[2] = sing;
@@ -779,7 +810,7 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
   if (fa.which == 3) {
     for (int it = threadIdx.x; it < tn * K * S; it += THREADS) {
       const int j = it / (K * S), e = it % (K * S), k = e / S, s = e % S;
-      const double *stj = st + (size_t)j * 3 * S;
+      const double *stj = st + (size_t)j * sst;
       double *te = tab + ((size_t)j * K * S + e) * 3;
       if ((hasm[j] >> s) & 1ull)
         term_entry(stj[s], stj[S + s], stj[2 * S + s], prm.phi2S[k], te[0], te[1], te[2]);
@@ -791,41 +822,65 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
     }
   }
   __syncthreads();
-  // ---------------- phase C1: thread per (pair, value): the 3L consistent values (+ S*K singleton values)
-  for (int it = threadIdx.x; it < tn * vals_per_pair; it += THREADS) {
-    const int j = it / vals_per_pair, e = it % vals_per_pair;
-    const long long pair = s_pair[j];
+  // ---------------- phase C1: thread per (value, pair): the 3L consistent values (+ S*K singleton values)
+  for (int it = threadIdx.x; it < (vals_per_pair << lgT); it += THREADS) {
+    const int e = it >> lgT, j = it & (T - 1);
+    if (j >= tn) continue;
     double v;
-    if (e < 3 * L) {
-      const double *a = agg + ((size_t)j * UL + gt.idxL[e]) * 3;
+    if (e < 3 * L) { // warp-uniform
+      const double *a = agg + (size_t)j * sag + 3 * gt.idxL[e];
       v = abf_from_sums(a[0], a[1], a[2], gt.omaL[e]);
-      fa.out_gen[pair * 3 * L + e] = v; // staged in global memory (L1/L2 resident), re-read in phase C2
     } else {
-      const int e2 = e - 3 * L, c = e2 / K, k = e2 % K;
-      const double *stj = st + (size_t)j * 3 * S;
+      const int e2 = e - 3 * L, c = e2 / K, k = e2 - c * K;
+      const double *stj = st + (size_t)j * sst;
       v = 0.0;
       if ((hasm[j] >> c) & 1ull) {
         double d, bd, sg;
         term_entry(stj[c], stj[S + c], stj[2 * S + c], prm.phi2S[k], d, bd, sg);
         v = abf_from_sums(d, bd, sg, prm.oma2S[k]);
       }
-      fa.out_cfg[(pair * C + c) * K + k] = v;
     }
+    vs[(size_t)e * T1 + j] = v;
   }
   __syncthreads();
   // ---------------- phase C2: log10_weighted_sum of each staged row (utils_math.cpp:100-131)
-  for (int it = threadIdx.x; it < tn * nrow_small; it += THREADS) {
-    const int j = it / nrow_small, r = it % nrow_small;
+  for (int it = threadIdx.x; it < (nrow_small << lgT); it += THREADS) {
+    const int r = it >> lgT, j = it & (T - 1);
+    if (j >= tn) continue;
     const int nk = (r < 3) ? L : K;
-    const double *v = (r < 3) ? fa.out_gen + (s_pair[j] * 3 + r) * L : fa.out_cfg + (s_pair[j] * C + (r - 3)) * K;
-    Lse a;
-    a.init();
-    for (int k = 0; k < nk; ++k) a.add(v[k], 1.0 / (double)nk, k == 0);
-    const double w = (nk > 0) ? a.result() : nan("");
+    const double *v = vs + (size_t)((r < 3) ? r * L : 3 * L + (r - 3) * K) * T1 + j;
+    // two passes exactly as the reference: max (seeded with element 0), then the weighted sum of 10^(x - max)
+    double w = nan("");
+    if (nk > 0) {
+      double mx = v[0];
+      for (int k = 1; k < nk; ++k) {
+        const double x = v[(size_t)k * T1];
+        mx = (x > mx) ? x : mx;
+      }
+      double sum = 0.0;
+      const double wk = 1.0 / (double)nk;
+      for (int k = 0; k < nk; ++k) {
+        const double x = v[(size_t)k * T1];
+        const double e = exp10(x - mx);
+        sum += isnan(x) ? 0.0 : wk * e;
+      }
+      w = mx + log10(sum);
+      if (fabs(w) <= DBL_EPSILON) w = 0.0;
+    }
     wrow[(size_t)j * (3 + S) + r] = w;
     double *o = fa.out_w + s_pair[j] * (5 + C);
     if (r < 3) o[r] = w;
     else o[5 + (r - 3)] = w;
+  }
+  // coalesced copy of the staged values to the output rows (warp per pair)
+  for (int j = warp; j < tn; j += WARPS) {
+    const long long pair = s_pair[j];
+    double *og = fa.out_gen + pair * 3 * L;
+    for (int e = lane; e < 3 * L; e += 32) og[e] = vs[(size_t)e * T1 + j];
+    if (fa.which == 2) {
+      double *oc = fa.out_cfg + pair * C * K;
+      for (int e = lane; e < S * K; e += 32) oc[e] = vs[(size_t)(3 * L + e) * T1 + j];
+    }
   }
   if (fa.which == 3) {
     // all configurations: thread per (pair, configuration), values from the shared table
@@ -904,8 +959,8 @@ __global__ void __launch_bounds__(THREADS) fast_pair_kernel(const DevParams *__r
 // shared-memory bytes of fast_pair_kernel for a tile of T pairs
 __host__ __device__ inline size_t fast_smem_bytes(int T, int S, int L, int K, int UL, int which)
 {
-  size_t d = (size_t)T * S + (size_t)T * 3 * S + (size_t)T * UL * 3 + (size_t)T * (3 + S);
-  (void)L;
+  const size_t vals = (size_t)3 * L + ((which == 2) ? (size_t)S * K : 0);
+  size_t d = (size_t)T * S + (size_t)T * ((3 * S) | 1) + (size_t)T * ((3 * UL) | 1) + (size_t)T * (3 + S) + vals * (T + 1);
   if (which == 3) d += (size_t)T * K * S * 3;
   return d * 8 + (size_t)T * (8 + 8 + 8 + 4) + 16;
 }
