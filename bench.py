@@ -34,9 +34,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(seed=1859, n_subgroups=3, n_inds=300, n_genes=5000, snps_per_gene=50, n_cov=11, dosage=True,
+WORKLOAD = dict(seed=1859, n_subgroups=3, n_inds=300, n_genes=5000, snps_per_gene=50, n_cov=11, cov_per_subgroup=True,
+                dosage=True,
                 radius=100, gene_spacing=201, far_snp=False, n_chr=22)
-WORKLOAD_DESC = ("c2: S=3 x N=300, Q=11 covariates, dosage genotypes, 5000 genes x ~50 cis SNPs, "
+WORKLOAD_DESC = ("c2: S=3 x N=300, Q=11 covariates (subgroup-specific values), dosage genotypes, 5000 genes x ~50 cis SNPs, "
                  "--analys join --bfs sin, gridL 25 / gridS 10, no permutations")
 PERM_WORKLOAD = dict(seed=1860, n_subgroups=9, n_inds=450, n_genes=40, snps_per_gene=200, ragged=True,
                      ragged_min_frac=0.34, radius=100, gene_spacing=201, far_snp=False, n_chr=2)

@@ -289,6 +289,7 @@ struct eqb_ctx {
   cudaStream_t stream = nullptr;
   bool finalized = false;
   int ldn = 0, Qmax = 0;
+  int n_sm = 148;
   std::vector<GenoHost> genos;
   std::vector<SubHost> subs;
   std::vector<double> phi2L, oma2L, phi2S, oma2S;
@@ -318,7 +319,13 @@ struct eqb_ctx {
   std::vector<int> dup_of;
   DevBuf<int> d_genes2;
   DevBuf<long long> d_pair_off2, d_fast_base;
-  DevBuf<double> d_bcat;
+  struct XChunk { // one prep_x_dmma launch: subgroups sharing a genotype variant, their basis / mask columns
+    PrepCols pc;
+    double *cat = nullptr; // Bcat [NTn*8][ldn] then Mcat [NMn*8][ldn]
+    int NTn = 0, NMn = 0, xvar = 0;
+  };
+  std::vector<XChunk> xchunks; // built by the first launch_prep_x (after prep_basis_kernel), constant afterwards
+  bool xchunks_built = false;
   DevBuf<unsigned long long> d_fix; // [0] = count, then (snp << 8 | subgroup) entries needing the explicit K1c pass
   GridTab gt;              // unique phi2 values of the consistent-configuration rows
   double *d_gt_d = nullptr; // uphi[UL] | omaL[3L]
@@ -513,7 +520,12 @@ cudaError_t launch_dmma(eqb_ctx *ctx, const double *X, const double *Bcat, const
   const size_t smem = ((size_t)(NT + NM) * 8 * (ctx->ldn + 1) + (size_t)WARPS * 8 * (NT + NM) * 8) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(prep_x_dmma_kernel<NT, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const unsigned grid = (unsigned)((M + 8 * WARPS - 1) / (8 * WARPS));
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prep_x_dmma_kernel<NT, NM>, THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  const long long want = (M + 8 * WARPS - 1) / (8 * WARPS);
+  const unsigned grid = (unsigned)std::min<long long>(want, (long long)ctx->n_sm * occ); // persistent CTAs
   prep_x_dmma_kernel<NT, NM><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, X, Bcat, Mcat, pc, xp, ctx->d_fix.p, (int)ctx->d_fix.cap);
   ctx->launches++;
   return cudaGetLastError();
@@ -529,54 +541,67 @@ int launch_prep_x(eqb_ctx *ctx)
   const int *dup = ctx->d_gt_i + 3 * (int)ctx->phi2L.size();
   CK(ctx->d_fix.ensure(1 << 16));
   CK(cudaMemsetAsync(ctx->d_fix.p, 0, sizeof(unsigned long long), ctx->stream));
-  // chunks of subgroups sharing a genotype variant, <= 8 basis tiles and <= 8 mask tiles, <= 16 subgroups
-  std::vector<char> done(S, 0);
-  for (int s0 = 0; s0 < S; ++s0) {
-    if (done[s0]) continue;
-    PrepCols pc;
-    memset(&pc, 0, sizeof(pc));
-    int ncols = 0, nmask = 0;
-    std::vector<int> members;
-    for (int s = s0; s < S; ++s) {
-      if (done[s] || ctx->subs[s].xvar != ctx->subs[s0].xvar) continue;
-      if (ctx->dup_of[s] >= 0) {
-        done[s] = 1; // shares the K1 output of an identical earlier subgroup
-        continue;
+  // chunks of subgroups sharing a genotype variant, <= 8 basis tiles and <= 8 mask tiles, <= 16 subgroups;
+  // the plan and its Bcat / Mcat matrices depend on the bases only: built once, after prep_basis_kernel
+  if (!ctx->xchunks_built) {
+    std::vector<char> done(S, 0);
+    for (int s0 = 0; s0 < S; ++s0) {
+      if (done[s0]) continue;
+      eqb_ctx::XChunk xc;
+      PrepCols &pc = xc.pc;
+      memset(&pc, 0, sizeof(pc));
+      int ncols = 0, nmask = 0;
+      std::vector<int> members;
+      for (int s = s0; s < S; ++s) {
+        if (done[s] || ctx->subs[s].xvar != ctx->subs[s0].xvar) continue;
+        if (ctx->dup_of[s] >= 0) {
+          done[s] = 1; // shares the K1 output of an identical earlier subgroup
+          continue;
+        }
+        const int nc = ctx->subs[s].Q + 1;
+        if ((int)members.size() == 16 || ncols + nc > 64 || nmask + 1 > 64) break;
+        pc.sub[members.size()] = s;
+        pc.col0[members.size()] = ncols;
+        pc.ncol[members.size()] = nc;
+        pc.mcol[members.size()] = nmask;
+        pc.sqrt_n[members.size()] = sqrt((double)ctx->hfp.sub[s].n);
+        ncols += nc;
+        nmask += 1;
+        members.push_back(s);
+        done[s] = 1;
       }
-      const int nc = ctx->subs[s].Q + 1;
-      if ((int)members.size() == 16 || ncols + nc > 64 || nmask + 1 > 64) break;
-      pc.sub[members.size()] = s;
-      pc.col0[members.size()] = ncols;
-      pc.ncol[members.size()] = nc;
-      pc.mcol[members.size()] = nmask;
-      pc.sqrt_n[members.size()] = sqrt((double)ctx->hfp.sub[s].n);
-      ncols += nc;
-      nmask += 1;
-      members.push_back(s);
-      done[s] = 1;
+      pc.n_sub = (int)members.size();
+      if (members.empty()) continue;
+      xc.NTn = (ncols + 7) / 8;
+      xc.NMn = (nmask + 7) / 8;
+      xc.xvar = ctx->subs[s0].xvar;
+      // Bcat / Mcat for the chunk (device-side gather of the basis rows; masks from q0 != 0)
+      const size_t bdoubles = (size_t)(xc.NTn + xc.NMn) * 8 * ldn;
+      CK(dmalloc(&xc.cat, bdoubles * sizeof(double)));
+      CK(cudaMemsetAsync(xc.cat, 0, bdoubles * sizeof(double), ctx->stream));
+      double *Bcat = xc.cat, *Mcat = xc.cat + (size_t)xc.NTn * 8 * ldn;
+      for (size_t i = 0; i < members.size(); ++i) {
+        const int s = members[i];
+        CK(cudaMemcpyAsync(Bcat + (size_t)pc.col0[i] * ldn, ctx->d_Bs[s], (size_t)pc.ncol[i] * ldn * sizeof(double),
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+        mask_from_basis_kernel<<<(ldn + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Bs[s], Mcat + (size_t)pc.mcol[i] * ldn, ldn);
+        ctx->launches++;
+      }
+      ctx->xchunks.push_back(xc);
     }
-    pc.n_sub = (int)members.size();
-    if (members.empty()) continue;
-    const int NTn = (ncols + 7) / 8, NMn = (nmask + 7) / 8;
-    // Bcat / Mcat for the chunk (device-side gather of the basis rows; masks from q0 != 0)
-    const size_t bdoubles = (size_t)(NTn + NMn) * 8 * ldn;
-    CK(ctx->d_bcat.ensure(bdoubles));
-    CK(cudaMemsetAsync(ctx->d_bcat.p, 0, bdoubles * sizeof(double), ctx->stream));
-    double *Bcat = ctx->d_bcat.p, *Mcat = ctx->d_bcat.p + (size_t)NTn * 8 * ldn;
-    for (size_t i = 0; i < members.size(); ++i) {
-      const int s = members[i];
-      CK(cudaMemcpyAsync(Bcat + (size_t)pc.col0[i] * ldn, ctx->d_Bs[s], (size_t)pc.ncol[i] * ldn * sizeof(double),
-                         cudaMemcpyDeviceToDevice, ctx->stream));
-      mask_from_basis_kernel<<<(ldn + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Bs[s], Mcat + (size_t)pc.mcol[i] * ldn, ldn);
-      ctx->launches++;
-    }
-    const double *X = ctx->d_X[ctx->subs[s0].xvar];
+    ctx->xchunks_built = true;
+  }
+  for (const eqb_ctx::XChunk &xc : ctx->xchunks) {
+    const double *X = ctx->d_X[xc.xvar];
+    const double *Bcat = xc.cat, *Mcat = xc.cat + (size_t)xc.NTn * 8 * ldn;
+    const int NTn = xc.NTn, NMn = xc.NMn;
     cudaError_t e;
-    if (NTn <= 1 && NMn <= 1) e = launch_dmma<1, 1>(ctx, X, Bcat, Mcat, pc, xp);
-    else if (NTn <= 2 && NMn <= 1) e = launch_dmma<2, 1>(ctx, X, Bcat, Mcat, pc, xp);
-    else if (NTn <= 2 && NMn <= 2) e = launch_dmma<2, 2>(ctx, X, Bcat, Mcat, pc, xp);
-    else if (NTn <= 4 && NMn <= 2) e = launch_dmma<4, 2>(ctx, X, Bcat, Mcat, pc, xp);
-    else e = launch_dmma<8, 2>(ctx, X, Bcat, Mcat, pc, xp);
+    if (NTn <= 1 && NMn <= 1) e = launch_dmma<1, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
+    else if (NTn <= 2 && NMn <= 1) e = launch_dmma<2, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
+    else if (NTn <= 3 && NMn <= 1) e = launch_dmma<3, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
+    else if (NTn <= 5 && NMn <= 1) e = launch_dmma<5, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
+    else if (NTn <= 8 && NMn <= 1) e = launch_dmma<8, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
+    else e = launch_dmma<8, 2>(ctx, X, Bcat, Mcat, xc.pc, xp);
     if (e != cudaSuccess) return fail(ctx, std::string("prep_x_dmma launch: ") + cudaGetErrorString(e));
   }
   // fix-up pass over the queued entries (a small persistent grid; the list is normally empty)
@@ -604,8 +629,29 @@ int launch_prep_yx(eqb_ctx *ctx)
   double **d_ptrs = ctx->d_prep_ptrs;
   if (!d_ptrs) return 0;
   if (G > 0) {
-    prep_y_kernel<<<(unsigned)((G * S + WARPS - 1) / WARPS), THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp,
-                                                                                      d_ptrs + S, d_ptrs + 2 * S);
+    int maxQ = 0;
+    for (int s = 0; s < S; ++s) maxQ = std::max(maxQ, ctx->subs[s].Q);
+    size_t smem = (size_t)(maxQ + 1) * ldn * sizeof(double);
+    const int in_smem = smem <= 96 * 1024;
+    if (!in_smem) smem = 0;
+    const int npl = (ldn + 31) / 32;
+#define EQB_PREP_Y(NPL, R)                                                                                           \
+  do {                                                                                                               \
+    CK(cudaFuncSetAttribute(prep_y_kernel<NPL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    int occ = 0;                                                                                                     \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prep_y_kernel<NPL, R>, THREADS, smem));                   \
+    const long long want = (G + WARPS * R - 1) / (WARPS * R);                                                        \
+    const long long fit = std::max<long long>(1, (long long)ctx->n_sm * std::max(occ, 1) / S); /* one wave */        \
+    const dim3 grid((unsigned)std::min(want, fit), (unsigned)S);                                                     \
+    prep_y_kernel<NPL, R><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, d_ptrs + S, d_ptrs + 2 * S, in_smem); \
+  } while (0)
+    if (npl <= 4) EQB_PREP_Y(4, 2);
+    else if (npl <= 8) EQB_PREP_Y(8, 2);
+    else if (npl <= 12) EQB_PREP_Y(12, 2);
+    else if (npl <= 16) EQB_PREP_Y(16, 2);
+    else if (npl <= 32) EQB_PREP_Y(32, 1);
+    else EQB_PREP_Y(64, 1);
+#undef EQB_PREP_Y
     ctx->launches++;
     CK(cudaGetLastError());
   }
@@ -801,6 +847,7 @@ int eqb_create(eqb_ctx **out, const eqb_config *cfg)
   CK(cudaSetDevice(cfg->device));
   configure_pool(cfg->device);
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
   AllocScope alloc_scope(ctx->stream);
   ctx->subs.resize(cfg->n_subgroups);
   {
@@ -849,7 +896,9 @@ void eqb_destroy(eqb_ctx *ctx)
   ctx->d_genes2.release();
   ctx->d_pair_off2.release();
   ctx->d_fast_base.release();
-  ctx->d_bcat.release();
+  for (auto &c : ctx->xchunks)
+    if (c.cat) dfree(c.cat);
+  ctx->xchunks.clear();
   ctx->d_fix.release();
   if (ctx->d_prm) dfree(ctx->d_prm);
   if (ctx->d_grids) dfree(ctx->d_grids);

@@ -127,90 +127,146 @@ __global__ void __launch_bounds__(32) prep_basis_kernel(const DevParams *__restr
 }
 
 // ---------------------------------------------------------------- K1b
+// One warp per R (gene, subgroup) expression rows, the rows held in registers (element lane + 32 j), the
+// subgroup's orthonormal basis staged once per CTA in shared memory when it fits (basis_in_smem), CTAs
+// persistent over the genes of their subgroup (blockIdx.y).  Projection = blocks of 4 independent dot
+// products, two passes (CGS2); every basis element read from shared memory is used for the R rows (the
+// kernel is bound by shared-memory bandwidth, not by HBM: Y is small).
+template <int NPL, int R>
 __global__ void __launch_bounds__(THREADS) prep_y_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
-                                                         double *const *Ytil_all, double *const *ystat_all)
+                                                         double *const *Ytil_all, double *const *ystat_all, int basis_in_smem)
 {
   const DevParams &prm = *prm_;
+  extern __shared__ double ysm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long item = (long long)blockIdx.x * WARPS + warp;
-  const int S = prm.S, ldn = prm.ldn;
-  if (item >= prm.G * S) return;
-  const long long g = item / S;
-  const int s = (int)(item % S);
+  const int s = blockIdx.y, ldn = prm.ldn;
   const SubDev &sb = prm.sub[s];
   const FastSub &fs = fp_->sub[s];
-  double *yt = Ytil_all[s] + (size_t)g * ldn;
-  double *ys = ystat_all[s] + (size_t)g * 4;
+  const int Q = sb.Q, n = fs.n;
   const double *q = fs.Bs;
-  const int n = fs.n;
-  bool generic = sb.gene_has[g] && n > 0 && !prm.qnorm; // --qnorm goes through the general path
-  double ysum = 0.0;
-  if (generic) {
-    const double *Yg = sb.Yall + (size_t)g * ldn;
-    int bad = 0;
-    for (int i = lane; i < ldn; i += 32) {
-      const bool keep = q[i] != 0.0;
-      const double v = keep ? Yg[i] : 0.0;
-      if (keep && isnan(v)) bad = 1;
-      yt[i] = v;
-      ysum += v;
-    }
-    if (__any_sync(0xffffffffu, bad)) generic = false;
+  if (basis_in_smem) {
+    for (int idx = threadIdx.x; idx < (Q + 1) * ldn; idx += THREADS) ysm[idx] = q[idx];
+    __syncthreads();
+    q = ysm;
   }
-  if (!generic) {
-    if (lane == 0) {
-      ys[0] = 0.0;
-      ys[1] = 0.0;
-      ys[2] = 0.0;
-      // 2 = nothing to compute in this cell (gene not expressed here / no individual), 0 = general path
-      ys[3] = (!sb.gene_has[g] || n == 0) ? 2.0 : 0.0;
-    }
-    for (int i = lane; i < ldn; i += 32) yt[i] = 0.0;
-    return;
+  unsigned long long keepm = 0ull; // bit j: element lane + 32 j belongs to the subgroup's individuals
+#pragma unroll
+  for (int j = 0; j < NPL; ++j) {
+    const int i = lane + 32 * j;
+    if ((i < ldn) && q[i] != 0.0) keepm |= 1ull << j;
   }
-  __syncwarp();
-  ysum = warp_sum(ysum);
-  const double ybar = ysum / n;
-  double tss = 0.0;
-  for (int i = lane; i < ldn; i += 32)
-    if (q[i] != 0.0) {
-      const double d = yt[i] - ybar;
-      tss += d * d;
+  for (long long g0 = ((long long)blockIdx.x * WARPS + warp) * R; g0 < prm.G; g0 += (long long)gridDim.x * WARPS * R) {
+    double yr[R][NPL], ybar[R], tss[R];
+    bool generic[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long g = g0 + r;
+      generic[r] = (g < prm.G) && sb.gene_has[g] && n > 0 && !prm.qnorm; // --qnorm goes through the general path
+      const double *Yg = sb.Yall + (size_t)min(g, prm.G - 1) * ldn;
+      int bad = 0;
+      double ysum = 0.0;
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) {
+        const bool keep = generic[r] && ((keepm >> j) & 1ull);
+        const double v = keep ? __ldcs(Yg + lane + 32 * j) : 0.0;
+        if (keep && isnan(v)) bad = 1;
+        yr[r][j] = v;
+        ysum += v;
+      }
+      if (__any_sync(0xffffffffu, bad)) {
+        generic[r] = false;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) yr[r][j] = 0.0;
+      }
+      ysum = warp_sum(ysum);
+      ybar[r] = generic[r] ? ysum / n : 0.0;
+      double ts = 0.0;
+#pragma unroll
+      for (int j = 0; j < NPL; ++j)
+        if ((keepm >> j) & 1ull) {
+          const double d = yr[r][j] - ybar[r];
+          ts += d * d;
+        }
+      tss[r] = warp_sum(ts);
     }
-  tss = warp_sum(tss);
-  const int Q = sb.Q;
-  // projection on the (orthonormal) basis: blocks of 4 independent dot products, two passes (CGS2)
-  for (int pass = 0; pass < 2; ++pass)
-    for (int k0 = 0; k0 <= Q; k0 += 4) {
-      double h[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int i = lane; i < ldn; i += 32) {
-        const double y = yt[i];
+    for (int pass = 0; pass < 2; ++pass)
+      for (int k0 = 0; k0 <= Q; k0 += 4) {
+        double h[R][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int a = 0; a < 4; ++a) h[r][a] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          const int i = lane + 32 * j;
+          if (i < ldn) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (k0 + a <= Q) {
+                const double qv = q[(size_t)(k0 + a) * ldn + i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) h[r][a] += qv * yr[r][j];
+              }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) h[r][a] += __shfl_xor_sync(0xffffffffu, h[r][a], o);
+        }
 #pragma unroll
         for (int a = 0; a < 4; ++a)
-          if (k0 + a <= Q) h[a] += q[(size_t)(k0 + a) * ldn + i] * y;
+          if (!(k0 + a <= Q && ((fs.colvalid >> (k0 + a)) & 1u))) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) h[r][a] = 0.0;
+          }
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+          const int i = lane + 32 * j;
+          if (i < ldn) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              if (k0 + a <= Q) {
+                const double qv = q[(size_t)(k0 + a) * ldn + i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) yr[r][j] -= h[r][a] * qv;
+              }
+          }
+        }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+    for (int r = 0; r < R; ++r) {
+      const long long g = g0 + r;
+      if (g >= prm.G) continue;
+      double *yt = Ytil_all[s] + (size_t)g * ldn;
+      double *ys = ystat_all[s] + (size_t)g * 4;
+      double yy = 0.0;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) h[a] += __shfl_xor_sync(0xffffffffu, h[a], o);
+      for (int j = 0; j < NPL; ++j) {
+        const int i = lane + 32 * j;
+        if (i < ldn) {
+          yt[i] = generic[r] ? yr[r][j] : 0.0;
+          yy += yr[r][j] * yr[r][j];
+        }
       }
-      for (int i = lane; i < ldn; i += 32) {
-        double y = yt[i];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          if (k0 + a <= Q && ((fs.colvalid >> (k0 + a)) & 1u)) y -= h[a] * q[(size_t)(k0 + a) * ldn + i];
-        yt[i] = y;
+      yy = warp_sum(yy);
+      if (lane == 0) {
+        if (generic[r]) {
+          ys[0] = yy;
+          ys[1] = tss[r];
+          ys[2] = ybar[r];
+          ys[3] = 1.0;
+        } else {
+          ys[0] = 0.0;
+          ys[1] = 0.0;
+          ys[2] = 0.0;
+          // 2 = nothing to compute in this cell (gene not expressed here / no individual), 0 = general path
+          ys[3] = (!sb.gene_has[g] || n == 0) ? 2.0 : 0.0;
+        }
       }
-      __syncwarp();
     }
-  double yy = 0.0;
-  for (int i = lane; i < ldn; i += 32) yy += yt[i] * yt[i];
-  yy = warp_sum(yy);
-  if (lane == 0) {
-    ys[0] = yy;
-    ys[1] = tss;
-    ys[2] = ybar;
-    ys[3] = 1.0;
   }
 }
 
@@ -351,6 +407,9 @@ __global__ void __launch_bounds__(THREADS) prep_x_dmma_kernel(const DevParams *_
                                                               const PrepCols pc, double *const *xstat_all,
                                                               unsigned long long *__restrict__ fix_list, int fix_cap)
 {
+  // Persistent CTAs: Bcat / Mcat are staged once per CTA, then every warp walks its blocks of 8 SNP rows.
+  // The genotype stream is register double-buffered in chunks of 8 x 16 bytes per lane, ACROSS block
+  // boundaries, so that a warp always has its next chunk in flight while the tensor pipe works.
   const DevParams &prm = *prm_;
   extern __shared__ double psm[];
   const int ldn = prm.ldn, ldn4 = ldn >> 2, strideB = ldn + 1;
@@ -367,90 +426,106 @@ __global__ void __launch_bounds__(THREADS) prep_x_dmma_kernel(const DevParams *_
     Msm[(size_t)c * strideB + i] = Mcat[idx];
   }
   __syncthreads();
-  const long long m0 = ((long long)blockIdx.x * WARPS + warp) * 8;
-  if (m0 >= prm.M) return;
-  const long long mrow = min(m0 + g, prm.M - 1);
-  const double *xrow = X + (size_t)mrow * ldn + (size_t)kk * ldn4;
+  constexpr int U = 8, CH = 2 * U;                    // doubles per lane per chunk
+  const long long M = prm.M, nblk = (M + 7) >> 3;
+  const long long bstep = (long long)gridDim.x * WARPS;
+  long long blk = (long long)blockIdx.x * WARPS + warp;
+  if (blk >= nblk) return;
+  const int nch = (ldn4 + CH - 1) / CH;
   const double *brow = Bsm + (size_t)g * strideB + (size_t)kk * ldn4;
   const double *mrowp = Msm + (size_t)g * strideB + (size_t)kk * ldn4;
+  const int W = (NT + NM) * 8;
+  double *Hw = Hsm + (size_t)warp * 8 * W;
   double c[NT][2], c2[NM][2];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) c[nt][0] = c[nt][1] = 0.0;
 #pragma unroll
   for (int nm = 0; nm < NM; ++nm) c2[nm][0] = c2[nm][1] = 0.0;
-  // software-pipelined main loop: 4 independent 16-byte genotype loads in flight per lane
-  int t = 0;
-  for (; t + 8 <= ldn4; t += 8) {
-    double2 a[4];
+  double2 cur[U], nxt[U];
+  {
+    const double *xr = X + (size_t)min(blk * 8 + g, M - 1) * ldn + (size_t)kk * ldn4;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = __ldcs(reinterpret_cast<const double2 *>(xrow + t + 2 * u));
+    for (int u = 0; u < U; ++u)
+      cur[u] = (2 * u < ldn4) ? __ldcs(reinterpret_cast<const double2 *>(xr + 2 * u)) : make_double2(0.0, 0.0);
+  }
+  int ch = 0;
+  while (true) {
+    // prefetch the next chunk (of this block, or the first one of the warp's next block)
+    const bool last = (ch + 1 == nch);
+    const long long nblk_id = last ? blk + bstep : blk;
+    const int nch_id = last ? 0 : ch + 1;
+    const bool more = nblk_id < nblk;
+    if (more) {
+      const double *xr = X + (size_t)min(nblk_id * 8 + g, M - 1) * ldn + (size_t)kk * ldn4 + nch_id * CH;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u)
+        nxt[u] = (nch_id * CH + 2 * u < ldn4) ? __ldcs(reinterpret_cast<const double2 *>(xr + 2 * u)) : make_double2(0.0, 0.0);
+    }
+    const int t = ch * CH;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (t + 2 * u < ldn4) { // warp-uniform
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          dmma_m8n8k4(c[nt][0], c[nt][1], cur[u].x, brow[(size_t)nt * 8 * strideB + t + 2 * u]);
+          dmma_m8n8k4(c[nt][0], c[nt][1], cur[u].y, brow[(size_t)nt * 8 * strideB + t + 2 * u + 1]);
+        }
+        const double ax2 = cur[u].x * cur[u].x, ay2 = cur[u].y * cur[u].y;
+#pragma unroll
+        for (int nm = 0; nm < NM; ++nm) {
+          dmma_m8n8k4(c2[nm][0], c2[nm][1], ax2, mrowp[(size_t)nm * 8 * strideB + t + 2 * u]);
+          dmma_m8n8k4(c2[nm][0], c2[nm][1], ay2, mrowp[(size_t)nm * 8 * strideB + t + 2 * u + 1]);
+        }
+      }
+    }
+    if (last) {
+      // epilogue through shared memory: per (row, subgroup) xx = R2 - sum H^2, xraw2 = R2, xsum = sqrt(n) H_0
+      const long long m0 = blk * 8;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        dmma_m8n8k4(c[nt][0], c[nt][1], a[u].x, brow[(size_t)nt * 8 * strideB + t + 2 * u]);
-        dmma_m8n8k4(c[nt][0], c[nt][1], a[u].y, brow[(size_t)nt * 8 * strideB + t + 2 * u + 1]);
+        Hw[g * W + nt * 8 + 2 * kk] = c[nt][0];
+        Hw[g * W + nt * 8 + 2 * kk + 1] = c[nt][1];
+        c[nt][0] = c[nt][1] = 0.0;
       }
-      const double ax2 = a[u].x * a[u].x, ay2 = a[u].y * a[u].y;
 #pragma unroll
       for (int nm = 0; nm < NM; ++nm) {
-        dmma_m8n8k4(c2[nm][0], c2[nm][1], ax2, mrowp[(size_t)nm * 8 * strideB + t + 2 * u]);
-        dmma_m8n8k4(c2[nm][0], c2[nm][1], ay2, mrowp[(size_t)nm * 8 * strideB + t + 2 * u + 1]);
+        Hw[g * W + NT * 8 + nm * 8 + 2 * kk] = c2[nm][0];
+        Hw[g * W + NT * 8 + nm * 8 + 2 * kk + 1] = c2[nm][1];
+        c2[nm][0] = c2[nm][1] = 0.0;
       }
+      __syncwarp();
+      for (int it = lane; it < 8 * pc.n_sub; it += 32) {
+        const int r = it / pc.n_sub, si = it % pc.n_sub;
+        const long long m = m0 + r;
+        if (m >= M) continue;
+        const int s = pc.sub[si];
+        double *xs = xstat_all[s] + (size_t)m * 3;
+        if (!prm.sub[s].snp_has[m]) {
+          xs[0] = 0.0;
+          xs[1] = 0.0;
+          xs[2] = 0.0;
+          continue;
+        }
+        const double *h = Hw + r * W + pc.col0[si];
+        double hh = 0.0;
+        for (int k = 0; k < pc.ncol[si]; ++k) hh += h[k] * h[k];
+        const double r2 = Hw[r * W + NT * 8 + pc.mcol[si]];
+        xs[0] = r2 - hh;
+        xs[1] = r2;
+        xs[2] = pc.sqrt_n[si] * h[0];
+        if (r2 > 0.0 && (r2 - hh) < 1e-2 * r2) {
+          // Gram-form residual lost accuracy (x nearly inside span([1, covariates])): queue for the explicit pass
+          const unsigned long long slot = atomicAdd(fix_list, 1ull);
+          if (slot + 1 < (unsigned long long)fix_cap) fix_list[slot + 1] = ((unsigned long long)m << 8) | (unsigned long long)s;
+        }
+      }
+      __syncwarp();
     }
-  }
-  for (; t < ldn4; t += 2) {
-    const double2 a = __ldcs(reinterpret_cast<const double2 *>(xrow + t));
+    if (!more) break;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      dmma_m8n8k4(c[nt][0], c[nt][1], a.x, brow[(size_t)nt * 8 * strideB + t]);
-      dmma_m8n8k4(c[nt][0], c[nt][1], a.y, brow[(size_t)nt * 8 * strideB + t + 1]);
-    }
-    const double ax2 = a.x * a.x, ay2 = a.y * a.y;
-#pragma unroll
-    for (int nm = 0; nm < NM; ++nm) {
-      dmma_m8n8k4(c2[nm][0], c2[nm][1], ax2, mrowp[(size_t)nm * 8 * strideB + t]);
-      dmma_m8n8k4(c2[nm][0], c2[nm][1], ay2, mrowp[(size_t)nm * 8 * strideB + t + 1]);
-    }
-  }
-  // epilogue through shared memory: per (row, subgroup) xx = R2 - sum H^2, xraw2 = R2, xsum = sqrt(n) H_0
-  const int W = (NT + NM) * 8;
-  double *Hw = Hsm + (size_t)warp * 8 * W;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    Hw[g * W + nt * 8 + 2 * kk] = c[nt][0];
-    Hw[g * W + nt * 8 + 2 * kk + 1] = c[nt][1];
-  }
-#pragma unroll
-  for (int nm = 0; nm < NM; ++nm) {
-    Hw[g * W + NT * 8 + nm * 8 + 2 * kk] = c2[nm][0];
-    Hw[g * W + NT * 8 + nm * 8 + 2 * kk + 1] = c2[nm][1];
-  }
-  __syncwarp();
-  for (int it = lane; it < 8 * pc.n_sub; it += 32) {
-    const int r = it / pc.n_sub, si = it % pc.n_sub;
-    const long long m = m0 + r;
-    if (m >= prm.M) continue;
-    const int s = pc.sub[si];
-    double *xs = xstat_all[s] + (size_t)m * 3;
-    if (!prm.sub[s].snp_has[m]) {
-      xs[0] = 0.0;
-      xs[1] = 0.0;
-      xs[2] = 0.0;
-      continue;
-    }
-    const double *h = Hw + r * W + pc.col0[si];
-    double hh = 0.0;
-    for (int k = 0; k < pc.ncol[si]; ++k) hh += h[k] * h[k];
-    const double r2 = Hw[r * W + NT * 8 + pc.mcol[si]];
-    xs[0] = r2 - hh;
-    xs[1] = r2;
-    xs[2] = pc.sqrt_n[si] * h[0];
-    if (r2 > 0.0 && (r2 - hh) < 1e-2 * r2) {
-      // Gram-form residual lost accuracy (x nearly inside span([1, covariates])): queue for the explicit pass
-      const unsigned long long slot = atomicAdd(fix_list, 1ull);
-      if (slot + 1 < (unsigned long long)fix_cap) fix_list[slot + 1] = ((unsigned long long)m << 8) | (unsigned long long)s;
-    }
+    for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+    blk = nblk_id;
+    ch = nch_id;
   }
 }
 

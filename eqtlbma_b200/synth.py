@@ -173,7 +173,7 @@ def _round(a, nd=6):
 
 
 def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene=2, n_chr=2,
-                 n_cov=0, ragged=False, ragged_min_frac=0.4, absent_gene_frac=0.0, nan_frac=0.0,
+                 n_cov=0, cov_per_subgroup=False, ragged=False, ragged_min_frac=0.4, absent_gene_frac=0.0, nan_frac=0.0,
                  dosage=False, maf=0.3, gridL=None, gridS=None, radius=None, anchor="TSS",
                  null_frac=0.3, separate_geno_files=False, missing_geno_frac=0.0,
                  pad_names=False, monomorphic_frac=0.0, gene_spacing=1000, far_snp=True) -> Dataset:
@@ -275,9 +275,16 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
     Cfull = np.zeros((n_cov, n_inds))
     for q, cn in enumerate(cov_names):
         Cfull[q] = rng.integers(0, 2, n_inds) if cn == "sex" else _round(rng.normal(0, 1, n_inds), 5)
+    Cshared = Cfull
     for s in range(S):
         name = f"s{s + 1}"
         gi = s if separate_geno_files else 0
+        if cov_per_subgroup and n_cov > 0 and s > 0:
+            # tissue-specific covariates (PEER-like factors); "sex" stays an attribute of the individual
+            Cfull = Cshared.copy()
+            for q, cn in enumerate(cov_names):
+                if cn != "sex":
+                    Cfull[q] = _round(rng.normal(0, 1, n_inds), 5)
         if ragged:
             n_s = int(rng.integers(int(ragged_min_frac * n_inds), n_inds + 1))
             cols = np.sort(rng.choice(n_inds, size=n_s, replace=False))

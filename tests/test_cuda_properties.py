@@ -95,3 +95,29 @@ def test_gtex_shape_slice_matches_oracle(cuda_lib, oracle_lib):
         pb = ora.run_permutations(25, 1859, pbf=pbf, wrtsize=3)
         assert np.array_equal(pa.count, pb.count)
         assert np.allclose(pa.perm_stats, pb.perm_stats, rtol=0, atol=1e-8, equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_sub,n_inds,n_cov", [(3, 300, 11), (9, 120, 6), (2, 700, 3)])
+def test_subgroup_specific_covariates_match_oracle(cuda_lib, oracle_lib, n_sub, n_inds, n_cov):
+    """c2 shape with tissue-specific covariate values (no duplicate-subgroup shortcut: one basis per
+    subgroup, several DMMA column tiles per launch), --bfs sin, plus permutations, against the CPU oracle."""
+    import eqtlbma_b200
+    from eqtlbma_b200._capi import Engine as AnyEngine
+    from eqtlbma_b200.synth import make_dataset
+    ds = make_dataset(seed=7 + n_sub, n_subgroups=n_sub, n_inds=n_inds, n_genes=12, snps_per_gene=9, n_cov=n_cov,
+                      cov_per_subgroup=True, dosage=True, ragged=(n_sub == 9), n_chr=2, radius=100, gene_spacing=201,
+                      far_snp=False)
+    eng = eqtlbma_b200.Engine(ds, analysis="join", bfs="sin")
+    ora = AnyEngine(oracle_lib, "eqo_", ds, analysis="join", bfs="sin")
+    assert eng.fast_gene_count() == ds.n_genes
+    a, b = eng.run(), ora.run()
+    assert np.array_equal(a.n, b.n)
+    assert np.allclose(a.sstats[..., 1:], b.sstats[..., 1:], rtol=1e-9, atol=0, equal_nan=True)
+    assert np.allclose(a.sstats[..., 0], b.sstats[..., 0], rtol=1e-9, atol=1e-12, equal_nan=True)
+    assert np.allclose(a.abf_gen, b.abf_gen, rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(a.abf_cfg, b.abf_cfg, rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(a.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
+    pa = eng.run_permutations(20, 1859, pbf="gen-sin", wrtsize=5)
+    pb = ora.run_permutations(20, 1859, pbf="gen-sin", wrtsize=5)
+    assert np.array_equal(pa.count, pb.count)
