@@ -326,6 +326,8 @@ struct eqb_ctx {
   };
   std::vector<XChunk> xchunks; // built by the first launch_prep_x (after prep_basis_kernel), constant afterwards
   bool xchunks_built = false;
+  bool x_explicit = false;  // rows too long for the DMMA tiles in shared memory: explicit CGS2 for every SNP
+  size_t dmma_budget = 0;
   DevBuf<unsigned long long> d_fix; // [0] = count, then (snp << 8 | subgroup) entries needing the explicit K1c pass
   GridTab gt;              // unique phi2 values of the consistent-configuration rows
   double *d_gt_d = nullptr; // uphi[UL] | omaL[3L]
@@ -512,21 +514,21 @@ int stat_kind_for(const eqb_ctx *ctx, const eqb_perm_config *pc)
 }
 
 
-template <int NT, int NM>
+template <int NT, int NM, int NW>
 cudaError_t launch_dmma(eqb_ctx *ctx, const double *X, const double *Bcat, const double *Mcat, const PrepCols &pc,
                         double **xp)
 {
   const long long M = ctx->cfg.n_snps;
-  const size_t smem = ((size_t)(NT + NM) * 8 * (ctx->ldn + 1) + (size_t)WARPS * 8 * (NT + NM) * 8) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(prep_x_dmma_kernel<NT, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = ((size_t)(NT + NM) * 8 * (ctx->ldn + 1) + (size_t)NW * 8 * (NT + NM) * 8) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(prep_x_dmma_kernel<NT, NM, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prep_x_dmma_kernel<NT, NM>, THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prep_x_dmma_kernel<NT, NM, NW>, NW * 32, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
-  const long long want = (M + 8 * WARPS - 1) / (8 * WARPS);
+  const long long want = (M + 8 * NW - 1) / (8 * NW);
   const unsigned grid = (unsigned)std::min<long long>(want, (long long)ctx->n_sm * occ); // persistent CTAs
-  prep_x_dmma_kernel<NT, NM><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, X, Bcat, Mcat, pc, xp, ctx->d_fix.p, (int)ctx->d_fix.cap);
+  prep_x_dmma_kernel<NT, NM, NW><<<grid, NW * 32, smem, ctx->stream>>>(ctx->d_prm, X, Bcat, Mcat, pc, xp, ctx->d_fix.p, (int)ctx->d_fix.cap);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -543,9 +545,16 @@ int launch_prep_x(eqb_ctx *ctx)
   CK(cudaMemsetAsync(ctx->d_fix.p, 0, sizeof(unsigned long long), ctx->stream));
   // chunks of subgroups sharing a genotype variant, <= 8 basis tiles and <= 8 mask tiles, <= 16 subgroups;
   // the plan and its Bcat / Mcat matrices depend on the bases only: built once, after prep_basis_kernel
+  auto dmma_smem = [&](int NT, int NW) {
+    return ((size_t)(NT + 1) * 8 * (ldn + 1) + (size_t)NW * 8 * (NT + 1) * 8) * sizeof(double);
+  };
+  auto tile_variant = [](int NTn) { return NTn <= 1 ? 1 : NTn <= 2 ? 2 : NTn <= 3 ? 3 : NTn <= 5 ? 5 : 8; };
   if (!ctx->xchunks_built) {
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->cfg.device));
+    ctx->dmma_budget = (size_t)std::max(0, optin - 1024);
     std::vector<char> done(S, 0);
-    for (int s0 = 0; s0 < S; ++s0) {
+    for (int s0 = 0; s0 < S && !ctx->x_explicit; ++s0) {
       if (done[s0]) continue;
       eqb_ctx::XChunk xc;
       PrepCols &pc = xc.pc;
@@ -559,7 +568,11 @@ int launch_prep_x(eqb_ctx *ctx)
           continue;
         }
         const int nc = ctx->subs[s].Q + 1;
-        if ((int)members.size() == 16 || ncols + nc > 64 || nmask + 1 > 64) break;
+        // one mask tile (8 subgroups), <= 8 basis tiles, and the tiles must fit in shared memory
+        if (nmask == 8 || ncols + nc > 64 || dmma_smem(tile_variant((ncols + nc + 7) / 8), 8) > ctx->dmma_budget) {
+          if (members.empty()) ctx->x_explicit = true; // not even one subgroup fits: explicit CGS2 pass for all
+          break;
+        }
         pc.sub[members.size()] = s;
         pc.col0[members.size()] = ncols;
         pc.ncol[members.size()] = nc;
@@ -572,8 +585,8 @@ int launch_prep_x(eqb_ctx *ctx)
       }
       pc.n_sub = (int)members.size();
       if (members.empty()) continue;
-      xc.NTn = (ncols + 7) / 8;
-      xc.NMn = (nmask + 7) / 8;
+      xc.NTn = tile_variant((ncols + 7) / 8);
+      xc.NMn = 1;
       xc.xvar = ctx->subs[s0].xvar;
       // Bcat / Mcat for the chunk (device-side gather of the basis rows; masks from q0 != 0)
       const size_t bdoubles = (size_t)(xc.NTn + xc.NMn) * 8 * ldn;
@@ -591,30 +604,33 @@ int launch_prep_x(eqb_ctx *ctx)
     }
     ctx->xchunks_built = true;
   }
-  for (const eqb_ctx::XChunk &xc : ctx->xchunks) {
-    const double *X = ctx->d_X[xc.xvar];
-    const double *Bcat = xc.cat, *Mcat = xc.cat + (size_t)xc.NTn * 8 * ldn;
-    const int NTn = xc.NTn, NMn = xc.NMn;
-    cudaError_t e;
-    if (NTn <= 1 && NMn <= 1) e = launch_dmma<1, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
-    else if (NTn <= 2 && NMn <= 1) e = launch_dmma<2, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
-    else if (NTn <= 3 && NMn <= 1) e = launch_dmma<3, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
-    else if (NTn <= 5 && NMn <= 1) e = launch_dmma<5, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
-    else if (NTn <= 8 && NMn <= 1) e = launch_dmma<8, 1>(ctx, X, Bcat, Mcat, xc.pc, xp);
-    else e = launch_dmma<8, 2>(ctx, X, Bcat, Mcat, xc.pc, xp);
-    if (e != cudaSuccess) return fail(ctx, std::string("prep_x_dmma launch: ") + cudaGetErrorString(e));
-  }
+  if (!ctx->x_explicit)
+    for (const eqb_ctx::XChunk &xc : ctx->xchunks) {
+      const double *X = ctx->d_X[xc.xvar];
+      const double *Bcat = xc.cat, *Mcat = xc.cat + (size_t)xc.NTn * 8 * ldn;
+      const bool wide = dmma_smem(xc.NTn, 16) <= ctx->dmma_budget; // 16 warps per CTA when one CTA fills the SM anyway
+      cudaError_t e;
+      switch (xc.NTn) {
+      case 1: e = launch_dmma<1, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
+      case 2: e = launch_dmma<2, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
+      case 3: e = wide ? launch_dmma<3, 1, 16>(ctx, X, Bcat, Mcat, xc.pc, xp) : launch_dmma<3, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
+      case 5: e = wide ? launch_dmma<5, 1, 16>(ctx, X, Bcat, Mcat, xc.pc, xp) : launch_dmma<5, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
+      default: e = launch_dmma<8, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
+      }
+      if (e != cudaSuccess) return fail(ctx, std::string("prep_x_dmma launch: ") + cudaGetErrorString(e));
+    }
   // fix-up pass over the queued entries (a small persistent grid; the list is normally empty)
-  const unsigned grid = 148 * 2;
+  const unsigned grid = (unsigned)ctx->n_sm * (ctx->x_explicit ? 8 : 2);
   const int npl = (ldn + 31) / 32;
   const unsigned long long *fl = ctx->d_fix.p;
   const int fc = (int)ctx->d_fix.cap;
-  if (npl <= 4) prep_x_kernel<4><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
-  else if (npl <= 8) prep_x_kernel<8><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
-  else if (npl <= 12) prep_x_kernel<12><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
-  else if (npl <= 16) prep_x_kernel<16><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
-  else if (npl <= 32) prep_x_kernel<32><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
-  else prep_x_kernel<64><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, 1, fl, fc);
+  const int mode = ctx->x_explicit ? 0 : 1;
+  if (npl <= 4) prep_x_kernel<4><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
+  else if (npl <= 8) prep_x_kernel<8><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
+  else if (npl <= 12) prep_x_kernel<12><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
+  else if (npl <= 16) prep_x_kernel<16><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
+  else if (npl <= 32) prep_x_kernel<32><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
+  else prep_x_kernel<64><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;

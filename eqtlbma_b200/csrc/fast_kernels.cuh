@@ -401,8 +401,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                : "d"(a), "d"(b));
 }
 
-template <int NT, int NM>
-__global__ void __launch_bounds__(THREADS) prep_x_dmma_kernel(const DevParams *__restrict__ prm_, const double *__restrict__ X,
+template <int NT, int NM, int NW>
+__global__ void __launch_bounds__(NW * 32) prep_x_dmma_kernel(const DevParams *__restrict__ prm_, const double *__restrict__ X,
                                                               const double *__restrict__ Bcat, const double *__restrict__ Mcat,
                                                               const PrepCols pc, double *const *xstat_all,
                                                               unsigned long long *__restrict__ fix_list, int fix_cap)
@@ -416,20 +416,20 @@ __global__ void __launch_bounds__(THREADS) prep_x_dmma_kernel(const DevParams *_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, kk = lane & 3;
   double *Bsm = psm;                                  // [NT*8][strideB]
   double *Msm = Bsm + (size_t)NT * 8 * strideB;       // [NM*8][strideB]
-  double *Hsm = Msm + (size_t)NM * 8 * strideB;       // [WARPS][8][(NT+NM)*8]
-  for (int idx = threadIdx.x; idx < NT * 8 * ldn; idx += THREADS) {
+  double *Hsm = Msm + (size_t)NM * 8 * strideB;       // [NW][8][(NT+NM)*8]
+  for (int idx = threadIdx.x; idx < NT * 8 * ldn; idx += NW * 32) {
     const int c = idx / ldn, i = idx % ldn;
     Bsm[(size_t)c * strideB + i] = Bcat[idx];
   }
-  for (int idx = threadIdx.x; idx < NM * 8 * ldn; idx += THREADS) {
+  for (int idx = threadIdx.x; idx < NM * 8 * ldn; idx += NW * 32) {
     const int c = idx / ldn, i = idx % ldn;
     Msm[(size_t)c * strideB + i] = Mcat[idx];
   }
   __syncthreads();
   constexpr int U = 8, CH = 2 * U;                    // doubles per lane per chunk
   const long long M = prm.M, nblk = (M + 7) >> 3;
-  const long long bstep = (long long)gridDim.x * WARPS;
-  long long blk = (long long)blockIdx.x * WARPS + warp;
+  const long long bstep = (long long)gridDim.x * NW;
+  long long blk = (long long)blockIdx.x * NW + warp;
   if (blk >= nblk) return;
   const int nch = (ldn4 + CH - 1) / CH;
   const double *brow = Bsm + (size_t)g * strideB + (size_t)kk * ldn4;
@@ -754,7 +754,10 @@ __device__ __forceinline__ void contract_shared_x(const double *__restrict__ Xm,
 // the data-independent branches (oma2 == 0 of the gen-fix row, phi2 == 0 of the gen-maxh row, consistent vs
 // singleton value) are warp-uniform.  Values are staged in shared memory ([value][T+1], conflict-free both ways),
 // reduced there, and written to the output rows with coalesced stores.
-__global__ void __launch_bounds__(THREADS, 3) fast_pair_kernel(const DevParams *__restrict__ prm_,
+#ifndef EQB_FAST_MINB
+#define EQB_FAST_MINB 3 // resident CTAs per SM the register allocation is capped for
+#endif
+__global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const DevParams *__restrict__ prm_,
                                                             const FastParams *__restrict__ fp_, const FastArgs fa,
                                                             const GridTab gt)
 {

@@ -98,7 +98,7 @@ def test_gtex_shape_slice_matches_oracle(cuda_lib, oracle_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_sub,n_inds,n_cov", [(3, 300, 11), (9, 120, 6), (2, 700, 3)])
+@pytest.mark.parametrize("n_sub,n_inds,n_cov", [(3, 300, 11), (9, 120, 6), (9, 450, 2), (2, 700, 3), (2, 1800, 2)])
 def test_subgroup_specific_covariates_match_oracle(cuda_lib, oracle_lib, n_sub, n_inds, n_cov):
     """c2 shape with tissue-specific covariate values (no duplicate-subgroup shortcut: one basis per
     subgroup, several DMMA column tiles per launch), --bfs sin, plus permutations, against the CPU oracle."""
