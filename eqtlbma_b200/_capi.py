@@ -89,12 +89,6 @@ class Engine:
                      BFS[bfs], ERROR[error], int(qnorm), device, float(fiterr))
         self.ctx = C.c_void_p()
         self._call("create", C.byref(self.ctx), C.byref(cfg), ctx_first=False)
-        for gi, G in enumerate(ds.genos):
-            if getattr(ds, "_clean", False) and G.flags.c_contiguous and G.dtype == np.float64:
-                Gc = G  # already NaN-free and contiguous (e.g. pinned by the caller): no host copy
-            else:
-                Gc = np.ascontiguousarray(np.nan_to_num(G, nan=0.0), dtype=np.float64)
-            self._call("set_genotypes", C.c_int32(gi), _ptr(Gc), C.c_int64(Gc.shape[0]), C.c_int32(Gc.shape[1]))
         for s, sg in enumerate(ds.subgroups):
             arrs = dict(all2geno=np.ascontiguousarray(sg.all2geno, dtype=np.int32),
                         all2exp=np.ascontiguousarray(sg.all2exp, dtype=np.int32),
@@ -123,6 +117,14 @@ class Engine:
         sp = np.ascontiguousarray(ds.snp_pos, dtype=np.int64)
         self._call("build_cis_windows", _ptr(gc), _ptr(gst), _ptr(gen), _ptr(sc_), _ptr(sp),
                    C.c_int32(ANCHOR[ds.anchor]), C.c_int64(ds.radius), _ptr(self.cis_begin), _ptr(self.cis_end))
+        # genotypes last: their upload is asynchronous and everything queued after it on the copy engine would wait
+        for gi, G in enumerate(ds.genos):
+            if getattr(ds, "_clean", False) and G.flags.c_contiguous and G.dtype == np.float64:
+                Gc = G  # already NaN-free and contiguous (e.g. pinned by the caller): no host copy
+            else:
+                Gc = np.ascontiguousarray(np.nan_to_num(G, nan=0.0), dtype=np.float64)
+            self._keep.append(Gc)  # the upload is asynchronous: valid until the first run returns
+            self._call("set_genotypes", C.c_int32(gi), _ptr(Gc), C.c_int64(Gc.shape[0]), C.c_int32(Gc.shape[1]))
         self._call("finalize")
         f = getattr(lib, prefix + "n_configs")
         f.restype = C.c_int64

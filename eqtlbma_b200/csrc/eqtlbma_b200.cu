@@ -15,6 +15,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -257,6 +258,7 @@ struct SubHost {
 struct GenoHost {
   double *d_raw = nullptr;
   int n_cols = 0;
+  std::vector<cudaEvent_t> ev; // upload of row chunk c complete (recorded on the copy stream)
 };
 
 template <class T>
@@ -287,6 +289,17 @@ struct eqb_ctx {
   eqb_config cfg;
   std::string err;
   cudaStream_t stream = nullptr;
+  // upload pipeline: genotype rows travel in row chunks on xcopy; xcomp re-indexes and projects each chunk as it
+  // lands (xready[c]); eqb_run launches the pair kernel per gene segment as soon as its rows are ready and
+  // returns the results on dstream while later chunks are still uploading
+  cudaStream_t xcopy = nullptr, xcomp = nullptr, dstream = nullptr;
+  std::vector<long long> xrow;      // chunk c = SNP rows [xrow[c], xrow[c+1]), boundaries multiples of 8
+  std::vector<cudaEvent_t> xready;  // chunk c expanded (and projected, on the fast path)
+  struct XVar { int geno_id; int *dmap; };
+  std::vector<XVar> xvars;          // genotype variants awaiting their expansion
+  bool x_enqueued = false, x_complete = false;
+  uint8_t *stage_h = nullptr, *stage_d = nullptr; // pinned staging buffer of h2d()
+  size_t stage_off = 0;
   bool finalized = false;
   int ldn = 0, Qmax = 0;
   int n_sm = 148;
@@ -341,6 +354,77 @@ struct eqb_ctx {
   int perm_slots = 0;
   int perm_N = 0;
 };
+
+// ---------------------------------------------------------------- small host -> device transfers
+// While the genotype matrix streams in on the copy engine (upload pipeline), a cudaMemcpyAsync of a few
+// kilobytes would queue behind hundreds of megabytes.  Small arrays therefore go through a pinned, mapped
+// staging buffer and a copy kernel that reads it over PCIe directly; the source is consumed before returning
+// (same guarantee as a pageable cudaMemcpyAsync).  Large arrays keep the DMA engine.
+namespace {
+struct StagePool {
+  std::mutex mu;
+  std::vector<std::pair<uint8_t *, uint8_t *> > free_list[64];
+};
+StagePool g_stage_pool;
+constexpr size_t STAGE_CAP = (size_t)8 << 20, STAGE_MAX = (size_t)1 << 20;
+
+__global__ void stage_copy_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, size_t bytes)
+{
+  const size_t n16 = bytes >> 4, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+    for (size_t i = i0; i < n16; i += st) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    for (size_t i = (n16 << 4) + i0; i < bytes; i += st) dst[i] = src[i];
+  } else
+    for (size_t i = i0; i < bytes; i += st) dst[i] = src[i];
+}
+
+cudaError_t h2d(eqb_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+  if (bytes == 0) return cudaSuccess;
+  if (bytes > STAGE_MAX) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (!ctx->stage_h) {
+    const int dev = ctx->cfg.device;
+    {
+      std::lock_guard<std::mutex> lk(g_stage_pool.mu);
+      if (dev >= 0 && dev < 64 && !g_stage_pool.free_list[dev].empty()) {
+        ctx->stage_h = g_stage_pool.free_list[dev].back().first;
+        ctx->stage_d = g_stage_pool.free_list[dev].back().second;
+        g_stage_pool.free_list[dev].pop_back();
+      }
+    }
+    if (!ctx->stage_h) {
+      cudaError_t e = cudaHostAlloc((void **)&ctx->stage_h, STAGE_CAP, cudaHostAllocMapped);
+      if (e != cudaSuccess) return e;
+      e = cudaHostGetDevicePointer((void **)&ctx->stage_d, ctx->stage_h, 0);
+      if (e != cudaSuccess) return e;
+    }
+    ctx->stage_off = 0;
+  }
+  size_t off = (ctx->stage_off + 15) & ~(size_t)15;
+  if (off + bytes > STAGE_CAP) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream); // every earlier staged copy has been consumed
+    if (e != cudaSuccess) return e;
+    off = 0;
+  }
+  memcpy(ctx->stage_h + off, src, bytes);
+  const unsigned grid = (unsigned)std::min<size_t>(32, (bytes + 4095) / 4096);
+  stage_copy_kernel<<<grid, 256, 0, ctx->stream>>>((uint8_t *)dst, ctx->stage_d + off, bytes);
+  ctx->stage_off = off + bytes;
+  return cudaGetLastError();
+}
+
+void release_stage(eqb_ctx *ctx)
+{
+  if (!ctx->stage_h) return;
+  const int dev = ctx->cfg.device;
+  std::lock_guard<std::mutex> lk(g_stage_pool.mu);
+  if (dev >= 0 && dev < 64 && g_stage_pool.free_list[dev].size() < 8)
+    g_stage_pool.free_list[dev].push_back(std::make_pair(ctx->stage_h, ctx->stage_d));
+  else
+    cudaFreeHost(ctx->stage_h);
+  ctx->stage_h = ctx->stage_d = nullptr;
+}
+} // namespace
 
 namespace {
 
@@ -515,10 +599,9 @@ int stat_kind_for(const eqb_ctx *ctx, const eqb_perm_config *pc)
 
 
 template <int NT, int NM, int NW>
-cudaError_t launch_dmma(eqb_ctx *ctx, const double *X, const double *Bcat, const double *Mcat, const PrepCols &pc,
-                        double **xp)
+cudaError_t launch_dmma(eqb_ctx *ctx, cudaStream_t st, long long m_lo, long long m_hi, const double *X, const double *Bcat,
+                        const double *Mcat, const PrepCols &pc, double **xp)
 {
-  const long long M = ctx->cfg.n_snps;
   const size_t smem = ((size_t)(NT + NM) * 8 * (ctx->ldn + 1) + (size_t)NW * 8 * (NT + NM) * 8) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(prep_x_dmma_kernel<NT, NM, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -526,84 +609,95 @@ cudaError_t launch_dmma(eqb_ctx *ctx, const double *X, const double *Bcat, const
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prep_x_dmma_kernel<NT, NM, NW>, NW * 32, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
-  const long long want = (M + 8 * NW - 1) / (8 * NW);
+  const long long blk_lo = m_lo >> 3, blk_hi = (m_hi + 7) >> 3; // m_lo is a multiple of 8
+  const long long want = (blk_hi - blk_lo + NW - 1) / NW;
+  if (want <= 0) return cudaSuccess;
   const unsigned grid = (unsigned)std::min<long long>(want, (long long)ctx->n_sm * occ); // persistent CTAs
-  prep_x_dmma_kernel<NT, NM, NW><<<grid, NW * 32, smem, ctx->stream>>>(ctx->d_prm, X, Bcat, Mcat, pc, xp, ctx->d_fix.p, (int)ctx->d_fix.cap);
+  prep_x_dmma_kernel<NT, NM, NW><<<grid, NW * 32, smem, st>>>(ctx->d_prm, X, Bcat, Mcat, pc, xp, ctx->d_fix.p,
+                                                             (int)ctx->d_fix.cap, blk_lo, blk_hi);
   ctx->launches++;
   return cudaGetLastError();
 }
 
-// K1c: DMMA projection of every SNP on the subgroup bases (chunks of <= 8 column tiles), then the
-// accuracy fix-up pass (explicit CGS2) for the few entries whose Gram-form residual cancelled.
-int launch_prep_x(eqb_ctx *ctx)
+// K1c plan: chunks of subgroups sharing a genotype variant, their concatenated basis / mask columns.
+// Depends on the bases only: built once, on the main stream, after prep_basis_kernel.
+int build_x_plan(eqb_ctx *ctx)
 {
   const int S = ctx->cfg.n_subgroups, ldn = ctx->ldn;
-  const long long M = ctx->cfg.n_snps;
-  double **xp = ctx->d_prep_ptrs + 3 * S;
-  const int *dup = ctx->d_gt_i + 3 * (int)ctx->phi2L.size();
-  CK(ctx->d_fix.ensure(1 << 16));
-  CK(cudaMemsetAsync(ctx->d_fix.p, 0, sizeof(unsigned long long), ctx->stream));
-  // chunks of subgroups sharing a genotype variant, <= 8 basis tiles and <= 8 mask tiles, <= 16 subgroups;
-  // the plan and its Bcat / Mcat matrices depend on the bases only: built once, after prep_basis_kernel
+  if (ctx->xchunks_built) return 0;
   auto dmma_smem = [&](int NT, int NW) {
     return ((size_t)(NT + 1) * 8 * (ldn + 1) + (size_t)NW * 8 * (NT + 1) * 8) * sizeof(double);
   };
   auto tile_variant = [](int NTn) { return NTn <= 1 ? 1 : NTn <= 2 ? 2 : NTn <= 3 ? 3 : NTn <= 5 ? 5 : 8; };
-  if (!ctx->xchunks_built) {
-    int optin = 0;
-    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->cfg.device));
-    ctx->dmma_budget = (size_t)std::max(0, optin - 1024);
-    std::vector<char> done(S, 0);
-    for (int s0 = 0; s0 < S && !ctx->x_explicit; ++s0) {
-      if (done[s0]) continue;
-      eqb_ctx::XChunk xc;
-      PrepCols &pc = xc.pc;
-      memset(&pc, 0, sizeof(pc));
-      int ncols = 0, nmask = 0;
-      std::vector<int> members;
-      for (int s = s0; s < S; ++s) {
-        if (done[s] || ctx->subs[s].xvar != ctx->subs[s0].xvar) continue;
-        if (ctx->dup_of[s] >= 0) {
-          done[s] = 1; // shares the K1 output of an identical earlier subgroup
-          continue;
-        }
-        const int nc = ctx->subs[s].Q + 1;
-        // one mask tile (8 subgroups), <= 8 basis tiles, and the tiles must fit in shared memory
-        if (nmask == 8 || ncols + nc > 64 || dmma_smem(tile_variant((ncols + nc + 7) / 8), 8) > ctx->dmma_budget) {
-          if (members.empty()) ctx->x_explicit = true; // not even one subgroup fits: explicit CGS2 pass for all
-          break;
-        }
-        pc.sub[members.size()] = s;
-        pc.col0[members.size()] = ncols;
-        pc.ncol[members.size()] = nc;
-        pc.mcol[members.size()] = nmask;
-        pc.sqrt_n[members.size()] = sqrt((double)ctx->hfp.sub[s].n);
-        ncols += nc;
-        nmask += 1;
-        members.push_back(s);
-        done[s] = 1;
+  CK(ctx->d_fix.ensure(1 << 16));
+  int optin = 0;
+  CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->cfg.device));
+  ctx->dmma_budget = (size_t)std::max(0, optin - 1024);
+  std::vector<char> done(S, 0);
+  for (int s0 = 0; s0 < S && !ctx->x_explicit; ++s0) {
+    if (done[s0]) continue;
+    eqb_ctx::XChunk xc;
+    PrepCols &pc = xc.pc;
+    memset(&pc, 0, sizeof(pc));
+    int ncols = 0, nmask = 0;
+    std::vector<int> members;
+    for (int s = s0; s < S; ++s) {
+      if (done[s] || ctx->subs[s].xvar != ctx->subs[s0].xvar) continue;
+      if (ctx->dup_of[s] >= 0) {
+        done[s] = 1; // shares the K1 output of an identical earlier subgroup
+        continue;
       }
-      pc.n_sub = (int)members.size();
-      if (members.empty()) continue;
-      xc.NTn = tile_variant((ncols + 7) / 8);
-      xc.NMn = 1;
-      xc.xvar = ctx->subs[s0].xvar;
-      // Bcat / Mcat for the chunk (device-side gather of the basis rows; masks from q0 != 0)
-      const size_t bdoubles = (size_t)(xc.NTn + xc.NMn) * 8 * ldn;
-      CK(dmalloc(&xc.cat, bdoubles * sizeof(double)));
-      CK(cudaMemsetAsync(xc.cat, 0, bdoubles * sizeof(double), ctx->stream));
-      double *Bcat = xc.cat, *Mcat = xc.cat + (size_t)xc.NTn * 8 * ldn;
-      for (size_t i = 0; i < members.size(); ++i) {
-        const int s = members[i];
-        CK(cudaMemcpyAsync(Bcat + (size_t)pc.col0[i] * ldn, ctx->d_Bs[s], (size_t)pc.ncol[i] * ldn * sizeof(double),
-                           cudaMemcpyDeviceToDevice, ctx->stream));
-        mask_from_basis_kernel<<<(ldn + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Bs[s], Mcat + (size_t)pc.mcol[i] * ldn, ldn);
-        ctx->launches++;
+      const int nc = ctx->subs[s].Q + 1;
+      // one mask tile (8 subgroups), <= 8 basis tiles, and the tiles must fit in shared memory
+      if (nmask == 8 || ncols + nc > 64 || dmma_smem(tile_variant((ncols + nc + 7) / 8), 8) > ctx->dmma_budget) {
+        if (members.empty()) ctx->x_explicit = true; // not even one subgroup fits: explicit CGS2 pass for all
+        break;
       }
-      ctx->xchunks.push_back(xc);
+      pc.sub[members.size()] = s;
+      pc.col0[members.size()] = ncols;
+      pc.ncol[members.size()] = nc;
+      pc.mcol[members.size()] = nmask;
+      pc.sqrt_n[members.size()] = sqrt((double)ctx->hfp.sub[s].n);
+      ncols += nc;
+      nmask += 1;
+      members.push_back(s);
+      done[s] = 1;
     }
-    ctx->xchunks_built = true;
+    pc.n_sub = (int)members.size();
+    if (members.empty()) continue;
+    xc.NTn = tile_variant((ncols + 7) / 8);
+    xc.NMn = 1;
+    xc.xvar = ctx->subs[s0].xvar;
+    // Bcat / Mcat for the chunk (device-side gather of the basis rows; masks from q0 != 0)
+    const size_t bdoubles = (size_t)(xc.NTn + xc.NMn) * 8 * ldn;
+    CK(dmalloc(&xc.cat, bdoubles * sizeof(double)));
+    CK(cudaMemsetAsync(xc.cat, 0, bdoubles * sizeof(double), ctx->stream));
+    double *Bcat = xc.cat, *Mcat = xc.cat + (size_t)xc.NTn * 8 * ldn;
+    for (size_t i = 0; i < members.size(); ++i) {
+      const int s = members[i];
+      stage_copy_kernel<<<32, 256, 0, ctx->stream>>>((uint8_t *)(Bcat + (size_t)pc.col0[i] * ldn), (const uint8_t *)ctx->d_Bs[s],
+                                                     (size_t)pc.ncol[i] * ldn * sizeof(double)); // (not the copy engine)
+      mask_from_basis_kernel<<<(ldn + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_Bs[s], Mcat + (size_t)pc.mcol[i] * ldn, ldn);
+      ctx->launches++;
+    }
+    ctx->xchunks.push_back(xc);
   }
+  ctx->xchunks_built = true;
+  return 0;
+}
+
+// K1c on stream st for the SNP rows [m_lo, m_hi) (m_lo a multiple of 8): DMMA projection on the subgroup
+// bases, then the accuracy fix-up pass (explicit CGS2) for the few entries whose Gram-form residual cancelled.
+int launch_prep_x(eqb_ctx *ctx, cudaStream_t st, long long m_lo, long long m_hi)
+{
+  const int S = ctx->cfg.n_subgroups, ldn = ctx->ldn;
+  if (m_hi <= m_lo) return 0;
+  double **xp = ctx->d_prep_ptrs + 3 * S;
+  const int *dup = ctx->d_gt_i + 3 * (int)ctx->phi2L.size();
+  auto dmma_smem = [&](int NT, int NW) {
+    return ((size_t)(NT + 1) * 8 * (ldn + 1) + (size_t)NW * 8 * (NT + 1) * 8) * sizeof(double);
+  };
+  CK(cudaMemsetAsync(ctx->d_fix.p, 0, sizeof(unsigned long long), st));
   if (!ctx->x_explicit)
     for (const eqb_ctx::XChunk &xc : ctx->xchunks) {
       const double *X = ctx->d_X[xc.xvar];
@@ -611,34 +705,92 @@ int launch_prep_x(eqb_ctx *ctx)
       const bool wide = dmma_smem(xc.NTn, 16) <= ctx->dmma_budget; // 16 warps per CTA when one CTA fills the SM anyway
       cudaError_t e;
       switch (xc.NTn) {
-      case 1: e = launch_dmma<1, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
-      case 2: e = launch_dmma<2, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
-      case 3: e = wide ? launch_dmma<3, 1, 16>(ctx, X, Bcat, Mcat, xc.pc, xp) : launch_dmma<3, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
-      case 5: e = wide ? launch_dmma<5, 1, 16>(ctx, X, Bcat, Mcat, xc.pc, xp) : launch_dmma<5, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
-      default: e = launch_dmma<8, 1, 8>(ctx, X, Bcat, Mcat, xc.pc, xp); break;
+      case 1: e = launch_dmma<1, 1, 8>(ctx, st, m_lo, m_hi, X, Bcat, Mcat, xc.pc, xp); break;
+      case 2: e = launch_dmma<2, 1, 8>(ctx, st, m_lo, m_hi, X, Bcat, Mcat, xc.pc, xp); break;
+      case 3:
+        e = wide ? launch_dmma<3, 1, 16>(ctx, st, m_lo, m_hi, X, Bcat, Mcat, xc.pc, xp)
+                 : launch_dmma<3, 1, 8>(ctx, st, m_lo, m_hi, X, Bcat, Mcat, xc.pc, xp);
+        break;
+      case 5:
+        e = wide ? launch_dmma<5, 1, 16>(ctx, st, m_lo, m_hi, X, Bcat, Mcat, xc.pc, xp)
+                 : launch_dmma<5, 1, 8>(ctx, st, m_lo, m_hi, X, Bcat, Mcat, xc.pc, xp);
+        break;
+      default: e = launch_dmma<8, 1, 8>(ctx, st, m_lo, m_hi, X, Bcat, Mcat, xc.pc, xp); break;
       }
       if (e != cudaSuccess) return fail(ctx, std::string("prep_x_dmma launch: ") + cudaGetErrorString(e));
     }
   // fix-up pass over the queued entries (a small persistent grid; the list is normally empty)
-  const unsigned grid = (unsigned)ctx->n_sm * (ctx->x_explicit ? 8 : 2);
+  const long long rows = m_hi - m_lo;
+  const unsigned grid = (unsigned)std::min<long long>((rows + WARPS - 1) / WARPS, (long long)ctx->n_sm * (ctx->x_explicit ? 8 : 2));
   const int npl = (ldn + 31) / 32;
   const unsigned long long *fl = ctx->d_fix.p;
   const int fc = (int)ctx->d_fix.cap;
   const int mode = ctx->x_explicit ? 0 : 1;
-  if (npl <= 4) prep_x_kernel<4><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
-  else if (npl <= 8) prep_x_kernel<8><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
-  else if (npl <= 12) prep_x_kernel<12><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
-  else if (npl <= 16) prep_x_kernel<16><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
-  else if (npl <= 32) prep_x_kernel<32><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
-  else prep_x_kernel<64><<<grid, THREADS, 0, ctx->stream>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc);
+  if (npl <= 4) prep_x_kernel<4><<<grid, THREADS, 0, st>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc, m_lo, m_hi);
+  else if (npl <= 8) prep_x_kernel<8><<<grid, THREADS, 0, st>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc, m_lo, m_hi);
+  else if (npl <= 12) prep_x_kernel<12><<<grid, THREADS, 0, st>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc, m_lo, m_hi);
+  else if (npl <= 16) prep_x_kernel<16><<<grid, THREADS, 0, st>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc, m_lo, m_hi);
+  else if (npl <= 32) prep_x_kernel<32><<<grid, THREADS, 0, st>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc, m_lo, m_hi);
+  else prep_x_kernel<64><<<grid, THREADS, 0, st>>>(ctx->d_prm, ctx->d_fp, xp, dup, mode, fl, fc, m_lo, m_hi);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
 }
 
+// The main stream may use every genotype row (general path, permutations, device-only timing) once the
+// last chunk of the upload pipeline is ready.
+int wait_x_all(eqb_ctx *ctx)
+{
+  if (!ctx->xready.empty()) CK(cudaStreamWaitEvent(ctx->stream, ctx->xready.back(), 0));
+  return 0;
+}
+
+// Upload pipeline, device side: for each row chunk, wait for its upload, re-index it into the all-sample
+// space (every genotype variant) and, on the fast path, project it (K1c); xready[c] marks the chunk usable.
+int enqueue_x_pipeline(eqb_ctx *ctx, bool with_prep)
+{
+  if (ctx->x_enqueued) return 0;
+  const int N = ctx->cfg.n_samples_all, ldn = ctx->ldn;
+  const long long M = ctx->cfg.n_snps;
+  cudaEvent_t ev_main;
+  CK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+  CK(cudaEventRecord(ev_main, ctx->stream)); // allocations, sample maps, bases, plan, parameter blocks
+  CK(cudaStreamWaitEvent(ctx->xcomp, ev_main, 0));
+  CK(cudaEventDestroy(ev_main));
+  const int nxc = (int)ctx->xrow.size() - 1;
+  for (int c = 0; c < nxc; ++c) {
+    const long long r0 = ctx->xrow[c], r1 = ctx->xrow[c + 1];
+    for (size_t v = 0; v < ctx->xvars.size(); ++v) {
+      const GenoHost &gh = ctx->genos[ctx->xvars[v].geno_id];
+      if ((size_t)c < gh.ev.size()) CK(cudaStreamWaitEvent(ctx->xcomp, gh.ev[c], 0));
+      if (r1 > r0) {
+        expand_rows_kernel<<<(unsigned)(r1 - r0), 128, 0, ctx->xcomp>>>(gh.d_raw + (size_t)r0 * gh.n_cols, gh.n_cols,
+                                                                       ctx->xvars[v].dmap, nullptr,
+                                                                       ctx->d_X[v] + (size_t)r0 * ldn, N, ldn, r1 - r0, 0.0, 0.0);
+        ctx->launches++;
+      }
+    }
+    CK(cudaGetLastError());
+    if (with_prep) {
+      int rc = launch_prep_x(ctx, ctx->xcomp, r0, r1);
+      if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->xready[c], ctx->xcomp));
+  }
+  for (auto &xv : ctx->xvars)
+    if (xv.dmap) cudaFreeAsync(xv.dmap, ctx->xcomp);
+  ctx->xvars.clear();
+  for (auto &g : ctx->genos) {
+    if (g.d_raw) cudaFreeAsync(g.d_raw, ctx->xcomp);
+    g.d_raw = nullptr;
+  }
+  ctx->x_enqueued = true;
+  return 0;
+}
+
 // K1b + K1c launches (residual phenotypes, residual genotype sums of squares); re-run by the
 // device-only benchmark entry so that the projection is inside the timed region.
-int launch_prep_yx(eqb_ctx *ctx)
+int launch_prep_yx(eqb_ctx *ctx, bool with_x)
 {
   const int S = ctx->cfg.n_subgroups, ldn = ctx->ldn;
   const long long M = ctx->cfg.n_snps, G = ctx->cfg.n_genes;
@@ -671,8 +823,8 @@ int launch_prep_yx(eqb_ctx *ctx)
     ctx->launches++;
     CK(cudaGetLastError());
   }
-  if (M > 0) {
-    int rc = launch_prep_x(ctx);
+  if (M > 0 && with_x) {
+    int rc = launch_prep_x(ctx, ctx->stream, 0, M);
     if (rc) return rc;
   }
   return 0;
@@ -701,7 +853,7 @@ int prepare_fast_path(eqb_ctx *ctx)
     CK(dmalloc(&ctx->d_emask[s], ldn));
     std::vector<uint8_t> em(ldn, 0);
     for (int i = 0; i < N; ++i) em[i] = sb.all2exp[i] >= 0;
-    CK(cudaMemcpyAsync(ctx->d_emask[s], em.data(), ldn, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, ctx->d_emask[s], em.data(), ldn));
     CK(cudaStreamSynchronize(ctx->stream));
   }
   // device arrays of pointers
@@ -718,8 +870,8 @@ int prepare_fast_path(eqb_ctx *ctx)
     hp[2 * S + s] = ctx->d_ystat[s];
     hp[3 * S + s] = ctx->d_xstat[s];
   }
-  CK(cudaMemcpyAsync(d_ptrs, hp.data(), hp.size() * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_eptr, ctx->d_emask.data(), S * sizeof(uint8_t *), cudaMemcpyHostToDevice, ctx->stream));
+  CK(h2d(ctx, d_ptrs, hp.data(), hp.size() * sizeof(double *)));
+  CK(h2d(ctx, d_eptr, ctx->d_emask.data(), S * sizeof(uint8_t *)));
   ctx->d_prep_ptrs = d_ptrs;
   // unique phi2 table of the gen / gen-fix / gen-maxh rows + duplicate-subgroup map
   {
@@ -762,8 +914,8 @@ int prepare_fast_path(eqb_ctx *ctx)
     gd.insert(gd.end(), omaL.begin(), omaL.end());
     CK(dmalloc(&ctx->d_gt_d, std::max<size_t>(gd.size(), 1) * sizeof(double)));
     CK(dmalloc(&ctx->d_gt_i, std::max<size_t>(idxL.size(), 1) * sizeof(int)));
-    CK(cudaMemcpyAsync(ctx->d_gt_d, gd.data(), gd.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_gt_i, idxL.data(), idxL.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, ctx->d_gt_d, gd.data(), gd.size() * sizeof(double)));
+    CK(h2d(ctx, ctx->d_gt_i, idxL.data(), idxL.size() * sizeof(int)));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->gt.uphi = ctx->d_gt_d;
     ctx->gt.omaL = ctx->d_gt_d + uphi.size();
@@ -801,8 +953,8 @@ int prepare_fast_path(eqb_ctx *ctx)
     }
     double *d_nus = base + (size_t)S * TZ_NI * TZ_NC, *d_wmax = d_nus + S;
     double **d_tzp = (double **)(d_wmax + S);
-    CK(cudaMemcpyAsync(d_nus, nus.data(), S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_tzp, tzp.data(), S * sizeof(double *), cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, d_nus, nus.data(), S * sizeof(double)));
+    CK(h2d(ctx, d_tzp, tzp.data(), S * sizeof(double *)));
     build_tz_kernel<<<S, TZ_NI * 16, 0, ctx->stream>>>(d_nus, d_tzp, d_wmax);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -815,9 +967,13 @@ int prepare_fast_path(eqb_ctx *ctx)
     }
   }
   CK(dmalloc(&ctx->d_fp, sizeof(FastParams)));
-  CK(cudaMemcpyAsync(ctx->d_fp, &ctx->hfp, sizeof(FastParams), cudaMemcpyHostToDevice, ctx->stream));
+  CK(h2d(ctx, ctx->d_fp, &ctx->hfp, sizeof(FastParams)));
   {
-    int rc2 = launch_prep_yx(ctx);
+    int rc2 = build_x_plan(ctx);
+    if (rc2) return rc2;
+    rc2 = launch_prep_yx(ctx, false); // K1b here; K1c rides the upload pipeline, chunk by chunk
+    if (rc2) return rc2;
+    rc2 = enqueue_x_pipeline(ctx, true);
     if (rc2) return rc2;
   }
   // which genes are generic in every subgroup where they are expressed
@@ -864,6 +1020,19 @@ int eqb_create(eqb_ctx **out, const eqb_config *cfg)
   configure_pool(cfg->device);
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+  CK(cudaStreamCreateWithFlags(&ctx->xcopy, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->xcomp, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->dstream, cudaStreamNonBlocking));
+  {
+    // row chunks of the upload pipeline (boundaries multiples of 8: one DMMA block = 8 SNP rows)
+    const long long M = cfg->n_snps;
+    const int nxc = M >= 65536 ? 8 : (M >= 8192 ? 4 : 1);
+    ctx->xrow.assign(nxc + 1, 0);
+    for (int c = 1; c < nxc; ++c) ctx->xrow[c] = ((M * c / nxc) + 7) / 8 * 8;
+    ctx->xrow[nxc] = M;
+    ctx->xready.assign(nxc, nullptr);
+    for (int c = 0; c < nxc; ++c) CK(cudaEventCreateWithFlags(&ctx->xready[c], cudaEventDisableTiming));
+  }
   AllocScope alloc_scope(ctx->stream);
   ctx->subs.resize(cfg->n_subgroups);
   {
@@ -883,10 +1052,20 @@ void eqb_destroy(eqb_ctx *ctx)
   AllocScope alloc_scope(ctx->stream);
   if (ctx->stream) {
     cudaSetDevice(ctx->cfg.device);
+    if (ctx->xcopy) cudaStreamSynchronize(ctx->xcopy);
+    if (ctx->xcomp) cudaStreamSynchronize(ctx->xcomp);
+    if (ctx->dstream) cudaStreamSynchronize(ctx->dstream);
     cudaStreamSynchronize(ctx->stream);
   }
-  for (auto &g : ctx->genos)
+  for (auto &xv : ctx->xvars)
+    if (xv.dmap) dfree(xv.dmap);
+  for (auto e : ctx->xready)
+    if (e) cudaEventDestroy(e);
+  for (auto &g : ctx->genos) {
+    for (auto e : g.ev)
+      if (e) cudaEventDestroy(e);
     if (g.d_raw) dfree(g.d_raw);
+  }
   for (auto &s : ctx->subs) {
     if (s.d_Yraw) dfree(s.d_Yraw);
     if (s.d_Craw) dfree(s.d_Craw);
@@ -945,6 +1124,10 @@ void eqb_destroy(eqb_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
   }
+  release_stage(ctx);
+  if (ctx->xcopy) cudaStreamDestroy(ctx->xcopy);
+  if (ctx->xcomp) cudaStreamDestroy(ctx->xcomp);
+  if (ctx->dstream) cudaStreamDestroy(ctx->dstream);
   delete ctx;
 }
 
@@ -954,15 +1137,36 @@ int eqb_set_genotypes(eqb_ctx *ctx, int32_t geno_id, const double *G, int64_t n_
 {
   AllocScope alloc_scope(ctx->stream);
   if (!ctx->stream) return fail(ctx, "context not usable");
+  if (ctx->finalized) return fail(ctx, "eqb_set_genotypes() after eqb_finalize()");
   if (geno_id < 0 || n_snps != ctx->cfg.n_snps || n_cols < 1) return fail(ctx, "bad genotype matrix");
   CK(cudaSetDevice(ctx->cfg.device));
   if ((size_t)geno_id >= ctx->genos.size()) ctx->genos.resize(geno_id + 1);
   GenoHost &gh = ctx->genos[geno_id];
-  if (gh.d_raw) dfree(gh.d_raw);
+  if (gh.d_raw) {
+    CK(cudaStreamSynchronize(ctx->xcopy)); // replacing a matrix whose upload may still be in flight
+    dfree(gh.d_raw);
+  }
   gh.n_cols = n_cols;
   const size_t bytes = (size_t)n_snps * n_cols * sizeof(double);
   CK(dmalloc(&gh.d_raw, std::max<size_t>(bytes, 8)));
-  CK(cudaMemcpyAsync(gh.d_raw, G, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // asynchronous upload in row chunks on the copy stream; the host matrix must stay valid until the first
+  // eqb_run* call on this context has returned (see include/eqtlbma_b200.h)
+  cudaEvent_t ev_alloc;
+  CK(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+  CK(cudaEventRecord(ev_alloc, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->xcopy, ev_alloc, 0));
+  CK(cudaEventDestroy(ev_alloc));
+  const int nxc = (int)ctx->xrow.size() - 1;
+  for (auto e : gh.ev) cudaEventDestroy(e);
+  gh.ev.assign(nxc, nullptr);
+  for (int c = 0; c < nxc; ++c) {
+    const long long r0 = ctx->xrow[c], r1 = ctx->xrow[c + 1];
+    if (r1 > r0)
+      CK(cudaMemcpyAsync(gh.d_raw + (size_t)r0 * n_cols, G + (size_t)r0 * n_cols, (size_t)(r1 - r0) * n_cols * sizeof(double),
+                         cudaMemcpyHostToDevice, ctx->xcopy));
+    CK(cudaEventCreateWithFlags(&gh.ev[c], cudaEventDisableTiming));
+    CK(cudaEventRecord(gh.ev[c], ctx->xcopy));
+  }
   return 0;
 }
 
@@ -994,7 +1198,7 @@ int eqb_set_subgroup(eqb_ctx *ctx, int32_t s, const eqb_subgroup *sg)
   sb.d_Yraw = sb.d_Craw = nullptr;
   const size_t yb = (size_t)G * sg->n_exp_cols * sizeof(double);
   CK(dmalloc(&sb.d_Yraw, std::max<size_t>(yb, 8)));
-  CK(cudaMemcpyAsync(sb.d_Yraw, sg->Y, yb, cudaMemcpyHostToDevice, ctx->stream));
+  CK(h2d(ctx, sb.d_Yraw, sg->Y, yb));
   sb.covkey.clear();
   if (sb.Q > 0) {
     sb.covkey.assign((size_t)sb.Q * N, 0.0);
@@ -1003,7 +1207,7 @@ int eqb_set_subgroup(eqb_ctx *ctx, int32_t s, const eqb_subgroup *sg)
         if (sb.all2cov[i] >= 0) sb.covkey[(size_t)q * N + i] = sg->C[(size_t)q * sb.n_cov_cols + sb.all2cov[i]];
     const size_t cbytes = (size_t)sb.Q * sb.n_cov_cols * sizeof(double);
     CK(dmalloc(&sb.d_Craw, cbytes));
-    CK(cudaMemcpyAsync(sb.d_Craw, sg->C, cbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, sb.d_Craw, sg->C, cbytes));
   }
   return 0;
 }
@@ -1061,12 +1265,12 @@ int eqb_build_cis_windows(eqb_ctx *ctx, const int32_t *gene_chr, const int64_t *
   CK(dmalloc(&d_pos, std::max<size_t>(M, 1) * 8));
   CK(dmalloc(&d_b, std::max<size_t>(G, 1) * 8));
   CK(dmalloc(&d_e, std::max<size_t>(G, 1) * 8));
-  CK(cudaMemcpyAsync(d_gc, gene_chr, G * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_gs, gene_start, G * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_ge, gene_end, G * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_lo, lo.data(), nchr * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_hi, hi.data(), nchr * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_pos, snp_pos, M * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(h2d(ctx, d_gc, gene_chr, G * sizeof(int)));
+  CK(h2d(ctx, d_gs, gene_start, G * 8));
+  CK(h2d(ctx, d_ge, gene_end, G * 8));
+  CK(h2d(ctx, d_lo, lo.data(), nchr * 8));
+  CK(h2d(ctx, d_hi, hi.data(), nchr * 8));
+  CK(h2d(ctx, d_pos, snp_pos, M * 8));
   cis_window_kernel<<<(unsigned)((G + 127) / 128), 128, 0, ctx->stream>>>(d_gc, d_gs, d_ge, d_lo, d_hi, d_pos, anchor,
                                                                          radius, G, d_b, d_e);
   ctx->launches++;
@@ -1117,25 +1321,14 @@ int eqb_finalize(eqb_ctx *ctx)
       int *dmap = nullptr;
       CK(dmalloc(&dX, std::max<size_t>((size_t)M * ldn, 1) * sizeof(double)));
       CK(dmalloc(&dmap, N * sizeof(int)));
-      CK(cudaMemcpyAsync(dmap, sb.all2geno.data(), N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-      if (M > 0) {
-        expand_rows_kernel<<<(unsigned)M, 128, 0, ctx->stream>>>(ctx->genos[sb.geno_id].d_raw,
-                                                                 ctx->genos[sb.geno_id].n_cols, dmap, nullptr, dX, N,
-                                                                 ldn, M, 0.0, 0.0);
-        ctx->launches++;
-      }
-      CK(cudaGetLastError());
-      CK(cudaStreamSynchronize(ctx->stream));
-      dfree(dmap);
+      CK(h2d(ctx, dmap, sb.all2geno.data(), N * sizeof(int)));
+      CK(cudaStreamSynchronize(ctx->stream)); // (the map is copied from pageable memory)
+      ctx->xvars.push_back({sb.geno_id, dmap}); // re-indexed chunk by chunk by enqueue_x_pipeline()
       ctx->d_X.push_back(dX);
       variants[key] = v;
       sb.xvar = v;
     } else
       sb.xvar = it->second;
-  }
-  for (auto &g : ctx->genos) {
-    if (g.d_raw) dfree(g.d_raw);
-    g.d_raw = nullptr;
   }
   const double qnan = std::numeric_limits<double>::quiet_NaN();
   for (int s = 0; s < S; ++s) {
@@ -1144,11 +1337,11 @@ int eqb_finalize(eqb_ctx *ctx)
     CK(dmalloc(&dmap, N * sizeof(int)));
     CK(dmalloc(&sb.d_gene_has, std::max<size_t>(G, 1)));
     CK(dmalloc(&sb.d_snp_has, std::max<size_t>(M, 1)));
-    CK(cudaMemcpyAsync(sb.d_gene_has, sb.gene_has.data(), G, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(sb.d_snp_has, sb.snp_has.data(), M, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, sb.d_gene_has, sb.gene_has.data(), G));
+    CK(h2d(ctx, sb.d_snp_has, sb.snp_has.data(), M));
     // expression -> all-sample space, NaN where the sample is absent or the gene is not expressed
     CK(dmalloc(&sb.d_Yall, std::max<size_t>((size_t)G * ldn, 1) * sizeof(double)));
-    CK(cudaMemcpyAsync(dmap, sb.all2exp.data(), N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, dmap, sb.all2exp.data(), N * sizeof(int)));
     if (G > 0) {
       expand_rows_kernel<<<(unsigned)G, 128, 0, ctx->stream>>>(sb.d_Yraw, sb.n_exp_cols, dmap, sb.d_gene_has,
                                                                sb.d_Yall, N, ldn, G, qnan, qnan);
@@ -1164,11 +1357,11 @@ int eqb_finalize(eqb_ctx *ctx)
     }
     CK(dmalloc(&sb.d_gmask, ldn));
     CK(dmalloc(&sb.d_cmask, ldn));
-    CK(cudaMemcpyAsync(sb.d_gmask, gm.data(), ldn, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(sb.d_cmask, cm.data(), ldn, cudaMemcpyHostToDevice, ctx->stream));
+    CK(h2d(ctx, sb.d_gmask, gm.data(), ldn));
+    CK(h2d(ctx, sb.d_cmask, cm.data(), ldn));
     if (sb.Q > 0) {
       CK(dmalloc(&sb.d_Call, (size_t)sb.Q * ldn * sizeof(double)));
-      CK(cudaMemcpyAsync(dmap, sb.all2cov.data(), N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      CK(h2d(ctx, dmap, sb.all2cov.data(), N * sizeof(int)));
       expand_rows_kernel<<<(unsigned)sb.Q, 128, 0, ctx->stream>>>(sb.d_Craw, sb.n_cov_cols, dmap, nullptr, sb.d_Call,
                                                                   N, ldn, sb.Q, 0.0, 0.0);
       ctx->launches++;
@@ -1209,19 +1402,19 @@ int eqb_finalize(eqb_ctx *ctx)
   grids.insert(grids.end(), ctx->phi2S.begin(), ctx->phi2S.end());
   grids.insert(grids.end(), ctx->oma2S.begin(), ctx->oma2S.end());
   CK(dmalloc(&ctx->d_grids, std::max<size_t>(grids.size(), 1) * sizeof(double)));
-  CK(cudaMemcpyAsync(ctx->d_grids, grids.data(), grids.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(h2d(ctx, ctx->d_grids, grids.data(), grids.size() * sizeof(double)));
   std::vector<unsigned long long> masks;
   std::vector<double> weights;
   if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.bfs == EQB_BFS_ALL) enumerate_configs(S, masks, weights);
   ctx->n_cfg_all = (long long)masks.size();
   CK(dmalloc(&ctx->d_cfg_mask, std::max<size_t>(masks.size(), 1) * 8));
   CK(dmalloc(&ctx->d_cfg_weight, std::max<size_t>(masks.size(), 1) * 8));
-  CK(cudaMemcpyAsync(ctx->d_cfg_mask, masks.data(), masks.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_cfg_weight, weights.data(), weights.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(h2d(ctx, ctx->d_cfg_mask, masks.data(), masks.size() * 8));
+  CK(h2d(ctx, ctx->d_cfg_weight, weights.data(), weights.size() * 8));
   CK(dmalloc(&ctx->d_cb, std::max<size_t>(G, 1) * 8));
   CK(dmalloc(&ctx->d_ce, std::max<size_t>(G, 1) * 8));
-  CK(cudaMemcpyAsync(ctx->d_cb, ctx->cb.data(), G * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_ce, ctx->ce.data(), G * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(h2d(ctx, ctx->d_cb, ctx->cb.data(), G * 8));
+  CK(h2d(ctx, ctx->d_ce, ctx->ce.data(), G * 8));
 
   DevParams &hp = ctx->hp;
   memset(&hp, 0, sizeof(hp));
@@ -1264,9 +1457,11 @@ int eqb_finalize(eqb_ctx *ctx)
     hp.sub[s].Q = sb.Q;
   }
   CK(dmalloc(&ctx->d_prm, sizeof(DevParams)));
-  CK(cudaMemcpyAsync(ctx->d_prm, &hp, sizeof(DevParams), cudaMemcpyHostToDevice, ctx->stream));
+  CK(h2d(ctx, ctx->d_prm, &hp, sizeof(DevParams)));
   CK(cudaStreamSynchronize(ctx->stream));
   int rc = prepare_fast_path(ctx);
+  if (rc) return rc;
+  rc = enqueue_x_pipeline(ctx, false); // general path only: the rows still have to be re-indexed
   if (rc) return rc;
   ctx->finalized = true;
   return 0;
@@ -1324,6 +1519,29 @@ int64_t eqb_fast_gene_count(const eqb_ctx *ctx)
   return n;
 }
 
+// device -> host copy of the output rows of pairs [o0, o1) of the current gene chunk
+static int copy_results(eqb_ctx *ctx, cudaStream_t st, eqb_results *res, long long pair_base, long long o0, long long o1,
+                        bool o_gen, bool o_cfg, long long C)
+{
+  const int S = ctx->cfg.n_subgroups;
+  const bool join = ctx->cfg.analysis == EQB_ANALYSIS_JOIN;
+  const int L = (int)ctx->phi2L.size(), K = (int)ctx->phi2S.size();
+  const size_t n = (size_t)(o1 - o0);
+  if (o1 <= o0) return 0;
+  const long long hb = pair_base + o0;
+  if (res->n)
+    CK(cudaMemcpyAsync(res->n + hb * S, ctx->d_out_n.p + o0 * S, n * S * 4, cudaMemcpyDeviceToHost, st));
+  if (res->sstats)
+    CK(cudaMemcpyAsync(res->sstats + hb * S * 5, ctx->d_ss.p + o0 * S * 5, n * S * 40, cudaMemcpyDeviceToHost, st));
+  if (o_gen)
+    CK(cudaMemcpyAsync(res->abf_gen + hb * 3 * L, ctx->d_gen.p + o0 * 3 * L, n * 3 * L * 8, cudaMemcpyDeviceToHost, st));
+  if (o_cfg)
+    CK(cudaMemcpyAsync(res->abf_cfg + hb * C * K, ctx->d_cfg.p + o0 * C * K, n * C * K * 8, cudaMemcpyDeviceToHost, st));
+  if (res->abf_w && join)
+    CK(cudaMemcpyAsync(res->abf_w + hb * (5 + C), ctx->d_w.p + o0 * (5 + C), n * (5 + C) * 8, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
 static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_results *res, bool want_raw,
                          bool device_only, float *ms)
 {
@@ -1349,6 +1567,7 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
   CK(cudaMemGetInfo(&free_b, &total_b));
   const size_t budget = std::max<size_t>(64u << 20, std::min<size_t>(free_b / 2, (size_t)24 << 30));
 
+  if (device_only && wait_x_all(ctx)) return 100;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ms) {
     CK(cudaEventCreate(&ev0));
@@ -1389,10 +1608,11 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
       if (join && C > 0) CK(ctx->d_cfg.ensure((size_t)n_pairs * C * K));
       if (join) CK(ctx->d_w.ensure((size_t)n_pairs * (5 + C)));
       if (!gs.empty()) {
+        if (wait_x_all(ctx)) return 100; // the general path reads any genotype row
         CK(ctx->d_genes.ensure(gs.size()));
         CK(ctx->d_pair_off.ensure(gs.size()));
-        CK(cudaMemcpyAsync(ctx->d_genes.p, gs.data(), gs.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_pair_off.p, ps.data(), gs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(h2d(ctx, ctx->d_genes.p, gs.data(), gs.size() * sizeof(int)));
+        CK(h2d(ctx, ctx->d_pair_off.p, ps.data(), gs.size() * 8));
         LaunchArgs la;
         memset(&la, 0, sizeof(la));
         la.genes = ctx->d_genes.p;
@@ -1414,8 +1634,8 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
       if (!gf.empty()) {
         CK(ctx->d_genes2.ensure(gf.size()));
         CK(ctx->d_pair_off2.ensure(gf.size()));
-        CK(cudaMemcpyAsync(ctx->d_genes2.p, gf.data(), gf.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_pair_off2.p, pf.data(), gf.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(h2d(ctx, ctx->d_genes2.p, gf.data(), gf.size() * sizeof(int)));
+        CK(h2d(ctx, ctx->d_pair_off2.p, pf.data(), gf.size() * 8));
         std::vector<long long> fbase(gf.size());
         long long nfp = 0;
         for (size_t i = 0; i < gf.size(); ++i) {
@@ -1423,13 +1643,12 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           nfp += ctx->ce[gf[i]] - ctx->cb[gf[i]];
         }
         CK(ctx->d_fast_base.ensure(gf.size()));
-        CK(cudaMemcpyAsync(ctx->d_fast_base.p, fbase.data(), gf.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(h2d(ctx, ctx->d_fast_base.p, fbase.data(), gf.size() * 8));
         FastArgs fa;
         memset(&fa, 0, sizeof(fa));
         fa.genes = ctx->d_genes2.p;
         fa.n_genes = (int)gf.size();
         fa.which = ctx->cfg.bfs + 1;
-        fa.n_pairs = nfp;
         fa.fast_base = ctx->d_fast_base.p;
         fa.pair_off = ctx->d_pair_off2.p;
         fa.out_n = o_n ? ctx->d_out_n.p : nullptr;
@@ -1447,16 +1666,66 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         if (smem > 200 * 1024) return fail(ctx, "configuration table does not fit in shared memory");
         CK(cudaFuncSetAttribute(fast_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (device_only && prep_in_timed_region) {
-          int rcp = launch_prep_yx(ctx);
+          int rcp = launch_prep_yx(ctx, true);
           if (rcp) return rcp;
         }
+        // Segments of consecutive fast genes.  Device-only timing: one launch.  Otherwise one launch per row chunk
+        // of the upload pipeline (a segment starts as soon as the genotype rows of its genes are ready) and the
+        // results of a segment travel back on dstream while the next one computes / uploads.
+        const int nxc = (int)ctx->xrow.size() - 1;
+        std::vector<size_t> seg_begin(1, 0);
+        std::vector<int> seg_chunk;
+        if (device_only || nxc <= 1) {
+          seg_chunk.push_back(nxc - 1);
+        } else {
+          auto chunk_of = [&](int g) {
+            const long long last_row = std::max(ctx->ce[g] - 1, ctx->cb[g]);
+            int c = 0;
+            while (c + 1 < nxc && last_row >= ctx->xrow[c + 1]) ++c;
+            return c;
+          };
+          int cur = chunk_of(gf[0]);
+          for (size_t i = 1; i < gf.size(); ++i) {
+            const int c = chunk_of(gf[i]);
+            if (c > cur) { // genes are in SNP order: a later chunk opens a new segment
+              seg_begin.push_back(i);
+              seg_chunk.push_back(cur);
+              cur = c;
+            }
+          }
+          seg_chunk.push_back(cur);
+        }
+        seg_begin.push_back(gf.size());
         cudaEvent_t k0 = nullptr, k1 = nullptr;
         if (device_only) {
           CK(cudaEventCreate(&k0));
           CK(cudaEventCreate(&k1));
           CK(cudaEventRecord(k0, ctx->stream));
         }
-        fast_pair_kernel<<<(unsigned)((nfp + T - 1) / T), THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt);
+        for (size_t sgi = 0; sgi + 1 < seg_begin.size(); ++sgi) {
+          const size_t i0 = seg_begin[sgi], i1 = seg_begin[sgi + 1];
+          fa.q_begin = fbase[i0];
+          fa.n_pairs = (i1 < gf.size()) ? fbase[i1] : nfp;
+          if (!device_only && !ctx->xready.empty()) CK(cudaStreamWaitEvent(ctx->stream, ctx->xready[seg_chunk[sgi]], 0));
+          if (fa.n_pairs > fa.q_begin) {
+            fast_pair_kernel<<<(unsigned)((fa.n_pairs - fa.q_begin + T - 1) / T), THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp,
+                                                                                                       fa, ctx->gt);
+            ctx->launches++;
+          }
+          CK(cudaGetLastError());
+          if (!device_only) {
+            // output pairs [o0, o1) are final: this segment's genes and every general-path gene before them
+            const long long o0 = (sgi == 0) ? 0 : pf[i0];
+            const long long o1 = (i1 < gf.size()) ? pf[i1] : n_pairs;
+            cudaEvent_t done;
+            CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+            CK(cudaEventRecord(done, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->dstream, done, 0));
+            CK(cudaEventDestroy(done));
+            int rcd = copy_results(ctx, ctx->dstream, res, pair_base, o0, o1, o_gen, o_cfg, C);
+            if (rcd) return rcd;
+          }
+        }
         if (device_only) {
           CK(cudaEventRecord(k1, ctx->stream));
           CK(cudaEventSynchronize(k1));
@@ -1464,20 +1733,12 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           cudaEventDestroy(k0);
           cudaEventDestroy(k1);
         }
-        ctx->launches++;
-        CK(cudaGetLastError());
+      } else if (!device_only) {
+        int rcd = copy_results(ctx, ctx->stream, res, pair_base, 0, n_pairs, o_gen, o_cfg, C);
+        if (rcd) return rcd;
       }
       if (!device_only) {
-        if (res->n)
-          CK(cudaMemcpyAsync(res->n + pair_base * S, ctx->d_out_n.p, (size_t)n_pairs * S * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (res->sstats)
-          CK(cudaMemcpyAsync(res->sstats + pair_base * S * 5, ctx->d_ss.p, (size_t)n_pairs * S * 40, cudaMemcpyDeviceToHost, ctx->stream));
-        if (o_gen)
-          CK(cudaMemcpyAsync(res->abf_gen + pair_base * 3 * L, ctx->d_gen.p, (size_t)n_pairs * 3 * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (o_cfg)
-          CK(cudaMemcpyAsync(res->abf_cfg + pair_base * C * K, ctx->d_cfg.p, (size_t)n_pairs * C * K * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (res->abf_w && join)
-          CK(cudaMemcpyAsync(res->abf_w + pair_base * (5 + C), ctx->d_w.p, (size_t)n_pairs * (5 + C) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->dstream));
         CK(cudaStreamSynchronize(ctx->stream)); // buffers are reused by the next chunk
       }
     }
@@ -1490,6 +1751,10 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
     CK(cudaEventElapsedTime(ms, ev0, ev1));
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+  }
+  if (!ctx->x_complete && !ctx->xready.empty()) {
+    CK(cudaEventSynchronize(ctx->xready.back())); // the caller's genotype matrices are no longer needed
+    ctx->x_complete = true;
   }
   return check_device_errors(ctx);
 }
@@ -1554,8 +1819,8 @@ static int eval_perm_items(eqb_ctx *ctx, const std::vector<int> &genes, const st
   if (n_items == 0) return 0;
   CK(ctx->d_genes.ensure(n_items));
   CK(ctx->d_slots.ensure(n_items));
-  CK(cudaMemcpyAsync(ctx->d_genes.p, genes.data(), n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_slots.p, tab_idx.data(), n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(h2d(ctx, ctx->d_genes.p, genes.data(), n_items * sizeof(int)));
+  CK(h2d(ctx, ctx->d_slots.p, tab_idx.data(), n_items * sizeof(int)));
   LaunchArgs la;
   memset(&la, 0, sizeof(la));
   la.genes = ctx->d_genes.p;
@@ -1603,6 +1868,7 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
   if (join && pc->pbf > ctx->cfg.bfs + 1) return fail(ctx, "--pbf needs Bayes factors that --bfs does not compute");
   if (!join && pc->permsep != 1 && pc->permsep != 2) return fail(ctx, "bad --permsep");
   CK(cudaSetDevice(ctx->cfg.device));
+  if (wait_x_all(ctx)) return 100;
   const int S = ctx->cfg.n_subgroups, N = ctx->cfg.n_samples_all;
   const long long P = pc->nperm;
   const int kind = stat_kind_for(ctx, pc);
@@ -1673,7 +1939,7 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
         }
       }
       CK(ctx->d_perm.ensure(tab.size()));
-      CK(cudaMemcpyAsync(ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
+      CK(h2d(ctx, ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short)));
       CK(cudaStreamSynchronize(ctx->stream));
       ctx->perm_seed = pc->seed;
       ctx->perm_P = P;
@@ -1736,7 +2002,7 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
           }
         }
         CK(ctx->d_perm.ensure(tab.size()));
-        CK(cudaMemcpyAsync(ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, ctx->stream));
+        CK(h2d(ctx, ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short)));
         CK(cudaStreamSynchronize(ctx->stream));
         // rows of this sub-batch are contiguous in a scratch region, then scattered to their items
         CK(ctx->d_stat2.ensure(bg.size() * (size_t)P));

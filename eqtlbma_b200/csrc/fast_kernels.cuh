@@ -47,7 +47,8 @@ struct FastArgs {
   int n_genes;
   int T;                       // pairs per tile
   int which;                   // 1 gen, 2 sin, 3 all
-  long long n_pairs;           // pairs of the fast genes
+  long long n_pairs;           // compact pair range of this launch: [q_begin, n_pairs)
+  long long q_begin;
   const long long *fast_base;  // [n_genes] first compact pair index of each fast gene
   const long long *pair_off;   // [n_genes] first OUTPUT pair index of each fast gene
   int *out_n;
@@ -279,7 +280,7 @@ template <int NPL>
 __global__ void __launch_bounds__(THREADS) prep_x_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
                                                          double *const *xstat_all, const int *__restrict__ dup_of,
                                                          const int fixup_only, const unsigned long long *__restrict__ fix_list,
-                                                         int fix_cap)
+                                                         int fix_cap, long long m_lo, long long m_hi)
 {
   const DevParams &prm = *prm_;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -287,9 +288,9 @@ __global__ void __launch_bounds__(THREADS) prep_x_kernel(const DevParams *__rest
   // fix-up mode: grid-stride walk over the entries queued by the DMMA pass (fix_list[0] = count; if the
   // list overflowed, every SNP is re-checked)
   const bool listed = fixup_only && fix_list != nullptr && fix_list[0] + 1 < (unsigned long long)fix_cap;
-  const long long n_items = listed ? (long long)fix_list[0] : prm.M;
+  const long long n_items = listed ? (long long)fix_list[0] : m_hi - m_lo; // unlisted: SNP rows [m_lo, m_hi)
   for (long long item = (long long)blockIdx.x * WARPS + warp; item < n_items; item += (long long)gridDim.x * WARPS) {
-  const long long m = listed ? (long long)(fix_list[item + 1] >> 8) : item;
+  const long long m = listed ? (long long)(fix_list[item + 1] >> 8) : m_lo + item;
   const int s_only = listed ? (int)(fix_list[item + 1] & 0xffull) : -1;
   for (int s = 0; s < S; ++s) {
     if (s_only >= 0 && s != s_only) continue;
@@ -405,8 +406,10 @@ template <int NT, int NM, int NW>
 __global__ void __launch_bounds__(NW * 32) prep_x_dmma_kernel(const DevParams *__restrict__ prm_, const double *__restrict__ X,
                                                               const double *__restrict__ Bcat, const double *__restrict__ Mcat,
                                                               const PrepCols pc, double *const *xstat_all,
-                                                              unsigned long long *__restrict__ fix_list, int fix_cap)
+                                                              unsigned long long *__restrict__ fix_list, int fix_cap,
+                                                              long long blk_lo, long long blk_hi)
 {
+  // Blocks of 8 SNP rows [blk_lo, blk_hi) (a row chunk of the upload pipeline, or every row).
   // Persistent CTAs: Bcat / Mcat are staged once per CTA, then every warp walks its blocks of 8 SNP rows.
   // The genotype stream is register double-buffered in chunks of 8 x 16 bytes per lane, ACROSS block
   // boundaries, so that a warp always has its next chunk in flight while the tensor pipe works.
@@ -427,9 +430,9 @@ __global__ void __launch_bounds__(NW * 32) prep_x_dmma_kernel(const DevParams *_
   }
   __syncthreads();
   constexpr int U = 8, CH = 2 * U;                    // doubles per lane per chunk
-  const long long M = prm.M, nblk = (M + 7) >> 3;
+  const long long M = prm.M, nblk = blk_hi;
   const long long bstep = (long long)gridDim.x * NW;
-  long long blk = (long long)blockIdx.x * NW + warp;
+  long long blk = blk_lo + (long long)blockIdx.x * NW + warp;
   if (blk >= nblk) return;
   const int nch = (ldn4 + CH - 1) / CH;
   const double *brow = Bsm + (size_t)g * strideB + (size_t)kk * ldn4;
@@ -783,7 +786,7 @@ __global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const
   long long *s_m = s_pair + T;                               // [T] SNP index
   int *s_gene = (int *)(s_m + T);                            // [T] gene id
 
-  const long long q0 = (long long)blockIdx.x * T;
+  const long long q0 = fa.q_begin + (long long)blockIdx.x * T;
   const int tn = (int)min((long long)T, fa.n_pairs - q0);
   // map the tile's pairs to (gene, SNP, output index)
   for (int j = threadIdx.x; j < tn; j += THREADS) {
@@ -870,16 +873,26 @@ __global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const
     const double *stj = st + (size_t)j * sst;
     unsigned long long mask = hasm[j];
     const double phi2 = gt.uphi[u];
-    double den = 0.0, num = 0.0, sing = 0.0;
+    // sum_s 0.5 log10(v_s / (v_s + phi2)) = 0.5 log10(prod_s v_s / (v_s + phi2)): ONE logarithm per (pair, phi2);
+    // the running product is folded into slog long before it could underflow
+    double den = 0.0, num = 0.0, tsum = 0.0, prod = 1.0, slog = 0.0;
     while (mask) {
       const int s = __ffsll((long long)mask) - 1;
       mask &= mask - 1;
-      double d, bd, sg;
-      term_entry(stj[s], stj[S + s], stj[2 * S + s], phi2, d, bd, sg);
-      den += d;
-      num += bd;
-      sing += sg;
+      const double b = stj[s], v = stj[S + s], tt = stj[2 * S + s];
+      if (!(fabs(tt) < 1e-8)) { // (gene_snp_pair.cpp:314: |t| < 1e-8 contributes nothing)
+        const double inv = 1.0 / (v + phi2);
+        den += inv;
+        num += b * inv;
+        tsum += tt * tt * inv;
+        prod *= v * inv;
+        if (prod < 1e-200) {
+          slog += log(prod);
+          prod = 1.0;
+        }
+      }
     }
+    const double sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log(prod)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
     double *a = agg + (size_t)j * sag + 3 * u;
     a[0] = den;
     a[1] = num;
@@ -913,9 +926,15 @@ __global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const
       const double *stj = st + (size_t)j * sst;
       v = 0.0;
       if ((hasm[j] >> c) & 1ull) {
-        double d, bd, sg;
-        term_entry(stj[c], stj[S + c], stj[2 * S + c], prm.phi2S[k], d, bd, sg);
-        v = abf_from_sums(d, bd, sg, prm.oma2S[k]);
+        // singleton configuration: term + ABF of one subgroup merged,
+        // 0.5 log10(v/(v+phi2)) - 0.5 log10(1 + oma2/(v+phi2)) = 0.5 log10(v / (v + phi2 + oma2))  (one logarithm)
+        const double b = stj[c], vv = stj[S + c], tt = stj[2 * S + c];
+        const double phi2 = prm.phi2S[k], oma2 = prm.oma2S[k];
+        const double inv = 1.0 / (vv + phi2);
+        if (!(fabs(tt) < 1e-8) && b != 0.0 && inv != 0.0 && inv == inv) { // guards of CalcLog10AbfUvlr (see abf_from_sums)
+          const double w = 1.0 / (vv + phi2 + oma2);
+          v = (0.5 * log(vv * w) + 0.5 * inv * (tt * tt * phi2 + b * b * oma2 * w)) * EQB_INV_LN10;
+        }
       }
     }
     vs[(size_t)e * T1 + j] = v;

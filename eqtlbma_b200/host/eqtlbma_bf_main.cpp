@@ -1056,8 +1056,6 @@ int main(int argc, char **argv)
     sub.C = Q ? Cmats[s].data() : NULL;
     check(ctx, eqb_set_subgroup(ctx, s, &sub), "eqb_set_subgroup");
   }
-  for (size_t j = 0; j < Gmats.size(); ++j)
-    check(ctx, eqb_set_genotypes(ctx, (int)j, Gmats[j].data(), M, Gcols[j]), "eqb_set_genotypes");
   if (join || !d.phi2L.empty())
     check(ctx, eqb_set_grids(ctx, d.phi2L.data(), d.oma2L.data(), (int)d.phi2L.size(), d.phi2S.data(), d.oma2S.data(),
                              (int)d.phi2S.size()),
@@ -1077,6 +1075,9 @@ int main(int argc, char **argv)
                                    o.anchor == "TSS" ? EQB_ANCHOR_TSS : EQB_ANCHOR_TSS_TES, (int64_t)o.radius, cb.data(),
                                    ce.data()),
         "eqb_build_cis_windows");
+  // genotypes last: the upload is asynchronous (row chunks), projection and results overlap with it
+  for (size_t j = 0; j < Gmats.size(); ++j)
+    check(ctx, eqb_set_genotypes(ctx, (int)j, Gmats[j].data(), M, Gcols[j]), "eqb_set_genotypes");
   check(ctx, eqb_finalize(ctx), "eqb_finalize");
 
   // ---- headers (writeRes(..., "only"), eqtlbma_bf.cpp:1510-1513)

@@ -122,7 +122,11 @@ void eqb_destroy(eqb_ctx *ctx);
 const char *eqb_last_error(const eqb_ctx *ctx);
 
 /* Snp::subgroup2genotypes_ (snp.hpp:45): dosages of one genotype file, SNP-major
- * G[snp * n_cols + col] (= column-major N x M); rows of SNPs the file lacks may hold anything. */
+ * G[snp * n_cols + col] (= column-major N x M); rows of SNPs the file lacks may hold anything.
+ * The upload is asynchronous (row chunks on a copy stream, overlapped with the projection of the
+ * chunks that already landed and with the results of eqb_run travelling back): G must stay valid
+ * and unchanged until the first eqb_run* call on this context has returned, or eqb_destroy();
+ * pinned host memory (cudaHostAlloc / cudaHostRegister) is what makes the overlap effective. */
 int eqb_set_genotypes(eqb_ctx *ctx, int32_t geno_id, const double *G, int64_t n_snps, int32_t n_cols);
 int eqb_set_subgroup(eqb_ctx *ctx, int32_t s, const eqb_subgroup *sg);
 /* Grid (grid.cpp:28-65): phi2/oma2 columns of --gridL (L points) and --gridS (K points). */
