@@ -1026,7 +1026,7 @@ int eqb_create(eqb_ctx **out, const eqb_config *cfg)
   {
     // row chunks of the upload pipeline (boundaries multiples of 8: one DMMA block = 8 SNP rows)
     const long long M = cfg->n_snps;
-    const int nxc = M >= 65536 ? 8 : (M >= 8192 ? 4 : 1);
+    const int nxc = M >= 131072 ? 16 : (M >= 65536 ? 8 : (M >= 8192 ? 4 : 1));
     ctx->xrow.assign(nxc + 1, 0);
     for (int c = 1; c < nxc; ++c) ctx->xrow[c] = ((M * c / nxc) + 7) / 8 * 8;
     ctx->xrow[nxc] = M;
@@ -1519,6 +1519,52 @@ int64_t eqb_fast_gene_count(const eqb_ctx *ctx)
   return n;
 }
 
+// Results of a list of genes written straight into the caller's (pinned, device-accessible) result arrays:
+// one CTA per gene copies its pair rows of every requested output with coalesced stores over PCIe.  Used by
+// the upload pipeline, where genes finish in genotype-chunk order and a DMA copy per gene would be too many.
+struct ScatterArgs {
+  const int *genes;
+  const long long *pair_off;
+  int n_genes;
+  long long host_base; // first output pair of the gene chunk in the host arrays
+  const int *d_n;
+  const double *d_ss, *d_gen, *d_cfg, *d_w;
+  int *h_n;
+  double *h_ss, *h_gen, *h_cfg, *h_w;
+  long long w_n, w_ss, w_gen, w_cfg, w_w; // words per pair
+};
+
+__global__ void __launch_bounds__(256) scatter_results_kernel(const DevParams *__restrict__ prm, const ScatterArgs a)
+{
+  const int i = blockIdx.x;
+  if (i >= a.n_genes) return;
+  const int g = a.genes[i];
+  const long long np = prm->cis_end[g] - prm->cis_begin[g], o = a.pair_off[i], h = a.host_base + o;
+  if (a.h_n)
+    for (long long k = threadIdx.x; k < np * a.w_n; k += blockDim.x) a.h_n[h * a.w_n + k] = a.d_n[o * a.w_n + k];
+  if (a.h_ss)
+    for (long long k = threadIdx.x; k < np * a.w_ss; k += blockDim.x) a.h_ss[h * a.w_ss + k] = a.d_ss[o * a.w_ss + k];
+  if (a.h_gen)
+    for (long long k = threadIdx.x; k < np * a.w_gen; k += blockDim.x) a.h_gen[h * a.w_gen + k] = a.d_gen[o * a.w_gen + k];
+  if (a.h_cfg)
+    for (long long k = threadIdx.x; k < np * a.w_cfg; k += blockDim.x) a.h_cfg[h * a.w_cfg + k] = a.d_cfg[o * a.w_cfg + k];
+  if (a.h_w)
+    for (long long k = threadIdx.x; k < np * a.w_w; k += blockDim.x) a.h_w[h * a.w_w + k] = a.d_w[o * a.w_w + k];
+}
+
+// device-side alias of a pinned host array (nullptr if the array is not device-accessible)
+static void *mapped_alias_v(const void *p)
+{
+  if (!p) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return at.devicePointer;
+}
+
 // device -> host copy of the output rows of pairs [o0, o1) of the current gene chunk
 static int copy_results(eqb_ctx *ctx, cudaStream_t st, eqb_results *res, long long pair_base, long long o0, long long o1,
                         bool o_gen, bool o_cfg, long long C)
@@ -1632,25 +1678,10 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         if (rc) return rc;
       }
       if (!gf.empty()) {
-        CK(ctx->d_genes2.ensure(gf.size()));
-        CK(ctx->d_pair_off2.ensure(gf.size()));
-        CK(h2d(ctx, ctx->d_genes2.p, gf.data(), gf.size() * sizeof(int)));
-        CK(h2d(ctx, ctx->d_pair_off2.p, pf.data(), gf.size() * 8));
-        std::vector<long long> fbase(gf.size());
-        long long nfp = 0;
-        for (size_t i = 0; i < gf.size(); ++i) {
-          fbase[i] = nfp;
-          nfp += ctx->ce[gf[i]] - ctx->cb[gf[i]];
-        }
-        CK(ctx->d_fast_base.ensure(gf.size()));
-        CK(h2d(ctx, ctx->d_fast_base.p, fbase.data(), gf.size() * 8));
         FastArgs fa;
         memset(&fa, 0, sizeof(fa));
-        fa.genes = ctx->d_genes2.p;
         fa.n_genes = (int)gf.size();
         fa.which = ctx->cfg.bfs + 1;
-        fa.fast_base = ctx->d_fast_base.p;
-        fa.pair_off = ctx->d_pair_off2.p;
         fa.out_n = o_n ? ctx->d_out_n.p : nullptr;
         fa.out_ss = o_ss ? ctx->d_ss.p : nullptr;
         fa.out_gen = join ? ctx->d_gen.p : nullptr; // also the staging area of phase C
@@ -1669,33 +1700,96 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           int rcp = launch_prep_yx(ctx, true);
           if (rcp) return rcp;
         }
-        // Segments of consecutive fast genes.  Device-only timing: one launch.  Otherwise one launch per row chunk
-        // of the upload pipeline (a segment starts as soon as the genotype rows of its genes are ready) and the
-        // results of a segment travel back on dstream while the next one computes / uploads.
+        // Device-only timing, small inputs or pageable result arrays: one launch in gene order, DMA copy back.
+        // Otherwise (upload pipeline): the fast genes are taken in the order of the genotype row chunk that
+        // completes their cis window, one launch per chunk as soon as it is ready, and each segment's results are
+        // scattered into the caller's pinned arrays on dstream while later chunks upload and compute.
         const int nxc = (int)ctx->xrow.size() - 1;
+        ScatterArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        bool pipelined = !device_only && nxc > 1 && getenv("EQB_NO_PIPELINE") == nullptr;
+        if (pipelined) {
+          sa.h_n = (int *)mapped_alias_v(res->n);
+          sa.h_ss = (double *)mapped_alias_v(res->sstats);
+          sa.h_gen = o_gen ? (double *)mapped_alias_v(res->abf_gen) : nullptr;
+          sa.h_cfg = o_cfg ? (double *)mapped_alias_v(res->abf_cfg) : nullptr;
+          sa.h_w = join ? (double *)mapped_alias_v(res->abf_w) : nullptr;
+          pipelined = (!res->n || sa.h_n) && (!res->sstats || sa.h_ss) && (!o_gen || sa.h_gen) && (!o_cfg || sa.h_cfg) &&
+                      (!(join && res->abf_w) || sa.h_w);
+          sa.host_base = pair_base;
+          sa.d_n = ctx->d_out_n.p;
+          sa.d_ss = ctx->d_ss.p;
+          sa.d_gen = ctx->d_gen.p;
+          sa.d_cfg = ctx->d_cfg.p;
+          sa.d_w = ctx->d_w.p;
+          sa.w_n = S;
+          sa.w_ss = (long long)S * 5;
+          sa.w_gen = 3LL * L;
+          sa.w_cfg = C * K;
+          sa.w_w = 5 + C;
+        }
         std::vector<size_t> seg_begin(1, 0);
         std::vector<int> seg_chunk;
-        if (device_only || nxc <= 1) {
-          seg_chunk.push_back(nxc - 1);
-        } else {
+        if (pipelined) {
           auto chunk_of = [&](int g) {
             const long long last_row = std::max(ctx->ce[g] - 1, ctx->cb[g]);
             int c = 0;
             while (c + 1 < nxc && last_row >= ctx->xrow[c + 1]) ++c;
             return c;
           };
-          int cur = chunk_of(gf[0]);
-          for (size_t i = 1; i < gf.size(); ++i) {
-            const int c = chunk_of(gf[i]);
-            if (c > cur) { // genes are in SNP order: a later chunk opens a new segment
+          std::vector<int> cidx(gf.size());
+          std::vector<size_t> order(gf.size());
+          for (size_t i = 0; i < gf.size(); ++i) {
+            cidx[i] = chunk_of(gf[i]);
+            order[i] = i;
+          }
+          std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cidx[a] < cidx[b]; });
+          std::vector<int> gf2(gf.size());
+          std::vector<long long> pf2(gf.size());
+          for (size_t i = 0; i < gf.size(); ++i) {
+            gf2[i] = gf[order[i]];
+            pf2[i] = pf[order[i]];
+            if (i > 0 && cidx[order[i]] != cidx[order[i - 1]]) {
               seg_begin.push_back(i);
-              seg_chunk.push_back(cur);
-              cur = c;
+              seg_chunk.push_back(cidx[order[i - 1]]);
             }
           }
-          seg_chunk.push_back(cur);
-        }
+          seg_chunk.push_back(cidx[order.back()]);
+          gf.swap(gf2);
+          pf.swap(pf2);
+        } else
+          seg_chunk.push_back(nxc - 1);
         seg_begin.push_back(gf.size());
+        if (!pipelined && !device_only && wait_x_all(ctx)) return 100;
+        CK(ctx->d_genes2.ensure(gf.size()));
+        CK(ctx->d_pair_off2.ensure(gf.size()));
+        CK(h2d(ctx, ctx->d_genes2.p, gf.data(), gf.size() * sizeof(int)));
+        CK(h2d(ctx, ctx->d_pair_off2.p, pf.data(), gf.size() * 8));
+        std::vector<long long> fbase(gf.size());
+        long long nfp = 0;
+        for (size_t i = 0; i < gf.size(); ++i) {
+          fbase[i] = nfp;
+          nfp += ctx->ce[gf[i]] - ctx->cb[gf[i]];
+        }
+        CK(ctx->d_fast_base.ensure(gf.size()));
+        CK(h2d(ctx, ctx->d_fast_base.p, fbase.data(), gf.size() * 8));
+        fa.genes = ctx->d_genes2.p;
+        fa.fast_base = ctx->d_fast_base.p;
+        fa.pair_off = ctx->d_pair_off2.p;
+        if (pipelined && !gs.empty()) {
+          // general-path genes of this chunk (already computed on the main stream)
+          cudaEvent_t done;
+          CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+          CK(cudaEventRecord(done, ctx->stream));
+          CK(cudaStreamWaitEvent(ctx->dstream, done, 0));
+          CK(cudaEventDestroy(done));
+          ScatterArgs s2 = sa;
+          s2.genes = ctx->d_genes.p;
+          s2.pair_off = ctx->d_pair_off.p;
+          s2.n_genes = (int)gs.size();
+          scatter_results_kernel<<<(unsigned)gs.size(), 256, 0, ctx->dstream>>>(ctx->d_prm, s2);
+          ctx->launches++;
+        }
         cudaEvent_t k0 = nullptr, k1 = nullptr;
         if (device_only) {
           CK(cudaEventCreate(&k0));
@@ -1706,24 +1800,26 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           const size_t i0 = seg_begin[sgi], i1 = seg_begin[sgi + 1];
           fa.q_begin = fbase[i0];
           fa.n_pairs = (i1 < gf.size()) ? fbase[i1] : nfp;
-          if (!device_only && !ctx->xready.empty()) CK(cudaStreamWaitEvent(ctx->stream, ctx->xready[seg_chunk[sgi]], 0));
+          if (pipelined) CK(cudaStreamWaitEvent(ctx->stream, ctx->xready[seg_chunk[sgi]], 0));
           if (fa.n_pairs > fa.q_begin) {
             fast_pair_kernel<<<(unsigned)((fa.n_pairs - fa.q_begin + T - 1) / T), THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp,
                                                                                                        fa, ctx->gt);
             ctx->launches++;
           }
           CK(cudaGetLastError());
-          if (!device_only) {
-            // output pairs [o0, o1) are final: this segment's genes and every general-path gene before them
-            const long long o0 = (sgi == 0) ? 0 : pf[i0];
-            const long long o1 = (i1 < gf.size()) ? pf[i1] : n_pairs;
+          if (pipelined && i1 > i0) {
             cudaEvent_t done;
             CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
             CK(cudaEventRecord(done, ctx->stream));
             CK(cudaStreamWaitEvent(ctx->dstream, done, 0));
             CK(cudaEventDestroy(done));
-            int rcd = copy_results(ctx, ctx->dstream, res, pair_base, o0, o1, o_gen, o_cfg, C);
-            if (rcd) return rcd;
+            ScatterArgs s2 = sa;
+            s2.genes = ctx->d_genes2.p + i0;
+            s2.pair_off = ctx->d_pair_off2.p + i0;
+            s2.n_genes = (int)(i1 - i0);
+            scatter_results_kernel<<<(unsigned)(i1 - i0), 256, 0, ctx->dstream>>>(ctx->d_prm, s2);
+            ctx->launches++;
+            CK(cudaGetLastError());
           }
         }
         if (device_only) {
@@ -1732,6 +1828,10 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           CK(cudaEventElapsedTime(&ctx->last_pair_ms, k0, k1));
           cudaEventDestroy(k0);
           cudaEventDestroy(k1);
+        }
+        if (!pipelined && !device_only) {
+          int rcd = copy_results(ctx, ctx->stream, res, pair_base, 0, n_pairs, o_gen, o_cfg, C);
+          if (rcd) return rcd;
         }
       } else if (!device_only) {
         int rcd = copy_results(ctx, ctx->stream, res, pair_base, 0, n_pairs, o_gen, o_cfg, C);

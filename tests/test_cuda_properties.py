@@ -121,3 +121,43 @@ def test_subgroup_specific_covariates_match_oracle(cuda_lib, oracle_lib, n_sub, 
     pa = eng.run_permutations(20, 1859, pbf="gen-sin", wrtsize=5)
     pb = ora.run_permutations(20, 1859, pbf="gen-sin", wrtsize=5)
     assert np.array_equal(pa.count, pb.count)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("analysis,bfs", [("join", "sin"), ("join", "all"), ("sep", "gen")])
+def test_upload_pipeline_matches_plain_path(cuda_lib, analysis, bfs, monkeypatch):
+    """Enough SNPs for the chunked upload pipeline (genes finish in genotype-chunk order and their results
+    are scattered into PINNED host arrays by a kernel): bit-identical to the plain path (pageable arrays,
+    DMA copy, gene order), for the whole range and for a sub-range of genes, and to a run with the
+    pipeline disabled."""
+    import eqtlbma_b200
+    from eqtlbma_b200.synth import make_dataset
+    ds = make_dataset(seed=21, n_subgroups=3, n_inds=40, n_genes=700, snps_per_gene=14, n_cov=2, cov_per_subgroup=True,
+                      dosage=True, n_chr=3, radius=100, gene_spacing=201, far_snp=False, absent_gene_frac=0.05)
+    assert ds.n_snps >= 8192
+    eng = eqtlbma_b200.Engine(ds, analysis=analysis, bfs=bfs)
+    plain = eng.run()
+    pinned = eng.run(out=eng.alloc_results(pinned=True))
+    for a, b in ((plain.n, pinned.n), (plain.sstats, pinned.sstats), (plain.abf_gen, pinned.abf_gen),
+                 (plain.abf_cfg, pinned.abf_cfg), (plain.abf_w, pinned.abf_w)):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert np.array_equal(a, b, equal_nan=True)
+    sub = eng.run(lo=100, hi=420, out=eng.alloc_results(100, 420, pinned=True))
+    off = eng.pair_offsets()
+    assert np.array_equal(sub.sstats, plain.sstats[off[100]:off[420]], equal_nan=True)
+    if plain.abf_w is not None:
+        assert np.array_equal(sub.abf_w, plain.abf_w[off[100]:off[420]], equal_nan=True)
+    eng.close()
+    # first run of a fresh context goes through the pipeline while the upload is still in flight
+    eng2 = eqtlbma_b200.Engine(ds, analysis=analysis, bfs=bfs)
+    first = eng2.run(out=eng2.alloc_results(pinned=True))
+    assert np.array_equal(first.sstats, plain.sstats, equal_nan=True)
+    if plain.abf_w is not None:
+        assert np.array_equal(first.abf_w, plain.abf_w, equal_nan=True)
+    eng2.close()
+    monkeypatch.setenv("EQB_NO_PIPELINE", "1")
+    eng3 = eqtlbma_b200.Engine(ds, analysis=analysis, bfs=bfs)
+    off_run = eng3.run(out=eng3.alloc_results(pinned=True))
+    assert np.array_equal(off_run.sstats, plain.sstats, equal_nan=True)
+    eng3.close()
