@@ -892,6 +892,7 @@ int prepare_fast_path(eqb_ctx *ctx)
         }
         idxL[r * L + k] = u;
         omaL[r * L + k] = oma2;
+        if (r == 0) ctx->gt.pad = (int)uphi.size(); // unique phi2 values of the "gen" row (they come first)
       }
     // dup_of[s]: an earlier subgroup with the same genotype variant, individuals and covariates
     ctx->dup_of.assign(S, -1);

@@ -684,7 +684,7 @@ struct GridTab {
   const int *idxL;
   const double *omaL;
   int UL;
-  int pad;
+  int pad; // number of leading entries of uphi used by the gen row (the permutation statistic needs only those)
 };
 
 // ES-model log10 ABF from the sums over the active subgroups (CalcLog10AbfUvlr, gene_snp_pair.cpp:332-355)
@@ -718,6 +718,78 @@ __device__ __forceinline__ void term_entry(double b, double v, double t, double 
     // -0.5 log10(1 + phi2/v) = 0.5 log10(v / (v + phi2)) = 0.5 log10(v * inv)
     sg = (phi2 == 0.0) ? 0.0 : (0.5 * log(v * inv) + 0.5 * t * t * phi2 * inv) * EQB_INV_LN10;
   }
+}
+
+// sums over the subgroups in `mask` for one phi2: den = sum 1/(v+phi2), num = sum b/(v+phi2) and the sum of
+// the single-subgroup log10 ABFs with ONE logarithm:
+//   sum_s 0.5 log10(v_s / (v_s + phi2)) = 0.5 log10(prod_s v_s / (v_s + phi2))
+// (the running product is folded into slog long before it could underflow).  st = {b[S], v[S], t[S]}.
+__device__ __forceinline__ void consistent_sums(const double *__restrict__ st, int S, unsigned long long mask, double phi2,
+                                                double &den, double &num, double &sing)
+{
+  double tsum = 0.0, prod = 1.0, slog = 0.0;
+  den = 0.0;
+  num = 0.0;
+  while (mask) {
+    const int s = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    const double b = st[s], v = st[S + s], tt = st[2 * S + s];
+    if (!(fabs(tt) < 1e-8)) { // (gene_snp_pair.cpp:314: |t| < 1e-8 contributes nothing)
+      const double inv = 1.0 / (v + phi2);
+      den += inv;
+      num += b * inv;
+      tsum += tt * tt * inv;
+      prod *= v * inv;
+      if (prod < 1e-200) {
+        slog += log(prod);
+        prod = 1.0;
+      }
+    }
+  }
+  sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log(prod)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
+}
+
+// singleton configuration: term + ABF of one subgroup merged,
+// 0.5 log10(v/(v+phi2)) - 0.5 log10(1 + oma2/(v+phi2)) = 0.5 log10(v / (v + phi2 + oma2))  (one logarithm);
+// guards of CalcLog10AbfUvlr as in abf_from_sums
+__device__ __forceinline__ double singleton_value(double b, double vv, double tt, double phi2, double oma2)
+{
+  const double inv = 1.0 / (vv + phi2);
+  if (!(fabs(tt) < 1e-8) && b != 0.0 && inv != 0.0 && inv == inv) {
+    const double w = 1.0 / (vv + phi2 + oma2);
+    return (0.5 * log(vv * w) + 0.5 * inv * (tt * tt * phi2 + b * b * oma2 * w)) * EQB_INV_LN10;
+  }
+  return 0.0;
+}
+
+// log10_weighted_sum (utils_math.cpp:100-131: max seeded with element 0, NaN elements skipped, |result| <=
+// DBL_EPSILON snapped to 0) of n values by the 4 adjacent lanes {4j .. 4j+3}; q = lane & 3.  Every lane of the
+// warp must call it (full-mask shuffles); val(k) / wt(k) give element k and its weight.
+template <class FV, class FW>
+__device__ __forceinline__ double lws_quad(int n, int q, FV val, FW wt)
+{
+  if (n <= 0) return nan("");
+  double mx = val(0);
+  for (int k = q; k < n; k += 4) {
+    const double x = val(k);
+    mx = (x > mx) ? x : mx;
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    const double y = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = (y > mx) ? y : mx;
+  }
+  double sum = 0.0;
+  for (int k = q; k < n; k += 4) {
+    const double x = val(k);
+    const double e = exp10(x - mx);
+    sum += isnan(x) ? 0.0 : wt(k) * e;
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  double r = mx + log10(sum);
+  if (fabs(r) <= DBL_EPSILON) r = 0.0;
+  return r;
 }
 
 // phase A helper: SN contractions of one genotype row against the SN residualised expression rows of the gene
@@ -873,26 +945,8 @@ __global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const
     const double *stj = st + (size_t)j * sst;
     unsigned long long mask = hasm[j];
     const double phi2 = gt.uphi[u];
-    // sum_s 0.5 log10(v_s / (v_s + phi2)) = 0.5 log10(prod_s v_s / (v_s + phi2)): ONE logarithm per (pair, phi2);
-    // the running product is folded into slog long before it could underflow
-    double den = 0.0, num = 0.0, tsum = 0.0, prod = 1.0, slog = 0.0;
-    while (mask) {
-      const int s = __ffsll((long long)mask) - 1;
-      mask &= mask - 1;
-      const double b = stj[s], v = stj[S + s], tt = stj[2 * S + s];
-      if (!(fabs(tt) < 1e-8)) { // (gene_snp_pair.cpp:314: |t| < 1e-8 contributes nothing)
-        const double inv = 1.0 / (v + phi2);
-        den += inv;
-        num += b * inv;
-        tsum += tt * tt * inv;
-        prod *= v * inv;
-        if (prod < 1e-200) {
-          slog += log(prod);
-          prod = 1.0;
-        }
-      }
-    }
-    const double sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log(prod)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
+    double den, num, sing;
+    consistent_sums(stj, S, mask, phi2, den, num, sing); // ONE logarithm per (pair, phi2)
     double *a = agg + (size_t)j * sag + 3 * u;
     a[0] = den;
     a[1] = num;
@@ -926,15 +980,7 @@ __global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const
       const double *stj = st + (size_t)j * sst;
       v = 0.0;
       if ((hasm[j] >> c) & 1ull) {
-        // singleton configuration: term + ABF of one subgroup merged,
-        // 0.5 log10(v/(v+phi2)) - 0.5 log10(1 + oma2/(v+phi2)) = 0.5 log10(v / (v + phi2 + oma2))  (one logarithm)
-        const double b = stj[c], vv = stj[S + c], tt = stj[2 * S + c];
-        const double phi2 = prm.phi2S[k], oma2 = prm.oma2S[k];
-        const double inv = 1.0 / (vv + phi2);
-        if (!(fabs(tt) < 1e-8) && b != 0.0 && inv != 0.0 && inv == inv) { // guards of CalcLog10AbfUvlr (see abf_from_sums)
-          const double w = 1.0 / (vv + phi2 + oma2);
-          v = (0.5 * log(vv * w) + 0.5 * inv * (tt * tt * phi2 + b * b * oma2 * w)) * EQB_INV_LN10;
-        }
+        v = singleton_value(stj[c], stj[S + c], stj[2 * S + c], prm.phi2S[k], prm.oma2S[k]);
       }
     }
     vs[(size_t)e * T1 + j] = v;

@@ -466,71 +466,81 @@ __global__ void __launch_bounds__(PW * 32) perm_kernel(const DevParams *__restri
       __syncwarp();
       continue;
     }
-    // 4b: per (SNP, unique phi2): sums over the subgroups with results (consistent configuration)
-    for (int it = lane; it < 8 * UL; it += 32) {
-      const int j = it / UL, u = it % UL;
+    // 4b: per (SNP, unique phi2 of the "gen" row): sums over the subgroups with results (consistent
+    // configuration), one logarithm per item (consistent_sums)
+    const int UG = gt.pad; // the unique phi2 values of the gen row come first in gt.uphi
+    for (int it = lane; it < 8 * UG; it += 32) {
+      const int j = it / UG, u = it % UG;
       if (j >= tn) continue;
-      const double *stj = stw + j * 3 * S;
-      unsigned long long mask = hasw[j];
-      const double phi2 = gt.uphi[u];
-      double den = 0.0, num = 0.0, sing = 0.0;
-      while (mask) {
-        const int s = __ffsll((long long)mask) - 1;
-        mask &= mask - 1;
-        double d, bd, sg;
-        term_entry(stj[s], stj[S + s], stj[2 * S + s], phi2, d, bd, sg);
-        den += d;
-        num += bd;
-        sing += sg;
-      }
+      double den, num, sing;
+      consistent_sums(stw + j * 3 * S, S, hasw[j], gt.uphi[u], den, num, sing);
       double *a = agg + (j * UL + u) * 3;
       a[0] = den;
       a[1] = num;
       a[2] = sing;
     }
     __syncwarp();
-    // 4c: "gen" values on gridL, then their log10_weighted_sum (one lane per SNP)
+    // 4c: "gen" values on gridL, then their log10_weighted_sum by 4 lanes per SNP (lane = 4 j + q)
+    const int qj = lane >> 2, qq = lane & 3;
     for (int it = lane; it < 8 * L; it += 32) {
       const int j = it / L, k = it % L;
-      if (j >= tn) continue;
       const double *a = agg + (j * UL + gt.idxL[k]) * 3;
-      valw[j * L + k] = abf_from_sums(a[0], a[1], a[2], gt.omaL[k]);
+      valw[j * L + k] = (j < tn) ? abf_from_sums(a[0], a[1], a[2], gt.omaL[k]) : 0.0;
     }
     __syncwarp();
-    if (lane < tn) {
-      Lse a;
-      a.init();
-      for (int k = 0; k < L; ++k) a.add(valw[lane * L + k], 1.0 / (double)L, k == 0);
-      wgw[lane] = (L > 0) ? a.result() : nan("");
+    {
+      const double *vj = valw + qj * L;
+      const double wL = 1.0 / (double)L;
+      const double w = lws_quad(L, qq, [&](int k) { return vj[k]; }, [&](int) { return wL; });
+      if (qq == 0) wgw[qj] = w;
     }
     __syncwarp();
     if (la.which == 2) {
-      // 4d: singletons on gridS: one lane per (SNP, subgroup), online log-sum-exp over the grid
+      // 4d: singletons on gridS: one lane per (SNP, subgroup); the K values stay in registers for the two-pass
+      // log10_weighted_sum (K <= 16; larger grids use the online form)
       for (int it = lane; it < 8 * S; it += 32) {
         const int j = it / S, c = it % S;
         if (j >= tn) continue;
         const double *stj = stw + j * 3 * S;
-        Lse b;
-        b.init();
         const bool has = (hasw[j] >> c) & 1ull;
-        for (int k = 0; k < K; ++k) {
-          double v = 0.0;
-          if (has) {
-            double d, bd, sg;
-            term_entry(stj[c], stj[S + c], stj[2 * S + c], prm.phi2S[k], d, bd, sg);
-            v = abf_from_sums(d, bd, sg, prm.oma2S[k]);
-          }
-          b.add(v, 1.0 / (double)K, k == 0);
+        const double b = stj[c], vv = stj[S + c], tt = stj[2 * S + c];
+        double res;
+        if (K <= 16) {
+          double v[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = (k < K && has) ? singleton_value(b, vv, tt, prm.phi2S[k], prm.oma2S[k]) : 0.0;
+          double mx = v[0];
+#pragma unroll
+          for (int k = 1; k < 16; ++k)
+            if (k < K) mx = (v[k] > mx) ? v[k] : mx;
+          double sum = 0.0;
+          const double wK = 1.0 / (double)K;
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k < K) {
+              const double e = exp10(v[k] - mx);
+              sum += isnan(v[k]) ? 0.0 : wK * e;
+            }
+          res = mx + log10(sum);
+          if (fabs(res) <= DBL_EPSILON) res = 0.0;
+          if (K == 0) res = nan("");
+        } else {
+          Lse acc;
+          acc.init();
+          for (int k = 0; k < K; ++k)
+            acc.add(has ? singleton_value(b, vv, tt, prm.phi2S[k], prm.oma2S[k]) : 0.0, 1.0 / (double)K, k == 0);
+          res = acc.result();
         }
-        wcw[j * S + c] = b.result();
+        wcw[j * S + c] = res;
       }
       __syncwarp();
-      if (lane < tn) { // CalcBMAlite (gene_snp_pair.cpp:552-570)
-        Lse lite;
-        lite.init();
-        for (int c = 0; c < S; ++c) lite.add(wcw[lane * S + c], 0.5 / (double)S, c == 0);
-        lite.add(wgw[lane], 0.5, false);
-        wgw[lane] = lite.result();
+      { // CalcBMAlite (gene_snp_pair.cpp:552-570): S singleton terms (0.5/S each) then the consistent one (0.5)
+        const double *wj = wcw + qj * S;
+        const double wg = wgw[qj], wS = 0.5 / (double)S;
+        __syncwarp();
+        const double w = lws_quad(S + 1, qq, [&](int k) { return (k < S) ? wj[k] : wg; },
+                                  [&](int k) { return (k < S) ? wS : 0.5; });
+        if (qq == 0) wgw[qj] = w;
       }
       __syncwarp();
     } else if (la.which == 3) {
