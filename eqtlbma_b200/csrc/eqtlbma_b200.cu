@@ -1000,6 +1000,58 @@ int prepare_fast_path(eqb_ctx *ctx)
 
 } // namespace
 
+
+// diagnostics: worst deviations of the short-latency elementary functions from the CUDA library versions
+__global__ void math_selftest_kernel(long long n, double *out)
+{
+  __shared__ double worst[6];
+  if (threadIdx.x < 6) worst[threadIdx.x] = 0.0;
+  __syncthreads();
+  double w[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long st = 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+  auto unif = [&]() { // xorshift64*, uniform in [0, 1)
+    st ^= st >> 12;
+    st ^= st << 25;
+    st ^= st >> 27;
+    return (double)((st * 0x2545F4914F6CDD1Dull) >> 11) * (1.0 / 9007199254740992.0);
+  };
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int kind = (int)(i % 3);
+    double x;
+    if (kind == 0) x = exp10(-280.0 + 560.0 * unif());
+    else if (kind == 1) x = exp10(-12.0 + 24.0 * unif());
+    else x = 1.0 + (unif() - 0.5) * ((i % 2) ? 2e-3 : 1.2);
+    const double r0 = 1.0 / x, r1 = eqb::rcp_fast(x);
+    w[0] = fmax(w[0], fabs(r1 - r0) / fabs(r0));
+    const double l0 = log(x), l1 = eqb::log_fast(x);
+    w[1] = fmax(w[1], fabs(l1 - l0));
+    w[2] = fmax(w[2], fabs(l1 - l0) / fmax(fabs(l0), 1e-300));
+    const double y = (kind == 0) ? -299.0 + 598.0 * unif() : ((kind == 1) ? -30.0 * unif() : 2.0 * unif() - 1.0);
+    const double e0 = exp10(y), e1 = eqb::exp10_fast(y);
+    w[3] = fmax(w[3], fabs(e1 - e0) / e0);
+  }
+  // special values must agree exactly in kind
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double sp[8] = {0.0, -1.0, INFINITY, nan(""), 1e-310, 1.0, 4.9e-324, 1e300};
+    double bad = 0.0;
+    for (int k = 0; k < 8; ++k) {
+      const double a = log(sp[k]), b = eqb::log_fast(sp[k]);
+      if (!((isnan(a) && isnan(b)) || a == b || fabs(a - b) <= 1e-13 * fabs(a))) bad += 1.0;
+      const double c = 1.0 / sp[k], d = eqb::rcp_fast(sp[k]);
+      if (!((isnan(c) && isnan(d)) || c == d || fabs(c - d) <= 1e-15 * fabs(c))) bad += 1.0;
+    }
+    const double se[6] = {-INFINITY, INFINITY, nan(""), -400.0, 400.0, 0.0};
+    for (int k = 0; k < 6; ++k) {
+      const double a = exp10(se[k]), b = eqb::exp10_fast(se[k]);
+      if (!((isnan(a) && isnan(b)) || a == b)) bad += 1.0;
+    }
+    w[4] = bad;
+  }
+  for (int k = 0; k < 5; ++k) atomicMax((unsigned long long *)&worst[k], (unsigned long long)__double_as_longlong(w[k])); // (non-negative doubles order like integers)
+  __syncthreads();
+  if (threadIdx.x < 5) atomicMax((unsigned long long *)&out[threadIdx.x], (unsigned long long)__double_as_longlong(worst[threadIdx.x]));
+}
+
 extern "C" {
 
 int eqb_create(eqb_ctx **out, const eqb_config *cfg)
@@ -2243,6 +2295,19 @@ int eqb_run_permutations_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene
 {
   if (!pc) return fail(ctx, "null argument");
   return run_perm_impl(ctx, gene_lo, gene_hi, pc, nullptr, true, ms);
+}
+
+int eqb_math_selftest(int32_t device, int64_t n, double *out5)
+{
+  if (!out5 || n <= 0) return 1;
+  if (cudaSetDevice(device) != cudaSuccess) return 2;
+  double *d = nullptr;
+  if (cudaMalloc((void **)&d, 5 * sizeof(double)) != cudaSuccess) return 3;
+  cudaMemset(d, 0, 5 * sizeof(double));
+  math_selftest_kernel<<<296, 256>>>(n, d);
+  cudaError_t e = cudaMemcpy(out5, d, 5 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : 4;
 }
 
 } // extern "C"

@@ -698,7 +698,7 @@ __device__ __forceinline__ double abf_from_sums(double den, double num, double s
   if (num != 0.0 && den != 0.0 && den == den) { // (a NaN denominator fails the reference's "V < +Inf")
     if (oma2 == 0.0) return sing; // (a zero numerator would take the slow division path)
     const double z = 1.0 + oma2 * den; // log(1 + x) has an ABSOLUTE error of ~1e-16 here: no log1p needed
-    return sing + (-0.5 * log(z) + 0.5 * num * num * oma2 / z) * EQB_INV_LN10;
+    return sing + (-0.5 * log_fast(z) + 0.5 * num * num * oma2 * rcp_fast(z)) * EQB_INV_LN10;
   }
   return 0.0;
 }
@@ -712,11 +712,11 @@ __device__ __forceinline__ void term_entry(double b, double v, double t, double 
     bd = 0.0;
     sg = 0.0;
   } else {
-    const double inv = 1.0 / (v + phi2);
+    const double inv = rcp_fast(v + phi2);
     d = inv;
     bd = b * inv;
     // -0.5 log10(1 + phi2/v) = 0.5 log10(v / (v + phi2)) = 0.5 log10(v * inv)
-    sg = (phi2 == 0.0) ? 0.0 : (0.5 * log(v * inv) + 0.5 * t * t * phi2 * inv) * EQB_INV_LN10;
+    sg = (phi2 == 0.0) ? 0.0 : (0.5 * log_fast(v * inv) + 0.5 * t * t * phi2 * inv) * EQB_INV_LN10;
   }
 }
 
@@ -735,7 +735,7 @@ __device__ __forceinline__ void consistent_sums(const double *__restrict__ st, i
     mask &= mask - 1;
     const double b = st[s], v = st[S + s], tt = st[2 * S + s];
     if (!(fabs(tt) < 1e-8)) { // (gene_snp_pair.cpp:314: |t| < 1e-8 contributes nothing)
-      const double inv = 1.0 / (v + phi2);
+      const double inv = rcp_fast(v + phi2);
       den += inv;
       num += b * inv;
       tsum += tt * tt * inv;
@@ -746,7 +746,7 @@ __device__ __forceinline__ void consistent_sums(const double *__restrict__ st, i
       }
     }
   }
-  sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log(prod)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
+  sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log_fast(prod)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
 }
 
 // singleton configuration: term + ABF of one subgroup merged,
@@ -754,10 +754,10 @@ __device__ __forceinline__ void consistent_sums(const double *__restrict__ st, i
 // guards of CalcLog10AbfUvlr as in abf_from_sums
 __device__ __forceinline__ double singleton_value(double b, double vv, double tt, double phi2, double oma2)
 {
-  const double inv = 1.0 / (vv + phi2);
+  const double inv = rcp_fast(vv + phi2);
   if (!(fabs(tt) < 1e-8) && b != 0.0 && inv != 0.0 && inv == inv) {
-    const double w = 1.0 / (vv + phi2 + oma2);
-    return (0.5 * log(vv * w) + 0.5 * inv * (tt * tt * phi2 + b * b * oma2 * w)) * EQB_INV_LN10;
+    const double w = rcp_fast(vv + phi2 + oma2);
+    return (0.5 * log_fast(vv * w) + 0.5 * inv * (tt * tt * phi2 + b * b * oma2 * w)) * EQB_INV_LN10;
   }
   return 0.0;
 }
@@ -782,7 +782,7 @@ __device__ __forceinline__ double lws_quad(int n, int q, FV val, FW wt)
   double sum = 0.0;
   for (int k = q; k < n; k += 4) {
     const double x = val(k);
-    const double e = exp10(x - mx);
+    const double e = exp10_fast(x - mx);
     sum += isnan(x) ? 0.0 : wt(k) * e;
   }
   sum += __shfl_xor_sync(0xffffffffu, sum, 1);
@@ -878,6 +878,15 @@ __global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const
   }
   __syncthreads();
   // ---------------- phase A: contraction x . ytil_s (one warp per pair)
+  // the genotype rows of the tile are requested from HBM up front (one L2 prefetch per 128-byte line), so that
+  // the per-pair loads below pay an L2 hit instead of a DRAM round trip each
+  for (int s0 = 0; s0 < S; s0 += 8) {
+    if (s0 > 0 && prm.sub[s0].X == prm.sub[0].X) continue;
+    for (int j = warp; j < tn; j += WARPS) {
+      const double *row = prm.sub[s0].X + (size_t)s_m[j] * ldn;
+      for (int l = lane; l < (ldn >> 4); l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 16 * l));
+    }
+  }
   for (int s0 = 0; s0 < S; s0 += 8) {
     const int sn = min(8, S - s0);
     bool same = true;
@@ -1004,7 +1013,7 @@ __global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const
       const double wk = 1.0 / (double)nk;
       for (int k = 0; k < nk; ++k) {
         const double x = v[(size_t)k * T1];
-        const double e = exp10(x - mx);
+        const double e = exp10_fast(x - mx);
         sum += isnan(x) ? 0.0 : wk * e;
       }
       w = mx + log10(sum);

@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(PW * 32) perm_kernel(const DevParams *__restri
 #pragma unroll
           for (int k = 0; k < 16; ++k)
             if (k < K) {
-              const double e = exp10(v[k] - mx);
+              const double e = exp10_fast(v[k] - mx);
               sum += isnan(v[k]) ? 0.0 : wK * e;
             }
           res = mx + log10(sum);

@@ -161,3 +161,19 @@ def test_upload_pipeline_matches_plain_path(cuda_lib, analysis, bfs, monkeypatch
     off_run = eng3.run(out=eng3.alloc_results(pinned=True))
     assert np.array_equal(off_run.sstats, plain.sstats, equal_nan=True)
     eng3.close()
+
+
+@pytest.mark.gpu
+def test_short_latency_math_against_cuda_library(cuda_lib):
+    """rcp_fast / log_fast / exp10_fast (device_math.cuh) against 1/x, log, exp10 of the CUDA math library over
+    3e6 pseudo-random arguments (wide range and around 1) and the special values."""
+    import ctypes
+    out = (ctypes.c_double * 5)()
+    f = cuda_lib.eqb_math_selftest
+    f.restype = ctypes.c_int
+    assert f(ctypes.c_int32(0), ctypes.c_int64(3_000_000), out) == 0
+    rcp_rel, log_abs, log_rel, exp_rel, special = list(out)
+    assert rcp_rel < 5e-16
+    assert log_abs < 2e-13 and log_rel < 1e-12   # |log x| up to 645: a few ulp; relative near x = 1 stays ~1e-16 * O(1)
+    assert exp_rel < 2e-15
+    assert special == 0.0
