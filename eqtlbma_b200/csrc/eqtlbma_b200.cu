@@ -1021,28 +1021,32 @@ __global__ void math_selftest_kernel(long long n, double *out)
     if (kind == 0) x = exp10(-280.0 + 560.0 * unif());
     else if (kind == 1) x = exp10(-12.0 + 24.0 * unif());
     else x = 1.0 + (unif() - 0.5) * ((i % 2) ? 2e-3 : 1.2);
-    const double r0 = 1.0 / x, r1 = eqb::rcp_fast(x);
+    const double r0 = 1.0 / x, r1 = eqb::rcp_fast_impl(x);
     w[0] = fmax(w[0], fabs(r1 - r0) / fabs(r0));
-    const double l0 = log(x), l1 = eqb::log_fast(x);
+    const double s0 = rsqrt(x), s1 = eqb::rsqrt_fast_nb(x);
+    w[0] = fmax(w[0], fabs(s1 - s0) / s0);
+    const double l0 = log(x), l1 = eqb::log_fast_impl(x);
     w[1] = fmax(w[1], fabs(l1 - l0));
     w[2] = fmax(w[2], fabs(l1 - l0) / fmax(fabs(l0), 1e-300));
     const double y = (kind == 0) ? -299.0 + 598.0 * unif() : ((kind == 1) ? -30.0 * unif() : 2.0 * unif() - 1.0);
-    const double e0 = exp10(y), e1 = eqb::exp10_fast(y);
+    const double e0 = exp10(y), e1 = eqb::exp10_fast_impl(y);
     w[3] = fmax(w[3], fabs(e1 - e0) / e0);
+    const double g0 = exp(2.302585092994046 * y), g1 = eqb::exp_fast_nb(2.302585092994046 * y);
+    w[3] = fmax(w[3], fabs(g1 - g0) / g0);
   }
   // special values must agree exactly in kind
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const double sp[8] = {0.0, -1.0, INFINITY, nan(""), 1e-310, 1.0, 4.9e-324, 1e300};
     double bad = 0.0;
     for (int k = 0; k < 8; ++k) {
-      const double a = log(sp[k]), b = eqb::log_fast(sp[k]);
+      const double a = log(sp[k]), b = eqb::log_fast_impl(sp[k]);
       if (!((isnan(a) && isnan(b)) || a == b || fabs(a - b) <= 1e-13 * fabs(a))) bad += 1.0;
-      const double c = 1.0 / sp[k], d = eqb::rcp_fast(sp[k]);
+      const double c = 1.0 / sp[k], d = eqb::rcp_fast_impl(sp[k]);
       if (!((isnan(c) && isnan(d)) || c == d || fabs(c - d) <= 1e-15 * fabs(c))) bad += 1.0;
     }
     const double se[6] = {-INFINITY, INFINITY, nan(""), -400.0, 400.0, 0.0};
     for (int k = 0; k < 6; ++k) {
-      const double a = exp10(se[k]), b = eqb::exp10_fast(se[k]);
+      const double a = exp10(se[k]), b = eqb::exp10_fast_impl(se[k]);
       if (!((isnan(a) && isnan(b)) || a == b)) bad += 1.0;
     }
     w[4] = bad;
@@ -1932,9 +1936,15 @@ static int run_perm_or_pair_kernel(eqb_ctx *ctx, const LaunchArgs &la, long long
   // dynamic shared memory available = opt-in maximum of the device minus the kernel's static shared memory
   int optin = 0;
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->cfg.device);
+  const bool allcfg = la.which == 3;
   cudaFuncAttributes fa16, fa8;
-  cudaFuncGetAttributes(&fa16, perm_kernel<16>);
-  cudaFuncGetAttributes(&fa8, perm_kernel<8>);
+  if (allcfg) {
+    cudaFuncGetAttributes(&fa16, perm_kernel<16, true>);
+    cudaFuncGetAttributes(&fa8, perm_kernel<8, true>);
+  } else {
+    cudaFuncGetAttributes(&fa16, perm_kernel<16, false>);
+    cudaFuncGetAttributes(&fa8, perm_kernel<8, false>);
+  }
   const size_t lim16 = (size_t)std::max(0, optin - (int)fa16.sharedSizeBytes - 1024);
   const size_t lim = (size_t)std::max(0, optin - (int)fa8.sharedSizeBytes - 1024);
   const size_t smem16 = perm_smem_doubles(S, ctx->Qmax, ctx->ldn, K, L, ctx->gt.UL, la.which, 16) * sizeof(double);
@@ -1944,15 +1954,19 @@ static int run_perm_or_pair_kernel(eqb_ctx *ctx, const LaunchArgs &la, long long
   if (!ok) return run_pair_kernel(ctx, la, n_ctas, ppg);
   const unsigned grid = (unsigned)((long long)la.n_genes * std::max(1, ppg));
   cudaError_t e;
-  if (smem16 <= lim16) { // 16 warps share the CTA's B matrix: twice the latency hiding
-    e = cudaFuncSetAttribute(perm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
-    if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel attribute: ") + cudaGetErrorString(e));
-    perm_kernel<16><<<grid, 16 * 32, smem16, ctx->stream>>>(ctx->d_prm, ctx->d_fp, la, ctx->gt);
-  } else {
-    e = cudaFuncSetAttribute(perm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8);
-    if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel attribute: ") + cudaGetErrorString(e));
-    perm_kernel<8><<<grid, 8 * 32, smem8, ctx->stream>>>(ctx->d_prm, ctx->d_fp, la, ctx->gt);
+#define EQB_PERM_LAUNCH(PWV, ALLV, SMEMV)                                                                            \
+  do {                                                                                                               \
+    e = cudaFuncSetAttribute(perm_kernel<PWV, ALLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEMV));     \
+    if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel attribute: ") + cudaGetErrorString(e));          \
+    perm_kernel<PWV, ALLV><<<grid, PWV * 32, SMEMV, ctx->stream>>>(ctx->d_prm, ctx->d_fp, la, ctx->gt);              \
+  } while (0)
+  if (smem16 <= lim16 && !allcfg) { // 16 warps share the CTA's B matrix: twice the latency hiding
+    EQB_PERM_LAUNCH(16, false, smem16);
+  } else { // (--pbf all keeps 8 warps: its per-lane configuration tables need the 255-register budget)
+    if (allcfg) EQB_PERM_LAUNCH(8, true, smem8);
+    else EQB_PERM_LAUNCH(8, false, smem8);
   }
+#undef EQB_PERM_LAUNCH
   ctx->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel launch: ") + cudaGetErrorString(e));

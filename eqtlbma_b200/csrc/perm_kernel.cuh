@@ -37,7 +37,7 @@ __host__ __device__ inline size_t perm_warp_doubles(int S, int Qmax, int K, int 
 {
   const int sa = perm_mitm_sa(S, K);
   size_t d = perm_u1_doubles(S, Qmax, UL) + 8 * 3 * S + 8 + (size_t)8 * L + (size_t)8 * S + 8 + 8;
-  if (which == 3) d += (size_t)3 * K * S + (sa >= 0 ? (size_t)3 * K * (1u << sa) : 0);
+  if (which == 3) d += (size_t)3 * K * S + (sa >= 0 ? (size_t)3 * ((K + 3) & ~3) * (1u << sa) : 0); // mitm padded to 4 grid points
   return d;
 }
 __host__ __device__ inline size_t perm_smem_doubles(int S, int Qmax, int ldn, int K, int L, int UL, int which, int pw)
@@ -94,7 +94,9 @@ __device__ __forceinline__ void dmma_block(const double *__restrict__ xrow, cons
   }
 }
 
-template <int PW>
+// ALLCFG: the instantiation that carries the 2^S-1 configuration code (--pbf all); the gen / gen-sin / separate
+// statistics use the other one, whose register allocation is not burdened by the meet-in-the-middle tables
+template <int PW, bool ALLCFG>
 __global__ void __launch_bounds__(PW * 32) perm_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
                                                        const LaunchArgs la, const GridTab gt)
 {
@@ -543,7 +545,7 @@ __global__ void __launch_bounds__(PW * 32) perm_kernel(const DevParams *__restri
         if (qq == 0) wgw[qj] = w;
       }
       __syncwarp();
-    } else if (la.which == 3) {
+    } else if (ALLCFG && la.which == 3) {
       // 4e: all 2^S-1 configurations, warp per SNP.  Fast form (S <= 10): meet in the middle -- lane b owns
       // the subset b of the high min(5,S) subgroups (its per-grid-point sums live in registers), the 2^SA
       // subsets of the low subgroups come from a shared table -- and the BMA sum is accumulated in the
@@ -580,16 +582,18 @@ __global__ void __launch_bounds__(PW * 32) perm_kernel(const DevParams *__restri
         if (fast_ok) {
           const int SB = S - SA;
           const int nA = 1 << SA;
-          for (int e = lane; e < K * nA; e += 32) { // sums over the subsets of the low subgroups
+          const int Kp = (K + 3) & ~3; // grid points are evaluated four at a time; the padding entries are neutral
+          for (int e = lane; e < Kp * nA; e += 32) { // sums over the subsets of the low subgroups
             const int k = e / nA, a = e % nA;
             double d = 0.0, n_ = 0.0, A = 0.0;
-            for (int s = 0; s < SA; ++s)
-              if ((a >> s) & 1) {
-                const double *te = tab + ((size_t)k * S + s) * 3;
-                d += te[0];
-                n_ += te[1];
-                A += te[2];
-              }
+            if (k < K)
+              for (int s = 0; s < SA; ++s)
+                if ((a >> s) & 1) {
+                  const double *te = tab + ((size_t)k * S + s) * 3;
+                  d += te[0];
+                  n_ += te[1];
+                  A += te[2];
+                }
             double *m3 = mitm + (size_t)e * 3;
             m3[0] = d;
             m3[1] = n_;
@@ -598,10 +602,12 @@ __global__ void __launch_bounds__(PW * 32) perm_kernel(const DevParams *__restri
           __syncwarp();
           double acc = 0.0;
           if (lane < (1 << SB)) {
-            double hd[12], hn[12], hA[12];
+            double hd[12], hn[12], hA[12], hom[12];
 #pragma unroll
             for (int k = 0; k < 12; ++k) {
-              hd[k] = hn[k] = hA[k] = 0.0;
+              hd[k] = hn[k] = 0.0;
+              hA[k] = (k < K) ? 0.0 : -1e300; // padding: exp(-inf) = 0
+              hom[k] = (k < K) ? prm.oma2S[k] : 0.0;
               if (k < K)
                 for (int s = 0; s < SB; ++s)
                   if ((lane >> s) & 1) {
@@ -617,13 +623,18 @@ __global__ void __launch_bounds__(PW * 32) perm_kernel(const DevParams *__restri
               const double w = prm.size_weight[pb + __popc(a)];
               double part = 0.0;
 #pragma unroll
-              for (int k = 0; k < 12; ++k)
-                if (k < K) {
-                  const double *m3 = mitm + ((size_t)k * nA + a) * 3;
-                  const double den = hd[k] + m3[0], num = hn[k] + m3[1], A = hA[k] + m3[2];
-                  const double om = prm.oma2S[k];
-                  const double r = rsqrt(1.0 + om * den);
-                  part += r * exp(A + 0.5 * num * num * om * r * r - Mref);
+              for (int k0 = 0; k0 < 12; k0 += 4)
+                if (k0 < K) { // warp-uniform; the four evaluations below are independent and branch-free
+                  double ev[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u;
+                    const double *m3 = mitm + ((size_t)k * nA + a) * 3;
+                    const double den = hd[k] + m3[0], num = hn[k] + m3[1], A = hA[k] + m3[2];
+                    const double r = rsqrt_fast_nb(fma(hom[k], den, 1.0));
+                    ev[u] = r * exp_fast_nb(A + 0.5 * num * num * hom[k] * r * r - Mref);
+                  }
+                  part += (ev[0] + ev[1]) + (ev[2] + ev[3]);
                 }
               acc += w * part;
             }
