@@ -330,7 +330,7 @@ struct eqb_ctx {
   std::vector<uint8_t *> d_emask;
   std::vector<uint8_t> gene_fast;
   std::vector<int> dup_of;
-  DevBuf<int> d_genes2;
+  DevBuf<int> d_genes2, d_tile_gene;
   DevBuf<long long> d_pair_off2, d_fast_base;
   struct XChunk { // one prep_x_dmma launch: subgroups sharing a genotype variant, their basis / mask columns
     PrepCols pc;
@@ -1152,6 +1152,7 @@ void eqb_destroy(eqb_ctx *ctx)
     if (c.cat) dfree(c.cat);
   ctx->xchunks.clear();
   ctx->d_fix.release();
+  ctx->d_tile_gene.release();
   if (ctx->d_prm) dfree(ctx->d_prm);
   if (ctx->d_grids) dfree(ctx->d_grids);
   if (ctx->d_cfg_mask) dfree(ctx->d_cfg_mask);
@@ -1833,6 +1834,22 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         fa.genes = ctx->d_genes2.p;
         fa.fast_base = ctx->d_fast_base.p;
         fa.pair_off = ctx->d_pair_off2.p;
+        // first gene of every tile of every segment (the kernel walks forward from it instead of searching)
+        std::vector<int> tile_gene;
+        std::vector<size_t> seg_tile0(seg_begin.size(), 0);
+        for (size_t sgi = 0; sgi + 1 < seg_begin.size(); ++sgi) {
+          seg_tile0[sgi] = tile_gene.size();
+          const size_t i0 = seg_begin[sgi], i1 = seg_begin[sgi + 1];
+          if (i1 <= i0) continue;
+          const long long qb = fbase[i0], qe = (i1 < gf.size()) ? fbase[i1] : nfp;
+          size_t gi = i0;
+          for (long long q = qb; q < qe; q += T) {
+            while (gi + 1 < gf.size() && fbase[gi + 1] <= q) ++gi;
+            tile_gene.push_back((int)gi);
+          }
+        }
+        CK(ctx->d_tile_gene.ensure(std::max<size_t>(tile_gene.size(), 1)));
+        CK(h2d(ctx, ctx->d_tile_gene.p, tile_gene.data(), tile_gene.size() * sizeof(int)));
         if (pipelined && !gs.empty()) {
           // general-path genes of this chunk (already computed on the main stream)
           cudaEvent_t done;
@@ -1856,6 +1873,7 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         for (size_t sgi = 0; sgi + 1 < seg_begin.size(); ++sgi) {
           const size_t i0 = seg_begin[sgi], i1 = seg_begin[sgi + 1];
           fa.q_begin = fbase[i0];
+          fa.tile_gene = ctx->d_tile_gene.p + seg_tile0[sgi];
           fa.n_pairs = (i1 < gf.size()) ? fbase[i1] : nfp;
           if (pipelined) CK(cudaStreamWaitEvent(ctx->stream, ctx->xready[seg_chunk[sgi]], 0));
           if (fa.n_pairs > fa.q_begin) {

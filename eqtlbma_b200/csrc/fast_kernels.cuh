@@ -49,6 +49,7 @@ struct FastArgs {
   int which;                   // 1 gen, 2 sin, 3 all
   long long n_pairs;           // compact pair range of this launch: [q_begin, n_pairs)
   long long q_begin;
+  const int *tile_gene;        // [tiles of this launch] index (into genes) of the gene holding the tile's first pair
   const long long *fast_base;  // [n_genes] first compact pair index of each fast gene
   const long long *pair_off;   // [n_genes] first OUTPUT pair index of each fast gene
   int *out_n;
@@ -863,12 +864,8 @@ __global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const
   // map the tile's pairs to (gene, SNP, output index)
   for (int j = threadIdx.x; j < tn; j += THREADS) {
     const long long q = q0 + j;
-    int lo = 0, hi = fa.n_genes; // last gene with fast_base <= q
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (fa.fast_base[mid] <= q) lo = mid;
-      else hi = mid;
-    }
+    int lo = fa.tile_gene[blockIdx.x]; // gene of the tile's first pair (host-computed); walk forward from it
+    while (lo + 1 < fa.n_genes && fa.fast_base[lo + 1] <= q) ++lo;
     const int g = fa.genes[lo];
     const long long off = q - fa.fast_base[lo];
     s_gene[j] = g;
