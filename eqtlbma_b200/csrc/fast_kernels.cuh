@@ -191,7 +191,30 @@ __global__ void __launch_bounds__(THREADS) prep_y_kernel(const DevParams *__rest
         }
       tss[r] = warp_sum(ts);
     }
-    for (int pass = 0; pass < 2; ++pass)
+    // sum of squares before the projection: the second (re-orthogonalisation) pass is only needed when the
+    // projection removes almost everything (|y~|^2 < 1e-3 |y|^2); otherwise one pass on the orthonormal basis is
+    // accurate to ~eps |y| / |y~| < 1e-14
+    double yraw2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double a = 0.0;
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) a += yr[r][j] * yr[r][j];
+      yraw2[r] = warp_sum(a);
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) {
+        bool need = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          double a = 0.0;
+#pragma unroll
+          for (int j = 0; j < NPL; ++j) a += yr[r][j] * yr[r][j];
+          a = warp_sum(a);
+          need = need || (a < 1e-3 * yraw2[r]);
+        }
+        if (!need) break; // warp-uniform
+      }
       for (int k0 = 0; k0 <= Q; k0 += 4) {
         double h[R][4];
 #pragma unroll
@@ -238,6 +261,7 @@ __global__ void __launch_bounds__(THREADS) prep_y_kernel(const DevParams *__rest
           }
         }
       }
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const long long g = g0 + r;
