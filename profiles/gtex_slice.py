@@ -1,4 +1,4 @@
-import sys, time; sys.path.insert(0,'.')
+import os, sys, time; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, eqtlbma_b200
 from eqtlbma_b200.synth import make_dataset, make_grid
 t=time.time()

@@ -18,8 +18,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 CAPTURES = [("fast_pair_kernel (K2+K3), c2 bench step", "r1_raw_fast_pair_kernel.csv"),
             ("prep_x_dmma_kernel<5,1,16> (K1c, FP64 mma.sync), c2 bench step", "r1_raw_prep_x_dmma.csv"),
             ("prep_y_kernel<12,2> (K1b), c2 bench step", "r1_raw_prep_y_kernel.csv"),
-            ("perm_kernel<16,false> (K4, c4 slice of bench.py, --pbf gen-sin)", "r1_raw_perm_kernel_gensin.csv"),
-            ("perm_kernel<8,true> (K4, same slice, --bfs all --pbf all)", "r1_raw_perm_kernel_all.csv")]
+            ("perm_kernel<16,false> (K4, c4 slice of bench.py, --pbf gen-sin; `python profiles/perm_slice_gensin.py`)", "r1_raw_perm_kernel_gensin.csv"),
+            ("perm_kernel<8,true> (K4, same slice, --bfs all --pbf all; `python profiles/perm_slice_all.py`)", "r1_raw_perm_kernel_all.csv")]
 
 
 def raw(path):

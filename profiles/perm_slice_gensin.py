@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0,'.')
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, eqtlbma_b200, numpy as np
 from eqtlbma_b200.synth import make_dataset
 pds = make_dataset(**bench.PERM_WORKLOAD)
