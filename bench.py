@@ -127,6 +127,25 @@ def pinned_copy(ds):
     return ds
 
 
+def fixed_point_copy(ds):
+    """What the front-end's text parser hands to the ABI for a dosage file written with 3 decimals
+    (eqtlbma_bf_main.cpp, eqb_set_genotypes_fixed): u16 numerators of 1000 in pinned memory.  Lossless:
+    k / 1000 (IEEE division) is checked here to reproduce every double of the matrix bit for bit."""
+    import copy
+    import torch
+    d2 = copy.copy(ds)
+    d2.genos, d2._pinned, d2.geno_denoms = [], list(getattr(ds, "_pinned", [])), []
+    for G in ds.genos:
+        k = np.rint(G * 1000.0)
+        if not (np.all(k >= 0) and np.all(k <= 65535) and np.array_equal(k / 1000.0, G)):
+            return None  # not representable: the caller keeps the double matrix
+        t = torch.from_numpy(k.astype(np.uint16)).pin_memory()
+        d2.genos.append(t.numpy())
+        d2._pinned.append(t)
+        d2.geno_denoms.append(1000.0)
+    return d2
+
+
 def h2d_bytes(ds):
     b = sum(G.nbytes for G in ds.genos)
     for sg in ds.subgroups:
@@ -183,15 +202,24 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the C ABI with host buffers ("e2e"): context creation, H2D of every
     # input from pinned host memory, layout build, kernels, D2H of every result into pinned buffers
     out_buf = eng.alloc_results(raw=True, pinned=True)
+    # host genotype buffers in the compact lossless transport format the front-end's parser produces for this
+    # dosage file (3 decimals -> u16 numerators of 1000); the plain double matrix is timed next to it ("e2e_f64")
+    ds_fx = fixed_point_copy(ds)
+    ds_e2e = ds_fx if ds_fx is not None else ds
 
-    def e2e_step():
-        e = eqtlbma_b200.Engine(ds, **kw)
+    def e2e_step(d=None):
+        e = eqtlbma_b200.Engine(ds_e2e if d is None else d, **kw)
         r_ = e.run(raw=True, out=out_buf)
         e.close()
         return r_
 
-    for _ in range(max(1, args.warmup)):  # untimed warm-up steps of the end-to-end path as well
+    for _ in range(0 if args.no_e2e else max(1, args.warmup)):  # untimed warm-up steps of the end-to-end path as well
         r = e2e_step()
+    if args.no_e2e:
+        r = eng.run(raw=True, out=out_buf)
+        args_steps_e2e = 0
+    else:
+        args_steps_e2e = args.steps
     d2h = int(r.n.nbytes + r.sstats.nbytes + r.abf_gen.nbytes + r.abf_cfg.nbytes + r.abf_w.nbytes)
     if dist:
         dist.barrier()
@@ -201,15 +229,26 @@ def run_ours(args, rank, world, local_rank):
         _E.timing = {}
     t0 = time.perf_counter()
     step_times = []
-    for _ in range(args.steps):
+    for _ in range(args_steps_e2e):
         ts = time.perf_counter()
         e2e_step()
         step_times.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
     e2e_mean_s = (time.perf_counter() - t0) / args.steps
+    if args.no_e2e:
+        step_times = [float("nan")]
     # the GPU box's host is shared: single steps are occasionally 2-3x slower (PCIe / memory contention from other
     # tenants); the per-step median is the robust estimate, the mean is reported next to it
     e2e_s = float(np.median(step_times))
+    e2e_f64_s = None
+    if ds_fx is not None and not args.no_e2e:
+        e2e_step(ds)
+        tt = []
+        for _ in range(args.steps):
+            ts = time.perf_counter()
+            e2e_step(ds)
+            tt.append(time.perf_counter() - ts)
+        e2e_f64_s = float(np.median(tt))
     if args.verbose:
         print("e2e per-step ms:", [round(t * 1e3, 2) for t in step_times], file=sys.stderr)
     if args.verbose:
@@ -265,9 +304,11 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs (genotypes %.0f MB per GPU) larger than the 126 MB L2" % (ds.genos[0].nbytes / 1e6),
                    "sharding": "genes sharded across ranks, no collective"},
         "clocks": clocks,
-        "e2e": {"value": tot_pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes(ds),
+        "e2e": {"value": tot_pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes(ds_e2e),
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "stat": "median of per-step wall times",
-                "mean_ms_per_step": e2e_mean_s * 1e3},
+                "mean_ms_per_step": e2e_mean_s * 1e3,
+                "genotype_transport": ("u16 numerators of 1000 (lossless for the 3-decimal dosage file; "
+                                       "eqb_set_genotypes_fixed)" if ds_fx is not None else "f64")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_kind": pk_kind,
@@ -275,6 +316,9 @@ def run_ours(args, rank, world, local_rank):
                      "step_achieved": achieved_step, "step_frac": achieved_step / pk["hbm_gbs"],
                      "step_kernels": "prep_y + prep_x_dmma + fix-up + fast_pair"},
     }
+    if e2e_f64_s is not None and world == 1:
+        out["e2e_f64"] = {"value": pairs / e2e_f64_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes(ds),
+                          "ms_per_step": e2e_f64_s * 1e3, "genotype_transport": "f64 (eqb_set_genotypes)"}
     if perm_info:
         out["perm"] = perm_info
     if world == 1 and not args.no_cpu:
@@ -414,6 +458,7 @@ def main():
     ap.add_argument("--cpu-genes", type=int, default=60, help="genes in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-perm", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel A/B runs only: skip the end-to-end loop (e2e = null)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -42,6 +42,10 @@ def load_library() -> ctypes.CDLL:
     """Load the CUDA library; raises if it has not been built (no fallback of any kind)."""
     global _lib
     if _lib is None:
+        path = os.environ.get("EQB_LIB", LIB_PATH)  # tuning builds (variants/), never a different implementation
+        if path != LIB_PATH:
+            _lib = ctypes.CDLL(path)
+            return _lib
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(the eqtlbma_b200 hot path has no CPU fallback)")

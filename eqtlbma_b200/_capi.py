@@ -118,7 +118,18 @@ class Engine:
         self._call("build_cis_windows", _ptr(gc), _ptr(gst), _ptr(gen), _ptr(sc_), _ptr(sp),
                    C.c_int32(ANCHOR[ds.anchor]), C.c_int64(ds.radius), _ptr(self.cis_begin), _ptr(self.cis_end))
         # genotypes last: their upload is asynchronous and everything queued after it on the copy engine would wait
+        denoms = getattr(ds, "geno_denoms", None) or [1.0] * len(ds.genos)
         for gi, G in enumerate(ds.genos):
+            if G.dtype in (np.uint8, np.uint16):
+                # compact lossless transport (eqb_set_genotypes_fixed): value = k / denom
+                if prefix == "eqb_":
+                    Gc = G if G.flags.c_contiguous else np.ascontiguousarray(G)
+                    self._keep.append(Gc)
+                    self._call("set_genotypes_fixed", C.c_int32(gi), Gc.ctypes.data_as(C.c_void_p),
+                               C.c_int32(Gc.dtype.itemsize), C.c_double(float(denoms[gi])), C.c_int64(Gc.shape[0]),
+                               C.c_int32(Gc.shape[1]))
+                    continue
+                G = G.astype(np.float64) / float(denoms[gi])  # the oracle takes doubles
             if getattr(ds, "_clean", False) and G.flags.c_contiguous and G.dtype == np.float64:
                 Gc = G  # already NaN-free and contiguous (e.g. pinned by the caller): no host copy
             else:

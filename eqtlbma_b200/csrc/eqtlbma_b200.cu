@@ -133,14 +133,17 @@ struct Mt19937 {
 // ---------------------------------------------------------------- small kernels
 
 // out[r][i] = map[i] >= 0 ? in[r][map[i]] : fill   (re-index a matrix into the all-sample space)
-__global__ void expand_rows_kernel(const double *__restrict__ in, int n_cols, const int *__restrict__ map,
+// in may also be the compact transport format of eqb_set_genotypes_fixed: unsigned integers k with value k / denom
+// (IEEE division of two exactly representable integers = the correctly rounded decimal the text parser produces)
+template <class T>
+__global__ void expand_rows_kernel(const T *__restrict__ in, int n_cols, const int *__restrict__ map,
                                    const uint8_t *__restrict__ row_ok, double *__restrict__ out, int N, int ldn,
-                                   long long n_rows, double fill, double fill_bad_row)
+                                   long long n_rows, double fill, double fill_bad_row, double denom = 1.0)
 {
   const long long r = blockIdx.x;
   if (r >= n_rows) return;
   const bool ok = row_ok ? row_ok[r] != 0 : true;
-  const double *src = in + (size_t)r * n_cols;
+  const T *src = in + (size_t)r * n_cols;
   double *dst = out + (size_t)r * ldn;
   for (int i = threadIdx.x; i < ldn; i += blockDim.x) {
     double v = fill;
@@ -149,7 +152,7 @@ __global__ void expand_rows_kernel(const double *__restrict__ in, int n_cols, co
       if (!ok)
         v = fill_bad_row;
       else if (c >= 0)
-        v = src[c];
+        v = sizeof(T) == 8 ? (double)src[c] : __ddiv_rn((double)src[c], denom);
     } else
       v = (fill != fill) ? fill : 0.0; // padding: NaN for expression rows, 0 otherwise
     dst[i] = v;
@@ -256,8 +259,10 @@ struct SubHost {
 };
 
 struct GenoHost {
-  double *d_raw = nullptr;
+  void *d_raw = nullptr;
   int n_cols = 0;
+  int elem_bytes = 8;  // 8: doubles; 1 / 2: unsigned fixed-point transport (eqb_set_genotypes_fixed)
+  double denom = 1.0;
   std::vector<cudaEvent_t> ev; // upload of row chunk c complete (recorded on the copy stream)
 };
 
@@ -344,7 +349,8 @@ struct eqb_ctx {
   DevBuf<unsigned long long> d_fix; // [0] = count, then (snp << 8 | subgroup) entries needing the explicit K1c pass
   GridTab gt;              // unique phi2 values of the consistent-configuration rows
   double *d_gt_d = nullptr; // uphi[UL] | omaL[3L]
-  int *d_gt_i = nullptr;    // idxL[3L] | dup_of[S]
+  int *d_gt_i = nullptr;    // idxL[3L] | dup_of[S] | ustart[UL+1] | uent[3L]
+  GridOrder go;             // grid entries grouped by unique phi2 (fast_pair_warp_kernel)
   double **d_prep_ptrs = nullptr;
   double *d_tz = nullptr;
   float last_pair_ms = 0.f;
@@ -764,9 +770,18 @@ int enqueue_x_pipeline(eqb_ctx *ctx, bool with_prep)
       const GenoHost &gh = ctx->genos[ctx->xvars[v].geno_id];
       if ((size_t)c < gh.ev.size()) CK(cudaStreamWaitEvent(ctx->xcomp, gh.ev[c], 0));
       if (r1 > r0) {
-        expand_rows_kernel<<<(unsigned)(r1 - r0), 128, 0, ctx->xcomp>>>(gh.d_raw + (size_t)r0 * gh.n_cols, gh.n_cols,
-                                                                       ctx->xvars[v].dmap, nullptr,
-                                                                       ctx->d_X[v] + (size_t)r0 * ldn, N, ldn, r1 - r0, 0.0, 0.0);
+        const size_t roff = (size_t)r0 * gh.n_cols;
+        double *dst = ctx->d_X[v] + (size_t)r0 * ldn;
+        const int *dmap = ctx->xvars[v].dmap;
+        if (gh.elem_bytes == 1)
+          expand_rows_kernel<uint8_t><<<(unsigned)(r1 - r0), 128, 0, ctx->xcomp>>>((const uint8_t *)gh.d_raw + roff, gh.n_cols, dmap,
+                                                                                   nullptr, dst, N, ldn, r1 - r0, 0.0, 0.0, gh.denom);
+        else if (gh.elem_bytes == 2)
+          expand_rows_kernel<uint16_t><<<(unsigned)(r1 - r0), 128, 0, ctx->xcomp>>>((const uint16_t *)gh.d_raw + roff, gh.n_cols, dmap,
+                                                                                    nullptr, dst, N, ldn, r1 - r0, 0.0, 0.0, gh.denom);
+        else
+          expand_rows_kernel<double><<<(unsigned)(r1 - r0), 128, 0, ctx->xcomp>>>((const double *)gh.d_raw + roff, gh.n_cols, dmap,
+                                                                                  nullptr, dst, N, ldn, r1 - r0, 0.0, 0.0);
         ctx->launches++;
       }
     }
@@ -911,10 +926,26 @@ int prepare_fast_path(eqb_ctx *ctx)
       idxL[3 * L + s] = dup;
       ctx->dup_of[s] = dup;
     }
+    // grid entries grouped by their unique phi2 value (rows in order inside a group)
+    const int UL0 = (int)uphi.size();
+    const size_t go_off = idxL.size();
+    idxL.resize(go_off + UL0 + 1 + 3 * L);
+    {
+      int *ustart = idxL.data() + go_off, *uent = ustart + UL0 + 1;
+      int n = 0;
+      for (int u = 0; u < UL0; ++u) {
+        ustart[u] = n;
+        for (int e = 0; e < 3 * L; ++e)
+          if (idxL[e] == u) uent[n++] = e;
+      }
+      ustart[UL0] = n;
+    }
     std::vector<double> gd(uphi);
     gd.insert(gd.end(), omaL.begin(), omaL.end());
     CK(dmalloc(&ctx->d_gt_d, std::max<size_t>(gd.size(), 1) * sizeof(double)));
     CK(dmalloc(&ctx->d_gt_i, std::max<size_t>(idxL.size(), 1) * sizeof(int)));
+    ctx->go.ustart = ctx->d_gt_i + go_off;
+    ctx->go.uent = ctx->d_gt_i + go_off + UL0 + 1;
     CK(h2d(ctx, ctx->d_gt_d, gd.data(), gd.size() * sizeof(double)));
     CK(h2d(ctx, ctx->d_gt_i, idxL.data(), idxL.size() * sizeof(int)));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1191,12 +1222,31 @@ void eqb_destroy(eqb_ctx *ctx)
 
 const char *eqb_last_error(const eqb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+static int set_genotypes_impl(eqb_ctx *ctx, int32_t geno_id, const void *G, int elem_bytes, double denom, int64_t n_snps,
+                              int32_t n_cols);
+
 int eqb_set_genotypes(eqb_ctx *ctx, int32_t geno_id, const double *G, int64_t n_snps, int32_t n_cols)
+{
+  return set_genotypes_impl(ctx, geno_id, G, 8, 1.0, n_snps, n_cols);
+}
+
+int eqb_set_genotypes_fixed(eqb_ctx *ctx, int32_t geno_id, const void *G, int32_t elem_bytes, double denom, int64_t n_snps,
+                            int32_t n_cols)
+{
+  if (elem_bytes != 1 && elem_bytes != 2) return fail(ctx, "eqb_set_genotypes_fixed(): elem_bytes must be 1 or 2");
+  if (!(denom >= 1.0) || denom != floor(denom) || denom > 4503599627370496.0)
+    return fail(ctx, "eqb_set_genotypes_fixed(): denom must be a positive integer");
+  return set_genotypes_impl(ctx, geno_id, G, elem_bytes, denom, n_snps, n_cols);
+}
+
+static int set_genotypes_impl(eqb_ctx *ctx, int32_t geno_id, const void *Gv, int elem_bytes, double denom, int64_t n_snps,
+                              int32_t n_cols)
 {
   AllocScope alloc_scope(ctx->stream);
   if (!ctx->stream) return fail(ctx, "context not usable");
   if (ctx->finalized) return fail(ctx, "eqb_set_genotypes() after eqb_finalize()");
-  if (geno_id < 0 || n_snps != ctx->cfg.n_snps || n_cols < 1) return fail(ctx, "bad genotype matrix");
+  if (geno_id < 0 || n_snps != ctx->cfg.n_snps || n_cols < 1 || !Gv) return fail(ctx, "bad genotype matrix");
+  const char *G = (const char *)Gv;
   CK(cudaSetDevice(ctx->cfg.device));
   if ((size_t)geno_id >= ctx->genos.size()) ctx->genos.resize(geno_id + 1);
   GenoHost &gh = ctx->genos[geno_id];
@@ -1205,8 +1255,11 @@ int eqb_set_genotypes(eqb_ctx *ctx, int32_t geno_id, const double *G, int64_t n_
     dfree(gh.d_raw);
   }
   gh.n_cols = n_cols;
-  const size_t bytes = (size_t)n_snps * n_cols * sizeof(double);
-  CK(dmalloc(&gh.d_raw, std::max<size_t>(bytes, 8)));
+  gh.elem_bytes = elem_bytes;
+  gh.denom = denom;
+  const size_t eb = (size_t)elem_bytes;
+  const size_t bytes = (size_t)n_snps * n_cols * eb;
+  CK(dmalloc((char **)&gh.d_raw, std::max<size_t>(bytes, 8)));
   // asynchronous upload in row chunks on the copy stream; the host matrix must stay valid until the first
   // eqb_run* call on this context has returned (see include/eqtlbma_b200.h)
   cudaEvent_t ev_alloc;
@@ -1220,7 +1273,7 @@ int eqb_set_genotypes(eqb_ctx *ctx, int32_t geno_id, const double *G, int64_t n_
   for (int c = 0; c < nxc; ++c) {
     const long long r0 = ctx->xrow[c], r1 = ctx->xrow[c + 1];
     if (r1 > r0)
-      CK(cudaMemcpyAsync(gh.d_raw + (size_t)r0 * n_cols, G + (size_t)r0 * n_cols, (size_t)(r1 - r0) * n_cols * sizeof(double),
+      CK(cudaMemcpyAsync((char *)gh.d_raw + (size_t)r0 * n_cols * eb, G + (size_t)r0 * n_cols * eb, (size_t)(r1 - r0) * n_cols * eb,
                          cudaMemcpyHostToDevice, ctx->xcopy));
     CK(cudaEventCreateWithFlags(&gh.ev[c], cudaEventDisableTiming));
     CK(cudaEventRecord(gh.ev[c], ctx->xcopy));
@@ -1750,10 +1803,33 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         size_t tile_budget = 72 * 1024;
         if (const char *e = getenv("EQB_FAST_SMEM_KB")) tile_budget = (size_t)std::max(8, atoi(e)) * 1024;
         while (T > 4 && ((T & (T - 1)) || fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which) > tile_budget)) T /= 2;
+        // --bfs gen|sin and --analys sep: warp-autonomous tiles of 32 pairs (no CTA barriers); --bfs all keeps the
+        // CTA-synchronous tile kernel (its per-pair term table lives in shared memory)
+        const bool warp_tiles = fa.which != 3 && getenv("EQB_FAST_TILE") == nullptr;
+        int nwarp = WARPS;
+        size_t smem;
+        if (warp_tiles) {
+          T = 32;
+          if (const char *e = getenv("EQB_FASTW_WARPS")) nwarp = std::min(WARPS, std::max(1, atoi(e)));
+          const size_t tb = fast_warp_table_bytes(L, K, ctx->gt.UL);
+          while (nwarp > 1 && tb + nwarp * fast_warp_smem_bytes(S) > tile_budget) nwarp /= 2;
+          // phenotype cache: as many genes as fit next to the rest in ~1/2 of an SM's shared memory (2 CTAs per SM)
+          size_t cache_budget = 104 * 1024;
+          if (const char *e = getenv("EQB_FASTW_CACHE_KB")) cache_budget = (size_t)std::max(0, atoi(e)) * 1024;
+          const size_t base = tb + nwarp * fast_warp_smem_bytes(S), yrow = fast_warp_ycache_bytes(1, S, ctx->ldn);
+          int slots = (cache_budget > base) ? (int)((cache_budget - base) / yrow) : 0;
+          slots = std::min(slots, 8);
+          fa.ycache_slots = slots;
+          fa.use_dmma = getenv("EQB_FASTW_NO_DMMA") == nullptr;
+          smem = base + fast_warp_ycache_bytes(slots, S, ctx->ldn);
+          if (smem > 200 * 1024) return fail(ctx, "grid tables do not fit in shared memory");
+          CK(cudaFuncSetAttribute(fast_pair_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else {
+          smem = fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which);
+          if (smem > 200 * 1024) return fail(ctx, "configuration table does not fit in shared memory");
+          CK(cudaFuncSetAttribute(fast_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         fa.T = T;
-        const size_t smem = fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which);
-        if (smem > 200 * 1024) return fail(ctx, "configuration table does not fit in shared memory");
-        CK(cudaFuncSetAttribute(fast_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (device_only && prep_in_timed_region) {
           int rcp = launch_prep_yx(ctx, true);
           if (rcp) return rcp;
@@ -1877,8 +1953,12 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           fa.n_pairs = (i1 < gf.size()) ? fbase[i1] : nfp;
           if (pipelined) CK(cudaStreamWaitEvent(ctx->stream, ctx->xready[seg_chunk[sgi]], 0));
           if (fa.n_pairs > fa.q_begin) {
-            fast_pair_kernel<<<(unsigned)((fa.n_pairs - fa.q_begin + T - 1) / T), THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp,
-                                                                                                       fa, ctx->gt);
+            const long long tiles = (fa.n_pairs - fa.q_begin + T - 1) / T;
+            if (warp_tiles)
+              fast_pair_warp_kernel<<<(unsigned)((tiles + nwarp - 1) / nwarp), nwarp * 32, smem, ctx->stream>>>(
+                  ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->go);
+            else
+              fast_pair_kernel<<<(unsigned)tiles, THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt);
             ctx->launches++;
           }
           CK(cudaGetLastError());

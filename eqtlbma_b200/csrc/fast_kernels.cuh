@@ -54,6 +54,8 @@ struct FastArgs {
   const long long *pair_off;   // [n_genes] first OUTPUT pair index of each fast gene
   int *out_n;
   double *out_ss, *out_gen, *out_cfg, *out_w;
+  int ycache_slots;            // fast_pair_warp_kernel: genes whose residual phenotype rows a CTA stages in shared memory
+  int use_dmma;                // fast_pair_warp_kernel: phase A on the FP64 tensor cores
 };
 
 // ---------------------------------------------------------------- K1a
@@ -1136,6 +1138,451 @@ __host__ __device__ inline size_t fast_smem_bytes(int T, int S, int L, int K, in
   size_t d = (size_t)T * S + (size_t)T * ((3 * S) | 1) + (size_t)T * ((3 * UL) | 1) + (size_t)T * (3 + S) + vals * (T + 1);
   if (which == 3) d += (size_t)T * K * S * 3;
   return d * 8 + (size_t)T * (8 + 8 + 8 + 4) + 16;
+}
+
+
+// =====================================================================================================
+// fast_pair_warp_kernel (K2+K3 for --bfs gen|sin and --analys sep): the same three phases, but every WARP
+// owns a tile of 32 pairs from the contraction to the last output row -- no CTA barrier anywhere, so the
+// memory-bound contraction of one warp overlaps the transcendental-bound ABF phase of its neighbours
+// (fast_pair_kernel's phases are CTA-synchronous: barrier stalls were a third of its issue slots, and its
+// thread-per-(pair, subgroup) phase B used 96 of 256 threads).
+//   A  lanes over the individuals, two pairs in flight: x . ytil_s                     (contraction)
+//   B  lane per (pair, subgroup): summary statistics + standardisation                  (S rounds of 32 items)
+//   C  lane per PAIR: loop over the unique phi2 values (the sums over the subgroups are computed once per
+//      phi2 and reused by every grid point of gen / gen-fix / gen-maxh that shares it), then over the singleton
+//      configurations; values go straight to their output rows, log10_weighted_sum is accumulated online in
+//      registers (utils_math.cpp:100-131; same NaN rules), BMAlite at the end.  The grid point / configuration
+//      is uniform across the warp (the pair varies across lanes), so grid-dependent branches never diverge.
+// Shared memory per warp: xy[32][S] + (b, v, t)[32][3S|1] + masks and pair indices.
+struct GridOrder {
+  const int *ustart; // [UL+1] entries of unique phi2 value u: uent[ustart[u] .. ustart[u+1])
+  const int *uent;   // [3L]   r * L + k of the entry (row r of gen / gen-fix / gen-maxh, grid point k)
+};
+
+struct LseOnline { // log10_weighted_sum accumulated one element at a time (max tracked with rescaling)
+  double m, acc;
+  bool poisoned; // element 0 was NaN: the reference's max is NaN and so is its result
+  __device__ __forceinline__ void init()
+  {
+    m = -INFINITY;
+    acc = 0.0;
+    poisoned = false;
+  }
+  __device__ __forceinline__ void add(double v, double w, bool is_first)
+  {
+    if (v != v) {
+      poisoned = poisoned || is_first;
+      return;
+    }
+    const double d = v - m; // +inf on the first element
+    const bool up = d > 0.0;
+    const double e = exp10_fast(up ? -d : d);
+    acc = up ? fma(acc, e, w) : fma(w, e, acc);
+    m = up ? v : m;
+  }
+  __device__ __forceinline__ double result() const
+  {
+    if (poisoned) return nan("");
+    double r = m + log10(acc);
+    if (fabs(r) <= DBL_EPSILON) r = 0.0;
+    return r;
+  }
+};
+
+// phase A helper: two genotype rows (two pairs) against their SN residual phenotype rows, one warp
+template <int SN>
+__device__ __forceinline__ void contract_two(const double *__restrict__ Xa, const double *__restrict__ Xb,
+                                             const FastSub *__restrict__ fsub, size_t growa, size_t growb, int ldn, int lane,
+                                             double *__restrict__ outa, double *__restrict__ outb)
+{
+  const double2 *xa2 = reinterpret_cast<const double2 *>(Xa), *xb2 = reinterpret_cast<const double2 *>(Xb);
+  double acca[SN], accb[SN];
+#pragma unroll
+  for (int a = 0; a < SN; ++a) acca[a] = accb[a] = 0.0;
+  const int h = ldn >> 1;
+  for (int i = lane; i < h; i += 32) {
+    const double2 xa = xa2[i], xb = xb2[i];
+#pragma unroll
+    for (int a = 0; a < SN; ++a) {
+      const double2 ya = reinterpret_cast<const double2 *>(fsub[a].Ytil + growa)[i];
+      const double2 yb = reinterpret_cast<const double2 *>(fsub[a].Ytil + growb)[i];
+      acca[a] = fma(xa.x, ya.x, acca[a]);
+      accb[a] = fma(xb.x, yb.x, accb[a]);
+      acca[a] = fma(xa.y, ya.y, acca[a]);
+      accb[a] = fma(xb.y, yb.y, accb[a]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < SN; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acca[a] += __shfl_xor_sync(0xffffffffu, acca[a], o);
+      accb[a] += __shfl_xor_sync(0xffffffffu, accb[a], o);
+    }
+    if (lane == a) {
+      outa[a] = acca[a];
+      outb[a] = accb[a];
+    }
+  }
+}
+
+template <int SN>
+__device__ __forceinline__ void contract_tile(const double *__restrict__ X, const FastSub *__restrict__ fsub, const long long *s_m,
+                                              const int *s_gene, int tn, int S, int ldn, int lane, double *__restrict__ xy)
+{
+  int j = 0;
+  for (; j + 1 < tn; j += 2)
+    contract_two<SN>(X + (size_t)s_m[j] * ldn, X + (size_t)s_m[j + 1] * ldn, fsub, (size_t)s_gene[j] * ldn,
+                     (size_t)s_gene[j + 1] * ldn, ldn, lane, xy + (size_t)j * S, xy + (size_t)(j + 1) * S);
+  if (j < tn) contract_shared_x<SN>(X + (size_t)s_m[j] * ldn, fsub, (size_t)s_gene[j] * ldn, ldn, lane, xy + (size_t)j * S);
+}
+
+// phase A, common case (one genotype matrix for the subgroups [s0, s0+sn), rows of at most 64*NI doubles): the
+// genotype row of pair j+1 is loaded into registers (NI 16-byte loads per lane, issued back to back) BEFORE pair j
+// is contracted, so a warp pays one memory round trip per pair instead of one per load, overlapped with the
+// previous pair's arithmetic.  Per-lane summation order = contract_shared_x (bit-identical results).
+template <int NI>
+__device__ __forceinline__ void contract_tile_regs(const double *__restrict__ X, const FastSub *__restrict__ fsub, int sn,
+                                                   const long long *s_m, const int *s_gene, int tn, int S, int ldn, int lane,
+                                                   double *__restrict__ xy, const double *ycache, const int *s_slot,
+                                                   int ncached, int s0)
+{
+  const int h = ldn >> 1;
+  double2 cur[NI], nxt[NI];
+  {
+    const double2 *row = reinterpret_cast<const double2 *>(X + (size_t)s_m[0] * ldn);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int idx = lane + 32 * i;
+      cur[i] = (idx < h) ? row[idx] : make_double2(0.0, 0.0);
+    }
+  }
+  for (int j = 0; j < tn; ++j) {
+    {
+      const int jn = (j + 1 < tn) ? j + 1 : j;
+      const double2 *row = reinterpret_cast<const double2 *>(X + (size_t)s_m[jn] * ldn);
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int idx = lane + 32 * i;
+        nxt[i] = (idx < h) ? row[idx] : make_double2(0.0, 0.0);
+      }
+    }
+    const size_t grow = (size_t)s_gene[j] * ldn;
+    const int slot = s_slot[j];
+    for (int a = 0; a < sn; ++a) {
+      // residual phenotype row: the CTA's shared-memory copy when the gene is one of the staged ones
+      const double2 *y = reinterpret_cast<const double2 *>(
+          (slot < ncached) ? ycache + ((size_t)slot * S + s0 + a) * ldn : fsub[a].Ytil + grow);
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < h) {
+          const double2 y2 = y[idx];
+          acc += cur[i].x * y2.x;
+          acc += cur[i].y * y2.y;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) xy[(size_t)j * S + a] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) cur[i] = nxt[i];
+  }
+}
+
+// phase A on the FP64 tensor cores: the tile's contraction IS a small matrix product
+//   xy[32 pairs][sn subgroups] = X_tile[32][ldn] . Ytil_gene[sn][ldn]^T
+// done as 4 row blocks of mma.sync.m8n8k4 (DMMA): A fragments straight from the genotype rows (one 16-byte load per
+// lane covers two k-steps: the k index inside a chunk of 8 individuals is permuted the same way for A and B),
+// B fragments from the CTA's shared-memory copy of the gene's residual phenotype rows (columns >= sn repeat the last
+// subgroup and are dropped).  The rows of a tile that belong to different genes are handled as runs: every run
+// multiplies the whole tile by ITS gene's phenotype block and keeps its own rows (1.6 runs per tile at 50 SNPs per
+// gene, 1 at the GTEx shape).  ~600 warp instructions per tile instead of ~8000 for the shuffle-reduced dot products.
+__device__ __forceinline__ void contract_tile_dmma(const double *__restrict__ X, const FastSub *__restrict__ fsub, int sn,
+                                                   const long long *s_m, const int *s_gene, const int *s_slot, int tn, int S,
+                                                   int ldn, int lane, double *__restrict__ xy, const double *ycache,
+                                                   int ncached, int s0)
+{
+  const int r = lane >> 2, kq = lane & 3;
+  const double *xp[4];
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb) {
+    const int j = min(mb * 8 + r, tn - 1); // rows past the end of the tile repeat the last one (results dropped)
+    xp[mb] = X + (size_t)s_m[j] * ldn + 2 * kq;
+  }
+  const int col = min(r, sn - 1);
+  const int nchunk = ldn >> 3;
+  int j0 = 0;
+  while (j0 < tn) {
+    const int gs = s_slot[j0];
+    const unsigned same = __ballot_sync(0xffffffffu, lane < tn && s_slot[lane < tn ? lane : 0] == gs);
+    const int j1 = j0 + __popc(same >> j0 << j0); // rows of a gene are consecutive
+    const double *yp = ((gs < ncached) ? ycache + ((size_t)gs * S + s0 + col) * ldn
+                                       : fsub[col].Ytil + (size_t)s_gene[j0] * ldn) + 2 * kq;
+    double acc[4][2];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) acc[mb][0] = acc[mb][1] = 0.0;
+    // only the row blocks that hold rows of this run
+    const int mb0 = j0 >> 3, mb1 = (j1 - 1) >> 3;
+#pragma unroll 2
+    for (int c = 0; c < nchunk; ++c) {
+      const double2 b2 = *reinterpret_cast<const double2 *>(yp + 8 * c);
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {
+        if (mb >= mb0 && mb <= mb1) { // warp-uniform
+          const double2 a2 = *reinterpret_cast<const double2 *>(xp[mb] + 8 * c);
+          dmma_m8n8k4(acc[mb][0], acc[mb][1], a2.x, b2.x);
+          dmma_m8n8k4(acc[mb][0], acc[mb][1], a2.y, b2.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const int j = mb * 8 + r;
+      if (j >= j0 && j < j1) {
+        if (2 * kq < sn) xy[(size_t)j * S + 2 * kq] = acc[mb][0];
+        if (2 * kq + 1 < sn) xy[(size_t)j * S + 2 * kq + 1] = acc[mb][1];
+      }
+    }
+    j0 = j1;
+  }
+}
+
+// shared memory of fast_pair_warp_kernel: CTA-wide grid tables, then one region per warp
+__host__ __device__ inline size_t fast_warp_table_bytes(int L, int K, int UL)
+{
+  const size_t b = (size_t)(UL + 3 * L + 2 * K) * 8 + (size_t)(UL + 1 + 3 * L) * 4;
+  return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t fast_warp_smem_bytes(int S)
+{
+  return ((size_t)32 * S + (size_t)32 * ((3 * S) | 1)) * 8 + (size_t)32 * (8 + 8 + 8 + 4 + 4);
+}
+__host__ __device__ inline size_t fast_warp_ycache_bytes(int slots, int S, int ldn) { return (size_t)slots * S * ldn * 8; }
+
+#ifndef EQB_FASTW_MINB
+#define EQB_FASTW_MINB 2
+#endif
+__global__ void __launch_bounds__(THREADS, EQB_FASTW_MINB) fast_pair_warp_kernel(const DevParams *__restrict__ prm_,
+                                                                 const FastParams *__restrict__ fp_, const FastArgs fa,
+                                                                 const GridTab gt, const GridOrder go)
+{
+  const DevParams &prm = *prm_;
+  extern __shared__ double fsm[];
+  const int S = prm.S, ldn = prm.ldn, L = prm.L, K = prm.K, UL = gt.UL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const long long tile = (long long)blockIdx.x * nwarp + warp;
+  const long long q0 = fa.q_begin + tile * 32;
+  // CTA-wide grid tables (a dependent chain of global loads per grid point otherwise): unique phi2 values, the grid
+  // entries grouped by them (destination index + omega2), the singleton grid
+  double *t_uphi = fsm;                     // [UL]
+  double *t_oma = t_uphi + UL;              // [3L] omega2 of entry i (grouped order)
+  double *t_phiS = t_oma + 3 * L;           // [K]
+  double *t_omaS = t_phiS + K;              // [K]
+  int *t_ustart = (int *)(t_omaS + K);      // [UL+1]
+  int *t_ent = t_ustart + UL + 1;           // [3L] r*L + k of entry i
+  for (int i = threadIdx.x; i < UL; i += blockDim.x) t_uphi[i] = gt.uphi[i];
+  for (int i = threadIdx.x; i <= UL; i += blockDim.x) t_ustart[i] = go.ustart[i];
+  for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) {
+    const int e = go.uent[i];
+    t_ent[i] = e;
+    t_oma[i] = gt.omaL[e];
+  }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    t_phiS[i] = prm.phi2S[i];
+    t_omaS[i] = prm.oma2S[i];
+  }
+  // CTA-wide cache of the residual phenotype rows: the nwarp tiles of a CTA are consecutive pairs, i.e. a handful of
+  // consecutive genes (ONE gene at the GTEx shape); their S rows are staged once instead of being re-read from
+  // L2 for every pair (the phenotype re-reads were 2/3 of the kernel's L2 -> SM traffic)
+  double *ycache = reinterpret_cast<double *>(reinterpret_cast<char *>(fsm) + fast_warp_table_bytes(L, K, UL));
+  int g_lo = 0, ncached = 0;
+  {
+    const long long tile0 = (long long)blockIdx.x * nwarp;
+    const long long qf = fa.q_begin + tile0 * 32;
+    if (qf < fa.n_pairs && fa.ycache_slots > 0) {
+      const long long ql = min(qf + (long long)nwarp * 32, fa.n_pairs) - 1;
+      g_lo = fa.tile_gene[tile0];
+      int g_hi = g_lo;
+      while (g_hi + 1 < fa.n_genes && fa.fast_base[g_hi + 1] <= ql && g_hi - g_lo + 1 < fa.ycache_slots) ++g_hi;
+      ncached = g_hi - g_lo + 1;
+      const int h = ldn >> 1;
+      const int per = S * h;
+      for (int i = threadIdx.x; i < ncached * per; i += blockDim.x) {
+        const int slot = i / per, r = i - slot * per, a = r / h, c = r - a * h;
+        reinterpret_cast<double2 *>(ycache)[i] =
+            reinterpret_cast<const double2 *>(fp_->sub[a].Ytil + (size_t)fa.genes[g_lo + slot] * ldn)[c];
+      }
+    }
+  }
+  __syncthreads(); // the only CTA-wide barrier
+  if (q0 >= fa.n_pairs) return;
+  const int tn = (int)min(32LL, fa.n_pairs - q0);
+  const long long C = (fa.which == 1) ? 0 : S;
+  const bool join = prm.analysis == 1;
+  const int sst = (3 * S) | 1;
+  // per-warp shared memory
+  char *wbase = reinterpret_cast<char *>(fsm) + fast_warp_table_bytes(L, K, UL) +
+                fast_warp_ycache_bytes(fa.ycache_slots, S, ldn) + (size_t)warp * fast_warp_smem_bytes(S);
+  double *xy = reinterpret_cast<double *>(wbase);            // [32][S]
+  double *st = xy + (size_t)32 * S;                          // [32][sst]  b, v, t per subgroup
+  unsigned long long *hasm = (unsigned long long *)(st + (size_t)32 * sst); // [32]
+  long long *s_pair = (long long *)(hasm + 32);              // [32] output pair index
+  long long *s_m = s_pair + 32;                              // [32] SNP index
+  int *s_gene = (int *)(s_m + 32);                           // [32] gene id
+  int *s_slot = s_gene + 32;                                 // [32] slot of the gene in the CTA's phenotype cache
+
+  long long my_pair = 0;
+  if (lane < tn) {
+    const long long q = q0 + lane;
+    int lo = fa.tile_gene[tile]; // gene of the tile's first pair (host-computed); walk forward from it
+    while (lo + 1 < fa.n_genes && fa.fast_base[lo + 1] <= q) ++lo;
+    const int g = fa.genes[lo];
+    const long long off = q - fa.fast_base[lo];
+    s_gene[lane] = g;
+    s_slot[lane] = lo - g_lo;
+    s_m[lane] = prm.cis_begin[g] + off;
+    my_pair = fa.pair_off[lo] + off;
+    s_pair[lane] = my_pair;
+    hasm[lane] = 0ull;
+  }
+  __syncwarp();
+  // ---------------- phase A: contraction x . ytil_s
+  // the genotype rows of the tile are requested from HBM up front (one L2 prefetch per 128-byte line)
+  for (int s0 = 0; s0 < S; s0 += 8) {
+    if (s0 > 0 && prm.sub[s0].X == prm.sub[0].X) continue;
+    for (int j = 0; j < tn; ++j) {
+      const double *row = prm.sub[s0].X + (size_t)s_m[j] * ldn;
+      for (int l = lane; l < (ldn >> 4); l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 16 * l));
+    }
+  }
+  for (int s0 = 0; s0 < S; s0 += 8) {
+    const int sn = min(8, S - s0);
+    bool same = true;
+    for (int a = 1; a < sn; ++a) same = same && (prm.sub[s0 + a].X == prm.sub[s0].X);
+    const FastSub *fsub = fp_->sub + s0;
+    if (same && fa.use_dmma) {
+      contract_tile_dmma(prm.sub[s0].X, fsub, sn, s_m, s_gene, s_slot, tn, S, ldn, lane, xy + s0, ycache, ncached, s0);
+    } else if (same && ldn <= 512) {
+      const double *X = prm.sub[s0].X;
+      switch ((ldn + 63) >> 6) {
+      case 1: contract_tile_regs<1>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
+      case 2: contract_tile_regs<2>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
+      case 3: contract_tile_regs<3>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
+      case 4: contract_tile_regs<4>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
+      case 5: contract_tile_regs<5>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
+      case 6: contract_tile_regs<6>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
+      case 7: contract_tile_regs<7>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
+      default: contract_tile_regs<8>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
+      }
+    } else if (same) {
+      const double *X = prm.sub[s0].X;
+      switch (sn) {
+      case 1: contract_tile<1>(X, fsub, s_m, s_gene, tn, S, ldn, lane, xy + s0); break;
+      case 2: contract_tile<2>(X, fsub, s_m, s_gene, tn, S, ldn, lane, xy + s0); break;
+      case 3: contract_tile<3>(X, fsub, s_m, s_gene, tn, S, ldn, lane, xy + s0); break;
+      case 4: contract_tile<4>(X, fsub, s_m, s_gene, tn, S, ldn, lane, xy + s0); break;
+      case 5: contract_tile<5>(X, fsub, s_m, s_gene, tn, S, ldn, lane, xy + s0); break;
+      case 6: contract_tile<6>(X, fsub, s_m, s_gene, tn, S, ldn, lane, xy + s0); break;
+      case 7: contract_tile<7>(X, fsub, s_m, s_gene, tn, S, ldn, lane, xy + s0); break;
+      default: contract_tile<8>(X, fsub, s_m, s_gene, tn, S, ldn, lane, xy + s0); break;
+      }
+    } else {
+      for (int a = 0; a < sn; ++a) contract_tile<1>(prm.sub[s0 + a].X, fsub + a, s_m, s_gene, tn, S, ldn, lane, xy + s0 + a);
+    }
+  }
+  __syncwarp();
+  // ---------------- phase B: lane per (pair, subgroup): summary statistics + standardisation
+  for (int it = lane; it < tn * S; it += 32) {
+    const int j = it / S, s = it - j * S;
+    const long long m = s_m[j];
+    const int g = s_gene[j];
+    const SubDev &sb = prm.sub[s];
+    const FastSub &fs = fp_->sub[s];
+    const double *ys = fs.ystat + (size_t)g * 4;
+    const bool have = sb.gene_has[g] && sb.snp_has[m] && fs.n > 0;
+    PairStat ps;
+    ps.pve = ps.sigmahat = ps.betahat = ps.se = ps.pval = nan("");
+    ps.b = ps.v = ps.t = nan("");
+    if (have) {
+      const double *xs = fs.xstat + (size_t)m * 3;
+      stats_from_dots(xy[(size_t)j * S + s], xs[0], xs[1], xs[2], ys[0], ys[1], ys[2], fs.n, sb.Q, fs.rankz, fs.tz, fs.tz_nu,
+                      fs.tz_wmax, ps);
+      atomicOr(&hasm[j], 1ull << s);
+    }
+    st[(size_t)j * sst + s] = ps.b;
+    st[(size_t)j * sst + S + s] = ps.v;
+    st[(size_t)j * sst + 2 * S + s] = ps.t;
+    const long long pair = s_pair[j];
+    if (fa.out_n) fa.out_n[pair * S + s] = have ? fs.n : 0;
+    if (fa.out_ss) {
+      double *o = fa.out_ss + (pair * S + s) * 5;
+      o[0] = ps.pve;
+      o[1] = ps.sigmahat;
+      o[2] = ps.betahat;
+      o[3] = ps.se;
+      o[4] = ps.pval;
+    }
+  }
+  __syncwarp();
+  if (!join || lane >= tn) return;
+  // ---------------- phase C: lane per pair
+  const double *stj = st + (size_t)lane * sst;
+  const unsigned long long mask = hasm[lane];
+  double *og = fa.out_gen + my_pair * 3 * L;
+  double *ow = fa.out_w + my_pair * (5 + C);
+  LseOnline r0, r1, r2;
+  r0.init();
+  r1.init();
+  r2.init();
+  const double wL = 1.0 / (double)L;
+  for (int u = 0; u < UL; ++u) {
+    double den, num, sing;
+    consistent_sums(stj, S, mask, t_uphi[u], den, num, sing); // ONE logarithm per (pair, phi2)
+    const int i1 = t_ustart[u + 1];
+    for (int i = t_ustart[u]; i < i1; ++i) {
+      const int e = t_ent[i]; // warp-uniform
+      const double v = abf_from_sums(den, num, sing, t_oma[i]);
+      og[e] = v;
+      if (e < L) r0.add(v, wL, e == 0);
+      else if (e < 2 * L) r1.add(v, wL, e == L);
+      else r2.add(v, wL, e == 2 * L);
+    }
+  }
+  const double wgen = r0.result();
+  ow[0] = wgen;
+  ow[1] = r1.result();
+  ow[2] = r2.result();
+  if (fa.which == 1) {
+    ow[3] = nan("");
+    ow[4] = nan("");
+    return;
+  }
+  // singleton configurations (CalcAbfsUvlrForSingletons, gene_snp_pair.cpp:422-463) + BMAlite (:552-570)
+  double *oc = fa.out_cfg + my_pair * C * K;
+  LseOnline lite;
+  lite.init();
+  const double wK = 1.0 / (double)K, wS = 0.5 / (double)S;
+  for (int c = 0; c < S; ++c) {
+    LseOnline rc;
+    rc.init();
+    const bool has = (mask >> c) & 1ull;
+    const double b = stj[c], vv = stj[S + c], tt = stj[2 * S + c];
+    for (int k = 0; k < K; ++k) {
+      const double v = has ? singleton_value(b, vv, tt, t_phiS[k], t_omaS[k]) : 0.0;
+      oc[c * K + k] = v;
+      rc.add(v, wK, k == 0);
+    }
+    const double wc = rc.result();
+    ow[5 + c] = wc;
+    lite.add(wc, wS, c == 0);
+  }
+  lite.add(wgen, 0.5, false);
+  ow[3] = lite.result();
+  ow[4] = nan("");
 }
 
 } // namespace eqb

@@ -1076,8 +1076,37 @@ int main(int argc, char **argv)
                                    ce.data()),
         "eqb_build_cis_windows");
   // genotypes last: the upload is asynchronous (row chunks), projection and results overlap with it
-  for (size_t j = 0; j < Gmats.size(); ++j)
-    check(ctx, eqb_set_genotypes(ctx, (int)j, Gmats[j].data(), M, Gcols[j]), "eqb_set_genotypes");
+  // Compact lossless transport when the parsed dosages allow it: hard calls (VCF GT, integer dose) travel as u8,
+  // dosages written with d <= 4 decimals as u8/u16 numerators of 10^d (k / 10^d correctly rounded = the parsed
+  // double, checked element by element below); anything else (NaN, more decimals) goes up as doubles.
+  vector<vector<uint8_t> > Gfix8(Gmats.size());
+  vector<vector<uint16_t> > Gfix16(Gmats.size());
+  for (size_t j = 0; j < Gmats.size(); ++j) {
+    const vector<double> &Gm = Gmats[j];
+    int width = 0;
+    double denom = 1.0;
+    for (int dgt = 0; dgt <= 4 && !width; ++dgt, denom *= 10.0) {
+      double mx = 0.0;
+      bool ok = true;
+      for (size_t i = 0; i < Gm.size() && ok; ++i) {
+        const double k = nearbyint(Gm[i] * denom);
+        ok = (k >= 0.0 && k <= 65535.0 && k / denom == Gm[i]);
+        if (k > mx) mx = k;
+      }
+      if (ok) width = (mx <= 255.0) ? 1 : 2;
+      if (width) break;
+    }
+    if (width == 1) {
+      Gfix8[j].resize(Gm.size());
+      for (size_t i = 0; i < Gm.size(); ++i) Gfix8[j][i] = (uint8_t)nearbyint(Gm[i] * denom);
+      check(ctx, eqb_set_genotypes_fixed(ctx, (int)j, Gfix8[j].data(), 1, denom, M, Gcols[j]), "eqb_set_genotypes_fixed");
+    } else if (width == 2) {
+      Gfix16[j].resize(Gm.size());
+      for (size_t i = 0; i < Gm.size(); ++i) Gfix16[j][i] = (uint16_t)nearbyint(Gm[i] * denom);
+      check(ctx, eqb_set_genotypes_fixed(ctx, (int)j, Gfix16[j].data(), 2, denom, M, Gcols[j]), "eqb_set_genotypes_fixed");
+    } else
+      check(ctx, eqb_set_genotypes(ctx, (int)j, Gmats[j].data(), M, Gcols[j]), "eqb_set_genotypes");
+  }
   check(ctx, eqb_finalize(ctx), "eqb_finalize");
 
   // ---- headers (writeRes(..., "only"), eqtlbma_bf.cpp:1510-1513)

@@ -128,6 +128,15 @@ const char *eqb_last_error(const eqb_ctx *ctx);
  * and unchanged until the first eqb_run* call on this context has returned, or eqb_destroy();
  * pinned host memory (cudaHostAlloc / cudaHostRegister) is what makes the overlap effective. */
 int eqb_set_genotypes(eqb_ctx *ctx, int32_t geno_id, const double *G, int64_t n_snps, int32_t n_cols);
+/* The same matrix in the compact, LOSSLESS transport format a text parser can produce for free: unsigned
+ * integers k of elem_bytes (1 or 2) bytes, element value = (double)k / denom.  Hard calls (VCF GT -> 0/1/2,
+ * snp.cpp:130-185) use denom 1; a dosage / IMPUTE file written with d decimals (snp.cpp:88-128,
+ * data_loader.cpp:570-1010) uses denom 10^d: the IEEE quotient of two exactly representable integers is the
+ * correctly rounded value of k/10^d, i.e. the very double strtod() yields for the decimal text, so the device
+ * sees bit-identical dosages while the host->device transfer (the end-to-end bound of a no-permutation run)
+ * shrinks 8x / 4x.  Same lifetime and asynchrony rules as eqb_set_genotypes(). */
+int eqb_set_genotypes_fixed(eqb_ctx *ctx, int32_t geno_id, const void *G, int32_t elem_bytes, double denom,
+                            int64_t n_snps, int32_t n_cols);
 int eqb_set_subgroup(eqb_ctx *ctx, int32_t s, const eqb_subgroup *sg);
 /* Grid (grid.cpp:28-65): phi2/oma2 columns of --gridL (L points) and --gridS (K points). */
 int eqb_set_grids(eqb_ctx *ctx, const double *phi2L, const double *oma2L, int32_t L,

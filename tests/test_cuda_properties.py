@@ -177,3 +177,40 @@ def test_short_latency_math_against_cuda_library(cuda_lib):
     assert log_abs < 2e-13 and log_rel < 1e-12   # |log x| up to 645: a few ulp; relative near x = 1 stays ~1e-16 * O(1)
     assert exp_rel < 2e-15
     assert special == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dosage,dtype,denom", [(True, np.uint16, 1000.0), (False, np.uint8, 1.0)])
+def test_fixed_point_genotype_transport_is_lossless(cuda_lib, dosage, dtype, denom):
+    """eqb_set_genotypes_fixed (u8 hard calls / u16 numerators of 10^d for a d-decimal dosage file) must give
+    bit-identical results to the double matrix: k / 10^d correctly rounded IS the parsed double."""
+    import copy
+    import eqtlbma_b200
+    ds = _ds(n_genes=120, dosage=dosage)
+    a = eqtlbma_b200.Engine(ds, analysis="join", bfs="sin").run(raw=True)
+    ds2 = copy.copy(ds)
+    ds2.genos = []
+    for G in ds.genos:
+        k = np.rint(G * denom)
+        assert np.array_equal(k / denom, G)
+        ds2.genos.append(k.astype(dtype))
+    ds2.geno_denoms = [denom] * len(ds.genos)
+    b = eqtlbma_b200.Engine(ds2, analysis="join", bfs="sin").run(raw=True)
+    assert np.array_equal(a.n, b.n)
+    for f in ("sstats", "abf_gen", "abf_cfg", "abf_w"):
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
+
+
+@pytest.mark.gpu
+def test_fixed_point_rejects_bad_arguments(cuda_lib):
+    import ctypes as C
+    import eqtlbma_b200
+    ds = _ds(n_genes=8)
+    eng = eqtlbma_b200.Engine(ds, analysis="join", bfs="gen")
+    f = cuda_lib.eqb_set_genotypes_fixed
+    f.restype = C.c_int
+    G = np.zeros((ds.n_snps, ds.genos[0].shape[1]), dtype=np.uint8)
+    # wrong element width, non-integer denominator, and a call after eqb_finalize() all fail with a message
+    assert f(eng.ctx, 0, G.ctypes.data_as(C.c_void_p), 4, C.c_double(1.0), C.c_int64(G.shape[0]), G.shape[1]) != 0
+    assert f(eng.ctx, 0, G.ctypes.data_as(C.c_void_p), 1, C.c_double(2.5), C.c_int64(G.shape[0]), G.shape[1]) != 0
+    assert f(eng.ctx, 0, G.ctypes.data_as(C.c_void_p), 1, C.c_double(1.0), C.c_int64(G.shape[0]), G.shape[1]) != 0
