@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+
 #include "fast_kernels.cuh"
 #include "mvlr_kernel.cuh"
 #include "perm_kernel.cuh"
@@ -258,6 +260,30 @@ struct SubHost {
   uint8_t *d_gmask = nullptr, *d_cmask = nullptr, *d_snp_has = nullptr, *d_gene_has = nullptr;
 };
 
+// host-side phase timing (EQB_TIMING=1: accumulated per label, printed by eqb_destroy)
+struct PhaseTimer {
+  bool on = getenv("EQB_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  static std::map<std::string, double> &acc()
+  {
+    static std::map<std::string, double> m;
+    return m;
+  }
+  void mark(const char *label)
+  {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    acc()[label] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+  static void report()
+  {
+    if (!getenv("EQB_TIMING")) return;
+    for (auto &kv : acc()) fprintf(stderr, "[eqb timing] %-28s %10.3f ms\n", kv.first.c_str(), kv.second);
+    acc().clear();
+  }
+};
+
 struct GenoHost {
   void *d_raw = nullptr;
   int n_cols = 0;
@@ -347,6 +373,7 @@ struct eqb_ctx {
   bool x_explicit = false;  // rows too long for the DMMA tiles in shared memory: explicit CGS2 for every SNP
   size_t dmma_budget = 0;
   DevBuf<unsigned long long> d_fix; // [0] = count, then (snp << 8 | subgroup) entries needing the explicit K1c pass
+  size_t free_bytes_at_create = 0; // see run_true_impl
   GridTab gt;              // unique phi2 values of the consistent-configuration rows
   double *d_gt_d = nullptr; // uphi[UL] | omaL[3L]
   int *d_gt_i = nullptr;    // idxL[3L] | dup_of[S] | ustart[UL+1] | uent[3L]
@@ -851,6 +878,7 @@ int prepare_fast_path(eqb_ctx *ctx)
 {
   const int S = ctx->cfg.n_subgroups, N = ctx->cfg.n_samples_all, ldn = ctx->ldn;
   const long long M = ctx->cfg.n_snps, G = ctx->cfg.n_genes;
+  PhaseTimer pt;
   ctx->gene_fast.assign(G, 0);
   ctx->d_Bs.assign(S, nullptr);
   ctx->d_Ytil.assign(S, nullptr);
@@ -961,6 +989,7 @@ int prepare_fast_path(eqb_ctx *ctx)
   std::vector<int> hi(3 * S);
   CK(cudaMemcpyAsync(hi.data(), d_ints, hi.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  pt.mark("fp.basis");
   memset(&ctx->hfp, 0, sizeof(ctx->hfp));
   for (int s = 0; s < S; ++s) {
     FastSub &fs = ctx->hfp.sub[s];
@@ -998,6 +1027,7 @@ int prepare_fast_path(eqb_ctx *ctx)
       ctx->hfp.sub[s].tz_wmax = wmax[s];
     }
   }
+  pt.mark("fp.tz");
   CK(dmalloc(&ctx->d_fp, sizeof(FastParams)));
   CK(h2d(ctx, ctx->d_fp, &ctx->hfp, sizeof(FastParams)));
   {
@@ -1008,6 +1038,7 @@ int prepare_fast_path(eqb_ctx *ctx)
     rc2 = enqueue_x_pipeline(ctx, true);
     if (rc2) return rc2;
   }
+  pt.mark("fp.plan_prepy_enqueue");
   // which genes are generic in every subgroup where they are expressed
   std::vector<double> ystat((size_t)G * 4);
   int herr[4] = {0, 0, 0, 0};
@@ -1023,6 +1054,7 @@ int prepare_fast_path(eqb_ctx *ctx)
   // a generic mask that keeps an individual without covariates is fatal in the reference only when
   // such a regression is actually run: let the general path find and report it
   if (herr[2]) std::fill(ok.begin(), ok.end(), 0);
+  pt.mark("fp.gene_fast");
   ctx->gene_fast = ok;
   dfree(d_eptr);
   dfree(d_ints);
@@ -1106,6 +1138,11 @@ int eqb_create(eqb_ctx **out, const eqb_config *cfg)
     return fail(ctx, "no CUDA device: the eqtlbma_b200 hot path has no CPU fallback");
   CK(cudaSetDevice(cfg->device));
   configure_pool(cfg->device);
+  {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    ctx->free_bytes_at_create = free_b;
+  }
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
   CK(cudaStreamCreateWithFlags(&ctx->xcopy, cudaStreamNonBlocking));
@@ -1137,6 +1174,7 @@ int eqb_create(eqb_ctx **out, const eqb_config *cfg)
 void eqb_destroy(eqb_ctx *ctx)
 {
   if (!ctx) return;
+  PhaseTimer pt;
   AllocScope alloc_scope(ctx->stream);
   if (ctx->stream) {
     cudaSetDevice(ctx->cfg.device);
@@ -1218,6 +1256,8 @@ void eqb_destroy(eqb_ctx *ctx)
   if (ctx->xcomp) cudaStreamDestroy(ctx->xcomp);
   if (ctx->dstream) cudaStreamDestroy(ctx->dstream);
   delete ctx;
+  pt.mark("destroy");
+  PhaseTimer::report();
 }
 
 const char *eqb_last_error(const eqb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -1407,6 +1447,7 @@ int eqb_build_cis_windows(eqb_ctx *ctx, const int32_t *gene_chr, const int64_t *
 int eqb_finalize(eqb_ctx *ctx)
 {
   AllocScope alloc_scope(ctx->stream);
+  PhaseTimer pt;
   if (!ctx->stream) return fail(ctx, "context not usable");
   CK(cudaSetDevice(ctx->cfg.device));
   const int S = ctx->cfg.n_subgroups, N = ctx->cfg.n_samples_all, ldn = ctx->ldn;
@@ -1433,7 +1474,7 @@ int eqb_finalize(eqb_ctx *ctx)
       CK(dmalloc(&dX, std::max<size_t>((size_t)M * ldn, 1) * sizeof(double)));
       CK(dmalloc(&dmap, N * sizeof(int)));
       CK(h2d(ctx, dmap, sb.all2geno.data(), N * sizeof(int)));
-      CK(cudaStreamSynchronize(ctx->stream)); // (the map is copied from pageable memory)
+      if ((size_t)N * sizeof(int) > STAGE_MAX) CK(cudaStreamSynchronize(ctx->stream)); // (not staged: pageable source)
       ctx->xvars.push_back({sb.geno_id, dmap}); // re-indexed chunk by chunk by enqueue_x_pipeline()
       ctx->d_X.push_back(dX);
       variants[key] = v;
@@ -1441,6 +1482,7 @@ int eqb_finalize(eqb_ctx *ctx)
     } else
       sb.xvar = it->second;
   }
+  pt.mark("finalize.variants");
   const double qnan = std::numeric_limits<double>::quiet_NaN();
   for (int s = 0; s < S; ++s) {
     SubHost &sb = ctx->subs[s];
@@ -1459,7 +1501,7 @@ int eqb_finalize(eqb_ctx *ctx)
       ctx->launches++;
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
+    // (no synchronisation inside this loop: small copies are staged when h2d() returns, frees are stream-ordered)
     // covariates
     std::vector<uint8_t> gm(ldn, 0), cm(ldn, 0);
     for (int i = 0; i < N; ++i) {
@@ -1478,13 +1520,13 @@ int eqb_finalize(eqb_ctx *ctx)
       ctx->launches++;
       CK(cudaGetLastError());
     }
-    CK(cudaStreamSynchronize(ctx->stream));
     dfree(dmap);
     if (sb.d_Yraw) dfree(sb.d_Yraw);
     if (sb.d_Craw) dfree(sb.d_Craw);
     sb.d_Yraw = sb.d_Craw = nullptr;
   }
 
+  pt.mark("finalize.expand_Y_C");
   // analysed genes (eqtlbma_bf.cpp:747-762) from per-subgroup prefix counts of genotyped SNPs
   ctx->analyzed.assign(G, 0);
   {
@@ -1505,6 +1547,7 @@ int eqb_finalize(eqb_ctx *ctx)
     }
   }
 
+  pt.mark("finalize.analyzed");
   // grids, configurations, windows, parameter block
   const int L = (int)ctx->phi2L.size(), K = (int)ctx->phi2S.size();
   std::vector<double> grids;
@@ -1570,10 +1613,13 @@ int eqb_finalize(eqb_ctx *ctx)
   CK(dmalloc(&ctx->d_prm, sizeof(DevParams)));
   CK(h2d(ctx, ctx->d_prm, &hp, sizeof(DevParams)));
   CK(cudaStreamSynchronize(ctx->stream));
+  pt.mark("finalize.params");
   int rc = prepare_fast_path(ctx);
   if (rc) return rc;
+  pt.mark("finalize.prepare_fast_path");
   rc = enqueue_x_pipeline(ctx, false); // general path only: the rows still have to be re-indexed
   if (rc) return rc;
+  pt.mark("finalize.enqueue_x");
   ctx->finalized = true;
   return 0;
 }
@@ -1703,6 +1749,7 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
                          bool device_only, float *ms)
 {
   AllocScope alloc_scope(ctx->stream);
+  PhaseTimer pt;
   const bool prep_in_timed_region = true; // K1 (projection) belongs to the measured hot path
   if (!ctx->finalized) return fail(ctx, "eqb_finalize() not called");
   if (gene_lo < 0 || gene_hi > ctx->cfg.n_genes || gene_lo > gene_hi) return fail(ctx, "bad gene range");
@@ -1720,9 +1767,9 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
   const bool o_cfg = join && C > 0 && (device_only ? want_raw : (res && res->abf_cfg));
   const size_t per_pair = (o_n ? S * 4 : 0) + (o_ss ? S * 40 : 0) + (o_gen ? 3 * L * 8 : 0) +
                           (join ? (size_t)C * K * 8 : 0) + (join ? (5 + C) * 8 : 0) + (join && !o_gen ? 3 * L * 8 : 0);
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  const size_t budget = std::max<size_t>(64u << 20, std::min<size_t>(free_b / 2, (size_t)24 << 30));
+  // free device memory was asked at eqb_create (cudaMemGetInfo waits for the copies in flight: here it would hold
+  // the first kernels of eqb_run back until the whole genotype upload has landed); a quarter of it bounds a chunk
+  const size_t budget = std::max<size_t>(64u << 20, std::min<size_t>(ctx->free_bytes_at_create / 4, (size_t)24 << 30));
 
   if (device_only && wait_x_all(ctx)) return 100;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1830,6 +1877,7 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           CK(cudaFuncSetAttribute(fast_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         fa.T = T;
+        pt.mark("run.setup");
         if (device_only && prep_in_timed_region) {
           int rcp = launch_prep_yx(ctx, true);
           if (rcp) return rcp;
@@ -1940,6 +1988,7 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           scatter_results_kernel<<<(unsigned)gs.size(), 256, 0, ctx->dstream>>>(ctx->d_prm, s2);
           ctx->launches++;
         }
+        pt.mark("run.worklists");
         cudaEvent_t k0 = nullptr, k1 = nullptr;
         if (device_only) {
           CK(cudaEventCreate(&k0));
@@ -1992,10 +2041,12 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         int rcd = copy_results(ctx, ctx->stream, res, pair_base, 0, n_pairs, o_gen, o_cfg, C);
         if (rcd) return rcd;
       }
+      pt.mark("run.enqueue");
       if (!device_only) {
         CK(cudaStreamSynchronize(ctx->dstream));
         CK(cudaStreamSynchronize(ctx->stream)); // buffers are reused by the next chunk
       }
+      pt.mark("run.wait_results");
     }
     pair_base += n_pairs;
     g0 = g1;
