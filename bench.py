@@ -288,14 +288,14 @@ def run_ours(args, rank, world, local_rank):
         return
 
     pk, pk_kind = peaks()
-    # dominant kernel = fast_pair_kernel (K2+K3): algorithmic bytes of SURVEY 8(d) / its own CUDA-event duration;
+    # dominant kernel = fast_pair_warp_kernel (K2+K3): algorithmic bytes of SURVEY 8(d) / its own CUDA-event duration;
     # the whole step (K1b + K1c + fix-up + K2+K3) is reported next to it
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     achieved_step = alg_bytes / (ms_step * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("fast_pair_kernel_dram_bytes_per_launch")
+        traffic = json.load(open(tpath)).get("fast_pair_warp_kernel_dram_bytes_per_launch")
     out = {
         "metric": "cis gene-SNP pair BFs/sec", "value": tot_pairs / (ms_step * 1e-3), "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -312,9 +312,9 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_kind": pk_kind,
-                     "kernel": "fast_pair_kernel", "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "fast_pair_warp_kernel", "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
                      "step_achieved": achieved_step, "step_frac": achieved_step / pk["hbm_gbs"],
-                     "step_kernels": "prep_y + prep_x_dmma + fix-up + fast_pair"},
+                     "step_kernels": "prep_y + prep_x_dmma + fix-up + fast_pair_warp"},
     }
     if e2e_f64_s is not None and world == 1:
         out["e2e_f64"] = {"value": pairs / e2e_f64_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes(ds),

@@ -362,6 +362,7 @@ struct eqb_ctx {
   std::vector<uint8_t> gene_fast;
   std::vector<int> dup_of;
   DevBuf<int> d_genes2, d_tile_gene;
+  DevBuf<long long> d_tile_q0;
   DevBuf<long long> d_pair_off2, d_fast_base;
   struct XChunk { // one prep_x_dmma launch: subgroups sharing a genotype variant, their basis / mask columns
     PrepCols pc;
@@ -378,6 +379,8 @@ struct eqb_ctx {
   double *d_gt_d = nullptr; // uphi[UL] | omaL[3L]
   int *d_gt_i = nullptr;    // idxL[3L] | dup_of[S] | ustart[UL+1] | uent[3L]
   GridOrder go;             // grid entries grouped by unique phi2 (fast_pair_warp_kernel)
+  GridConst gc;             // the same tables by value (kernel parameter) when they fit
+  bool gc_ok = false;
   double **d_prep_ptrs = nullptr;
   double *d_tz = nullptr;
   float last_pair_ms = 0.f;
@@ -974,6 +977,24 @@ int prepare_fast_path(eqb_ctx *ctx)
     CK(dmalloc(&ctx->d_gt_i, std::max<size_t>(idxL.size(), 1) * sizeof(int)));
     ctx->go.ustart = ctx->d_gt_i + go_off;
     ctx->go.uent = ctx->d_gt_i + go_off + UL0 + 1;
+    {
+      const int K = (int)ctx->phi2S.size();
+      memset(&ctx->gc, 0, sizeof(ctx->gc));
+      ctx->gc_ok = UL0 <= GC_UL && 3 * L <= GC_3L && K <= GC_K;
+      if (ctx->gc_ok) {
+        const int *ustart = idxL.data() + go_off, *uent = ustart + UL0 + 1;
+        for (int u = 0; u < UL0; ++u) ctx->gc.uphi[u] = uphi[u];
+        for (int u = 0; u <= UL0; ++u) ctx->gc.ustart[u] = (short)ustart[u];
+        for (int i = 0; i < 3 * L; ++i) {
+          ctx->gc.ent[i] = (unsigned char)uent[i];
+          ctx->gc.oma[i] = omaL[uent[i]];
+        }
+        for (int k = 0; k < K; ++k) {
+          ctx->gc.phiS[k] = ctx->phi2S[k];
+          ctx->gc.omaS[k] = ctx->oma2S[k];
+        }
+      }
+    }
     CK(h2d(ctx, ctx->d_gt_d, gd.data(), gd.size() * sizeof(double)));
     CK(h2d(ctx, ctx->d_gt_i, idxL.data(), idxL.size() * sizeof(int)));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1222,6 +1243,7 @@ void eqb_destroy(eqb_ctx *ctx)
   ctx->xchunks.clear();
   ctx->d_fix.release();
   ctx->d_tile_gene.release();
+  ctx->d_tile_q0.release();
   if (ctx->d_prm) dfree(ctx->d_prm);
   if (ctx->d_grids) dfree(ctx->d_grids);
   if (ctx->d_cfg_mask) dfree(ctx->d_cfg_mask);
@@ -1858,19 +1880,19 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         if (warp_tiles) {
           T = 32;
           if (const char *e = getenv("EQB_FASTW_WARPS")) nwarp = std::min(WARPS, std::max(1, atoi(e)));
-          const size_t tb = fast_warp_table_bytes(L, K, ctx->gt.UL);
-          while (nwarp > 1 && tb + nwarp * fast_warp_smem_bytes(S) > tile_budget) nwarp /= 2;
-          // phenotype cache: as many genes as fit next to the rest in ~1/2 of an SM's shared memory (2 CTAs per SM)
-          size_t cache_budget = 104 * 1024;
-          if (const char *e = getenv("EQB_FASTW_CACHE_KB")) cache_budget = (size_t)std::max(0, atoi(e)) * 1024;
-          const size_t base = tb + nwarp * fast_warp_smem_bytes(S), yrow = fast_warp_ycache_bytes(1, S, ctx->ldn);
-          int slots = (cache_budget > base) ? (int)((cache_budget - base) / yrow) : 0;
-          slots = std::min(slots, 8);
-          fa.ycache_slots = slots;
+          while (nwarp > 1 && nwarp * fast_warp_smem_bytes(S) > tile_budget) nwarp /= 2;
           fa.use_dmma = getenv("EQB_FASTW_NO_DMMA") == nullptr;
-          smem = base + fast_warp_ycache_bytes(slots, S, ctx->ldn);
-          if (smem > 200 * 1024) return fail(ctx, "grid tables do not fit in shared memory");
-          CK(cudaFuncSetAttribute(fast_pair_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          if (const char *e = getenv("EQB_FASTW_DEBUG")) fa.debug = atoi(e);
+          smem = nwarp * fast_warp_smem_bytes(S);
+          if (smem > 200 * 1024) return fail(ctx, "too many subgroups for the shared memory of one warp tile");
+          // phase A on the tensor cores when every group of 8 subgroups shares one genotype matrix
+          for (int s0 = 0; s0 < S; s0 += 8)
+            for (int a = s0 + 1; a < std::min(S, s0 + 8); ++a)
+              if (ctx->hp.sub[a].X != ctx->hp.sub[s0].X) fa.use_dmma = 0;
+          CK(cudaFuncSetAttribute(fast_pair_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CK(cudaFuncSetAttribute(fast_pair_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CK(cudaFuncSetAttribute(fast_pair_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CK(cudaFuncSetAttribute(fast_pair_warp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         } else {
           smem = fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which);
           if (smem > 200 * 1024) return fail(ctx, "configuration table does not fit in shared memory");
@@ -1959,21 +1981,36 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         fa.fast_base = ctx->d_fast_base.p;
         fa.pair_off = ctx->d_pair_off2.p;
         // first gene of every tile of every segment (the kernel walks forward from it instead of searching)
+        // Warp kernel: the tile list itself (tile_q0, one sentinel per segment).  (Measured dead ends: splitting the
+        // tiles of the last, partially filled wave, and staggering the tile sizes of the first wave so that the
+        // memory-bound and the arithmetic-bound phases of co-resident CTAs interleave -- a tile costs the same time
+        // whatever its pair count, so both only add tiles: 0.58 -> 0.58 ms and 0.58 -> 0.67 ms.)
         std::vector<int> tile_gene;
-        std::vector<size_t> seg_tile0(seg_begin.size(), 0);
+        std::vector<long long> tile_q0;
+        std::vector<size_t> seg_tile0(seg_begin.size(), 0), seg_ntiles(seg_begin.size(), 0);
         for (size_t sgi = 0; sgi + 1 < seg_begin.size(); ++sgi) {
-          seg_tile0[sgi] = tile_gene.size();
+          seg_tile0[sgi] = tile_gene.size() + (warp_tiles ? sgi : 0); // (+ one sentinel per earlier segment in tile_q0)
           const size_t i0 = seg_begin[sgi], i1 = seg_begin[sgi + 1];
-          if (i1 <= i0) continue;
-          const long long qb = fbase[i0], qe = (i1 < gf.size()) ? fbase[i1] : nfp;
+          const long long qb = (i0 < gf.size()) ? fbase[i0] : nfp, qe = (i1 < gf.size()) ? fbase[i1] : nfp;
           size_t gi = i0;
-          for (long long q = qb; q < qe; q += T) {
+          long long q = qb;
+          long long t = 0;
+          while (q < qe) {
             while (gi + 1 < gf.size() && fbase[gi + 1] <= q) ++gi;
             tile_gene.push_back((int)gi);
+            tile_q0.push_back(q);
+            q += T;
+            ++t;
           }
+          seg_ntiles[sgi] = (size_t)t;
+          tile_q0.push_back(qe); // sentinel (also the end of the segment's last tile)
         }
         CK(ctx->d_tile_gene.ensure(std::max<size_t>(tile_gene.size(), 1)));
         CK(h2d(ctx, ctx->d_tile_gene.p, tile_gene.data(), tile_gene.size() * sizeof(int)));
+        if (warp_tiles) {
+          CK(ctx->d_tile_q0.ensure(std::max<size_t>(tile_q0.size(), 1)));
+          CK(h2d(ctx, ctx->d_tile_q0.p, tile_q0.data(), tile_q0.size() * 8));
+        }
         if (pipelined && !gs.empty()) {
           // general-path genes of this chunk (already computed on the main stream)
           cudaEvent_t done;
@@ -1998,14 +2035,24 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         for (size_t sgi = 0; sgi + 1 < seg_begin.size(); ++sgi) {
           const size_t i0 = seg_begin[sgi], i1 = seg_begin[sgi + 1];
           fa.q_begin = fbase[i0];
-          fa.tile_gene = ctx->d_tile_gene.p + seg_tile0[sgi];
+          fa.tile_gene = ctx->d_tile_gene.p + seg_tile0[sgi] - (warp_tiles ? sgi : 0);
+          fa.tile_q0 = warp_tiles ? ctx->d_tile_q0.p + seg_tile0[sgi] : nullptr;
+          fa.n_tiles = (long long)seg_ntiles[sgi];
           fa.n_pairs = (i1 < gf.size()) ? fbase[i1] : nfp;
           if (pipelined) CK(cudaStreamWaitEvent(ctx->stream, ctx->xready[seg_chunk[sgi]], 0));
           if (fa.n_pairs > fa.q_begin) {
             const long long tiles = (fa.n_pairs - fa.q_begin + T - 1) / T;
-            if (warp_tiles)
-              fast_pair_warp_kernel<<<(unsigned)((tiles + nwarp - 1) / nwarp), nwarp * 32, smem, ctx->stream>>>(
-                  ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->go);
+            if (warp_tiles) {
+              const bool tp = ctx->gc_ok && getenv("EQB_FASTW_NO_CONST") == nullptr;
+              const unsigned grid = (unsigned)((fa.n_tiles + nwarp - 1) / nwarp);
+#define EQB_FASTW_LAUNCH(TPV, DMV)                                                                                    \
+  fast_pair_warp_kernel<TPV, DMV><<<grid, nwarp * 32, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->go, ctx->gc)
+              if (tp && fa.use_dmma) EQB_FASTW_LAUNCH(true, true);
+              else if (tp) EQB_FASTW_LAUNCH(true, false);
+              else if (fa.use_dmma) EQB_FASTW_LAUNCH(false, true);
+              else EQB_FASTW_LAUNCH(false, false);
+#undef EQB_FASTW_LAUNCH
+            }
             else
               fast_pair_kernel<<<(unsigned)tiles, THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt);
             ctx->launches++;

@@ -54,8 +54,10 @@ struct FastArgs {
   const long long *pair_off;   // [n_genes] first OUTPUT pair index of each fast gene
   int *out_n;
   double *out_ss, *out_gen, *out_cfg, *out_w;
-  int ycache_slots;            // fast_pair_warp_kernel: genes whose residual phenotype rows a CTA stages in shared memory
   int use_dmma;                // fast_pair_warp_kernel: phase A on the FP64 tensor cores
+  int debug;                   // timing experiments only (EQB_FASTW_DEBUG): 1 no raw-value stores, 2 no phase A, 4 no phase C
+  long long n_tiles;           // fast_pair_warp_kernel: tiles of this launch
+  const long long *tile_q0;    // [n_tiles + 1] first compact pair index of each tile (variable size, <= 32 pairs)
 };
 
 // ---------------------------------------------------------------- K1a
@@ -1142,22 +1144,38 @@ __host__ __device__ inline size_t fast_smem_bytes(int T, int S, int L, int K, in
 
 
 // =====================================================================================================
-// fast_pair_warp_kernel (K2+K3 for --bfs gen|sin and --analys sep): the same three phases, but every WARP
-// owns a tile of 32 pairs from the contraction to the last output row -- no CTA barrier anywhere, so the
-// memory-bound contraction of one warp overlaps the transcendental-bound ABF phase of its neighbours
-// (fast_pair_kernel's phases are CTA-synchronous: barrier stalls were a third of its issue slots, and its
+// fast_pair_warp_kernel (K2+K3 for --bfs gen|sin and --analys sep): the same three phases as fast_pair_kernel, but
+// every WARP owns a tile of up to 32 pairs from the contraction to the last output row.  There is no barrier and no
+// per-CTA prologue: the memory-bound contraction of one warp overlaps the transcendental-bound ABF phase of its
+// neighbours (fast_pair_kernel's phases are CTA-synchronous: barrier stalls were a third of its issue slots and its
 // thread-per-(pair, subgroup) phase B used 96 of 256 threads).
-//   A  lanes over the individuals, two pairs in flight: x . ytil_s                     (contraction)
+//   A  mma.sync.m8n8k4 (DMMA) tile product  xy[pairs][S] = X_tile . Ytil_gene^T            (contraction)
 //   B  lane per (pair, subgroup): summary statistics + standardisation                  (S rounds of 32 items)
 //   C  lane per PAIR: loop over the unique phi2 values (the sums over the subgroups are computed once per
 //      phi2 and reused by every grid point of gen / gen-fix / gen-maxh that shares it), then over the singleton
 //      configurations; values go straight to their output rows, log10_weighted_sum is accumulated online in
 //      registers (utils_math.cpp:100-131; same NaN rules), BMAlite at the end.  The grid point / configuration
 //      is uniform across the warp (the pair varies across lanes), so grid-dependent branches never diverge.
+// The grid tables of phase C are warp-uniform reads: they travel as a kernel parameter (constant bank, GridConst)
+// when they fit, else they are read from global memory.  Tiles come from a host-built list (tile_q0, <= 32 pairs).
+// Measured on the c2 step (EQB_FASTW_DEBUG): phase B alone 0.10 ms, A + B 0.26 ms, everything 0.58 ms, of which the
+// uncoalesced raw-value stores 0.05 ms -- the phases add up, i.e. the warps of a wave move through them together.
+// Neither occupancy (64 / 80 / 128 registers: 0.57 / 0.61 / 0.56 ms) nor persistent warps that request their next
+// tile's genotype rows from HBM before phase C (0.65 ms) changed that.
 // Shared memory per warp: xy[32][S] + (b, v, t)[32][3S|1] + masks and pair indices.
 struct GridOrder {
   const int *ustart; // [UL+1] entries of unique phi2 value u: uent[ustart[u] .. ustart[u+1])
   const int *uent;   // [3L]   r * L + k of the entry (row r of gen / gen-fix / gen-maxh, grid point k)
+};
+
+// the same tables by value (kernel parameter -> constant bank): limits UL <= 64, 3L <= 192, K <= 32
+constexpr int GC_UL = 64, GC_3L = 192, GC_K = 32;
+struct GridConst {
+  double uphi[GC_UL];
+  double oma[GC_3L]; // omega2 of entry i (grouped order)
+  double phiS[GC_K], omaS[GC_K];
+  short ustart[GC_UL + 1];
+  unsigned char ent[GC_3L]; // r * L + k of entry i
 };
 
 struct LseOnline { // log10_weighted_sum accumulated one element at a time (max tracked with rescaling)
@@ -1238,73 +1256,19 @@ __device__ __forceinline__ void contract_tile(const double *__restrict__ X, cons
   if (j < tn) contract_shared_x<SN>(X + (size_t)s_m[j] * ldn, fsub, (size_t)s_gene[j] * ldn, ldn, lane, xy + (size_t)j * S);
 }
 
-// phase A, common case (one genotype matrix for the subgroups [s0, s0+sn), rows of at most 64*NI doubles): the
-// genotype row of pair j+1 is loaded into registers (NI 16-byte loads per lane, issued back to back) BEFORE pair j
-// is contracted, so a warp pays one memory round trip per pair instead of one per load, overlapped with the
-// previous pair's arithmetic.  Per-lane summation order = contract_shared_x (bit-identical results).
-template <int NI>
-__device__ __forceinline__ void contract_tile_regs(const double *__restrict__ X, const FastSub *__restrict__ fsub, int sn,
-                                                   const long long *s_m, const int *s_gene, int tn, int S, int ldn, int lane,
-                                                   double *__restrict__ xy, const double *ycache, const int *s_slot,
-                                                   int ncached, int s0)
-{
-  const int h = ldn >> 1;
-  double2 cur[NI], nxt[NI];
-  {
-    const double2 *row = reinterpret_cast<const double2 *>(X + (size_t)s_m[0] * ldn);
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int idx = lane + 32 * i;
-      cur[i] = (idx < h) ? row[idx] : make_double2(0.0, 0.0);
-    }
-  }
-  for (int j = 0; j < tn; ++j) {
-    {
-      const int jn = (j + 1 < tn) ? j + 1 : j;
-      const double2 *row = reinterpret_cast<const double2 *>(X + (size_t)s_m[jn] * ldn);
-#pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const int idx = lane + 32 * i;
-        nxt[i] = (idx < h) ? row[idx] : make_double2(0.0, 0.0);
-      }
-    }
-    const size_t grow = (size_t)s_gene[j] * ldn;
-    const int slot = s_slot[j];
-    for (int a = 0; a < sn; ++a) {
-      // residual phenotype row: the CTA's shared-memory copy when the gene is one of the staged ones
-      const double2 *y = reinterpret_cast<const double2 *>(
-          (slot < ncached) ? ycache + ((size_t)slot * S + s0 + a) * ldn : fsub[a].Ytil + grow);
-      double acc = 0.0;
-#pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < h) {
-          const double2 y2 = y[idx];
-          acc += cur[i].x * y2.x;
-          acc += cur[i].y * y2.y;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) xy[(size_t)j * S + a] = acc;
-    }
-#pragma unroll
-    for (int i = 0; i < NI; ++i) cur[i] = nxt[i];
-  }
-}
-
 // phase A on the FP64 tensor cores: the tile's contraction IS a small matrix product
 //   xy[32 pairs][sn subgroups] = X_tile[32][ldn] . Ytil_gene[sn][ldn]^T
 // done as 4 row blocks of mma.sync.m8n8k4 (DMMA): A fragments straight from the genotype rows (one 16-byte load per
 // lane covers two k-steps: the k index inside a chunk of 8 individuals is permuted the same way for A and B),
-// B fragments from the CTA's shared-memory copy of the gene's residual phenotype rows (columns >= sn repeat the last
+// B fragments from the gene's residual phenotype rows (L1/L2 hits: 7 KB per gene; columns >= sn repeat the last
 // subgroup and are dropped).  The rows of a tile that belong to different genes are handled as runs: every run
-// multiplies the whole tile by ITS gene's phenotype block and keeps its own rows (1.6 runs per tile at 50 SNPs per
-// gene, 1 at the GTEx shape).  ~600 warp instructions per tile instead of ~8000 for the shuffle-reduced dot products.
+// multiplies the row blocks it touches by ITS gene's phenotype block and keeps its own rows (1.6 runs per tile at
+// 50 SNPs per gene, 1 at the GTEx shape).  ~600 warp instructions per tile instead of ~8000 for shuffle-reduced
+// dot products.  (Measured dead ends: a cp.async ring for the fragments, 0.65 vs 0.58 ms; a CTA-wide shared-memory
+// copy of the phenotype rows, same time as the L1 path but it needs a barrier and a per-CTA prologue.)
 __device__ __forceinline__ void contract_tile_dmma(const double *__restrict__ X, const FastSub *__restrict__ fsub, int sn,
-                                                   const long long *s_m, const int *s_gene, const int *s_slot, int tn, int S,
-                                                   int ldn, int lane, double *__restrict__ xy, const double *ycache,
-                                                   int ncached, int s0)
+                                                   const long long *s_m, const int *s_gene, int tn, int S, int ldn, int lane,
+                                                   double *__restrict__ xy)
 {
   const int r = lane >> 2, kq = lane & 3;
   const double *xp[4];
@@ -1317,22 +1281,20 @@ __device__ __forceinline__ void contract_tile_dmma(const double *__restrict__ X,
   const int nchunk = ldn >> 3;
   int j0 = 0;
   while (j0 < tn) {
-    const int gs = s_slot[j0];
-    const unsigned same = __ballot_sync(0xffffffffu, lane < tn && s_slot[lane < tn ? lane : 0] == gs);
+    const int g = s_gene[j0];
+    const unsigned same = __ballot_sync(0xffffffffu, lane < tn && s_gene[lane < tn ? lane : 0] == g);
     const int j1 = j0 + __popc(same >> j0 << j0); // rows of a gene are consecutive
-    const double *yp = ((gs < ncached) ? ycache + ((size_t)gs * S + s0 + col) * ldn
-                                       : fsub[col].Ytil + (size_t)s_gene[j0] * ldn) + 2 * kq;
+    const double *yp = fsub[col].Ytil + (size_t)g * ldn + 2 * kq;
     double acc[4][2];
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb) acc[mb][0] = acc[mb][1] = 0.0;
-    // only the row blocks that hold rows of this run
-    const int mb0 = j0 >> 3, mb1 = (j1 - 1) >> 3;
+    const int mb0 = j0 >> 3, mb1 = (j1 - 1) >> 3; // only the row blocks that hold rows of this run (warp-uniform)
 #pragma unroll 2
     for (int c = 0; c < nchunk; ++c) {
       const double2 b2 = *reinterpret_cast<const double2 *>(yp + 8 * c);
 #pragma unroll
       for (int mb = 0; mb < 4; ++mb) {
-        if (mb >= mb0 && mb <= mb1) { // warp-uniform
+        if (mb >= mb0 && mb <= mb1) {
           const double2 a2 = *reinterpret_cast<const double2 *>(xp[mb] + 8 * c);
           dmma_m8n8k4(acc[mb][0], acc[mb][1], a2.x, b2.x);
           dmma_m8n8k4(acc[mb][0], acc[mb][1], a2.y, b2.y);
@@ -1351,89 +1313,44 @@ __device__ __forceinline__ void contract_tile_dmma(const double *__restrict__ X,
   }
 }
 
-// shared memory of fast_pair_warp_kernel: CTA-wide grid tables, then one region per warp
-__host__ __device__ inline size_t fast_warp_table_bytes(int L, int K, int UL)
-{
-  const size_t b = (size_t)(UL + 3 * L + 2 * K) * 8 + (size_t)(UL + 1 + 3 * L) * 4;
-  return (b + 15) & ~(size_t)15;
-}
+// shared memory of fast_pair_warp_kernel: one region per warp
 __host__ __device__ inline size_t fast_warp_smem_bytes(int S)
 {
-  return ((size_t)32 * S + (size_t)32 * ((3 * S) | 1)) * 8 + (size_t)32 * (8 + 8 + 8 + 4 + 4);
+  return ((size_t)32 * S + (size_t)32 * ((3 * S) | 1)) * 8 + (size_t)32 * (8 + 8 + 8 + 4);
 }
-__host__ __device__ inline size_t fast_warp_ycache_bytes(int slots, int S, int ldn) { return (size_t)slots * S * ldn * 8; }
 
 #ifndef EQB_FASTW_MINB
 #define EQB_FASTW_MINB 2
 #endif
-__global__ void __launch_bounds__(THREADS, EQB_FASTW_MINB) fast_pair_warp_kernel(const DevParams *__restrict__ prm_,
+// TP: grid tables from the GridConst kernel parameter (constant bank) instead of global memory.
+// DM: every group of 8 subgroups shares one genotype matrix and phase A runs on the tensor cores (the common case);
+//     the instantiation without DM carries the shuffle-reduced fallbacks, whose register needs would otherwise
+//     set the allocation (and the occupancy) of the common case too.
+template <bool TP, bool DM>
+__global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_warp_kernel(const DevParams *__restrict__ prm_,
                                                                  const FastParams *__restrict__ fp_, const FastArgs fa,
-                                                                 const GridTab gt, const GridOrder go)
+                                                                 const GridTab gt, const GridOrder go,
+                                                                 const __grid_constant__ GridConst gc)
 {
   const DevParams &prm = *prm_;
   extern __shared__ double fsm[];
   const int S = prm.S, ldn = prm.ldn, L = prm.L, K = prm.K, UL = gt.UL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const long long tile = (long long)blockIdx.x * nwarp + warp;
-  const long long q0 = fa.q_begin + tile * 32;
-  // CTA-wide grid tables (a dependent chain of global loads per grid point otherwise): unique phi2 values, the grid
-  // entries grouped by them (destination index + omega2), the singleton grid
-  double *t_uphi = fsm;                     // [UL]
-  double *t_oma = t_uphi + UL;              // [3L] omega2 of entry i (grouped order)
-  double *t_phiS = t_oma + 3 * L;           // [K]
-  double *t_omaS = t_phiS + K;              // [K]
-  int *t_ustart = (int *)(t_omaS + K);      // [UL+1]
-  int *t_ent = t_ustart + UL + 1;           // [3L] r*L + k of entry i
-  for (int i = threadIdx.x; i < UL; i += blockDim.x) t_uphi[i] = gt.uphi[i];
-  for (int i = threadIdx.x; i <= UL; i += blockDim.x) t_ustart[i] = go.ustart[i];
-  for (int i = threadIdx.x; i < 3 * L; i += blockDim.x) {
-    const int e = go.uent[i];
-    t_ent[i] = e;
-    t_oma[i] = gt.omaL[e];
-  }
-  for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    t_phiS[i] = prm.phi2S[i];
-    t_omaS[i] = prm.oma2S[i];
-  }
-  // CTA-wide cache of the residual phenotype rows: the nwarp tiles of a CTA are consecutive pairs, i.e. a handful of
-  // consecutive genes (ONE gene at the GTEx shape); their S rows are staged once instead of being re-read from
-  // L2 for every pair (the phenotype re-reads were 2/3 of the kernel's L2 -> SM traffic)
-  double *ycache = reinterpret_cast<double *>(reinterpret_cast<char *>(fsm) + fast_warp_table_bytes(L, K, UL));
-  int g_lo = 0, ncached = 0;
-  {
-    const long long tile0 = (long long)blockIdx.x * nwarp;
-    const long long qf = fa.q_begin + tile0 * 32;
-    if (qf < fa.n_pairs && fa.ycache_slots > 0) {
-      const long long ql = min(qf + (long long)nwarp * 32, fa.n_pairs) - 1;
-      g_lo = fa.tile_gene[tile0];
-      int g_hi = g_lo;
-      while (g_hi + 1 < fa.n_genes && fa.fast_base[g_hi + 1] <= ql && g_hi - g_lo + 1 < fa.ycache_slots) ++g_hi;
-      ncached = g_hi - g_lo + 1;
-      const int h = ldn >> 1;
-      const int per = S * h;
-      for (int i = threadIdx.x; i < ncached * per; i += blockDim.x) {
-        const int slot = i / per, r = i - slot * per, a = r / h, c = r - a * h;
-        reinterpret_cast<double2 *>(ycache)[i] =
-            reinterpret_cast<const double2 *>(fp_->sub[a].Ytil + (size_t)fa.genes[g_lo + slot] * ldn)[c];
-      }
-    }
-  }
-  __syncthreads(); // the only CTA-wide barrier
-  if (q0 >= fa.n_pairs) return;
-  const int tn = (int)min(32LL, fa.n_pairs - q0);
+  if (tile >= fa.n_tiles) return; // (no barrier anywhere below)
+  const long long q0 = fa.tile_q0[tile];
+  const int tn = (int)(fa.tile_q0[tile + 1] - q0); // 1 .. 32
   const long long C = (fa.which == 1) ? 0 : S;
   const bool join = prm.analysis == 1;
   const int sst = (3 * S) | 1;
   // per-warp shared memory
-  char *wbase = reinterpret_cast<char *>(fsm) + fast_warp_table_bytes(L, K, UL) +
-                fast_warp_ycache_bytes(fa.ycache_slots, S, ldn) + (size_t)warp * fast_warp_smem_bytes(S);
+  char *wbase = reinterpret_cast<char *>(fsm) + (size_t)warp * fast_warp_smem_bytes(S);
   double *xy = reinterpret_cast<double *>(wbase);            // [32][S]
   double *st = xy + (size_t)32 * S;                          // [32][sst]  b, v, t per subgroup
   unsigned long long *hasm = (unsigned long long *)(st + (size_t)32 * sst); // [32]
   long long *s_pair = (long long *)(hasm + 32);              // [32] output pair index
   long long *s_m = s_pair + 32;                              // [32] SNP index
   int *s_gene = (int *)(s_m + 32);                           // [32] gene id
-  int *s_slot = s_gene + 32;                                 // [32] slot of the gene in the CTA's phenotype cache
 
   long long my_pair = 0;
   if (lane < tn) {
@@ -1443,7 +1360,6 @@ __global__ void __launch_bounds__(THREADS, EQB_FASTW_MINB) fast_pair_warp_kernel
     const int g = fa.genes[lo];
     const long long off = q - fa.fast_base[lo];
     s_gene[lane] = g;
-    s_slot[lane] = lo - g_lo;
     s_m[lane] = prm.cis_begin[g] + off;
     my_pair = fa.pair_off[lo] + off;
     s_pair[lane] = my_pair;
@@ -1464,20 +1380,10 @@ __global__ void __launch_bounds__(THREADS, EQB_FASTW_MINB) fast_pair_warp_kernel
     bool same = true;
     for (int a = 1; a < sn; ++a) same = same && (prm.sub[s0 + a].X == prm.sub[s0].X);
     const FastSub *fsub = fp_->sub + s0;
-    if (same && fa.use_dmma) {
-      contract_tile_dmma(prm.sub[s0].X, fsub, sn, s_m, s_gene, s_slot, tn, S, ldn, lane, xy + s0, ycache, ncached, s0);
-    } else if (same && ldn <= 512) {
-      const double *X = prm.sub[s0].X;
-      switch ((ldn + 63) >> 6) {
-      case 1: contract_tile_regs<1>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
-      case 2: contract_tile_regs<2>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
-      case 3: contract_tile_regs<3>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
-      case 4: contract_tile_regs<4>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
-      case 5: contract_tile_regs<5>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
-      case 6: contract_tile_regs<6>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
-      case 7: contract_tile_regs<7>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
-      default: contract_tile_regs<8>(X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0, ycache, s_slot, ncached, s0); break;
-      }
+    if (fa.debug & 2) {
+      for (int i = lane; i < tn * sn; i += 32) xy[(size_t)(i / sn) * S + s0 + i % sn] = 0.1;
+    } else if (DM) {
+      contract_tile_dmma(prm.sub[s0].X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0);
     } else if (same) {
       const double *X = prm.sub[s0].X;
       switch (sn) {
@@ -1528,7 +1434,8 @@ __global__ void __launch_bounds__(THREADS, EQB_FASTW_MINB) fast_pair_warp_kernel
     }
   }
   __syncwarp();
-  if (!join || lane >= tn) return;
+  if (!join || lane >= tn || (fa.debug & 4)) return;
+  const bool st_raw = !(fa.debug & 1);
   // ---------------- phase C: lane per pair
   const double *stj = st + (size_t)lane * sst;
   const unsigned long long mask = hasm[lane];
@@ -1541,12 +1448,12 @@ __global__ void __launch_bounds__(THREADS, EQB_FASTW_MINB) fast_pair_warp_kernel
   const double wL = 1.0 / (double)L;
   for (int u = 0; u < UL; ++u) {
     double den, num, sing;
-    consistent_sums(stj, S, mask, t_uphi[u], den, num, sing); // ONE logarithm per (pair, phi2)
-    const int i1 = t_ustart[u + 1];
-    for (int i = t_ustart[u]; i < i1; ++i) {
-      const int e = t_ent[i]; // warp-uniform
-      const double v = abf_from_sums(den, num, sing, t_oma[i]);
-      og[e] = v;
+    consistent_sums(stj, S, mask, TP ? gc.uphi[u] : gt.uphi[u], den, num, sing); // ONE logarithm per (pair, phi2)
+    const int i0 = TP ? (int)gc.ustart[u] : go.ustart[u], i1 = TP ? (int)gc.ustart[u + 1] : go.ustart[u + 1];
+    for (int i = i0; i < i1; ++i) {
+      const int e = TP ? (int)gc.ent[i] : go.uent[i]; // warp-uniform
+      const double v = abf_from_sums(den, num, sing, TP ? gc.oma[i] : gt.omaL[e]);
+      if (st_raw) og[e] = v;
       if (e < L) r0.add(v, wL, e == 0);
       else if (e < 2 * L) r1.add(v, wL, e == L);
       else r2.add(v, wL, e == 2 * L);
@@ -1572,8 +1479,8 @@ __global__ void __launch_bounds__(THREADS, EQB_FASTW_MINB) fast_pair_warp_kernel
     const bool has = (mask >> c) & 1ull;
     const double b = stj[c], vv = stj[S + c], tt = stj[2 * S + c];
     for (int k = 0; k < K; ++k) {
-      const double v = has ? singleton_value(b, vv, tt, t_phiS[k], t_omaS[k]) : 0.0;
-      oc[c * K + k] = v;
+      const double v = has ? singleton_value(b, vv, tt, TP ? gc.phiS[k] : prm.phi2S[k], TP ? gc.omaS[k] : prm.oma2S[k]) : 0.0;
+      if (st_raw) oc[c * K + k] = v;
       rc.add(v, wK, k == 0);
     }
     const double wc = rc.result();

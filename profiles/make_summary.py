@@ -15,7 +15,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
-CAPTURES = [("fast_pair_kernel (K2+K3), c2 bench step", "r1_raw_fast_pair_kernel.csv"),
+CAPTURES = [("fast_pair_warp_kernel (K2+K3 for --bfs gen|sin: warp-autonomous tiles, DMMA contraction), c2 bench step",
+             "r1_raw_fast_pair_warp_kernel.csv"),
+            ("fast_pair_kernel (K2+K3, CTA-synchronous tile kernel: the --bfs all path; captured on the c2 step with "
+             "EQB_FAST_TILE=1 before the warp kernel replaced it there)", "r1_raw_fast_pair_kernel.csv"),
             ("prep_x_dmma_kernel<5,1,16> (K1c, FP64 mma.sync), c2 bench step", "r1_raw_prep_x_dmma.csv"),
             ("prep_y_kernel<12,2> (K1b), c2 bench step", "r1_raw_prep_y_kernel.csv"),
             ("perm_kernel<16,false> (K4, c4 slice of bench.py, --pbf gen-sin; `python profiles/perm_slice_gensin.py`)", "r1_raw_perm_kernel_gensin.csv"),
@@ -34,7 +37,7 @@ def main():
            "cold-cache and serialised -- compare SHARES. Bench numbers come from `bench.py` (CUDA events), not from these "
            "runs.  Regenerate with `python profiles/make_summary.py` from the exports in `profiles/`.", "",
            "## Launch list of the bench command", "",
-           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv python bench.py --steps 2 --warmup 3 "
+           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv python bench.py --steps 2 --warmup 3 "
            "--no-cpu` -> `profiles/r1_launches_bench_c2.csv`", ""]
     rows = [r for r in csv.reader(open(os.path.join(HERE, "r1_launches_bench_c2.csv"))) if len(r) > 10]
     hdr = rows[0]
