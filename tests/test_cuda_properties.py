@@ -214,3 +214,41 @@ def test_fixed_point_rejects_bad_arguments(cuda_lib):
     assert f(eng.ctx, 0, G.ctypes.data_as(C.c_void_p), 4, C.c_double(1.0), C.c_int64(G.shape[0]), G.shape[1]) != 0
     assert f(eng.ctx, 0, G.ctypes.data_as(C.c_void_p), 1, C.c_double(2.5), C.c_int64(G.shape[0]), G.shape[1]) != 0
     assert f(eng.ctx, 0, G.ctypes.data_as(C.c_void_p), 1, C.c_double(1.0), C.c_int64(G.shape[0]), G.shape[1]) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["s44_sin", "big_grid", "separate_files", "sep_analysis"])
+def test_warp_kernel_variants_match_oracle(cuda_lib, oracle_lib, case):
+    """fast_pair_warp_kernel instantiations the c2 bench does not reach: 44 subgroups (--bfs sin, the c5 shape: six
+    groups of 8 subgroups in the DMMA contraction), a grid too large for the constant-bank tables (tables read from
+    global memory), separate genotype files per subgroup (shuffle-reduced fallback contraction) and --analys sep."""
+    import eqtlbma_b200
+    from eqtlbma_b200._capi import Engine as AnyEngine
+    from eqtlbma_b200.synth import make_dataset
+    kw = dict(seed=91, n_subgroups=3, n_inds=150, n_genes=14, snps_per_gene=13, n_cov=2, dosage=True, n_chr=2, radius=100,
+              gene_spacing=201, far_snp=False)
+    analysis, bfs = "join", "sin"
+    if case == "s44_sin":
+        kw.update(n_subgroups=44, n_inds=90, n_cov=1, ragged=True, ragged_min_frac=0.5)
+    elif case == "big_grid":
+        rng = np.random.default_rng(5)
+        gl = np.abs(rng.normal(0.3, 0.3, size=(70, 2))) + 1e-3   # 70 points: 3L = 210 > 192 entries
+        gl[::7, 1] = 0.0
+        gl[3::9, 0] = 0.0
+        kw.update(gridL=gl, gridS=np.abs(rng.normal(0.3, 0.3, size=(40, 2))) + 1e-3)   # K = 40 > 32
+    elif case == "separate_files":
+        kw.update(separate_geno_files=True, missing_geno_frac=0.1)
+    else:
+        analysis, bfs = "sep", "gen"
+    ds = make_dataset(**kw)
+    eng = eqtlbma_b200.Engine(ds, analysis=analysis, bfs=bfs)
+    ora = AnyEngine(oracle_lib, "eqo_", ds, analysis=analysis, bfs=bfs)
+    assert eng.fast_gene_count() > 0
+    a, b = eng.run(), ora.run()
+    assert np.array_equal(a.n, b.n)
+    assert np.allclose(a.sstats[..., 1:], b.sstats[..., 1:], rtol=1e-9, atol=0, equal_nan=True)
+    assert np.allclose(a.sstats[..., 0], b.sstats[..., 0], rtol=1e-9, atol=1e-12, equal_nan=True)
+    if analysis == "join":
+        assert np.allclose(a.abf_gen, b.abf_gen, rtol=0, atol=1e-8, equal_nan=True)
+        assert np.allclose(a.abf_cfg, b.abf_cfg, rtol=0, atol=1e-8, equal_nan=True)
+        assert np.allclose(a.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
