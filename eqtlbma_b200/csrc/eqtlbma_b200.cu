@@ -1883,6 +1883,15 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           while (nwarp > 1 && nwarp * fast_warp_smem_bytes(S) > tile_budget) nwarp /= 2;
           fa.use_dmma = getenv("EQB_FASTW_NO_DMMA") == nullptr;
           if (const char *e = getenv("EQB_FASTW_DEBUG")) fa.debug = atoi(e);
+          if (const char *e = getenv("EQB_FASTW_DELAY_US")) {
+            int ctas_per_sm = 1, n_sm = 148;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fast_pair_warp_kernel<true, true>, nwarp * 32,
+                                                             nwarp * fast_warp_smem_bytes(S)));
+            CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->cfg.device));
+            fa.delay_sm = n_sm;
+            fa.delay_ctas = ctas_per_sm * n_sm;
+            fa.delay_ns = atoi(e) * 1000 / std::max(1, ctas_per_sm);
+          }
           smem = nwarp * fast_warp_smem_bytes(S);
           if (smem > 200 * 1024) return fail(ctx, "too many subgroups for the shared memory of one warp tile");
           // phase A on the tensor cores when every group of 8 subgroups shares one genotype matrix

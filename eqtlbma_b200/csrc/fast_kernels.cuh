@@ -55,6 +55,7 @@ struct FastArgs {
   int *out_n;
   double *out_ss, *out_gen, *out_cfg, *out_w;
   int use_dmma;                // fast_pair_warp_kernel: phase A on the FP64 tensor cores
+  int delay_ns, delay_ctas, delay_sm; // timing experiment only (EQB_FASTW_DELAY_US)
   int debug;                   // timing experiments only (EQB_FASTW_DEBUG): 1 no raw-value stores, 2 no phase A, 4 no phase C
   long long n_tiles;           // fast_pair_warp_kernel: tiles of this launch
   const long long *tile_q0;    // [n_tiles + 1] first compact pair index of each tile (variable size, <= 32 pairs)
@@ -1338,6 +1339,11 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const long long tile = (long long)blockIdx.x * nwarp + warp;
   if (tile >= fa.n_tiles) return; // (no barrier anywhere below)
+  if (fa.delay_ns > 0 && (int)blockIdx.x < fa.delay_ctas) {
+    // timing experiment (EQB_FASTW_DELAY_US): CTAs of the first wave that share an SM start out of phase
+    const long long t_end = clock64() + (long long)(blockIdx.x / fa.delay_sm) * fa.delay_ns * 2; // ~2 cycles per ns
+    while (clock64() < t_end) __nanosleep(2000);
+  }
   const long long q0 = fa.tile_q0[tile];
   const int tn = (int)(fa.tile_q0[tile + 1] - q0); // 1 .. 32
   const long long C = (fa.which == 1) ? 0 : S;
