@@ -253,6 +253,7 @@ struct SubHost {
   std::vector<int> all2geno, all2exp, all2cov;
   std::vector<uint8_t> snp_has, gene_has;
   double *d_Yraw = nullptr, *d_Craw = nullptr;
+  cudaEvent_t y_uploaded = nullptr; // the expression matrix has landed in d_Yraw (recorded on the copy stream)
   std::vector<double> covkey; // covariates in all-sample space (host copy, for duplicate detection)
   // finalized
   int xvar = -1;
@@ -1112,9 +1113,11 @@ __global__ void math_selftest_kernel(long long n, double *out)
     const double l0 = log(x), l1 = eqb::log_fast_impl(x);
     w[1] = fmax(w[1], fabs(l1 - l0));
     w[2] = fmax(w[2], fabs(l1 - l0) / fmax(fabs(l0), 1e-300));
+    w[1] = fmax(w[1], fabs(eqb::log_tab(x) - l0)); // table-driven form: absolute accuracy (what the ABFs need)
     const double y = (kind == 0) ? -299.0 + 598.0 * unif() : ((kind == 1) ? -30.0 * unif() : 2.0 * unif() - 1.0);
     const double e0 = exp10(y), e1 = eqb::exp10_fast_impl(y);
     w[3] = fmax(w[3], fabs(e1 - e0) / e0);
+    w[3] = fmax(w[3], fabs(eqb::exp10_tab(y) - e0) / e0);
     const double g0 = exp(2.302585092994046 * y), g1 = eqb::exp_fast_nb(2.302585092994046 * y);
     w[3] = fmax(w[3], fabs(g1 - g0) / g0);
   }
@@ -1160,9 +1163,20 @@ int eqb_create(eqb_ctx **out, const eqb_config *cfg)
   CK(cudaSetDevice(cfg->device));
   configure_pool(cfg->device);
   {
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    ctx->free_bytes_at_create = free_b;
+    // cudaMemGetInfo costs ~0.5 ms: one query per device every 2 s is enough for a chunking heuristic
+    static std::mutex mu;
+    static size_t cached[64];
+    static std::chrono::steady_clock::time_point when[64];
+    std::lock_guard<std::mutex> lk(mu);
+    const int d = (cfg->device >= 0 && cfg->device < 64) ? cfg->device : 0;
+    const auto now = std::chrono::steady_clock::now();
+    if (cached[d] == 0 || std::chrono::duration<double>(now - when[d]).count() > 2.0) {
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      cached[d] = std::max<size_t>(free_b, 1);
+      when[d] = now;
+    }
+    ctx->free_bytes_at_create = cached[d];
   }
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -1214,6 +1228,7 @@ void eqb_destroy(eqb_ctx *ctx)
     if (g.d_raw) dfree(g.d_raw);
   }
   for (auto &s : ctx->subs) {
+    if (s.y_uploaded) cudaEventDestroy(s.y_uploaded);
     if (s.d_Yraw) dfree(s.d_Yraw);
     if (s.d_Craw) dfree(s.d_Craw);
     if (s.d_Yall) dfree(s.d_Yall);
@@ -1366,12 +1381,29 @@ int eqb_set_subgroup(eqb_ctx *ctx, int32_t s, const eqb_subgroup *sg)
   else sb.snp_has.assign(M, 1);
   if (sg->gene_has_exp) sb.gene_has.assign(sg->gene_has_exp, sg->gene_has_exp + G);
   else sb.gene_has.assign(G, 1);
+  if (sb.d_Yraw && sb.y_uploaded) CK(cudaStreamWaitEvent(ctx->stream, sb.y_uploaded, 0)); // (upload still in flight)
   if (sb.d_Yraw) dfree(sb.d_Yraw);
   if (sb.d_Craw) dfree(sb.d_Craw);
   sb.d_Yraw = sb.d_Craw = nullptr;
   const size_t yb = (size_t)G * sg->n_exp_cols * sizeof(double);
   CK(dmalloc(&sb.d_Yraw, std::max<size_t>(yb, 8)));
-  CK(h2d(ctx, sb.d_Yraw, sg->Y, yb));
+  // large expression matrices go up on the copy stream: the main stream (cis windows, sample maps, their
+  // synchronisations) does not queue behind tens of MB of PCIe traffic; eqb_finalize waits for y_uploaded
+  if (sb.y_uploaded) {
+    cudaEventDestroy(sb.y_uploaded);
+    sb.y_uploaded = nullptr;
+  }
+  if (yb > STAGE_MAX) {
+    cudaEvent_t ev_alloc;
+    CK(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev_alloc, ctx->stream)); // (stream-ordered allocation)
+    CK(cudaStreamWaitEvent(ctx->xcopy, ev_alloc, 0));
+    CK(cudaEventDestroy(ev_alloc));
+    CK(cudaMemcpyAsync(sb.d_Yraw, sg->Y, yb, cudaMemcpyHostToDevice, ctx->xcopy));
+    CK(cudaEventCreateWithFlags(&sb.y_uploaded, cudaEventDisableTiming));
+    CK(cudaEventRecord(sb.y_uploaded, ctx->xcopy));
+  } else
+    CK(h2d(ctx, sb.d_Yraw, sg->Y, yb));
   sb.covkey.clear();
   if (sb.Q > 0) {
     sb.covkey.assign((size_t)sb.Q * N, 0.0);
@@ -1517,6 +1549,7 @@ int eqb_finalize(eqb_ctx *ctx)
     // expression -> all-sample space, NaN where the sample is absent or the gene is not expressed
     CK(dmalloc(&sb.d_Yall, std::max<size_t>((size_t)G * ldn, 1) * sizeof(double)));
     CK(h2d(ctx, dmap, sb.all2exp.data(), N * sizeof(int)));
+    if (sb.y_uploaded) CK(cudaStreamWaitEvent(ctx->stream, sb.y_uploaded, 0));
     if (G > 0) {
       expand_rows_kernel<<<(unsigned)G, 128, 0, ctx->stream>>>(sb.d_Yraw, sb.n_exp_cols, dmap, sb.d_gene_has,
                                                                sb.d_Yall, N, ldn, G, qnan, qnan);
@@ -1552,9 +1585,14 @@ int eqb_finalize(eqb_ctx *ctx)
   // analysed genes (eqtlbma_bf.cpp:747-762) from per-subgroup prefix counts of genotyped SNPs
   ctx->analyzed.assign(G, 0);
   {
-    std::vector<std::vector<int> > cum(S, std::vector<int>(M + 1, 0));
-    for (int s = 0; s < S; ++s)
-      for (long long m = 0; m < M; ++m) cum[s][m + 1] = cum[s][m] + (ctx->subs[s].snp_has[m] ? 1 : 0);
+    // (prefix counts only for the subgroups whose genotype file lacks some SNP)
+    std::vector<std::vector<int> > cum(S);
+    for (int s = 0; s < S; ++s) {
+      const std::vector<uint8_t> &sh = ctx->subs[s].snp_has;
+      if (M > 0 && memchr(sh.data(), 0, (size_t)M) == nullptr) continue; // every SNP genotyped
+      cum[s].assign(M + 1, 0);
+      for (long long m = 0; m < M; ++m) cum[s][m + 1] = cum[s][m] + (sh[m] ? 1 : 0);
+    }
     for (long long g = 0; g < G; ++g) {
       bool any = false, all_exp = true;
       for (int s = 0; s < S; ++s) {
@@ -1562,7 +1600,7 @@ int eqb_finalize(eqb_ctx *ctx)
           all_exp = false;
           continue;
         }
-        if (ctx->ce[g] > ctx->cb[g] && cum[s][ctx->ce[g]] - cum[s][ctx->cb[g]] > 0) any = true;
+        if (ctx->ce[g] > ctx->cb[g] && (cum[s].empty() || cum[s][ctx->ce[g]] - cum[s][ctx->cb[g]] > 0)) any = true;
       }
       if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model != EQB_ERROR_UVLR && !all_exp) any = false;
       ctx->analyzed[g] = any ? 1 : 0;

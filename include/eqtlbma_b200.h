@@ -137,6 +137,8 @@ int eqb_set_genotypes(eqb_ctx *ctx, int32_t geno_id, const double *G, int64_t n_
  * shrinks 8x / 4x.  Same lifetime and asynchrony rules as eqb_set_genotypes(). */
 int eqb_set_genotypes_fixed(eqb_ctx *ctx, int32_t geno_id, const void *G, int32_t elem_bytes, double denom,
                             int64_t n_snps, int32_t n_cols);
+/* The expression matrix sg->Y is uploaded asynchronously too: it must stay valid and unchanged until
+ * eqb_finalize() has returned (the small arrays of the struct are copied before eqb_set_subgroup returns). */
 int eqb_set_subgroup(eqb_ctx *ctx, int32_t s, const eqb_subgroup *sg);
 /* Grid (grid.cpp:28-65): phi2/oma2 columns of --gridL (L points) and --gridS (K points). */
 int eqb_set_grids(eqb_ctx *ctx, const double *phi2L, const double *oma2L, int32_t L,
