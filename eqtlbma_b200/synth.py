@@ -66,6 +66,7 @@ class Dataset:
     anchor: str = "TSS"
     radius: int = 100000
     maf: np.ndarray | None = None  # [n_genos][M] folded MAF as the reference computes it
+    geno_format: str = "custom"  # "custom" (dose matrix + --scoord BED), "vcf" or "impute" (hard calls only)
 
     @property
     def n_all(self):
@@ -122,6 +123,31 @@ class Dataset:
             f"{self.chr_names[self.snp_chr[m]]}\t{int(self.snp_pos[m]) - 1}\t{int(self.snp_pos[m])}\t{self.snp_names[m]}"
             for m in range(self.n_snps)])
         for gi, G in enumerate(self.genos):
+            if self.geno_format == "vcf":
+                # Snp::AddSubgroupFromVcfLine (snp.cpp:118-150): dosage = number of "1" alleles of GT
+                lines = ["##fileformat=VCFv4.1", "##source=eqtlbma_b200.synth",
+                         "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(self.geno_samples[gi])]
+                gts = (("0|0", "0|1", "1|1"), ("0/0", "1/0", "1/1"))
+                for m in range(self.n_snps):
+                    if np.all(np.isnan(G[m])):
+                        continue
+                    extra = m % 2  # every other line carries a second FORMAT field before GT
+                    cells = [("7:" if extra else "") + gts[(m + i) % 2][int(v)] for i, v in enumerate(G[m])]
+                    lines.append(f"{self.chr_names[self.snp_chr[m]]}\t{int(self.snp_pos[m])}\t{self.snp_names[m]}\tA\tG\t.\tPASS\t.\t"
+                                 + ("DP:GT" if extra else "GT") + "\t" + "\t".join(cells))
+                w(f"genotypes_{gi}.txt.gz", lines)
+                continue
+            if self.geno_format == "impute":
+                # Snp::AddSubgroupFromImputeLine (snp.cpp:152-185): dosage = P(a1a2) + 2 P(a2a2)
+                lines = ["chr name coord a1 a2 " + " ".join(f"{s}_a1a1 {s}_a1a2 {s}_a2a2" for s in self.geno_samples[gi])]
+                trip = ("1 0 0", "0 1 0", "0 0 1")
+                for m in range(self.n_snps):
+                    if np.all(np.isnan(G[m])):
+                        continue
+                    lines.append(f"{self.chr_names[self.snp_chr[m]]} {self.snp_names[m]} {int(self.snp_pos[m])} A G "
+                                 + " ".join(trip[int(v)] for v in G[m]))
+                w(f"genotypes_{gi}.txt.gz", lines)
+                continue
             lines = ["id\t" + "\t".join(self.geno_samples[gi])]
             for m in range(self.n_snps):
                 if np.all(np.isnan(G[m])):
@@ -158,8 +184,10 @@ class Dataset:
 
     def ref_args(self, d: str, out_prefix: str):
         """Command-line arguments of the reference eqtlbma_bf for the files of write_files()."""
-        a = ["--geno", f"{d}/list_genotypes.txt", "--scoord", f"{d}/snp_coords.bed.gz",
-             "--exp", f"{d}/list_phenotypes.txt", "--gcoord", f"{d}/gene_coords.bed.gz",
+        a = ["--geno", f"{d}/list_genotypes.txt"]
+        if self.geno_format == "custom":
+            a += ["--scoord", f"{d}/snp_coords.bed.gz"]
+        a += ["--exp", f"{d}/list_phenotypes.txt", "--gcoord", f"{d}/gene_coords.bed.gz",
              "--anchor", self.anchor, "--cis", str(self.radius), "--out", out_prefix,
              "--gridL", f"{d}/grid_phi2_oma2_general.txt.gz",
              "--gridS", f"{d}/grid_phi2_oma2_with-configs.txt.gz"]
@@ -176,7 +204,8 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
                  n_cov=0, cov_per_subgroup=False, ragged=False, ragged_min_frac=0.4, absent_gene_frac=0.0, nan_frac=0.0,
                  dosage=False, maf=0.3, gridL=None, gridS=None, radius=None, anchor="TSS",
                  null_frac=0.3, separate_geno_files=False, missing_geno_frac=0.0,
-                 pad_names=False, monomorphic_frac=0.0, gene_spacing=1000, far_snp=True) -> Dataset:
+                 pad_names=False, monomorphic_frac=0.0, gene_spacing=1000, far_snp=True,
+                 geno_format="custom") -> Dataset:
     """Generate a dataset. One SNP stream per chromosome at uniform spacing; each gene's +-radius
     TSS window holds ~snps_per_gene SNPs; expression y = mu_s + b_s*g + N(0,1) with ES-model
     effects from the first cis SNP of the gene (simul_flutre_et_al.cpp:682-743)."""
@@ -263,7 +292,7 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
                  snp_names=snp_names, snp_chr=snp_chr, snp_pos=snp_pos,
                  snp_bed_start=snp_pos - 1, gene_names=gene_names, gene_chr=gene_chr,
                  gene_start=gene_start, gene_end=gene_end, chr_names=chr_names, gridL=gridL,
-                 gridS=gridS, anchor=anchor, radius=radius, maf=maf_arr)
+                 gridS=gridS, anchor=anchor, radius=radius, maf=maf_arr, geno_format=geno_format)
     beg, end = ds.cis_windows()
 
     # effects

@@ -52,6 +52,13 @@ SCENARIOS = {
     # degenerate inputs: monomorphic SNPs (rank-deficient designs)
     "monomorphic": dict(data=dict(BASE, seed=81, monomorphic_frac=0.3, snps_per_gene=4), analysis="join",
                         bfs="all", wrtsize=3),
+    # genotype decoders other than the custom dose matrix (data_loader.cpp:570-1010, snp.cpp:118-185): no --scoord,
+    # coordinates come from the genotype files themselves
+    "vcf_input": dict(data=dict(BASE, seed=101, snps_per_gene=3, geno_format="vcf", separate_geno_files=True,
+                                missing_geno_frac=0.1), analysis="join", bfs="all", wrtsize=4,
+                      perm=dict(nperm=30, pbf="all", seed=8)),
+    "impute_input": dict(data=dict(BASE, seed=102, snps_per_gene=3, n_cov=2, geno_format="impute"), analysis="join",
+                         bfs="sin", wrtsize=10),
     # TSS+TES anchor
     "anchor_tss_tes": dict(data=dict(BASE, seed=91, anchor="TSS+TES", radius=150, snps_per_gene=3),
                            analysis="join", bfs="gen", wrtsize=10),
