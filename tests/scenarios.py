@@ -64,6 +64,28 @@ SCENARIOS = {
                            analysis="join", bfs="gen", wrtsize=10),
 }
 
+# Front-end filters (command line only: they change what the loader hands to the hot path, so these have the
+# reference's text outputs as golden but no engine-level dump test): --sbgrp, --maf, --snp
+# (--outm is declared by the reference's option table but never handled: eqtlbma_bf.cpp:275 falls through to the help text)
+CLI_SCENARIOS = {
+    "cli_sbgrp_maf": dict(data=dict(BASE, seed=111, snps_per_gene=4, maf=0.25), analysis="join", bfs="sin",
+                          wrtsize=10, extra=["--sbgrp", "s1+s3", "--maf", "0.24"]),
+    "cli_snp_list": dict(data=dict(BASE, seed=112, snps_per_gene=4), analysis="sep", bfs="gen", wrtsize=10,
+                         snp_list_every=2),
+}
+
+
+def cli_extra(sc, ds, d):
+    """Extra command-line flags of a CLI-only scenario; writes the --snp list next to the input files."""
+    f = list(sc.get("extra", []))
+    k = sc.get("snp_list_every")
+    if k:
+        path = f"{d}/snps_to_keep.txt"
+        with open(path, "w") as fh:
+            fh.write("\n".join(ds.snp_names[::k]) + "\n")
+        f += ["--snp", path]
+    return f
+
 
 def build_dataset(sc):
     return make_dataset(**sc["data"])

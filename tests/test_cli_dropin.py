@@ -11,7 +11,7 @@ import subprocess
 
 import pytest
 
-from scenarios import SCENARIOS, build_dataset, ref_flags
+from scenarios import CLI_SCENARIOS, SCENARIOS, build_dataset, cli_extra, ref_flags
 from test_oracle_vs_reference import GOLD
 
 pytestmark = pytest.mark.gpu
@@ -49,12 +49,12 @@ def test_cli_parallel_encoder_is_byte_identical_after_gunzip(tmp_path, name):
 def _run_and_compare(tmp_path, name, threads):
     if not os.path.exists(EXE):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "eqtlbma_b200", "host")])
-    sc = SCENARIOS[name]
+    sc = SCENARIOS.get(name) or CLI_SCENARIOS[name]
     ds = build_dataset(sc)
     d = str(tmp_path / "in")
     ds.write_files(d)
     out = str(tmp_path / "obs")
-    cmd = [EXE] + ds.ref_args(d, out) + ref_flags(sc) + ["-v", "0", "--thread", str(threads)]
+    cmd = [EXE] + ds.ref_args(d, out) + ref_flags(sc) + cli_extra(sc, ds, d) + ["-v", "0", "--thread", str(threads)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     gold = json.loads(gzip.open(os.path.join(GOLD, name + ".text.json.gz"), "rt").read())

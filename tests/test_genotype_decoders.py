@@ -5,6 +5,7 @@ files: data_loader.cpp:570-1010, snp.cpp:118-185).  Outputs are compared with th
 outputs on the same files (tests/golden/{vcf,impute}_input.text.json.gz)."""
 import pytest
 
+from scenarios import CLI_SCENARIOS
 from test_cli_dropin import DECODERS, _run_and_compare
 
 pytestmark = pytest.mark.gpu
@@ -12,4 +13,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("name", sorted(DECODERS))
 def test_cli_reads_vcf_and_impute_like_the_reference(tmp_path, name):
+    _run_and_compare(tmp_path, name, threads=1)
+
+
+@pytest.mark.parametrize("name", sorted(CLI_SCENARIOS))
+def test_cli_loader_filters_like_the_reference(tmp_path, name):
+    """--sbgrp / --maf / --snp (eqtlbma_bf.cpp:130,193-198): loader-side filters ahead of the hot path."""
     _run_and_compare(tmp_path, name, threads=1)
