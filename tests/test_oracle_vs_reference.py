@@ -131,3 +131,18 @@ def test_oracle_matches_reference_dump(oracle_lib, name):
     perm = eng.run_permutations(**pk) if pk else None
     check_against_dump(eng, ds, sc, dump, res, perm)
     eng.close()
+
+
+def test_cli_only_goldens_belong_to_the_current_generator():
+    """The command-line-only scenarios (loader filters) have no dump; their text goldens must still come from
+    the dataset the generator produces today and from the flags the GPU drop-in test will pass."""
+    import gzip
+
+    from scenarios import CLI_SCENARIOS, ref_flags
+
+    for name, sc in CLI_SCENARIOS.items():
+        ds = build_dataset(sc)
+        assert dataset_digest(ds) == MANIFEST[name]["digest"], "synthetic data changed: regenerate the goldens"
+        assert MANIFEST[name]["flags"] == ref_flags(sc)
+        texts = json.loads(gzip.open(os.path.join(GOLD, name + ".text.json.gz"), "rt").read())
+        assert texts and all(len(t.splitlines()) > 1 for t in texts.values())
