@@ -11,7 +11,6 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
-#include "math_tables.cuh"
 
 namespace eqb {
 
@@ -23,7 +22,7 @@ __device__ __forceinline__ double lgam_corr(double z)
 }
 
 // ln[Gamma(a+b) / (Gamma(a) Gamma(b))] without cancelling three large lgamma values
-__device__ __noinline__ double ln_inv_beta(double a, double b)
+static __device__ __noinline__ double ln_inv_beta(double a, double b)
 {
   if (a < b) {
     const double t = a;
@@ -39,7 +38,7 @@ __device__ __noinline__ double ln_inv_beta(double a, double b)
 }
 
 // continued fraction of the incomplete beta function, modified Lentz
-__device__ __noinline__ double beta_cf(double a, double b, double x)
+static __device__ __noinline__ double beta_cf(double a, double b, double x)
 {
   const double tiny = 1e-300, eps = 1e-16;
   const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
@@ -94,7 +93,7 @@ __device__ inline void beta_inc_pair(double a, double b, double x, double y, dou
 }
 
 // two-sided Student tail Pr(|T_nu| > |t|) and its complement
-__device__ __noinline__ void tdist_tails(double t, double nu, double &tail, double &central)
+static __device__ __noinline__ void tdist_tails(double t, double nu, double &tail, double &central)
 {
   const double t2 = t * t;
   if (t2 == 0.0) {
@@ -141,7 +140,7 @@ __device__ inline double fdist_Q(double x, double nu1, double nu2)
 }
 
 // gsl_cdf_ugaussian_Pinv: lower-tail standard normal quantile
-__device__ __noinline__ double ugaussian_Pinv(double P)
+static __device__ __noinline__ double ugaussian_Pinv(double P)
 {
   if (isnan(P)) return nan("");
   if (P <= 0.0) return (P == 0.0) ? -INFINITY : nan("");
@@ -280,47 +279,7 @@ __device__ __forceinline__ double exp10_fast_impl(double x)
   return p * __hiloint2double((n + 1023) << 20, 0);
 }
 
-// Table-driven forms (math_tables.cuh, generated by profiles/gen_math_tables.py): the argument reduction goes
-// through a 128-entry reciprocal / logarithm table (log) or a 64-entry 2^(j/64) table (exp10), which leaves a
-// degree-6 / degree-5 polynomial on |r| <= 2^-8 -- 9-10 FP64 operations instead of ~22, the same ~1e-16 accuracy
-// (the dropped terms are below 1e-17; checked by eqb_math_selftest against the library).
-__device__ __forceinline__ double log_tab(double x)
-{
-  const int hi = __double2hiint(x);
-  if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x); // zero, subnormal, negative, Inf, NaN
-  const int e = (hi >> 20) - 1023;
-  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x)); // [1, 2)
-  const double2 t = LOG_TAB[(hi >> 13) & 0x7f]; // {1/m_i, log m_i}, m_i the centre of the mantissa's 1/128 interval
-  const double r = fma(m, t.x, -1.0);           // |r| <= 2^-8
-  const double r2 = r * r;
-  const double q0 = fma(r, 1.0 / 3.0, -0.5), q1 = fma(r, 0.2, -0.25);
-  const double lp = fma(r2, fma(r2, fma(r2, -1.0 / 6.0, q1), q0), r); // log1p(r) to r^6
-  const double de = (double)e;
-  return fma(de, 6.93147180369123816490e-01, fma(de, 1.90821492927058770002e-10, t.y + lp)); // ln2 = hi + lo
-}
-__device__ __forceinline__ double exp10_tab(double x)
-{
-  if (!(x > -300.0 && x < 300.0)) return exp10(x); // also NaN
-  const double C_HI = 64.0 * 3.321928094887362182e+00, C_LO = 64.0 * 1.661617516973592e-16; // 64 log2(10)
-  const double magic = 6755399441055744.0; // 1.5 * 2^52
-  const double tm = fma(x, C_HI, magic);
-  const int k = __double2loint(tm); // rint(64 x log2 10)
-  const double kd = tm - magic;
-  double f = fma(x, C_HI, -kd);
-  f = fma(x, C_LO, f);                            // |f| <= 1/2, in units of 1/64 octave
-  const double g = f * (6.93147180559945309417e-01 / 64.0); // |g| <= 0.0055
-  const double g2 = g * g;
-  const double s = fma(g2, fma(g, 1.0 / 120.0, 1.0 / 24.0), fma(g, 1.0 / 6.0, 0.5));
-  const double T = EXP2_TAB[k & 63];
-  const double v = fma(T, fma(g2, s, g), T);      // 2^(j/64) e^g
-  return v * __hiloint2double(((k >> 6) + 1023) << 20, 0);
-}
-
-#if defined(EQB_TABLE_MATH)
-__device__ __forceinline__ double rcp_fast(double x) { return rcp_fast_impl(x); }
-__device__ __forceinline__ double log_fast(double x) { return log_tab(x); }
-__device__ __forceinline__ double exp10_fast(double x) { return exp10_tab(x); }
-#elif defined(EQB_SHORT_LATENCY_MATH)
+#if defined(EQB_SHORT_LATENCY_MATH)
 __device__ __forceinline__ double rcp_fast(double x) { return rcp_fast_impl(x); }
 __device__ __forceinline__ double log_fast(double x) { return log_fast_impl(x); }
 __device__ __forceinline__ double exp10_fast(double x) { return exp10_fast_impl(x); }

@@ -55,14 +55,14 @@ struct FastArgs {
   int *out_n;
   double *out_ss, *out_gen, *out_cfg, *out_w;
   int use_dmma;                // fast_pair_warp_kernel: phase A on the FP64 tensor cores
-  int delay_ns, delay_ctas, delay_sm; // timing experiment only (EQB_FASTW_DELAY_US)
-  int debug;                   // timing experiments only (EQB_FASTW_DEBUG): 1 no raw-value stores, 2 no phase A, 4 no phase C
+  int delay_ns, delay_ctas, delay_sm; // timing experiment only (-DEQB_TUNING, EQB_FASTW_DELAY_US)
+  int debug;                   // timing experiments only (-DEQB_TUNING, EQB_FASTW_DEBUG): 1 no raw-value stores, 2 no phase A, 4 no phase C
   long long n_tiles;           // fast_pair_warp_kernel: tiles of this launch
   const long long *tile_q0;    // [n_tiles + 1] first compact pair index of each tile (variable size, <= 32 pairs)
 };
 
 // ---------------------------------------------------------------- K1a
-__global__ void __launch_bounds__(32) prep_basis_kernel(const DevParams *__restrict__ prm_, double *const *Bs_all,
+static __global__ void __launch_bounds__(32) prep_basis_kernel(const DevParams *__restrict__ prm_, double *const *Bs_all,
                                                         const uint8_t *const *emask_all, int *__restrict__ n_out,
                                                         int *__restrict__ rankz_out, unsigned int *__restrict__ colvalid_out,
                                                         int *__restrict__ err_flag)
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(NW * 32) prep_x_dmma_kernel(const DevParams *_
 // subgroup on this path) as piecewise Chebyshev series fitted to the exact evaluation
 // (tdist_P + ugaussian_Pinv), |error| ~ 1e-13, so that the per-pair cost is one short Clenshaw
 // recurrence instead of a data-dependent continued fraction.  p-value = 2 Phi(z) = erfc(|z|/sqrt 2).
-__global__ void __launch_bounds__(TZ_NI * 16) build_tz_kernel(const double *__restrict__ nus, double *const *tz_all,
+static __global__ void __launch_bounds__(TZ_NI * 16) build_tz_kernel(const double *__restrict__ nus, double *const *tz_all,
                                                               double *__restrict__ wmax_out)
 {
   __shared__ double f[TZ_NI][16];
@@ -625,7 +625,7 @@ struct PairStat {
   double b, v, t;                          // standardised (gene_snp_pair.cpp:256-290)
 };
 
-__device__ __noinline__ void stats_from_dots(double xy, double xx, double xraw2, double xsum, double yy, double tss,
+static __device__ __noinline__ void stats_from_dots(double xy, double xx, double xraw2, double xsum, double yy, double tss,
                                              double ybar, int n, int Q, int rankz, const double *__restrict__ tz,
                                              double tz_nu, double tz_wmax, PairStat &o)
 {
@@ -862,7 +862,7 @@ __device__ __forceinline__ void contract_shared_x(const double *__restrict__ Xm,
 #ifndef EQB_FAST_MINB
 #define EQB_FAST_MINB 3 // resident CTAs per SM the register allocation is capped for
 #endif
-__global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const DevParams *__restrict__ prm_,
+static __global__ void __launch_bounds__(THREADS, EQB_FAST_MINB) fast_pair_kernel(const DevParams *__restrict__ prm_,
                                                             const FastParams *__restrict__ fp_, const FastArgs fa,
                                                             const GridTab gt)
 {
@@ -1339,11 +1339,16 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const long long tile = (long long)blockIdx.x * nwarp + warp;
   if (tile >= fa.n_tiles) return; // (no barrier anywhere below)
+#ifdef EQB_TUNING
   if (fa.delay_ns > 0 && (int)blockIdx.x < fa.delay_ctas) {
     // timing experiment (EQB_FASTW_DELAY_US): CTAs of the first wave that share an SM start out of phase
     const long long t_end = clock64() + (long long)(blockIdx.x / fa.delay_sm) * fa.delay_ns * 2; // ~2 cycles per ns
     while (clock64() < t_end) __nanosleep(2000);
   }
+  const int dbg = fa.debug;
+#else
+  constexpr int dbg = 0; // the phase-skipping switches of the timing experiments do not exist in the product build
+#endif
   const long long q0 = fa.tile_q0[tile];
   const int tn = (int)(fa.tile_q0[tile + 1] - q0); // 1 .. 32
   const long long C = (fa.which == 1) ? 0 : S;
@@ -1386,7 +1391,7 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
     bool same = true;
     for (int a = 1; a < sn; ++a) same = same && (prm.sub[s0 + a].X == prm.sub[s0].X);
     const FastSub *fsub = fp_->sub + s0;
-    if (fa.debug & 2) {
+    if (dbg & 2) {
       for (int i = lane; i < tn * sn; i += 32) xy[(size_t)(i / sn) * S + s0 + i % sn] = 0.1;
     } else if (DM) {
       contract_tile_dmma(prm.sub[s0].X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0);
@@ -1440,8 +1445,8 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
     }
   }
   __syncwarp();
-  if (!join || lane >= tn || (fa.debug & 4)) return;
-  const bool st_raw = !(fa.debug & 1);
+  if (!join || lane >= tn || (dbg & 4)) return;
+  const bool st_raw = !(dbg & 1);
   // ---------------- phase C: lane per pair
   const double *stj = st + (size_t)lane * sst;
   const unsigned long long mask = hasm[lane];

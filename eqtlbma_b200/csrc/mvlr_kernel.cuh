@@ -89,7 +89,7 @@ struct MvGene {       // per (gene, permutation), shared memory
 };
 
 // ABFs of one configuration over a grid; writes raw values (optional) and returns the weighted ABF
-__device__ __noinline__ double mvlr_config(const MvGene &G, int S, unsigned long long gamma, double k, const double *b0,
+static __device__ __noinline__ double mvlr_config(const MvGene &G, int S, unsigned long long gamma, double k, const double *b0,
                                            double alpha, const double *phi2, const double *oma2, int nk, int variant,
                                            double *raw_out)
 {

@@ -151,7 +151,7 @@ __device__ inline Lse warp_merge(Lse a)
 
 // CalcLog10AbfUvlr (gene_snp_pair.cpp:297-356) from the per-(grid point, subgroup) table
 // tab[(k*S+s)*3 + {0,1,2}] = { 1/(v+phi2), bhat/(v+phi2), single-subgroup log10 ABF }
-__device__ __noinline__ double abf_from_table(const double *tab_k, unsigned long long mask, double oma2)
+static __device__ __noinline__ double abf_from_table(const double *tab_k, unsigned long long mask, double oma2)
 {
   double num = 0.0, den = 0.0, sing = 0.0;
   while (mask) {
@@ -188,7 +188,7 @@ __device__ __forceinline__ void table_entry(double b, double v, double t, double
 }
 
 // direct evaluation for the consistent configuration (one use per grid point: no table)
-__device__ __noinline__ double abf_direct(const double *st, int S, unsigned long long mask, double phi2, double oma2)
+static __device__ __noinline__ double abf_direct(const double *st, int S, unsigned long long mask, double phi2, double oma2)
 {
   double num = 0.0, den = 0.0, sing = 0.0;
   while (mask) {

@@ -193,6 +193,19 @@ int64_t eqb_launch_count(const eqb_ctx *ctx);
  * n pseudo-random arguments: out5 = { rcp rel, log abs, log rel, exp10 rel, special-value mismatches }. */
 int eqb_math_selftest(int32_t device, int64_t n, double *out5);
 
+/* FP64 pipe peaks of the device measured with register-resident loops (the denominators of the FP64 rooflines,
+ * BASELINE.md section 1): out4 = { DFMA TFLOP/s, DMMA (mma.sync.m8n8k4.f64) TFLOP/s, implied SM clock in MHz, SMs }. */
+int eqb_measure_fp64_peaks(int32_t device, double *out4);
+/* Self-test + throughput of the TMA / DMMA product kernel of the permutation path on pseudo-random operands
+ * (n_rows genotype rows x n_cols operand rows of ldn doubles, ldn a multiple of 16):
+ * out3 = { worst |D - reference| / sum |terms|, TFLOP/s (CUDA events, best of 3), tiles }. */
+int eqb_selftest_perm_gemm(int32_t device, int64_t n_rows, int64_t n_cols, int32_t ldn, double *out3);
+/* Per-kernel device time of the permutation path (Gene::MakePermutations*, gene.cpp:380-717), for roofline accounting:
+ * enable before eqb_run_permutations*(); out8 = { prep ms, GEMM ms, BF ms, merge ms, GEMM flop issued, GEMM flop
+ * useful (rows x columns that belong to a (SNP, subgroup, permutation)), (SNP, permutation) items, path }. */
+int eqb_set_perm_timing(eqb_ctx *ctx, int32_t on);
+int eqb_last_perm_timing(const eqb_ctx *ctx, double *out8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,8 +2,8 @@
  * the split K1/K2+K3 fast path and the general fused kernel are two independent implementations of
    the same statistics: they must agree on every pair of a large workload;
  * results do not depend on how genes are sharded (gene ranges processed separately = all at once);
- * permutation statistics are invariant to the chunking of the permutation dimension and the DMMA
-   permutation kernel agrees with the general kernel (exceedance counts identical)."""
+ * permutation statistics do not depend on the sharding either, and the batched-GEMM permutation path agrees
+   with the CPU oracle when every permutation changes the kept rows (ragged individuals with covariates)."""
 import os
 
 import numpy as np
@@ -58,16 +58,18 @@ def test_results_independent_of_gene_sharding(cuda_lib):
     assert np.array_equal(np.concatenate([p.perm_stats for p in pparts]), pfull.perm_stats, equal_nan=True)
 
 
-def test_dmma_permutation_kernel_equals_general_kernel(cuda_lib):
+def test_gemm_permutation_path_matches_oracle_with_covariates(cuda_lib, oracle_lib):
+    """Ragged individuals WITH covariates: every permutation changes the kept rows of every subgroup, so the
+    per-(gene, permutation) bases are rebuilt (perm_prep_kernel, general case) and x~'x~ comes from the Gram form of
+    the batched GEMM; against the CPU oracle."""
     import eqtlbma_b200
-    ds = _ds(n_genes=60, n_subgroups=5, n_inds=200, n_cov=3, ragged=True, snps_per_gene=30)
+    from eqtlbma_b200._capi import Engine as AnyEngine
+    ds = _ds(n_genes=30, n_subgroups=5, n_inds=200, n_cov=3, ragged=True, snps_per_gene=30)
     eng = eqtlbma_b200.Engine(ds, analysis="join", bfs="sin")
+    ora = AnyEngine(oracle_lib, "eqo_", ds, analysis="join", bfs="sin")
     a = eng.run_permutations(64, 7, pbf="gen-sin", wrtsize=7)
-    os.environ["EQB_NO_PERM_DMMA"] = "1"
-    try:
-        b = eng.run_permutations(64, 7, pbf="gen-sin", wrtsize=7)
-    finally:
-        del os.environ["EQB_NO_PERM_DMMA"]
+    b = ora.run_permutations(64, 7, pbf="gen-sin", wrtsize=7)
+    assert eng.last_perm_timing()["path"] == 1
     assert np.array_equal(a.count, b.count)
     assert np.allclose(a.perm_stats, b.perm_stats, rtol=0, atol=1e-8, equal_nan=True)
     assert np.allclose(a.true_stat, b.true_stat, rtol=0, atol=1e-8, equal_nan=True)
@@ -128,8 +130,7 @@ def test_subgroup_specific_covariates_match_oracle(cuda_lib, oracle_lib, n_sub, 
 def test_upload_pipeline_matches_plain_path(cuda_lib, analysis, bfs, monkeypatch):
     """Enough SNPs for the chunked upload pipeline (genes finish in genotype-chunk order and their results
     are scattered into PINNED host arrays by a kernel): bit-identical to the plain path (pageable arrays,
-    DMA copy, gene order), for the whole range and for a sub-range of genes, and to a run with the
-    pipeline disabled."""
+    DMA copy, gene order), for the whole range and for a sub-range of genes."""
     import eqtlbma_b200
     from eqtlbma_b200.synth import make_dataset
     ds = make_dataset(seed=21, n_subgroups=3, n_inds=40, n_genes=700, snps_per_gene=14, n_cov=2, cov_per_subgroup=True,
@@ -156,11 +157,6 @@ def test_upload_pipeline_matches_plain_path(cuda_lib, analysis, bfs, monkeypatch
     if plain.abf_w is not None:
         assert np.array_equal(first.abf_w, plain.abf_w, equal_nan=True)
     eng2.close()
-    monkeypatch.setenv("EQB_NO_PIPELINE", "1")
-    eng3 = eqtlbma_b200.Engine(ds, analysis=analysis, bfs=bfs)
-    off_run = eng3.run(out=eng3.alloc_results(pinned=True))
-    assert np.array_equal(off_run.sstats, plain.sstats, equal_nan=True)
-    eng3.close()
 
 
 @pytest.mark.gpu
