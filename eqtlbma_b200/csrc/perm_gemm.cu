@@ -82,6 +82,7 @@ struct Perm2State {
   Buf<unsigned int> sc_colvalid;
   Buf<uint8_t> complete;
   Buf<long long> lls; // drow0 | mg
+  Buf<unsigned long long> counter; // next BF task (persistent warps)
   Buf<PgTile> tiles;
   Buf<BfTask> tasks;
   Buf<BfPartial> part;
@@ -112,6 +113,7 @@ void perm2_destroy(Perm2State *st, cudaStream_t s)
   st->sc_colvalid.release(s);
   st->complete.release(s);
   st->lls.release(s);
+  st->counter.release(s);
   st->tiles.release(s);
   st->tasks.release(s);
   st->part.release(s);
@@ -158,10 +160,24 @@ static bool build_grid(const Perm2Env &env, PermGrid &pg)
       }
   }
   pg.ustart[uphi.size()] = (unsigned char)n;
-  for (int k = 0; k < K; ++k) {
-    pg.phiS[k] = pS[k];
-    pg.omaS[k] = oS[k];
+  // gridS grouped by phi2 + oma2 (the singleton configurations share one logarithm per group)
+  std::vector<double> utot;
+  for (int k = 0; k < K; ++k)
+    if (std::find(utot.begin(), utot.end(), pS[k] + oS[k]) == utot.end()) utot.push_back(pS[k] + oS[k]);
+  n = 0;
+  for (size_t u = 0; u < utot.size(); ++u) {
+    pg.utot[u] = utot[u];
+    pg.tstart[u] = (unsigned char)n;
+    for (int k = 0; k < K; ++k)
+      if (pS[k] + oS[k] == utot[u]) {
+        pg.phiS[n] = pS[k];
+        pg.omaS[n] = oS[k];
+        pg.kS[n] = (unsigned char)k;
+        ++n;
+      }
   }
+  pg.tstart[utot.size()] = (unsigned char)n;
+  pg.UT = (int)utot.size();
   for (int k = 0; k <= S && k < PGR_S; ++k) pg.size_weight[k] = env.hp->size_weight[k];
   pg.size_weight[0] = 0.0;
   pg.UG = (int)uphi.size();
@@ -339,8 +355,10 @@ int perm2_eval(Perm2State *st, const Perm2Env &env, const int *genes, const int 
     {
       const int ncg = (PB + 31) / 32;
       const double units = (double)rows * ncg;
-      int chunk = (int)std::ceil(units / (32.0 * env.n_sm));
-      chunk = std::max(which == 3 ? 1 : 4, std::min(chunk, 256));
+      // fixed chunk lengths: the merge order of the chunk partials (hence the last bits of a statistic) must not
+      // depend on which other genes share the batch (results independent of the sharding)
+      (void)units;
+      const int chunk = (join && which == 3) ? 4 : 16;
       for (int il = 0; il < n_items; ++il) {
         const int g = h_genes[il];
         const long long mb = env.cb[g], me = env.ce[g];
@@ -369,6 +387,7 @@ int perm2_eval(Perm2State *st, const Perm2Env &env, const int *genes, const int 
     P2CK(st->tiles.ensure(h_tiles.size(), sm));
     P2CK(st->tasks.ensure(n_tasks, sm));
     P2CK(st->part.ensure(n_tasks * 32, sm));
+    P2CK(st->counter.ensure(1, sm));
     if (stat_kind == STAT_SEP_PER) P2CK(st->part_sep.ensure(n_tasks * 2 * S * 32, sm));
     P2CK(st->sc_n.ensure(sc_count, sm));
     P2CK(st->sc_rankz.ensure(sc_count, sm));
@@ -466,14 +485,18 @@ int perm2_eval(Perm2State *st, const Perm2Env &env, const int *genes, const int 
       {
         // tasks of column groups past the batch's last column do nothing useful but are cheap to skip in-kernel:
         // restrict the grid instead (tasks are ordered item, column group, chunk -> not contiguous): keep them all
-        const unsigned grid = (unsigned)((n_tasks + bw - 1) / bw);
         const size_t smem = (size_t)bw * bf_warp_doubles(S, pb.which, stat_kind) * sizeof(double);
+        int occ = 1;
+        if (pb.which == 3) P2CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, perm_bf_kernel<true>, bw * 32, smem));
+        else P2CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, perm_bf_kernel<false>, bw * 32, smem));
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n_tasks + bw - 1) / bw, (size_t)env.n_sm * std::max(occ, 1)));
+        P2CK(cudaMemsetAsync(st->counter.p, 0, sizeof(unsigned long long), sm));
         if (pb.which == 3)
-          perm_bf_kernel<true><<<grid, bw * 32, smem, sm>>>(env.d_prm, env.d_fp, pb, pg, st->tasks.p, (long long)n_tasks, bw, st->part.p,
-                                                            st->part_sep.p);
+          perm_bf_kernel<true><<<grid, bw * 32, smem, sm>>>(env.d_prm, env.d_fp, pb, pg, st->tasks.p, (long long)n_tasks, bw,
+                                                            st->counter.p, st->part.p, st->part_sep.p);
         else
-          perm_bf_kernel<false><<<grid, bw * 32, smem, sm>>>(env.d_prm, env.d_fp, pb, pg, st->tasks.p, (long long)n_tasks, bw, st->part.p,
-                                                             st->part_sep.p);
+          perm_bf_kernel<false><<<grid, bw * 32, smem, sm>>>(env.d_prm, env.d_fp, pb, pg, st->tasks.p, (long long)n_tasks, bw,
+                                                             st->counter.p, st->part.p, st->part_sep.p);
         st->last.bf_items += rows * pb.PB;
       }
       if (tm) P2CK(cudaEventRecord(st->ev[3], sm));

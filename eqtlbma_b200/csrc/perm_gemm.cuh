@@ -262,9 +262,12 @@ struct PermGrid { // kernel parameter (constant bank): the "gen" row of gridL gr
   double omaL[PGR_L];       // oma2 of gen-row entry i (grouped order)
   double phiS[PGR_K], omaS[PGR_K];
   double size_weight[PGR_S]; // (1/S)(1/choose(S, size)); [0] = 0 (the empty configuration is not part of the model)
+  double utot[PGR_K];       // unique values of phi2 + oma2 on gridS; phiS / omaS / kS are stored grouped by them
   unsigned char ustart[PGR_U + 1];
   unsigned char kL[PGR_L];  // grid point k of entry i (element 0 carries the NaN rule of log10_weighted_sum)
-  int UG, L, K;
+  unsigned char tstart[PGR_K + 1];
+  unsigned char kS[PGR_K];  // grid point k of gridS entry i
+  int UG, L, K, UT;
 };
 
 struct PermBatch {
@@ -501,34 +504,59 @@ struct BfPartial {
   int flags;       // bit 0: the first SNP's value is NaN, bit 1: at least one value accumulated
 };
 
-constexpr int PBF_SA = 3; // subgroups of the low part of a configuration (2^3 subsets tabulated in shared memory)
+constexpr int PBF_SA = 3; // subgroups of the low part of a configuration (their 2^3 subset sums live in registers)
 
-// shared memory (doubles) of one warp of perm_bf_kernel: st[3S][32] + lo[8][3][32] + hi[SB][3][32] (--pbf all) + sep[2S][32]
+// shared memory (doubles) of one warp of perm_bf_kernel: st[3S][32] + hi[S-3][3][32] (--pbf all) + sep[2S][32]
 __host__ __device__ inline size_t bf_warp_doubles(int S, int which, int stat_kind)
 {
   size_t d = (size_t)3 * S * 32;
-  if (which == 3) d += (size_t)(1 << PBF_SA) * 3 * 32 + (size_t)(S > PBF_SA ? S - PBF_SA : 0) * 3 * 32;
+  if (which == 3) d += (size_t)(S > PBF_SA ? S - PBF_SA : 0) * 3 * 32;
   if (stat_kind == STAT_SEP_PER) d += (size_t)2 * S * 32;
   return d;
 }
 
-// exp(x) for x <= ~700 (lower clamp only; callers exclude NaN): 2^(k/16) = 2^(k >> 4) * tab[k & 15], remainder
-// |g| <= ln2/32 through a degree-4 polynomial: relative error < 6e-11
-__device__ __forceinline__ double exp_tab16(double x, const double *__restrict__ tab)
+// ---------------------------------------------------------------- throughput-oriented elementary functions
+// The BF kernel is bound by the FP64 pipe and the issue slots, every lane runs the same instruction stream, and a
+// log10 BF needs 1e-8 ABSOLUTE accuracy: the CUDA library's log / exp10 / division (full range, < 1 ulp) are replaced by
+// table + short-polynomial forms good to ~1e-12 (16-entry tables in shared memory: entry j occupies its own bank
+// pair, so a warp's 32 independent lookups never conflict).
+struct BfTabs {
+  double exp16[16];  // 2^(j/16)
+  double2 log16[16]; // { 1/m_j, ln m_j }, m_j = 1 + (j + 1/2)/16
+};
+
+// e^x.  FPCLAMP: any x (-inf, NaN -> ~1e-304); otherwise x must be finite with |x| < 1e7 (integer clamp of the binary
+// exponent: results below 2^-1000 come out as ~1e-301, i.e. zero for every sum they enter)
+template <bool FPCLAMP>
+__device__ __forceinline__ double exp_tab16(double x, const BfTabs &T)
 {
-  x = fmax(x, -700.0);
+  if (FPCLAMP) x = fmax(x, -700.0);
   const double magic = 6755399441055744.0; // 1.5 * 2^52
   const double tm = fma(x, 23.083120654223414, magic); // 16 / ln 2
   const int k = __double2loint(tm);
   const double kd = tm - magic;
-  const double gg = fma(kd, -0.043321698784996581, x); // ln 2 / 16
+  const double gg = fma(kd, -0.043321698784996581, x); // ln 2 / 16: |gg| <= ln2/32
   const double g2 = gg * gg;
   double s = fma(gg, 1.0 / 24.0, 1.0 / 6.0);
   s = fma(gg, s, 0.5);
-  const double pp = fma(g2, s, gg);
-  const double T = tab[k & 15];
-  const double v = fma(T, pp, T);
-  return __hiloint2double(__double2hiint(v) + ((k >> 4) << 20), __double2loint(v));
+  const double pp = fma(g2, s, gg); // e^g - 1 to g^4: relative error < 4e-11
+  const double tj = T.exp16[k & 15];
+  const double v = fma(tj, pp, tj);
+  const int e2 = FPCLAMP ? (k >> 4) : max(k >> 4, -1000);
+  return __hiloint2double(__double2hiint(v) + (e2 << 20), __double2loint(v));
+}
+template <bool FPCLAMP>
+__device__ __forceinline__ double exp10_tab16(double x, const BfTabs &T)
+{
+  return exp_tab16<FPCLAMP>(x * 2.302585092994045684, T);
+}
+
+// 1/x for a positive normal x: MUFU seed + one Newton step (relative error < 1e-12)
+__device__ __forceinline__ double rcp_n(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return fma(r, fma(-x, r, 1.0), r);
 }
 
 // 1/sqrt(x), x normal positive: MUFU seed + one Newton step (relative error ~4e-13)
@@ -541,10 +569,91 @@ __device__ __forceinline__ double rsqrt_newton1(double x)
   return fma(0.5 * y, e, y);
 }
 
+// ln x (absolute error < 2e-13 for normal positive x; everything else through the library)
+__device__ __forceinline__ double log_tab16(double x, const BfTabs &T)
+{
+  const int hi = __double2hiint(x);
+  if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x); // zero, subnormal, negative, Inf, NaN
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x)); // [1, 2)
+  const double2 t = T.log16[(hi >> 16) & 15];
+  const double r = fma(m, t.x, -1.0); // |r| <= 1/33
+  double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+  p = fma(r, p, 0.2);
+  p = fma(r, p, -0.25);
+  p = fma(r, p, 1.0 / 3.0);
+  p = fma(r, p, -0.5);
+  const double lp = fma(r * r, p, r); // log1p(r) to r^7
+  return fma((double)((hi >> 20) - 1023), 0.69314718055994530942, t.y + lp);
+}
+
+// log10_weighted_sum accumulated online (utils_math.cpp:100-131) with the table exponential
+struct LseTab {
+  double m, acc;
+  bool poisoned;
+  __device__ __forceinline__ void init()
+  {
+    m = -INFINITY;
+    acc = 0.0;
+    poisoned = false;
+  }
+  __device__ __forceinline__ void add(double v, double w, bool is_first, const BfTabs &T)
+  {
+    if (v != v) {
+      poisoned = poisoned || is_first;
+      return;
+    }
+    const double d = v - m; // +inf on the first element
+    const bool up = d > 0.0;
+    const double e = exp10_tab16<true>(up ? -d : d, T);
+    acc = up ? fma(acc, e, w) : fma(w, e, acc);
+    m = up ? v : m;
+  }
+  __device__ __forceinline__ double result(const BfTabs &T) const
+  {
+    if (poisoned) return nan("");
+    double r = m + log_tab16(acc, T) * EQB_INV_LN10;
+    if (fabs(r) <= DBL_EPSILON) r = 0.0;
+    return r;
+  }
+};
+
+// Standardised statistics of one (SNP, subgroup, column) in the regular case -- full-rank design, residual sum of
+// squares > 0, tabulated t -> z map valid -- with b = sign(x~'y~) |z| / sqrt(x~'x~), v = 1 / x~'x~, t = z
+// (gene_snp_pair.cpp:256-290 after substituting se = sigmahat / sqrt(x~'x~): sigmahat cancels).  |t|^2 / nu =
+// ess / rss, so w^2 = nu log1p(t^2 / nu) = -nu log(rss / yy).  Returns false for everything else (NaN rules, rank
+// deficiency, far tail): the caller then takes stats_from_dots.
+__device__ __forceinline__ bool stats_lean(double xy, double xx, double xraw2, double yy, int n, int Q, int rankz,
+                                           const double *__restrict__ tz, double tz_nu, double tz_wmax, const BfTabs &T,
+                                           double &b, double &v, double &t)
+{
+  const double nu = (double)(n - 2 - Q);
+  if (tz == nullptr || n < Q + 3 || rankz != Q + 1 || nu != tz_nu || !(xraw2 > 0.0) || !(xx > 1e-24 * xraw2) || !(yy > 0.0))
+    return false;
+  const double ixx = rcp_n(xx);
+  const double ess = xy * xy * ixx;
+  const double rss = yy - ess;
+  if (!(rss > 0.0)) return false;
+  double w2 = -nu * log_tab16(rss * rcp_n(yy), T);
+  w2 = (w2 > 0.0) ? w2 : 0.0;
+  const double w = (w2 > 0.0) ? w2 * rsqrt_newton1(w2) : 0.0;
+  if (!(w < tz_wmax)) return false;
+  const double z = (w > 0.0) ? -w * tz_eval(tz, w) : 0.0;
+  if (fabs(z) > 1e-8) {
+    const double sbh = fabs(z) * rsqrt_newton1(xx); // |z| / sqrt(x~'x~)
+    b = (xy < 0.0) ? -sbh : sbh;
+    v = ixx;
+  } else {
+    b = 0.0;
+    v = INFINITY;
+  }
+  t = z;
+  return true;
+}
+
 // log-domain evaluation of the BMA over all configurations for ONE lane (fallback of the linear-domain form: NaN /
 // infinite statistics, or a sum outside the representable window); st = b, v, t of the lane, stride 32
-__device__ __noinline__ double bma_all_logdomain(const double *__restrict__ st, int S, unsigned long long has_mask,
-                                                 const PermGrid &pg)
+static __device__ __noinline__ double bma_all_logdomain(const double *__restrict__ st, int S, unsigned long long has_mask,
+                                                        const PermGrid &pg)
 {
   Lse bma;
   bma.init();
@@ -564,7 +673,7 @@ __device__ __noinline__ double bma_all_logdomain(const double *__restrict__ st, 
         num += bd;
         sing += sg;
       }
-      b.add(abf_from_sums(den, num, sing, pg.omaS[k]), 1.0 / (double)pg.K, k == 0);
+      b.add(abf_from_sums(den, num, sing, pg.omaS[k]), 1.0 / (double)pg.K, pg.kS[k] == 0);
     }
     // CalcBMA (gene_snp_pair.cpp:572-602); the order of the configurations does not matter for a weighted sum, except
     // for the NaN rule of element 0 (configuration "1" = subgroup 0 alone = cfg 1 here as well)
@@ -574,8 +683,9 @@ __device__ __noinline__ double bma_all_logdomain(const double *__restrict__ st, 
 }
 
 // explicit residual sum of squares of one genotype row against the basis rows kept in B (Gram form cancelled)
-__device__ __noinline__ void explicit_xx(const double *__restrict__ Xm, const double *__restrict__ brow0, size_t jstride, int Q,
-                                         unsigned int colvalid, int n, int ldn, double &xx, double &xraw2, double &xsum)
+static __device__ __noinline__ void explicit_xx(const double *__restrict__ Xm, const double *__restrict__ brow0, size_t jstride,
+                                                int Q, unsigned int colvalid, int n, int ldn, double &xx, double &xraw2,
+                                                double &xsum)
 {
   // row j of the basis: brow0 + j * jstride (row 0 = 0/1 mask, unit direction mask / sqrt(n))
   double h[MAXQ + 1], h2[MAXQ + 1];
@@ -613,273 +723,323 @@ __device__ __noinline__ void explicit_xx(const double *__restrict__ Xm, const do
   }
 }
 
+// Persistent warps: every warp draws tasks from a global counter (uniform cost per SNP, but the number of tasks is
+// not a multiple of the resident warps: a static grid left a fifth of the SM time idle in its last wave).
 template <bool ALLCFG>
-__global__ void __launch_bounds__(256) perm_bf_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
-                                                      const PermBatch pb, const __grid_constant__ PermGrid pg,
-                                                      const BfTask *__restrict__ tasks, long long n_tasks, int warps_per_cta,
-                                                      BfPartial *__restrict__ part, double *__restrict__ part_sep)
+__global__ void __launch_bounds__(256, 2) perm_bf_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
+                                                         const PermBatch pb, const __grid_constant__ PermGrid pg,
+                                                         const BfTask *__restrict__ tasks, long long n_tasks, int warps_per_cta,
+                                                         unsigned long long *__restrict__ next_task,
+                                                         BfPartial *__restrict__ part, double *__restrict__ part_sep)
 {
   const DevParams &prm = *prm_;
   extern __shared__ double bf_smem[];
-  __shared__ double exp_tab[16];
-  if (threadIdx.x < 16) exp_tab[threadIdx.x] = exp2((double)threadIdx.x / 16.0);
+  __shared__ BfTabs T;
+  if (threadIdx.x < 16) {
+    const double mj = 1.0 + ((double)threadIdx.x + 0.5) / 16.0;
+    T.exp16[threadIdx.x] = exp2((double)threadIdx.x / 16.0);
+    T.log16[threadIdx.x] = make_double2(1.0 / mj, log(mj));
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long task = (long long)blockIdx.x * warps_per_cta + warp;
-  if (warp >= warps_per_cta || task >= n_tasks) return;
-  const BfTask tk = tasks[task];
-  if (tk.c_lo >= pb.PB) return; // column group past the (shorter) last batch
+  if (warp >= warps_per_cta) return;
   const int S = prm.S, ldn = prm.ldn;
-  const int il = tk.il, c = tk.c_lo + lane; // this lane's column
-  const int g = pb.genes[il];
-  const bool col_ok = c < pb.PB;
-  const int cc = col_ok ? c : pb.PB - 1; // lanes past the last column repeat it (results dropped)
   const bool join = prm.analysis == 1;
   const int which = pb.which, kind = pb.stat_kind;
   double *wsm = bf_smem + (size_t)warp * bf_warp_doubles(S, which, kind);
-  double *st = wsm + lane;                       // st[(r * S + s) * 32]: r = 0 b, 1 v, 2 t
-  double *lo = wsm + (size_t)3 * S * 32 + lane;  // lo[(a * 3 + r) * 32]
+  double *st = wsm + lane;                         // st[(r * S + s) * 32]: r = 0 b, 1 v, 2 t
+  double *hi = wsm + (size_t)3 * S * 32 + lane;    // hi[(sbit * 3 + r) * 32]  (--pbf all)
   const int SA = (S < PBF_SA) ? S : PBF_SA, SB = S - SA;
-  double *hi = lo + (size_t)(1 << PBF_SA) * 3 * 32; // hi[(sbit * 3 + r) * 32]
   double *sepm = wsm + bf_warp_doubles(S, which, 0) + lane; // sepm[s * 32] minima, sepm[(S + s) * 32] NaN flags
-  const long long mbeg = prm.cis_begin[g];
-  const double *Drow = pb.D + (size_t)(pb.drow0[il] + (tk.m_begin - mbeg)) * pb.ldd + cc;
-  const size_t scb = (size_t)il * S * pb.PBpad + cc;
 
-  Lse acc_stat;
-  acc_stat.init();
-  double max_stat = -INFINITY, sep_all_min = 1.0;
-  bool first_nan = false;
-  int cnt_nonnan = 0;
-  if (kind == STAT_SEP_PER)
-    for (int s = 0; s < S; ++s) {
-      sepm[s * 32] = INFINITY;
-      sepm[(S + s) * 32] = 0.0;
-    }
+  while (true) {
+    unsigned long long t64 = 0;
+    if (lane == 0) t64 = atomicAdd(next_task, 1ull);
+    t64 = __shfl_sync(0xffffffffu, t64, 0);
+    if (t64 >= (unsigned long long)n_tasks) break;
+    const long long task = (long long)t64;
+    const BfTask tk = tasks[task];
+    if (tk.c_lo >= pb.PB) continue; // column group past the (shorter) last batch
+    const int il = tk.il, c = tk.c_lo + lane; // this lane's column
+    const int g = pb.genes[il];
+    const int cc = (c < pb.PB) ? c : pb.PB - 1; // lanes past the last column repeat it (results dropped)
+    const long long mbeg = prm.cis_begin[g];
+    const double *Drow = pb.D + (size_t)(pb.drow0[il] + (tk.m_begin - mbeg)) * pb.ldd + cc;
+    const size_t scb = (size_t)il * S * pb.PBpad + cc;
 
-  for (long long m = tk.m_begin; m < tk.m_end; ++m, Drow += pb.ldd) {
-    // ---- summary statistics + standardisation of every subgroup
-    unsigned long long has_mask = 0ull;
-    double snp_pmin = 1.0;
-    for (int s = 0; s < S; ++s) {
-      const SubDev &sb = prm.sub[s];
-      const FastSub &fs = fp_->sub[s];
-      const int n = pb.sc_n[scb + (size_t)s * pb.PBpad];
-      const bool have = (n > 0) && sb.snp_has[m];
-      PairStat ps;
-      ps.b = ps.v = ps.t = ps.pval = nan("");
-      if (have) {
-        const double *d = Drow + (size_t)pb.dbase[(size_t)il * S + s] * pb.PBpad;
-        const int Q = sb.Q;
-        double xy;
-        const int rankz = pb.sc_rankz[scb + (size_t)s * pb.PBpad];
-        double xx, r2, xsum;
-        if (pb.complete[(size_t)il * S + s]) {
-          const double *xs = fs.xstat + (size_t)m * 3; // K1c output: permutation-invariant
-          xy = d[0];
-          xx = xs[0];
-          r2 = xs[1];
-          xsum = xs[2];
-        } else {
-          xsum = d[0];
-          xy = d[(size_t)(Q + 1) * pb.PBpad];
-          r2 = d[(size_t)(Q + 2) * pb.PBpad];
-          double hh = xsum * xsum / (double)n;
-          for (int k = 1; k <= Q; ++k) {
-            const double h = d[(size_t)k * pb.PBpad];
-            hh = fma(h, h, hh);
+    Lse acc_stat;
+    acc_stat.init();
+    double max_stat = -INFINITY, sep_all_min = 1.0;
+    bool first_nan = false;
+    int cnt_nonnan = 0;
+    if (kind == STAT_SEP_PER)
+      for (int s = 0; s < S; ++s) {
+        sepm[s * 32] = INFINITY;
+        sepm[(S + s) * 32] = 0.0;
+      }
+
+    for (long long m = tk.m_begin; m < tk.m_end; ++m, Drow += pb.ldd) {
+      // ---- summary statistics + standardisation of every subgroup
+      unsigned long long has_mask = 0ull;
+      double snp_pmin = 1.0;
+      for (int s = 0; s < S; ++s) {
+        const SubDev &sb = prm.sub[s];
+        const FastSub &fs = fp_->sub[s];
+        const int n = pb.sc_n[scb + (size_t)s * pb.PBpad];
+        const bool have = (n > 0) && sb.snp_has[m];
+        double sb_b = nan(""), sb_v = nan(""), sb_t = nan(""), sb_p = nan("");
+        if (have) {
+          const double *d = Drow + (size_t)pb.dbase[(size_t)il * S + s] * pb.PBpad;
+          const int Q = sb.Q;
+          const int rankz = pb.sc_rankz[scb + (size_t)s * pb.PBpad];
+          double xy, xx, r2, xsum;
+          if (pb.complete[(size_t)il * S + s]) {
+            const double *xs = fs.xstat + (size_t)m * 3; // K1c output: permutation-invariant
+            xy = d[0];
+            xx = xs[0];
+            r2 = xs[1];
+            xsum = xs[2];
+          } else {
+            xsum = d[0];
+            xy = d[(size_t)(Q + 1) * pb.PBpad];
+            r2 = d[(size_t)(Q + 2) * pb.PBpad];
+            double hh = xsum * xsum / (double)n;
+            for (int k = 1; k <= Q; ++k) {
+              const double h = d[(size_t)k * pb.PBpad];
+              hh = fma(h, h, hh);
+            }
+            xx = r2 - hh;
+            if (r2 > 0.0 && xx < 1e-5 * r2) {
+              // Gram form cancelled (genotype nearly inside span([1, covariates]) on the kept rows): explicit CGS2
+              const double *b0 = pb.Bmat + ((size_t)pb.bbase[(size_t)il * S + s] * pb.PBpad + cc) * ldn;
+              explicit_xx(sb.X + (size_t)m * ldn, b0, (size_t)pb.PBpad * ldn, Q, pb.sc_colvalid[scb + (size_t)s * pb.PBpad], n,
+                          ldn, xx, r2, xsum);
+            }
           }
-          xx = r2 - hh;
-          if (r2 > 0.0 && xx < 1e-5 * r2) {
-            // Gram form cancelled (genotype nearly inside span([1, covariates]) on the kept rows): explicit CGS2
-            const double *b0 = pb.Bmat + ((size_t)pb.bbase[(size_t)il * S + s] * pb.PBpad + cc) * ldn;
-            explicit_xx(sb.X + (size_t)m * ldn, b0, (size_t)pb.PBpad * ldn, Q, pb.sc_colvalid[scb + (size_t)s * pb.PBpad], n,
-                        ldn, xx, r2, xsum);
+          const double yy = pb.sc_yy[scb + (size_t)s * pb.PBpad];
+          if (!join || !stats_lean(xy, xx, r2, yy, n, Q, rankz, fs.tz, fs.tz_nu, fs.tz_wmax, T, sb_b, sb_v, sb_t)) {
+            const double nu = (double)n - 2.0 - Q;
+            const bool use_tab = (fs.tz != nullptr) && (fs.tz_nu == nu);
+            PairStat ps;
+            stats_from_dots(xy, xx, r2, xsum, yy, pb.sc_tss[scb + (size_t)s * pb.PBpad], pb.sc_ybar[scb + (size_t)s * pb.PBpad], n,
+                            Q, rankz, use_tab ? fs.tz : nullptr, fs.tz_nu, fs.tz_wmax, ps);
+            sb_b = ps.b;
+            sb_v = ps.v;
+            sb_t = ps.t;
+            sb_p = ps.pval;
+          }
+          has_mask |= 1ull << s;
+        }
+        st[s * 32] = sb_b;
+        st[(S + s) * 32] = sb_v;
+        st[(2 * S + s) * 32] = sb_t;
+        if (!join) {
+          const double pval = have ? sb_p : nan("");
+          if (pval < snp_pmin) snp_pmin = pval;
+          if (kind == STAT_SEP_PER) {
+            const double v = (sb.gene_has[g] && sb.snp_has[m]) ? pval : 1.0;
+            if (isnan(v)) {
+              if (m == mbeg) sepm[(S + s) * 32] = 1.0;
+            } else if (v < sepm[s * 32])
+              sepm[s * 32] = v;
           }
         }
-        const double nu = (double)n - 2.0 - Q;
-        const bool use_tab = (fs.tz != nullptr) && (fs.tz_nu == nu);
-        stats_from_dots(xy, xx, r2, xsum, pb.sc_yy[scb + (size_t)s * pb.PBpad], pb.sc_tss[scb + (size_t)s * pb.PBpad],
-                        pb.sc_ybar[scb + (size_t)s * pb.PBpad], n, Q, rankz, use_tab ? fs.tz : nullptr, fs.tz_nu, fs.tz_wmax, ps);
-        has_mask |= 1ull << s;
       }
-      st[s * 32] = ps.b;
-      st[(S + s) * 32] = ps.v;
-      st[(2 * S + s) * 32] = ps.t;
       if (!join) {
-        const double pval = have ? ps.pval : nan("");
-        if (pval < snp_pmin) snp_pmin = pval;
-        if (kind == STAT_SEP_PER) {
-          const double v = (sb.gene_has[g] && sb.snp_has[m]) ? pval : 1.0;
-          if (isnan(v)) {
-            if (m == mbeg) sepm[(S + s) * 32] = 1.0;
-          } else if (v < sepm[s * 32])
-            sepm[s * 32] = v;
+        if (snp_pmin < sep_all_min) sep_all_min = snp_pmin;
+        continue;
+      }
+      double val; // the SNP's weighted ABF of the requested kind
+      if (!ALLCFG || which != 3) {
+        // ---- "gen": consistent configuration on gridL, one pass per unique phi2 (gene_snp_pair.cpp:364-416)
+        LseTab rg;
+        rg.init();
+        const double wL = 1.0 / (double)pg.L;
+        for (int u = 0; u < pg.UG; ++u) {
+          const double phi2 = pg.uphi[u];
+          double den = 0.0, num = 0.0, tsum = 0.0, prod = 1.0, slog = 0.0;
+          for (int s = 0; s < S; ++s) {
+            const double tt = st[(2 * S + s) * 32];
+            if (((has_mask >> s) & 1ull) && !(fabs(tt) < 1e-8)) {
+              const double b = st[s * 32], v = st[(S + s) * 32];
+              const double inv = rcp_n(v + phi2);
+              den += inv;
+              num = fma(b, inv, num);
+              tsum = fma(tt * tt, inv, tsum);
+              prod *= v * inv;
+              if (prod < 1e-200) {
+                slog += log(prod);
+                prod = 1.0;
+              }
+            }
+          }
+          const double sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log_tab16(prod, T)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
+          const bool live = num != 0.0 && den != 0.0 && den == den; // (CalcLog10AbfUvlr's guards, see abf_from_sums)
+          for (int i = pg.ustart[u]; i < pg.ustart[u + 1]; ++i) {
+            const double oma2 = pg.omaL[i];
+            double x = 0.0;
+            if (live) {
+              x = sing;
+              if (oma2 != 0.0) {
+                const double z = fma(oma2, den, 1.0);
+                x += (-0.5 * log_tab16(z, T) + 0.5 * num * num * oma2 * rcp_n(z)) * EQB_INV_LN10;
+              }
+            }
+            rg.add(x, wL, pg.kL[i] == 0, T);
+          }
         }
+        val = rg.result(T);
+        if (which == 2) {
+          // ---- singletons on gridS + BMAlite (gene_snp_pair.cpp:422-463, 552-570): grid points grouped by
+          // phi2 + oma2 (the logarithm 0.5 log(v / (v + phi2 + oma2)) is shared inside a group)
+          LseTab lite;
+          lite.init();
+          const double wK = 1.0 / (double)pg.K, wS = 0.5 / (double)S;
+          for (int s = 0; s < S; ++s) {
+            LseTab rc;
+            rc.init();
+            const double b = st[s * 32], vv = st[(S + s) * 32], tt = st[(2 * S + s) * 32];
+            const bool live = ((has_mask >> s) & 1ull) && !(fabs(tt) < 1e-8) && b != 0.0 && vv == vv && vv < INFINITY;
+            const double t2 = tt * tt, b2 = b * b;
+            for (int u = 0; u < pg.UT; ++u) {
+              double w = 0.0, lg = 0.0;
+              if (live) {
+                w = rcp_n(vv + pg.utot[u]);
+                lg = 0.5 * log_tab16(vv * w, T);
+              }
+              for (int i = pg.tstart[u]; i < pg.tstart[u + 1]; ++i) {
+                double x = 0.0;
+                if (live) {
+                  const double inv = rcp_n(vv + pg.phiS[i]);
+                  x = (lg + 0.5 * inv * fma(t2, pg.phiS[i], b2 * pg.omaS[i] * w)) * EQB_INV_LN10;
+                }
+                rc.add(x, wK, pg.kS[i] == 0, T);
+              }
+            }
+            lite.add(pg.K > 0 ? rc.result(T) : nan(""), wS, s == 0, T);
+          }
+          lite.add(val, 0.5, false, T);
+          val = lite.result(T);
+        }
+      } else {
+        // ---- all 2^S - 1 configurations, linear domain against Mref = sum_s t_s^2 / 2 - 350 (>= every exponent - 350):
+        //   10^abf = exp(A) (1 + oma2 den)^-1/2 exp(num^2 oma2 / (2 (1 + oma2 den)))      gene_snp_pair.cpp:504-602
+        bool fast_ok = true;
+        double Mref = 0.0;
+        for (int s = 0; s < S; ++s)
+          if ((has_mask >> s) & 1ull) {
+            const double t = st[(2 * S + s) * 32], b = st[s * 32], v = st[(S + s) * 32];
+            if (isnan(t) || isnan(b) || isnan(v) || isinf(b)) fast_ok = false;
+            else if (fabs(t) >= 1e-8) Mref += 0.5 * t * t;
+          }
+        Mref -= 350.0;
+        double total = 0.0;
+        if (fast_ok) {
+          for (int k = 0; k < pg.K; ++k) {
+            const double phi2 = pg.phiS[k], oma2 = pg.omaS[k], hom2 = 0.5 * oma2;
+            // per-subgroup terms { oma2 / (v + phi2), b / (v + phi2), ln of the single-subgroup ABF }
+            auto term = [&](int s, double &dz, double &dn, double &dA) {
+              dz = dn = dA = 0.0;
+              const double tt = st[(2 * S + s) * 32];
+              if (((has_mask >> s) & 1ull) && !(fabs(tt) < 1e-8)) {
+                const double b = st[s * 32], v = st[(S + s) * 32];
+                const double inv = rcp_n(v + phi2);
+                dz = oma2 * inv;
+                dn = b * inv;
+                dA = (phi2 == 0.0) ? 0.0 : 0.5 * log_tab16(v * inv, T) + 0.5 * tt * tt * phi2 * inv;
+              }
+            };
+            // low part: the 2^SA subset sums of the subgroups 0..SA-1, in registers
+            double lz[1 << PBF_SA], ln_[1 << PBF_SA], lA[1 << PBF_SA];
+            {
+              double tz_[PBF_SA], tn_[PBF_SA], tA_[PBF_SA];
+#pragma unroll
+              for (int s = 0; s < PBF_SA; ++s) {
+                tz_[s] = tn_[s] = tA_[s] = 0.0;
+                if (s < SA) term(s, tz_[s], tn_[s], tA_[s]);
+              }
+#pragma unroll
+              for (int a = 0; a < (1 << PBF_SA); ++a) {
+                lz[a] = ln_[a] = lA[a] = 0.0;
+#pragma unroll
+                for (int s = 0; s < PBF_SA; ++s)
+                  if ((a >> s) & 1) {
+                    lz[a] += tz_[s];
+                    ln_[a] += tn_[s];
+                    lA[a] += tA_[s];
+                  }
+              }
+            }
+            for (int s = 0; s < SB; ++s) {
+              double dz, dn, dA;
+              term(SA + s, dz, dn, dA);
+              hi[(s * 3 + 0) * 32] = dz;
+              hi[(s * 3 + 1) * 32] = dn;
+              hi[(s * 3 + 2) * 32] = dA;
+            }
+            // high part: Gray code over the 2^SB subsets of the subgroups SA..S-1, sums kept in registers
+            double hz = 1.0, hn = 0.0, hA = -Mref, ksum = 0.0;
+            unsigned int gray = 0;
+            const unsigned int nhi = 1u << SB;
+            for (unsigned int ih = 0; ih < nhi; ++ih) {
+              if (ih > 0) {
+                const int bit = __ffs(ih) - 1; // warp-uniform
+                gray ^= 1u << bit;
+                const double sg = ((gray >> bit) & 1u) ? 1.0 : -1.0;
+                hz = fma(sg, hi[(bit * 3 + 0) * 32], hz);
+                hn = fma(sg, hi[(bit * 3 + 1) * 32], hn);
+                hA = fma(sg, hi[(bit * 3 + 2) * 32], hA);
+              }
+              const double *wq = pg.size_weight + __popc(gray);
+#pragma unroll
+              for (int a = 0; a < (1 << PBF_SA); ++a) {
+                if (a >= (1 << SA)) break; // (S < 3)
+                const double num = hn + ln_[a];
+                const double r = rsqrt_newton1(hz + lz[a]);
+                const double e = exp_tab16<false>(fma(num * num * (r * r), hom2, hA + lA[a]), T);
+                ksum = fma(wq[__popc(a)], r * e, ksum);
+              }
+            }
+            total += ksum;
+          }
+        }
+        if (fast_ok && total > 1e-280 && total < INFINITY) {
+          val = (Mref + log(total / (double)pg.K)) * EQB_INV_LN10;
+          if (fabs(val) <= DBL_EPSILON) val = 0.0;
+        } else
+          val = bma_all_logdomain(st, S, has_mask, pg);
+      }
+      // ---- running statistic over the SNPs of the gene (gene.cpp:643-697)
+      if (isnan(val)) {
+        if (m == mbeg) first_nan = true;
+      } else {
+        cnt_nonnan++;
+        if (val > max_stat) max_stat = val;
+        acc_stat.add(val, 1.0, false);
       }
     }
-    if (!join) {
-      if (snp_pmin < sep_all_min) sep_all_min = snp_pmin;
+    if (kind == STAT_SEP_PER) {
+      for (int s = 0; s < S; ++s) {
+        part_sep[((size_t)task * 2 * S + s) * 32 + lane] = sepm[s * 32];
+        part_sep[((size_t)task * 2 * S + S + s) * 32 + lane] = sepm[(S + s) * 32];
+      }
       continue;
     }
-    double val; // the SNP's weighted ABF of the requested kind
-    if (!ALLCFG || which != 3) {
-      // ---- "gen": consistent configuration on gridL, one pass per unique phi2 (gene_snp_pair.cpp:364-416)
-      LseOnline rg;
-      rg.init();
-      const double wL = 1.0 / (double)pg.L;
-      for (int u = 0; u < pg.UG; ++u) {
-        const double phi2 = pg.uphi[u];
-        double den = 0.0, num = 0.0, tsum = 0.0, prod = 1.0, slog = 0.0;
-        for (int s = 0; s < S; ++s) {
-          const double tt = st[(2 * S + s) * 32];
-          if (((has_mask >> s) & 1ull) && !(fabs(tt) < 1e-8)) {
-            const double b = st[s * 32], v = st[(S + s) * 32];
-            const double inv = rcp_fast(v + phi2);
-            den += inv;
-            num += b * inv;
-            tsum += tt * tt * inv;
-            prod *= v * inv;
-            if (prod < 1e-200) {
-              slog += log(prod);
-              prod = 1.0;
-            }
-          }
-        }
-        const double sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log_fast(prod)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
-        for (int i = pg.ustart[u]; i < pg.ustart[u + 1]; ++i)
-          rg.add(abf_from_sums(den, num, sing, pg.omaL[i]), wL, pg.kL[i] == 0);
-      }
-      val = rg.result();
-      if (which == 2) {
-        // ---- singletons on gridS + BMAlite (gene_snp_pair.cpp:422-463, 552-570)
-        LseOnline lite;
-        lite.init();
-        const double wK = 1.0 / (double)pg.K, wS = 0.5 / (double)S;
-        for (int s = 0; s < S; ++s) {
-          LseOnline rc;
-          rc.init();
-          const bool has = (has_mask >> s) & 1ull;
-          const double b = st[s * 32], vv = st[(S + s) * 32], tt = st[(2 * S + s) * 32];
-          for (int k = 0; k < pg.K; ++k) rc.add(has ? singleton_value(b, vv, tt, pg.phiS[k], pg.omaS[k]) : 0.0, wK, k == 0);
-          lite.add(pg.K > 0 ? rc.result() : nan(""), wS, s == 0);
-        }
-        lite.add(val, 0.5, false);
-        val = lite.result();
-      }
+    BfPartial o;
+    if (kind == STAT_JOIN_MAX) {
+      o.m = max_stat;
+      o.acc = 0.0;
+    } else if (kind == STAT_JOIN_AVG) {
+      o.m = acc_stat.m;
+      o.acc = acc_stat.acc;
     } else {
-      // ---- all 2^S - 1 configurations, linear domain against Mref = sum_s t_s^2 / 2 - 350 (>= every exponent - 350):
-      //   10^abf = exp(A) (1 + oma2 den)^-1/2 exp(num^2 oma2 / (2 (1 + oma2 den)))      gene_snp_pair.cpp:504-602
-      bool fast_ok = true;
-      double Mref = 0.0;
-      for (int s = 0; s < S; ++s)
-        if ((has_mask >> s) & 1ull) {
-          const double t = st[(2 * S + s) * 32], b = st[s * 32], v = st[(S + s) * 32];
-          if (isnan(t) || isnan(b) || isnan(v) || isinf(b)) fast_ok = false;
-          else if (fabs(t) >= 1e-8) Mref += 0.5 * t * t;
-        }
-      Mref -= 350.0;
-      double total = 0.0;
-      if (fast_ok) {
-        for (int k = 0; k < pg.K; ++k) {
-          const double phi2 = pg.phiS[k], hom2 = 0.5 * pg.omaS[k], oma2 = pg.omaS[k];
-          // per-subgroup terms {1/(v+phi2), b/(v+phi2), ln of the single-subgroup ABF}: low part in registers -> table
-          double ld[PBF_SA], ln_[PBF_SA], lA[PBF_SA];
-#pragma unroll
-          for (int s = 0; s < PBF_SA; ++s) {
-            ld[s] = ln_[s] = lA[s] = 0.0;
-            if (s < SA && ((has_mask >> s) & 1ull)) {
-              term_entry(st[s * 32], st[(S + s) * 32], st[(2 * S + s) * 32], phi2, ld[s], ln_[s], lA[s]);
-              lA[s] *= LN10;
-            }
-          }
-#pragma unroll
-          for (int a = 0; a < (1 << PBF_SA); ++a) {
-            double d = 0.0, n_ = 0.0, A = 0.0;
-#pragma unroll
-            for (int s = 0; s < PBF_SA; ++s)
-              if ((a >> s) & 1) {
-                d += ld[s];
-                n_ += ln_[s];
-                A += lA[s];
-              }
-            lo[(a * 3 + 0) * 32] = d;
-            lo[(a * 3 + 1) * 32] = n_;
-            lo[(a * 3 + 2) * 32] = A;
-          }
-          for (int s = 0; s < SB; ++s) {
-            double d = 0.0, n_ = 0.0, A = 0.0;
-            if ((has_mask >> (SA + s)) & 1ull) {
-              term_entry(st[(SA + s) * 32], st[(S + SA + s) * 32], st[(2 * S + SA + s) * 32], phi2, d, n_, A);
-              A *= LN10;
-            }
-            hi[(s * 3 + 0) * 32] = d;
-            hi[(s * 3 + 1) * 32] = n_;
-            hi[(s * 3 + 2) * 32] = A;
-          }
-          // high part: Gray code over the 2^SB subsets of the subgroups SA..S-1, sums kept in registers
-          double hd = 0.0, hn = 0.0, hA = -Mref;
-          unsigned int gray = 0;
-          double ksum = 0.0;
-          const unsigned int nhi = 1u << SB;
-          for (unsigned int ih = 0; ih < nhi; ++ih) {
-            if (ih > 0) {
-              const int bit = __ffs(ih) - 1; // warp-uniform
-              gray ^= 1u << bit;
-              const double sg = ((gray >> bit) & 1u) ? 1.0 : -1.0;
-              hd = fma(sg, hi[(bit * 3 + 0) * 32], hd);
-              hn = fma(sg, hi[(bit * 3 + 1) * 32], hn);
-              hA = fma(sg, hi[(bit * 3 + 2) * 32], hA);
-            }
-            const int pch = __popc(gray);
-#pragma unroll
-            for (int a = 0; a < (1 << PBF_SA); ++a) {
-              if (a >= (1 << SA)) break; // (S < 3)
-              const double den = hd + lo[(a * 3 + 0) * 32], num = hn + lo[(a * 3 + 1) * 32], A = hA + lo[(a * 3 + 2) * 32];
-              const double r = rsqrt_newton1(fma(oma2, den, 1.0));
-              const double e = exp_tab16(fma(num * num * (r * r), hom2, A), exp_tab);
-              ksum = fma(pg.size_weight[pch + __popc(a)], r * e, ksum);
-            }
-          }
-          total += ksum;
-        }
-      }
-      if (fast_ok && total > 0.0 && total < INFINITY) {
-        val = (Mref + log(total / (double)pg.K)) * EQB_INV_LN10;
-        if (fabs(val) <= DBL_EPSILON) val = 0.0;
-      } else
-        val = bma_all_logdomain(st, S, has_mask, pg);
+      o.m = sep_all_min;
+      o.acc = 0.0;
     }
-    // ---- running statistic over the SNPs of the gene (gene.cpp:643-697)
-    if (isnan(val)) {
-      if (m == mbeg) first_nan = true;
-    } else {
-      cnt_nonnan++;
-      if (val > max_stat) max_stat = val;
-      acc_stat.add(val, 1.0, false);
-    }
+    o.cnt_nonnan = cnt_nonnan;
+    o.flags = (first_nan ? 1 : 0) | (acc_stat.any ? 2 : 0);
+    part[(size_t)task * 32 + lane] = o;
   }
-  if (kind == STAT_SEP_PER) {
-    for (int s = 0; s < S; ++s) {
-      part_sep[((size_t)task * 2 * S + s) * 32 + lane] = sepm[s * 32];
-      part_sep[((size_t)task * 2 * S + S + s) * 32 + lane] = sepm[(S + s) * 32];
-    }
-    return;
-  }
-  BfPartial o;
-  if (kind == STAT_JOIN_MAX) {
-    o.m = max_stat;
-    o.acc = 0.0;
-  } else if (kind == STAT_JOIN_AVG) {
-    o.m = acc_stat.m;
-    o.acc = acc_stat.acc;
-  } else {
-    o.m = sep_all_min;
-    o.acc = 0.0;
-  }
-  o.cnt_nonnan = cnt_nonnan;
-  o.flags = (first_nan ? 1 : 0) | (acc_stat.any ? 2 : 0);
-  part[(size_t)task * 32 + lane] = o;
 }
 
 // thread per (item, column): merges the chunk partials of the gene in SNP order and applies the reference's rules
