@@ -206,126 +206,13 @@ __device__ inline double chisq_Qinv_1df(double Q)
   return z * z;
 }
 
-// warp reductions ---------------------------------------------------------------------------
-// ---------------------------------------------------------------- short-latency elementary functions
-// The ABF phases spend most of their instructions in log / exp10 / division.  The forms below (MUFU seed +
-// one correction step, Estrin polynomials, library fallback outside the plain positive / finite range) are
-// accurate to a few 1e-16 and have shorter dependency chains than the CUDA library versions -- but measured
-// on B200 they only pay where several INDEPENDENT evaluations can be interleaved without a branch in between
-// (exp_fast_nb / rsqrt_fast_nb in the linear-domain BMA of the permutation kernel: +18%); as drop-in
-// replacements inside the branchy per-item ABF code they were a wash (fast_pair_kernel +1%, perm_kernel -8%),
-// so rcp_fast / log_fast / exp10_fast forward to the library unless EQB_SHORT_LATENCY_MATH is defined.
-// eqb_math_selftest() checks all of them against the library either way.
-
-// 1/x: MUFU seed (upper 20 mantissa bits) + one cubic correction step
-__device__ __forceinline__ double rcp_fast_impl(double x)
-{
-  if (!(fabs(x) >= 1e-290 && fabs(x) <= 1e290)) return 1.0 / x;
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  const double e = fma(-x, r, 1.0); // |e| <= ~2^-20
-  const double q = fma(e, e, e);    // 1/(1-e) = 1 + e + e^2 + O(e^3), e^3 <= 2^-60
-  return fma(r, q, r);
-}
-
-// natural logarithm: x = 2^e m, m in [sqrt(1/2), sqrt(2)), log m = 2 atanh(s), s = (m-1)/(m+1), series to s^17
-__device__ __forceinline__ double log_fast_impl(double x)
-{
-  const int hi = __double2hiint(x);
-  if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x); // zero, subnormal, negative, Inf, NaN
-  int e = (hi >> 20) - 1023;
-  int mhi = (hi & 0x000fffff) | 0x3ff00000;
-  if (mhi >= 0x3ff6a09f) { // m >= ~sqrt(2): halve
-    mhi -= 0x00100000;
-    e += 1;
-  }
-  const double m = __hiloint2double(mhi, __double2loint(x));
-  const double f = m - 1.0;
-  const double s = f * rcp_fast_impl(2.0 + f);
-  const double z = s * s;
-  // Estrin evaluation (short dependency chain): p = sum_{k=0..7} c_k z^k, c_k = 2/(2k+3)
-  const double z2 = z * z, z4 = z2 * z2;
-  const double p01 = fma(2.0 / 5.0, z, 2.0 / 3.0), p23 = fma(2.0 / 9.0, z, 2.0 / 7.0);
-  const double p45 = fma(2.0 / 13.0, z, 2.0 / 11.0), p67 = fma(2.0 / 17.0, z, 2.0 / 15.0);
-  const double p = fma(z4, fma(z2, p67, p45), fma(z2, p23, p01));
-  const double lm = fma(s * z, p, 2.0 * s);
-  const double de = (double)e;
-  return fma(de, 6.93147180369123816490e-01, fma(de, 1.90821492927058770002e-10, lm)); // ln2 = hi + lo
-}
-
-// 10^x = 2^n 2^f, n = rint(x log2 10), f in [-1/2, 1/2]: degree-12 Taylor polynomial of 2^f
-__device__ __forceinline__ double exp10_fast_impl(double x)
-{
-  if (!(x > -300.0 && x < 300.0)) return exp10(x); // also NaN
-  const double L2_10_HI = 3.321928094887362182e+00, L2_10_LO = 1.661617516973592e-16;
-  const double t = x * L2_10_HI;
-  const double magic = 6755399441055744.0; // 1.5 * 2^52: (t + magic) - magic = rint(t), integer in the low word
-  const double tm = t + magic;
-  const int n = __double2loint(tm);
-  const double nd = tm - magic;
-  double f = fma(x, L2_10_HI, -nd);
-  f = fma(x, L2_10_LO, f);
-  // Estrin evaluation of sum_{k=0..12} (ln2^k / k!) f^k
-  const double f2 = f * f, f4 = f2 * f2, f8 = f4 * f4;
-  const double q01 = fma(6.9314718055994531e-01, f, 1.0);
-  const double q23 = fma(5.5504108664821580e-02, f, 2.4022650695910071e-01);
-  const double q45 = fma(1.3333558146428443e-03, f, 9.6181291076284772e-03);
-  const double q67 = fma(1.5252733804059840e-05, f, 1.5403530393381610e-04);
-  const double q89 = fma(1.0178086009239700e-07, f, 1.3215486790144309e-06);
-  const double qab = fma(4.4455382718708115e-10, f, 7.0549116208011233e-09);
-  const double q03 = fma(f2, q23, q01), q47 = fma(f2, q67, q45), q8b = fma(f2, qab, q89);
-  const double qhi = fma(f4, 2.5678435993488205e-11, q8b); // + c12 f^12 = f^8 * (f^4 c12)
-  const double p = fma(f8, qhi, fma(f4, q47, q03));
-  return p * __hiloint2double((n + 1023) << 20, 0);
-}
-
-#if defined(EQB_SHORT_LATENCY_MATH)
-__device__ __forceinline__ double rcp_fast(double x) { return rcp_fast_impl(x); }
-__device__ __forceinline__ double log_fast(double x) { return log_fast_impl(x); }
-__device__ __forceinline__ double exp10_fast(double x) { return exp10_fast_impl(x); }
-#else
+// elementary functions of the true-pass kernels: the CUDA math library (full range, < 1 ulp).  The permutation BF
+// kernel, which is bound by the FP64 pipe and has no divergence, uses the table-driven forms of perm_gemm.cuh.
 __device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
 __device__ __forceinline__ double log_fast(double x) { return log(x); }
 __device__ __forceinline__ double exp10_fast(double x) { return exp10(x); }
-#endif
 
-// e^x without a branch (arguments clamped to [-708, 708]; callers exclude NaN): same scheme as exp10_fast.
-// Used by the linear-domain BMA of the permutation kernel, where the K grid points of a configuration are
-// independent evaluations the compiler can interleave once no branch separates them.
-__device__ __forceinline__ double exp_fast_nb(double x)
-{
-  x = fmin(fmax(x, -708.0), 708.0);
-  const double L2E_HI = 1.4426950408889634e+00, L2E_LO = 2.0355273740931033e-17;
-  const double magic = 6755399441055744.0;
-  const double tm = fma(x, L2E_HI, magic);
-  const int n = __double2loint(tm);
-  const double nd = tm - magic;
-  double f = fma(x, L2E_HI, -nd);
-  f = fma(x, L2E_LO, f);
-  const double f2 = f * f, f4 = f2 * f2, f8 = f4 * f4;
-  const double q01 = fma(6.9314718055994531e-01, f, 1.0);
-  const double q23 = fma(5.5504108664821580e-02, f, 2.4022650695910071e-01);
-  const double q45 = fma(1.3333558146428443e-03, f, 9.6181291076284772e-03);
-  const double q67 = fma(1.5252733804059840e-05, f, 1.5403530393381610e-04);
-  const double q89 = fma(1.0178086009239700e-07, f, 1.3215486790144309e-06);
-  const double qab = fma(4.4455382718708115e-10, f, 7.0549116208011233e-09);
-  const double q03 = fma(f2, q23, q01), q47 = fma(f2, q67, q45), q8b = fma(f2, qab, q89);
-  const double qhi = fma(f4, 2.5678435993488205e-11, q8b);
-  const double p = fma(f8, qhi, fma(f4, q47, q03));
-  return p * __hiloint2double((n + 1023) << 20, 0);
-}
-
-// 1/sqrt(x) for a normal positive x, without a branch: MUFU seed + one cubic correction step
-__device__ __forceinline__ double rsqrt_fast_nb(double x)
-{
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double h = x * y;
-  const double e = fma(-h, y, 1.0);             // 1 - x y^2
-  const double q = e * fma(e, 0.375, 0.5);      // (1 - e)^(-1/2) = 1 + e/2 + 3 e^2/8 + O(e^3)
-  return fma(y, q, y);
-}
-
+// warp reductions ---------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

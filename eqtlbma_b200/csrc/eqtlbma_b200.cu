@@ -24,7 +24,6 @@
 #include "fast_kernels.cuh"
 #include "mvlr_kernel.cuh"
 #include "perm_gemm.h"
-#include "perm_kernel.cuh"
 
 using namespace eqb;
 
@@ -404,7 +403,7 @@ struct eqb_ctx {
   std::vector<uint8_t> sub_complete;               // [S] every sample of the union has genotype, expression, covariates
   std::vector<int> sub_xvar;                       // [S]
   bool perm_timing = false;
-  int perm_path = 0;                               // path taken by the last permutation run: 1 GEMM, 2 fused kernels
+  int perm_path = 0;                               // path taken by the last permutation run: 1 GEMM, 2 general fused kernel
   // cached permutation table key
   uint64_t perm_seed = 0;
   long long perm_P = -1;
@@ -1117,61 +1116,6 @@ int prepare_fast_path(eqb_ctx *ctx)
 
 } // namespace
 
-
-// diagnostics: worst deviations of the short-latency elementary functions from the CUDA library versions
-__global__ void math_selftest_kernel(long long n, double *out)
-{
-  __shared__ double worst[6];
-  if (threadIdx.x < 6) worst[threadIdx.x] = 0.0;
-  __syncthreads();
-  double w[6] = {0, 0, 0, 0, 0, 0};
-  unsigned long long st = 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
-  auto unif = [&]() { // xorshift64*, uniform in [0, 1)
-    st ^= st >> 12;
-    st ^= st << 25;
-    st ^= st >> 27;
-    return (double)((st * 0x2545F4914F6CDD1Dull) >> 11) * (1.0 / 9007199254740992.0);
-  };
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int kind = (int)(i % 3);
-    double x;
-    if (kind == 0) x = exp10(-280.0 + 560.0 * unif());
-    else if (kind == 1) x = exp10(-12.0 + 24.0 * unif());
-    else x = 1.0 + (unif() - 0.5) * ((i % 2) ? 2e-3 : 1.2);
-    const double r0 = 1.0 / x, r1 = eqb::rcp_fast_impl(x);
-    w[0] = fmax(w[0], fabs(r1 - r0) / fabs(r0));
-    const double s0 = rsqrt(x), s1 = eqb::rsqrt_fast_nb(x);
-    w[0] = fmax(w[0], fabs(s1 - s0) / s0);
-    const double l0 = log(x), l1 = eqb::log_fast_impl(x);
-    w[1] = fmax(w[1], fabs(l1 - l0));
-    w[2] = fmax(w[2], fabs(l1 - l0) / fmax(fabs(l0), 1e-300));
-    const double y = (kind == 0) ? -299.0 + 598.0 * unif() : ((kind == 1) ? -30.0 * unif() : 2.0 * unif() - 1.0);
-    const double e0 = exp10(y), e1 = eqb::exp10_fast_impl(y);
-    w[3] = fmax(w[3], fabs(e1 - e0) / e0);
-    const double g0 = exp(2.302585092994046 * y), g1 = eqb::exp_fast_nb(2.302585092994046 * y);
-    w[3] = fmax(w[3], fabs(g1 - g0) / g0);
-  }
-  // special values must agree exactly in kind
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const double sp[8] = {0.0, -1.0, INFINITY, nan(""), 1e-310, 1.0, 4.9e-324, 1e300};
-    double bad = 0.0;
-    for (int k = 0; k < 8; ++k) {
-      const double a = log(sp[k]), b = eqb::log_fast_impl(sp[k]);
-      if (!((isnan(a) && isnan(b)) || a == b || fabs(a - b) <= 1e-13 * fabs(a))) bad += 1.0;
-      const double c = 1.0 / sp[k], d = eqb::rcp_fast_impl(sp[k]);
-      if (!((isnan(c) && isnan(d)) || c == d || fabs(c - d) <= 1e-15 * fabs(c))) bad += 1.0;
-    }
-    const double se[6] = {-INFINITY, INFINITY, nan(""), -400.0, 400.0, 0.0};
-    for (int k = 0; k < 6; ++k) {
-      const double a = exp10(se[k]), b = eqb::exp10_fast_impl(se[k]);
-      if (!((isnan(a) && isnan(b)) || a == b)) bad += 1.0;
-    }
-    w[4] = bad;
-  }
-  for (int k = 0; k < 5; ++k) atomicMax((unsigned long long *)&worst[k], (unsigned long long)__double_as_longlong(w[k])); // (non-negative doubles order like integers)
-  __syncthreads();
-  if (threadIdx.x < 5) atomicMax((unsigned long long *)&out[threadIdx.x], (unsigned long long)__double_as_longlong(worst[threadIdx.x]));
-}
 
 extern "C" {
 
@@ -2202,52 +2146,6 @@ int eqb_run_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int32_t 
   return run_true_impl(ctx, gene_lo, gene_hi, nullptr, want_raw != 0, true, ms);
 }
 
-// K4 on the tensor cores when the shape allows it, else the general fused kernel
-static int run_perm_or_pair_kernel(eqb_ctx *ctx, const LaunchArgs &la, long long n_ctas, int ppg)
-{
-  const int S = ctx->cfg.n_subgroups;
-  const bool mvlr = ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model == EQB_ERROR_MVLR;
-  const int K = (int)ctx->phi2S.size(), L = (int)ctx->phi2L.size();
-  // dynamic shared memory available = opt-in maximum of the device minus the kernel's static shared memory
-  int optin = 0;
-  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->cfg.device);
-  const bool allcfg = la.which == 3;
-  cudaFuncAttributes fa16, fa8;
-  if (allcfg) {
-    cudaFuncGetAttributes(&fa16, perm_kernel<16, true>);
-    cudaFuncGetAttributes(&fa8, perm_kernel<8, true>);
-  } else {
-    cudaFuncGetAttributes(&fa16, perm_kernel<16, false>);
-    cudaFuncGetAttributes(&fa8, perm_kernel<8, false>);
-  }
-  const size_t lim16 = (size_t)std::max(0, optin - (int)fa16.sharedSizeBytes - 1024);
-  const size_t lim = (size_t)std::max(0, optin - (int)fa8.sharedSizeBytes - 1024);
-  const size_t smem16 = perm_smem_doubles(S, ctx->Qmax, ctx->ldn, K, L, ctx->gt.UL, la.which, 16) * sizeof(double);
-  const size_t smem8 = perm_smem_doubles(S, ctx->Qmax, ctx->ldn, K, L, ctx->gt.UL, la.which, 8) * sizeof(double);
-  const bool ok = !mvlr && ctx->d_fp != nullptr && ctx->ldn <= 512 && smem8 <= lim &&
-                  (!ctx->cfg.qnorm || ctx->Qmax >= 2) && !tuning_env("EQB_NO_PERM_DMMA");
-  if (!ok) return run_pair_kernel(ctx, la, n_ctas, ppg);
-  const unsigned grid = (unsigned)((long long)la.n_genes * std::max(1, ppg));
-  cudaError_t e;
-#define EQB_PERM_LAUNCH(PWV, ALLV, SMEMV)                                                                            \
-  do {                                                                                                               \
-    e = cudaFuncSetAttribute(perm_kernel<PWV, ALLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEMV));     \
-    if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel attribute: ") + cudaGetErrorString(e));          \
-    perm_kernel<PWV, ALLV><<<grid, PWV * 32, SMEMV, ctx->stream>>>(ctx->d_prm, ctx->d_fp, la, ctx->gt);              \
-  } while (0)
-  if (smem16 <= lim16 && !allcfg) { // 16 warps share the CTA's B matrix: twice the latency hiding
-    EQB_PERM_LAUNCH(16, false, smem16);
-  } else { // (--pbf all keeps 8 warps: its per-lane configuration tables need the 255-register budget)
-    if (allcfg) EQB_PERM_LAUNCH(8, true, smem8);
-    else EQB_PERM_LAUNCH(8, false, smem8);
-  }
-#undef EQB_PERM_LAUNCH
-  ctx->launches++;
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(ctx, std::string("perm_kernel launch: ") + cudaGetErrorString(e));
-  return 0;
-}
-
 // device evaluation of a set of (gene, permutation table) items: statistic of the true data, the P
 // permuted statistics, and the exceedance counters
 static int eval_perm_items(eqb_ctx *ctx, const std::vector<int> &genes, const std::vector<int> &tab_idx,
@@ -2312,7 +2210,7 @@ static int eval_perm_items(eqb_ctx *ctx, const std::vector<int> &genes, const st
     la.perms_per_gene = 0;
     la.true_rules = 1; // statistic of the true data: identity permutation, the reference's true-data rules
     la.out_stat = ctx->d_true.p + row0 * 1;
-    rc = run_perm_or_pair_kernel(ctx, la, (long long)n_items, 1);
+    rc = run_pair_kernel(ctx, la, (long long)n_items, 1);
     if (rc) return rc;
     la.true_rules = 0;
     la.out_stat = ctx->d_stat.p + row0 * (size_t)P;
@@ -2321,7 +2219,7 @@ static int eval_perm_items(eqb_ctx *ctx, const std::vector<int> &genes, const st
     for (long long p0 = 0; p0 < P; p0 += pcnk) {
       la.p0 = p0;
       la.perms_per_gene = (int)std::min<long long>(pcnk, P - p0);
-      rc = run_perm_or_pair_kernel(ctx, la, (long long)n_items * la.perms_per_gene, la.perms_per_gene);
+      rc = run_pair_kernel(ctx, la, (long long)n_items * la.perms_per_gene, la.perms_per_gene);
       if (rc) return rc;
     }
   }
@@ -2648,19 +2546,6 @@ int eqb_set_perm_timing(eqb_ctx *ctx, int32_t on)
   if (!ctx) return 1;
   ctx->perm_timing = on != 0;
   return 0;
-}
-
-int eqb_math_selftest(int32_t device, int64_t n, double *out5)
-{
-  if (!out5 || n <= 0) return 1;
-  if (cudaSetDevice(device) != cudaSuccess) return 2;
-  double *d = nullptr;
-  if (cudaMalloc((void **)&d, 5 * sizeof(double)) != cudaSuccess) return 3;
-  cudaMemset(d, 0, 5 * sizeof(double));
-  math_selftest_kernel<<<296, 256>>>(n, d);
-  cudaError_t e = cudaMemcpy(out5, d, 5 * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(d);
-  return e == cudaSuccess ? 0 : 4;
 }
 
 } // extern "C"

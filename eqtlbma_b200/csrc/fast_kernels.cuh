@@ -792,36 +792,6 @@ __device__ __forceinline__ double singleton_value(double b, double vv, double tt
   return 0.0;
 }
 
-// log10_weighted_sum (utils_math.cpp:100-131: max seeded with element 0, NaN elements skipped, |result| <=
-// DBL_EPSILON snapped to 0) of n values by the 4 adjacent lanes {4j .. 4j+3}; q = lane & 3.  Every lane of the
-// warp must call it (full-mask shuffles); val(k) / wt(k) give element k and its weight.
-template <class FV, class FW>
-__device__ __forceinline__ double lws_quad(int n, int q, FV val, FW wt)
-{
-  if (n <= 0) return nan("");
-  double mx = val(0);
-  for (int k = q; k < n; k += 4) {
-    const double x = val(k);
-    mx = (x > mx) ? x : mx;
-  }
-#pragma unroll
-  for (int o = 1; o <= 2; o <<= 1) {
-    const double y = __shfl_xor_sync(0xffffffffu, mx, o);
-    mx = (y > mx) ? y : mx;
-  }
-  double sum = 0.0;
-  for (int k = q; k < n; k += 4) {
-    const double x = val(k);
-    const double e = exp10_fast(x - mx);
-    sum += isnan(x) ? 0.0 : wt(k) * e;
-  }
-  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-  double r = mx + log10(sum);
-  if (fabs(r) <= DBL_EPSILON) r = 0.0;
-  return r;
-}
-
 // phase A helper: SN contractions of one genotype row against the SN residualised expression rows of the gene
 // (one warp; 16-byte loads -- rows are ldn*8 bytes apart with ldn a multiple of 16)
 template <int SN>

@@ -574,6 +574,21 @@ int eqb_measure_fp64_peaks(int32_t device, double *out4)
   return e == cudaSuccess ? 0 : 4;
 }
 
+// worst deviation of the permutation BF kernel's table-driven elementary functions from the CUDA library versions over
+// n pseudo-random arguments: out5 = { rcp rel, log abs, rsqrt rel, exp / exp10 rel, special-value mismatches }
+int eqb_math_selftest(int32_t device, int64_t n, double *out5)
+{
+  if (!out5 || n <= 0) return 1;
+  if (cudaSetDevice(device) != cudaSuccess) return 2;
+  double *d = nullptr;
+  if (cudaMalloc((void **)&d, 5 * sizeof(double)) != cudaSuccess) return 3;
+  cudaMemset(d, 0, 5 * sizeof(double));
+  eqb::math_selftest_kernel<<<296, 256>>>(n, d);
+  cudaError_t e = cudaMemcpy(out5, d, 5 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? 0 : 4;
+}
+
 // Self-test and throughput of perm_gemm_kernel on pseudo-random operands: D = X . B^T (and the squared variant) for
 // n_rows genotype rows x n_cols operand rows of length ldn (a multiple of 16); out3 = { worst |D - reference| / sum
 // |terms|, TFLOP/s of the GEMM kernel (CUDA events, best of 3), tiles }.

@@ -586,6 +586,63 @@ __device__ __forceinline__ double log_tab16(double x, const BfTabs &T)
   return fma((double)((hi >> 20) - 1023), 0.69314718055994530942, t.y + lp);
 }
 
+// diagnostics: worst deviation of the table-driven forms from the CUDA library over n pseudo-random arguments
+__global__ void math_selftest_kernel(long long n, double *out)
+{
+  __shared__ BfTabs T;
+  __shared__ double worst[5];
+  if (threadIdx.x < 16) {
+    const double mj = 1.0 + ((double)threadIdx.x + 0.5) / 16.0;
+    T.exp16[threadIdx.x] = exp2((double)threadIdx.x / 16.0);
+    T.log16[threadIdx.x] = make_double2(1.0 / mj, log(mj));
+  }
+  if (threadIdx.x < 5) worst[threadIdx.x] = 0.0;
+  __syncthreads();
+  double w[5] = {0, 0, 0, 0, 0};
+  unsigned long long st = 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+  auto unif = [&]() { // xorshift64*, uniform in [0, 1)
+    st ^= st >> 12;
+    st ^= st << 25;
+    st ^= st >> 27;
+    return (double)((st * 0x2545F4914F6CDD1Dull) >> 11) * (1.0 / 9007199254740992.0);
+  };
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int kind = (int)(i % 3);
+    double x;
+    if (kind == 0) x = exp10(-280.0 + 560.0 * unif());
+    else if (kind == 1) x = exp10(-12.0 + 24.0 * unif());
+    else x = 1.0 + (unif() - 0.5) * ((i % 2) ? 2e-3 : 1.2);
+    w[0] = fmax(w[0], fabs(rcp_n(x) - 1.0 / x) * x);
+    w[1] = fmax(w[1], fabs(log_tab16(x, T) - log(x)));
+    w[2] = fmax(w[2], fabs(rsqrt_newton1(x) - rsqrt(x)) * sqrt(x));
+    const double y = (kind == 0) ? -690.0 + 1380.0 * unif() : ((kind == 1) ? -60.0 * unif() : 2.0 * unif() - 1.0);
+    const double e0 = exp(y);
+    w[3] = fmax(w[3], fabs(exp_tab16<true>(y, T) - e0) / e0);
+    w[3] = fmax(w[3], fabs(exp_tab16<false>(y, T) - e0) / e0);
+    const double d0 = exp10(y * 0.4342944819032518);
+    w[3] = fmax(w[3], fabs(exp10_tab16<true>(y * 0.4342944819032518, T) - d0) / d0);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // special values: the clamped exponential must return (nearly) zero, never NaN; the logarithm forwards to the library
+    double bad = 0.0;
+    const double se[4] = {-INFINITY, -1e300, -5000.0, nan("")};
+    for (int k = 0; k < 4; ++k) {
+      const double v = exp_tab16<true>(se[k], T);
+      if (!(v >= 0.0 && v < 1e-300)) bad += 1.0;
+    }
+    if (!(exp_tab16<false>(-5000.0, T) < 1e-290)) bad += 1.0;
+    const double sl[5] = {0.0, -1.0, INFINITY, nan(""), 1e-310};
+    for (int k = 0; k < 5; ++k) {
+      const double a = log(sl[k]), b = log_tab16(sl[k], T);
+      if (!((isnan(a) && isnan(b)) || a == b)) bad += 1.0;
+    }
+    w[4] = bad;
+  }
+  for (int k = 0; k < 5; ++k) atomicMax((unsigned long long *)&worst[k], (unsigned long long)__double_as_longlong(w[k]));
+  __syncthreads();
+  if (threadIdx.x < 5) atomicMax((unsigned long long *)&out[threadIdx.x], (unsigned long long)__double_as_longlong(worst[threadIdx.x]));
+}
+
 // log10_weighted_sum accumulated online (utils_math.cpp:100-131) with the table exponential
 struct LseTab {
   double m, acc;

@@ -85,21 +85,19 @@ class Dataset:
         Gene::SetCisSnps (gene.cpp:140-157) with integer arithmetic."""
         beg = np.zeros(self.n_genes, dtype=np.int64)
         end = np.zeros(self.n_genes, dtype=np.int64)
-        chr_rng = {}
         for c in np.unique(self.snp_chr):
             idx = np.nonzero(self.snp_chr == c)[0]
-            chr_rng[int(c)] = (int(idx[0]), int(idx[-1]) + 1)
-        for g in range(self.n_genes):
-            if int(self.gene_chr[g]) not in chr_rng:
-                continue
-            lo_chr, hi_chr = chr_rng[int(self.gene_chr[g])]
+            lo_chr, hi_chr = int(idx[0]), int(idx[-1]) + 1
             pos = self.snp_pos[lo_chr:hi_chr]
-            start, endc = int(self.gene_start[g]), int(self.gene_end[g])
-            lo = start - self.radius if start >= self.radius else 0
+            gs = np.nonzero(self.gene_chr == c)[0]
+            if len(gs) == 0:
+                continue
+            start, endc = self.gene_start[gs], self.gene_end[gs]
+            lo = np.where(start >= self.radius, start - self.radius, 0)
             hi = (start if self.anchor == "TSS" else endc) + self.radius
-            b = int(np.searchsorted(pos, lo, side="left"))
-            e = int(np.searchsorted(pos, hi, side="right"))
-            beg[g], end[g] = lo_chr + b, lo_chr + max(b, e)
+            b = np.searchsorted(pos, lo, side="left")
+            e = np.searchsorted(pos, hi, side="right")
+            beg[gs], end[gs] = lo_chr + b, lo_chr + np.maximum(b, e)
         return beg, end
 
     # ------------------------------------------------------------------ files
@@ -205,7 +203,7 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
                  dosage=False, maf=0.3, gridL=None, gridS=None, radius=None, anchor="TSS",
                  null_frac=0.3, separate_geno_files=False, missing_geno_frac=0.0,
                  pad_names=False, monomorphic_frac=0.0, gene_spacing=1000, far_snp=True,
-                 geno_format="custom") -> Dataset:
+                 geno_format="custom", layout_only=False) -> Dataset:
     """Generate a dataset. One SNP stream per chromosome at uniform spacing; each gene's +-radius
     TSS window holds ~snps_per_gene SNPs; expression y = mu_s + b_s*g + N(0,1) with ES-model
     effects from the first cis SNP of the gene (simul_flutre_et_al.cpp:682-743)."""
@@ -264,6 +262,12 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
     gene_start = np.array([t[2] for t in genes], dtype=np.int64)
     gene_end = np.array([t[3] for t in genes], dtype=np.int64)
 
+    if layout_only:
+        # coordinates only (cis-window sizes for a cost partition): no genotypes, no expression levels
+        return Dataset(samples=samples, subgroups=[], genos=[], geno_samples=[], snp_names=snp_names, snp_chr=snp_chr,
+                       snp_pos=snp_pos, snp_bed_start=snp_pos - 1, gene_names=gene_names, gene_chr=gene_chr,
+                       gene_start=gene_start, gene_end=gene_end, chr_names=chr_names, gridL=gridL, gridS=gridS,
+                       anchor=anchor, radius=radius, geno_format=geno_format)
     # genotypes (file column order = ind1..indN, i.e. NOT the sorted order)
     p = np.array([(1 - maf) ** 2, 2 * maf * (1 - maf), maf ** 2])
     G = rng.choice(3, size=(M, n_inds), p=p).astype(np.float64)

@@ -189,8 +189,9 @@ int64_t eqb_fast_gene_count(const eqb_ctx *ctx);
 float eqb_last_pair_kernel_ms(const eqb_ctx *ctx);
 /* Number of kernel launches issued by this context so far. */
 int64_t eqb_launch_count(const eqb_ctx *ctx);
-/* diagnostics: worst deviation of the kernels' short-latency rcp / log / exp10 from the CUDA library versions over
- * n pseudo-random arguments: out5 = { rcp rel, log abs, log rel, exp10 rel, special-value mismatches }. */
+/* diagnostics: worst deviation of the table-driven rcp / log / rsqrt / exp of the permutation BF kernel (perm_gemm.cuh)
+ * from the CUDA library versions over n pseudo-random arguments:
+ * out5 = { rcp rel, log abs, rsqrt rel, exp rel, special-value mismatches }. */
 int eqb_math_selftest(int32_t device, int64_t n, double *out5);
 
 /* FP64 pipe peaks of the device measured with register-resident loops (the denominators of the FP64 rooflines,
