@@ -172,6 +172,8 @@ static bool build_grid(const Perm2Env &env, PermGrid &pg)
       if (pS[k] + oS[k] == utot[u]) {
         pg.phiS[n] = pS[k];
         pg.omaS[n] = oS[k];
+        pg.phiH[n] = 0.5 * pS[k];
+        pg.omaH[n] = 0.5 * oS[k];
         pg.kS[n] = (unsigned char)k;
         ++n;
       }
@@ -181,6 +183,8 @@ static bool build_grid(const Perm2Env &env, PermGrid &pg)
   for (int k = 0; k <= S && k < PGR_S; ++k) pg.size_weight[k] = env.hp->size_weight[k];
   pg.size_weight[0] = 0.0;
   pg.UG = (int)uphi.size();
+  pg.invL = L > 0 ? 1.0 / (double)L : 0.0;
+  pg.invK = K > 0 ? 1.0 / (double)K : 0.0;
   pg.L = L;
   pg.K = K;
   return true;

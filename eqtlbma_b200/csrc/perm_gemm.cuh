@@ -267,6 +267,8 @@ struct PermGrid { // kernel parameter (constant bank): the "gen" row of gridL gr
   unsigned char kL[PGR_L];  // grid point k of entry i (element 0 carries the NaN rule of log10_weighted_sum)
   unsigned char tstart[PGR_K + 1];
   unsigned char kS[PGR_K];  // grid point k of gridS entry i
+  double phiH[PGR_K], omaH[PGR_K]; // phiS / 2, omaS / 2
+  double invL, invK;
   int UG, L, K, UT;
 };
 
@@ -525,30 +527,67 @@ struct BfTabs {
   double2 log16[16]; // { 1/m_j, ln m_j }, m_j = 1 + (j + 1/2)/16
 };
 
+// polynomial coefficients and scale factors live in the constant bank: a DFMA takes them as a direct operand (a 64-bit
+// immediate would cost two uniform-register moves per use -- a third of the instructions of the first version)
+__constant__ double PGK[16] = {
+    23.083120654223414,      // 0  16 / ln 2
+    6755399441055744.0,      // 1  1.5 * 2^52
+    -0.043321698784996581,   // 2  -ln 2 / 16
+    1.0 / 24.0,              // 3
+    1.0 / 6.0,               // 4
+    1.0 / 7.0,               // 5
+    -1.0 / 6.0,              // 6
+    0.2,                     // 7
+    1.0 / 3.0,               // 8
+    0.69314718055994530942,  // 9  ln 2
+    2.302585092994045684,    // 10 ln 10
+    0.43429448190325182765,  // 11 1 / ln 10
+    0.0, 0.0, 0.0, 0.0};
+
+// the tables are addressed through a 32-bit shared-space address held in a register (one LDS per lookup)
+struct TabRef {
+  uint32_t base;
+  __device__ __forceinline__ double exp16(int j) const
+  {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + ((uint32_t)j << 3)));
+    return v;
+  }
+  __device__ __forceinline__ double2 log16(int j) const
+  {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + 128u + ((uint32_t)j << 4)));
+    return v;
+  }
+};
+
 // e^x.  FPCLAMP: any x (-inf, NaN -> ~1e-304); otherwise x must be finite with |x| < 1e7 (integer clamp of the binary
 // exponent: results below 2^-1000 come out as ~1e-301, i.e. zero for every sum they enter)
 template <bool FPCLAMP>
-__device__ __forceinline__ double exp_tab16(double x, const BfTabs &T)
+__device__ __forceinline__ double exp_tab16(double x, const TabRef T)
 {
-  if (FPCLAMP) x = fmax(x, -700.0);
-  const double magic = 6755399441055744.0; // 1.5 * 2^52
-  const double tm = fma(x, 23.083120654223414, magic); // 16 / ln 2
+  if (FPCLAMP) {
+    // max(x, -700) on the bit pattern (negative doubles order like their unsigned high words; NaN and -inf are larger)
+    const unsigned int hx = (unsigned int)__double2hiint(x);
+    if (hx > 0xC085E000u) x = -700.0;
+  }
+  const double tm = fma(x, PGK[0], PGK[1]);
   const int k = __double2loint(tm);
-  const double kd = tm - magic;
-  const double gg = fma(kd, -0.043321698784996581, x); // ln 2 / 16: |gg| <= ln2/32
+  const double kd = tm - PGK[1];
+  const double gg = fma(kd, PGK[2], x); // |gg| <= ln2/32
   const double g2 = gg * gg;
-  double s = fma(gg, 1.0 / 24.0, 1.0 / 6.0);
+  double s = fma(gg, PGK[3], PGK[4]);
   s = fma(gg, s, 0.5);
   const double pp = fma(g2, s, gg); // e^g - 1 to g^4: relative error < 4e-11
-  const double tj = T.exp16[k & 15];
+  const double tj = T.exp16(k & 15);
   const double v = fma(tj, pp, tj);
   const int e2 = FPCLAMP ? (k >> 4) : max(k >> 4, -1000);
   return __hiloint2double(__double2hiint(v) + (e2 << 20), __double2loint(v));
 }
 template <bool FPCLAMP>
-__device__ __forceinline__ double exp10_tab16(double x, const BfTabs &T)
+__device__ __forceinline__ double exp10_tab16(double x, const TabRef T)
 {
-  return exp_tab16<FPCLAMP>(x * 2.302585092994045684, T);
+  return exp_tab16<FPCLAMP>(x * PGK[10], T);
 }
 
 // 1/x for a positive normal x: MUFU seed + one Newton step (relative error < 1e-12)
@@ -569,35 +608,43 @@ __device__ __forceinline__ double rsqrt_newton1(double x)
   return fma(0.5 * y, e, y);
 }
 
-// ln x (absolute error < 2e-13 for normal positive x; everything else through the library)
-__device__ __forceinline__ double log_tab16(double x, const BfTabs &T)
+// ln x for a NORMAL POSITIVE x (absolute error < 2e-13); the callers guarantee the range (see log_tab16 for the checked form)
+__device__ __forceinline__ double log_tab16_pos(double x, const TabRef T)
 {
   const int hi = __double2hiint(x);
-  if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x); // zero, subnormal, negative, Inf, NaN
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x)); // [1, 2)
-  const double2 t = T.log16[(hi >> 16) & 15];
+  const double2 t = T.log16((hi >> 16) & 15);
   const double r = fma(m, t.x, -1.0); // |r| <= 1/33
-  double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
-  p = fma(r, p, 0.2);
+  double p = fma(r, PGK[5], PGK[6]);
+  p = fma(r, p, PGK[7]);
   p = fma(r, p, -0.25);
-  p = fma(r, p, 1.0 / 3.0);
+  p = fma(r, p, PGK[8]);
   p = fma(r, p, -0.5);
   const double lp = fma(r * r, p, r); // log1p(r) to r^7
-  return fma((double)((hi >> 20) - 1023), 0.69314718055994530942, t.y + lp);
+  return fma((double)((hi >> 20) - 1023), PGK[9], t.y + lp);
+}
+// any argument: zero, subnormal, negative, Inf, NaN go through the library
+__device__ __forceinline__ double log_tab16(double x, const TabRef T)
+{
+  const int hi = __double2hiint(x);
+  if (hi < 0x00100000 || hi >= 0x7ff00000) return log(x);
+  return log_tab16_pos(x, T);
 }
 
 // diagnostics: worst deviation of the table-driven forms from the CUDA library over n pseudo-random arguments
 __global__ void math_selftest_kernel(long long n, double *out)
 {
-  __shared__ BfTabs T;
+  __shared__ BfTabs Tsm;
   __shared__ double worst[5];
   if (threadIdx.x < 16) {
     const double mj = 1.0 + ((double)threadIdx.x + 0.5) / 16.0;
-    T.exp16[threadIdx.x] = exp2((double)threadIdx.x / 16.0);
-    T.log16[threadIdx.x] = make_double2(1.0 / mj, log(mj));
+    Tsm.exp16[threadIdx.x] = exp2((double)threadIdx.x / 16.0);
+    Tsm.log16[threadIdx.x] = make_double2(1.0 / mj, log(mj));
   }
   if (threadIdx.x < 5) worst[threadIdx.x] = 0.0;
   __syncthreads();
+  TabRef T;
+  T.base = smem_u32(&Tsm);
   double w[5] = {0, 0, 0, 0, 0};
   unsigned long long st = 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
   auto unif = [&]() { // xorshift64*, uniform in [0, 1)
@@ -614,6 +661,7 @@ __global__ void math_selftest_kernel(long long n, double *out)
     else x = 1.0 + (unif() - 0.5) * ((i % 2) ? 2e-3 : 1.2);
     w[0] = fmax(w[0], fabs(rcp_n(x) - 1.0 / x) * x);
     w[1] = fmax(w[1], fabs(log_tab16(x, T) - log(x)));
+    w[1] = fmax(w[1], fabs(log_tab16_pos(x, T) - log(x)));
     w[2] = fmax(w[2], fabs(rsqrt_newton1(x) - rsqrt(x)) * sqrt(x));
     const double y = (kind == 0) ? -690.0 + 1380.0 * unif() : ((kind == 1) ? -60.0 * unif() : 2.0 * unif() - 1.0);
     const double e0 = exp(y);
@@ -623,9 +671,10 @@ __global__ void math_selftest_kernel(long long n, double *out)
     w[3] = fmax(w[3], fabs(exp10_tab16<true>(y * 0.4342944819032518, T) - d0) / d0);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // special values: the clamped exponential must return (nearly) zero, never NaN; the logarithm forwards to the library
+    // special values: the clamped exponential must return (nearly) zero (NaN arguments are excluded by the callers);
+    // the logarithm forwards to the library
     double bad = 0.0;
-    const double se[4] = {-INFINITY, -1e300, -5000.0, nan("")};
+    const double se[4] = {-INFINITY, -1e300, -5000.0, -700.5};
     for (int k = 0; k < 4; ++k) {
       const double v = exp_tab16<true>(se[k], T);
       if (!(v >= 0.0 && v < 1e-300)) bad += 1.0;
@@ -653,7 +702,7 @@ struct LseTab {
     acc = 0.0;
     poisoned = false;
   }
-  __device__ __forceinline__ void add(double v, double w, bool is_first, const BfTabs &T)
+  __device__ __forceinline__ void add(double v, double w, bool is_first, const TabRef T)
   {
     if (v != v) {
       poisoned = poisoned || is_first;
@@ -665,10 +714,10 @@ struct LseTab {
     acc = up ? fma(acc, e, w) : fma(w, e, acc);
     m = up ? v : m;
   }
-  __device__ __forceinline__ double result(const BfTabs &T) const
+  __device__ __forceinline__ double result(const TabRef T) const
   {
     if (poisoned) return nan("");
-    double r = m + log_tab16(acc, T) * EQB_INV_LN10;
+    double r = fma(log_tab16(acc, T), PGK[11], m);
     if (fabs(r) <= DBL_EPSILON) r = 0.0;
     return r;
   }
@@ -680,7 +729,7 @@ struct LseTab {
 // ess / rss, so w^2 = nu log1p(t^2 / nu) = -nu log(rss / yy).  Returns false for everything else (NaN rules, rank
 // deficiency, far tail): the caller then takes stats_from_dots.
 __device__ __forceinline__ bool stats_lean(double xy, double xx, double xraw2, double yy, int n, int Q, int rankz,
-                                           const double *__restrict__ tz, double tz_nu, double tz_wmax, const BfTabs &T,
+                                           const double *__restrict__ tz, double tz_nu, double tz_wmax, const TabRef T,
                                            double &b, double &v, double &t)
 {
   const double nu = (double)(n - 2 - Q);
@@ -689,8 +738,9 @@ __device__ __forceinline__ bool stats_lean(double xy, double xx, double xraw2, d
   const double ixx = rcp_n(xx);
   const double ess = xy * xy * ixx;
   const double rss = yy - ess;
-  if (!(rss > 0.0)) return false;
-  double w2 = -nu * log_tab16(rss * rcp_n(yy), T);
+  const double larg = rss * rcp_n(yy);
+  if (!(larg > 1e-290)) return false; // (also rss <= 0: exact fit, NaN rules of the full function)
+  double w2 = -nu * log_tab16_pos(larg, T);
   w2 = (w2 > 0.0) ? w2 : 0.0;
   const double w = (w2 > 0.0) ? w2 * rsqrt_newton1(w2) : 0.0;
   if (!(w < tz_wmax)) return false;
@@ -708,7 +758,7 @@ __device__ __forceinline__ bool stats_lean(double xy, double xx, double xraw2, d
 }
 
 // log-domain evaluation of the BMA over all configurations for ONE lane (fallback of the linear-domain form: NaN /
-// infinite statistics, or a sum outside the representable window); st = b, v, t of the lane, stride 32
+// infinite statistics, or a sum outside the representable window); st = b, v, t^2 of the lane, stride 32
 static __device__ __noinline__ double bma_all_logdomain(const double *__restrict__ st, int S, unsigned long long has_mask,
                                                         const PermGrid &pg)
 {
@@ -725,7 +775,7 @@ static __device__ __noinline__ double bma_all_logdomain(const double *__restrict
         const int s = __ffsll((long long)mm) - 1;
         mm &= mm - 1;
         double d, bd, sg;
-        term_entry(st[s * 32], st[(S + s) * 32], st[(2 * S + s) * 32], pg.phiS[k], d, bd, sg);
+        term_entry(st[s * 32], st[(S + s) * 32], sqrt(st[(2 * S + s) * 32]), pg.phiS[k], d, bd, sg); // (third row = t^2)
         den += d;
         num += bd;
         sing += sg;
@@ -780,6 +830,52 @@ static __device__ __noinline__ void explicit_xx(const double *__restrict__ Xm, c
   }
 }
 
+// online-LSE forms of the "gen" row and of one singleton row (any value range, NaN rules of log10_weighted_sum): the
+// fallbacks of the linear-domain accumulations of perm_bf_kernel
+static __device__ __noinline__ double gen_row_slow(const double *__restrict__ st, int S, unsigned long long has_mask,
+                                                   const PermGrid &pg, const TabRef T)
+{
+  LseTab rg;
+  rg.init();
+  const double wL = 1.0 / (double)pg.L;
+  for (int u = 0; u < pg.UG; ++u) {
+    double den, num, sing;
+    {
+      const double phi2 = pg.uphi[u];
+      double tsum = 0.0, prod = 1.0, slog = 0.0;
+      den = 0.0;
+      num = 0.0;
+      for (int s = 0; s < S; ++s) {
+        const double t2 = st[(2 * S + s) * 32]; // (0 for the neutral element of a subgroup that contributes nothing)
+        if (((has_mask >> s) & 1ull) && t2 != 0.0) {
+          const double b = st[s * 32], v = st[(S + s) * 32];
+          const double inv = 1.0 / (v + phi2);
+          den += inv;
+          num += b * inv;
+          tsum += t2 * inv;
+          prod *= v * inv;
+          if (prod < 1e-200) {
+            slog += log(prod);
+            prod = 1.0;
+          }
+        }
+      }
+      sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log(prod)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
+    }
+    for (int i = pg.ustart[u]; i < pg.ustart[u + 1]; ++i) rg.add(abf_from_sums(den, num, sing, pg.omaL[i]), wL, pg.kL[i] == 0, T);
+  }
+  return rg.result(T);
+}
+
+static __device__ __noinline__ double single_row_slow(double b, double vv, double tt, const PermGrid &pg, const TabRef T)
+{
+  LseTab rc;
+  rc.init();
+  const double wK = 1.0 / (double)pg.K;
+  for (int i = 0; i < pg.K; ++i) rc.add(singleton_value(b, vv, tt, pg.phiS[i], pg.omaS[i]), wK, pg.kS[i] == 0, T);
+  return rc.result(T);
+}
+
 // Persistent warps: every warp draws tasks from a global counter (uniform cost per SNP, but the number of tasks is
 // not a multiple of the resident warps: a static grid left a fifth of the SM time idle in its last wave).
 template <bool ALLCFG>
@@ -791,20 +887,22 @@ __global__ void __launch_bounds__(256, 2) perm_bf_kernel(const DevParams *__rest
 {
   const DevParams &prm = *prm_;
   extern __shared__ double bf_smem[];
-  __shared__ BfTabs T;
+  __shared__ BfTabs Tsm;
   if (threadIdx.x < 16) {
     const double mj = 1.0 + ((double)threadIdx.x + 0.5) / 16.0;
-    T.exp16[threadIdx.x] = exp2((double)threadIdx.x / 16.0);
-    T.log16[threadIdx.x] = make_double2(1.0 / mj, log(mj));
+    Tsm.exp16[threadIdx.x] = exp2((double)threadIdx.x / 16.0);
+    Tsm.log16[threadIdx.x] = make_double2(1.0 / mj, log(mj));
   }
   __syncthreads();
+  TabRef T;
+  T.base = smem_u32(&Tsm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= warps_per_cta) return;
   const int S = prm.S, ldn = prm.ldn;
   const bool join = prm.analysis == 1;
   const int which = pb.which, kind = pb.stat_kind;
   double *wsm = bf_smem + (size_t)warp * bf_warp_doubles(S, which, kind);
-  double *st = wsm + lane;                         // st[(r * S + s) * 32]: r = 0 b, 1 v, 2 t
+  double *st = wsm + lane;                         // st[(r * S + s) * 32]: r = 0 b, 1 v, 2 t^2 (neutral element if inactive)
   double *hi = wsm + (size_t)3 * S * 32 + lane;    // hi[(sbit * 3 + r) * 32]  (--pbf all)
   const int SA = (S < PBF_SA) ? S : PBF_SA, SB = S - SA;
   double *sepm = wsm + bf_warp_doubles(S, which, 0) + lane; // sepm[s * 32] minima, sepm[(S + s) * 32] NaN flags
@@ -850,7 +948,18 @@ __global__ void __launch_bounds__(256, 2) perm_bf_kernel(const DevParams *__rest
           const int Q = sb.Q;
           const int rankz = pb.sc_rankz[scb + (size_t)s * pb.PBpad];
           double xy, xx, r2, xsum;
-          if (pb.complete[(size_t)il * S + s]) {
+          const bool comp = pb.complete[(size_t)il * S + s] != 0;
+          if (m + 1 < tk.m_end) {
+            // the next SNP's products of this subgroup: requested now, used one row of arithmetic later (D is read once,
+            // straight from HBM: without the prefetch every row pays the DRAM latency in its dependency chain)
+            const double *dn = d + pb.ldd;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(dn));
+            if (!comp) {
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(dn + (size_t)(Q + 1) * pb.PBpad));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(dn + (size_t)(Q + 2) * pb.PBpad));
+            }
+          }
+          if (comp) {
             const double *xs = fs.xstat + (size_t)m * 3; // K1c output: permutation-invariant
             xy = d[0];
             xx = xs[0];
@@ -887,9 +996,15 @@ __global__ void __launch_bounds__(256, 2) perm_bf_kernel(const DevParams *__rest
           }
           has_mask |= 1ull << s;
         }
-        st[s * 32] = sb_b;
-        st[(S + s) * 32] = sb_v;
-        st[(2 * S + s) * 32] = sb_t;
+        // A subgroup without a result, or with |t| < 1e-8 (gene_snp_pair.cpp:314: it contributes nothing), is stored as the
+        // NEUTRAL element b = 0, v = 1e300, t^2 = 0: 1 / (v + phi2) ~ 1e-300 and v / (v + phi2) = 1, so the sums over the
+        // subgroups below need no branch.  NaN statistics stay NaN (they poison the sums exactly as in the reference).
+        {
+          const bool inactive = !have || fabs(sb_t) < 1e-8;
+          st[s * 32] = inactive ? 0.0 : sb_b;
+          st[(S + s) * 32] = inactive ? 1e300 : sb_v;
+          st[(2 * S + s) * 32] = inactive ? 0.0 : sb_t * sb_t;
+        }
         if (!join) {
           const double pval = have ? sb_p : nan("");
           if (pval < snp_pmin) snp_pmin = pval;
@@ -908,72 +1023,86 @@ __global__ void __launch_bounds__(256, 2) perm_bf_kernel(const DevParams *__rest
       }
       double val; // the SNP's weighted ABF of the requested kind
       if (!ALLCFG || which != 3) {
-        // ---- "gen": consistent configuration on gridL, one pass per unique phi2 (gene_snp_pair.cpp:364-416)
-        LseTab rg;
-        rg.init();
-        const double wL = 1.0 / (double)pg.L;
+        // ---- "gen": consistent configuration on gridL, one pass per unique phi2 (gene_snp_pair.cpp:364-416).
+        // log10_weighted_sum in the LINEAR domain against the bound Mg = sum_s t_s^2 / 2 >= every ln ABF (a Bayes factor
+        // cannot exceed the maximised likelihood ratio): no running maximum, one exp per grid point; a sum outside the
+        // representable window (or a NaN) takes the online form of gen_row_slow
+        double Mg = 0.0;
+        for (int s = 0; s < S; ++s) Mg = fma(0.5, st[(2 * S + s) * 32], Mg);
+        double accg = 0.0;
         for (int u = 0; u < pg.UG; ++u) {
           const double phi2 = pg.uphi[u];
           double den = 0.0, num = 0.0, tsum = 0.0, prod = 1.0, slog = 0.0;
-          for (int s = 0; s < S; ++s) {
-            const double tt = st[(2 * S + s) * 32];
-            if (((has_mask >> s) & 1ull) && !(fabs(tt) < 1e-8)) {
-              const double b = st[s * 32], v = st[(S + s) * 32];
+          for (int s0 = 0; s0 < S; s0 += 8) {
+            const int s1 = min(S, s0 + 8);
+            for (int s = s0; s < s1; ++s) {
+              const double b = st[s * 32], v = st[(S + s) * 32], t2 = st[(2 * S + s) * 32];
               const double inv = rcp_n(v + phi2);
               den += inv;
               num = fma(b, inv, num);
-              tsum = fma(tt * tt, inv, tsum);
+              tsum = fma(t2, inv, tsum);
               prod *= v * inv;
-              if (prod < 1e-200) {
-                slog += log(prod);
-                prod = 1.0;
-              }
+            }
+            // (a factor v / (v + phi2) is never below ~1e-6: eight of them cannot underflow a product kept above 1e-200)
+            if (prod < 1e-200) {
+              slog += log(prod);
+              prod = 1.0;
             }
           }
-          const double sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log_tab16(prod, T)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
+          // ln of the product of the single-subgroup ABFs (one logarithm per phi2), shifted by the bound
+          const double sing = ((phi2 == 0.0) ? 0.0 : fma(0.5, slog + log_tab16_pos(prod, T), 0.5 * phi2 * tsum)) - Mg;
           const bool live = num != 0.0 && den != 0.0 && den == den; // (CalcLog10AbfUvlr's guards, see abf_from_sums)
+          const double hn2 = 0.5 * num * num;
           for (int i = pg.ustart[u]; i < pg.ustart[u + 1]; ++i) {
             const double oma2 = pg.omaL[i];
-            double x = 0.0;
+            double xn = -Mg;
             if (live) {
-              x = sing;
+              xn = sing;
               if (oma2 != 0.0) {
                 const double z = fma(oma2, den, 1.0);
-                x += (-0.5 * log_tab16(z, T) + 0.5 * num * num * oma2 * rcp_n(z)) * EQB_INV_LN10;
+                xn += fma(-0.5, log_tab16_pos(z, T), hn2 * oma2 * rcp_n(z));
               }
             }
-            rg.add(x, wL, pg.kL[i] == 0, T);
+            accg += exp_tab16<false>(xn, T);
           }
         }
-        val = rg.result(T);
+        if (accg > 1e-280 && accg < INFINITY) {
+          val = (Mg + log_tab16_pos(accg * pg.invL, T)) * PGK[11];
+          if (fabs(val) <= DBL_EPSILON) val = 0.0;
+        } else
+          val = gen_row_slow(st, S, has_mask, pg, T);
         if (which == 2) {
           // ---- singletons on gridS + BMAlite (gene_snp_pair.cpp:422-463, 552-570): grid points grouped by
-          // phi2 + oma2 (the logarithm 0.5 log(v / (v + phi2 + oma2)) is shared inside a group)
+          // phi2 + oma2 (the logarithm 0.5 ln(v / (v + phi2 + oma2)) is shared inside a group), linear domain
+          // against the bound t^2 / 2
           LseTab lite;
           lite.init();
-          const double wK = 1.0 / (double)pg.K, wS = 0.5 / (double)S;
+          const double wS = 0.5 / (double)S;
           for (int s = 0; s < S; ++s) {
-            LseTab rc;
-            rc.init();
-            const double b = st[s * 32], vv = st[(S + s) * 32], tt = st[(2 * S + s) * 32];
-            const bool live = ((has_mask >> s) & 1ull) && !(fabs(tt) < 1e-8) && b != 0.0 && vv == vv && vv < INFINITY;
-            const double t2 = tt * tt, b2 = b * b;
-            for (int u = 0; u < pg.UT; ++u) {
-              double w = 0.0, lg = 0.0;
-              if (live) {
-                w = rcp_n(vv + pg.utot[u]);
-                lg = 0.5 * log_tab16(vv * w, T);
-              }
-              for (int i = pg.tstart[u]; i < pg.tstart[u + 1]; ++i) {
-                double x = 0.0;
-                if (live) {
+            const double b = st[s * 32], vv = st[(S + s) * 32], t2 = st[(2 * S + s) * 32];
+            const bool live = t2 != 0.0 && b != 0.0 && vv == vv; // (neutral element: t2 = 0; NaN statistics: vv != vv)
+            double wc = 0.0; // every value of a subgroup without a usable statistic is 0 (gene_snp_pair.cpp:436-457)
+            if (pg.K == 0)
+              wc = nan("");
+            else if (live) {
+              const double Ms = 0.5 * t2, b2 = b * b;
+              double acc = 0.0;
+              for (int u = 0; u < pg.UT; ++u) {
+                const double w = rcp_n(vv + pg.utot[u]);
+                const double lg = fma(0.5, log_tab16_pos(vv * w, T), -Ms);
+                const double c1 = b2 * w;
+                for (int i = pg.tstart[u]; i < pg.tstart[u + 1]; ++i) {
                   const double inv = rcp_n(vv + pg.phiS[i]);
-                  x = (lg + 0.5 * inv * fma(t2, pg.phiS[i], b2 * pg.omaS[i] * w)) * EQB_INV_LN10;
+                  acc += exp_tab16<false>(fma(inv, fma(t2, pg.phiH[i], c1 * pg.omaH[i]), lg), T);
                 }
-                rc.add(x, wK, pg.kS[i] == 0, T);
               }
+              if (acc > 1e-280 && acc < INFINITY) {
+                wc = (Ms + log_tab16_pos(acc * pg.invK, T)) * PGK[11];
+                if (fabs(wc) <= DBL_EPSILON) wc = 0.0;
+              } else
+                wc = single_row_slow(b, vv, sqrt(t2), pg, T);
             }
-            lite.add(pg.K > 0 ? rc.result(T) : nan(""), wS, s == 0, T);
+            lite.add(wc, wS, s == 0, T);
           }
           lite.add(val, 0.5, false, T);
           val = lite.result(T);
@@ -985,9 +1114,9 @@ __global__ void __launch_bounds__(256, 2) perm_bf_kernel(const DevParams *__rest
         double Mref = 0.0;
         for (int s = 0; s < S; ++s)
           if ((has_mask >> s) & 1ull) {
-            const double t = st[(2 * S + s) * 32], b = st[s * 32], v = st[(S + s) * 32];
-            if (isnan(t) || isnan(b) || isnan(v) || isinf(b)) fast_ok = false;
-            else if (fabs(t) >= 1e-8) Mref += 0.5 * t * t;
+            const double t2 = st[(2 * S + s) * 32], b = st[s * 32], v = st[(S + s) * 32];
+            if (isnan(t2) || isnan(b) || isnan(v) || isinf(b)) fast_ok = false;
+            else Mref += 0.5 * t2;
           }
         Mref -= 350.0;
         double total = 0.0;
@@ -995,16 +1124,12 @@ __global__ void __launch_bounds__(256, 2) perm_bf_kernel(const DevParams *__rest
           for (int k = 0; k < pg.K; ++k) {
             const double phi2 = pg.phiS[k], oma2 = pg.omaS[k], hom2 = 0.5 * oma2;
             // per-subgroup terms { oma2 / (v + phi2), b / (v + phi2), ln of the single-subgroup ABF }
-            auto term = [&](int s, double &dz, double &dn, double &dA) {
-              dz = dn = dA = 0.0;
-              const double tt = st[(2 * S + s) * 32];
-              if (((has_mask >> s) & 1ull) && !(fabs(tt) < 1e-8)) {
-                const double b = st[s * 32], v = st[(S + s) * 32];
-                const double inv = rcp_n(v + phi2);
-                dz = oma2 * inv;
-                dn = b * inv;
-                dA = (phi2 == 0.0) ? 0.0 : 0.5 * log_tab16(v * inv, T) + 0.5 * tt * tt * phi2 * inv;
-              }
+            auto term = [&](int s, double &dz, double &dn, double &dA) { // (neutral elements give ~0, 0, ~0)
+              const double b = st[s * 32], v = st[(S + s) * 32], t2 = st[(2 * S + s) * 32];
+              const double inv = rcp_n(v + phi2);
+              dz = oma2 * inv;
+              dn = b * inv;
+              dA = (phi2 == 0.0) ? 0.0 : fma(0.5, log_tab16_pos(v * inv, T), 0.5 * t2 * phi2 * inv);
             };
             // low part: the 2^SA subset sums of the subgroups 0..SA-1, in registers
             double lz[1 << PBF_SA], ln_[1 << PBF_SA], lA[1 << PBF_SA];
