@@ -218,7 +218,9 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
 
     ind_names = [nm("ind", i + 1) for i in range(n_inds)]
     samples = sorted(ind_names)
-    chr_names_unsorted = [f"chr{c + 1}" for c in range(n_chr)]
+    # (zero-padded with pad_names: the byte-wise chromosome order of the loader then equals the numeric one, so genes that
+    # are contiguous in name order have contiguous genotype rows)
+    chr_names_unsorted = [f"chr{c + 1:0{len(str(n_chr))}d}" if pad_names else f"chr{c + 1}" for c in range(n_chr)]
     chr_names = sorted(chr_names_unsorted)
 
     # genes: equally spread over chromosomes, spacing 1000 bp, length 200
