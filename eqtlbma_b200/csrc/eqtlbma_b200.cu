@@ -1119,6 +1119,16 @@ int prepare_fast_path(eqb_ctx *ctx)
 
 extern "C" {
 
+int eqb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
 int eqb_create(eqb_ctx **out, const eqb_config *cfg)
 {
   if (!out || !cfg) return 1;
@@ -2298,8 +2308,7 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
     CK(cudaEventRecord(ev0, ctx->stream));
   }
   const int n_slots = max_slot + 1;
-  if (pc->trick != 1 || kind == STAT_SEP_PER) {
-    if (pc->trick == 1) return fail(ctx, "--trick 1 with --permsep 2 is not implemented on the device yet");
+  if (pc->trick != 1) {
     // --trick 0|2: every gene consumes exactly P shuffles, so the k-th analysed gene of any
     // write-group sees table[k][p] = cumulative gsl_ran_shuffle of the identity, the generator being
     // seeded once per write-group and running on across its genes (eqtlbma_bf.cpp:847, gene.cpp:617-639)
@@ -2330,6 +2339,9 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
     // next gene of the write-group starts depends on the data.  Write-groups are
     // independent (each re-seeds): rounds over the slot index, per-gene tables built from the master
     // stream of Fisher-Yates swap targets at the offset where the previous gene of the group stopped.
+    // --permsep 2 runs the whole scheme once per subgroup (the generator is re-seeded for every subgroup,
+    // eqtlbma_bf.cpp:806-822, and a gene's stopping point is its own in every subgroup, gene.cpp:380-450): pass sl
+    // keeps row sl of every item.
     ctx->perm_P = -1; // the cached --trick 0|2 tables are overwritten
     Mt19937 rng;
     rng.seed(pc->seed);
@@ -2341,88 +2353,91 @@ static int run_perm_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
         swaps.push_back(sw);
       }
     };
-    std::vector<long long> group_off(n_groups, 0);
     std::vector<long long> h_consumed;
-    for (int k = 0; k < n_slots; ++k) {
-      std::vector<int> it_idx;
-      for (size_t i = 0; i < n_items; ++i)
-        if (slots[i] == k) it_idx.push_back((int)i);
-      // process the round in sub-batches of distinct offsets to bound the table memory
-      size_t pos = 0;
-      while (pos < it_idx.size()) {
-        std::map<long long, int> off2tab;
-        std::vector<int> bg, bt;
-        std::vector<int> bidx;
-        const size_t max_tabs = std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)P * N * 2));
+    for (int sl = 0; sl < per; ++sl) {
+      std::vector<long long> group_off(n_groups, 0);
+      for (int k = 0; k < n_slots; ++k) {
+        std::vector<int> it_idx;
+        for (size_t i = 0; i < n_items; ++i)
+          if (slots[i] == k) it_idx.push_back((int)i);
+        // process the round in sub-batches of distinct offsets to bound the table memory
+        size_t pos = 0;
         while (pos < it_idx.size()) {
-          const int i = it_idx[pos];
-          const long long o = group_off[group_of[i]];
-          if (off2tab.find(o) == off2tab.end()) {
-            if (off2tab.size() >= max_tabs) break;
-            const int t = (int)off2tab.size();
-            off2tab[o] = t;
+          std::map<long long, int> off2tab;
+          std::vector<int> bg, bt;
+          std::vector<int> bidx;
+          const size_t max_tabs = std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)P * N * 2));
+          while (pos < it_idx.size()) {
+            const int i = it_idx[pos];
+            const long long o = group_off[group_of[i]];
+            if (off2tab.find(o) == off2tab.end()) {
+              if (off2tab.size() >= max_tabs) break;
+              const int t = (int)off2tab.size();
+              off2tab[o] = t;
+            }
+            bg.push_back(genes[i]);
+            bt.push_back(off2tab[o]);
+            bidx.push_back(i);
+            ++pos;
           }
-          bg.push_back(genes[i]);
-          bt.push_back(off2tab[o]);
-          bidx.push_back(i);
-          ++pos;
-        }
-        std::vector<unsigned short> tab(off2tab.size() * (size_t)P * N);
-        std::vector<unsigned short> perm(N);
-        for (auto &kv : off2tab) {
-          need_swaps((size_t)(kv.first + P));
-          for (int i = 0; i < N; ++i) perm[i] = (unsigned short)i;
-          for (long long p = 0; p < P; ++p) {
-            const std::vector<unsigned short> &sw = swaps[(size_t)(kv.first + p)];
-            for (int i = N - 1; i > 0; --i) std::swap(perm[i], perm[sw[i]]);
-            memcpy(&tab[((size_t)kv.second * P + p) * N], perm.data(), N * sizeof(unsigned short));
+          std::vector<unsigned short> tab(off2tab.size() * (size_t)P * N);
+          std::vector<unsigned short> perm(N);
+          for (auto &kv : off2tab) {
+            need_swaps((size_t)(kv.first + P));
+            for (int i = 0; i < N; ++i) perm[i] = (unsigned short)i;
+            for (long long p = 0; p < P; ++p) {
+              const std::vector<unsigned short> &sw = swaps[(size_t)(kv.first + p)];
+              for (int i = N - 1; i > 0; --i) std::swap(perm[i], perm[sw[i]]);
+              memcpy(&tab[((size_t)kv.second * P + p) * N], perm.data(), N * sizeof(unsigned short));
+            }
           }
+          CK(ctx->d_perm.ensure(tab.size()));
+          CK(h2d(ctx, ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short)));
+          CK(cudaStreamSynchronize(ctx->stream));
+          // rows of this sub-batch are contiguous in a scratch region, then scattered to their items
+          const size_t brows = bg.size() * (size_t)per;
+          CK(ctx->d_stat2.ensure(brows * (size_t)P));
+          std::swap(ctx->d_stat.p, ctx->d_stat2.p);
+          std::swap(ctx->d_stat.cap, ctx->d_stat2.cap);
+          // evaluate into scratch rows [0, brows)
+          DevBuf<double> keep_true;
+          DevBuf<long long> kc, kd, kt, ku;
+          std::swap(keep_true.p, ctx->d_true.p); std::swap(keep_true.cap, ctx->d_true.cap);
+          std::swap(kc.p, ctx->d_count.p); std::swap(kc.cap, ctx->d_count.cap);
+          std::swap(kd.p, ctx->d_done.p); std::swap(kd.cap, ctx->d_done.cap);
+          std::swap(kt.p, ctx->d_total.p); std::swap(kt.cap, ctx->d_total.cap);
+          std::swap(ku.p, ctx->d_consumed.p); std::swap(ku.cap, ctx->d_consumed.cap);
+          CK(ctx->d_true.ensure(brows));
+          CK(ctx->d_count.ensure(brows));
+          CK(ctx->d_done.ensure(brows));
+          CK(ctx->d_total.ensure(brows));
+          CK(ctx->d_consumed.ensure(brows));
+          int rc = eval_perm_items(ctx, bg, bt, pc, kind, 0);
+          if (rc) return rc;
+          // scatter row sl of every item of the sub-batch to its final row
+          for (size_t b = 0; b < bg.size(); ++b) {
+            const size_t r = (size_t)bidx[b] * per + sl, q = b * per + sl;
+            CK(cudaMemcpyAsync(ctx->d_stat2.p + r * (size_t)P, ctx->d_stat.p + q * (size_t)P, (size_t)P * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(keep_true.p + r, ctx->d_true.p + q, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(kc.p + r, ctx->d_count.p + q, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(kd.p + r, ctx->d_done.p + q, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(kt.p + r, ctx->d_total.p + q, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ku.p + r, ctx->d_consumed.p + q, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+          }
+          h_consumed.resize(brows);
+          CK(cudaMemcpyAsync(h_consumed.data(), ctx->d_consumed.p, brows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+          CK(cudaStreamSynchronize(ctx->stream));
+          for (size_t b = 0; b < bg.size(); ++b) group_off[group_of[bidx[b]]] += h_consumed[b * per + sl];
+          // restore the full-size buffers
+          ctx->d_true.release(); ctx->d_count.release(); ctx->d_done.release(); ctx->d_total.release(); ctx->d_consumed.release();
+          std::swap(keep_true.p, ctx->d_true.p); std::swap(keep_true.cap, ctx->d_true.cap);
+          std::swap(kc.p, ctx->d_count.p); std::swap(kc.cap, ctx->d_count.cap);
+          std::swap(kd.p, ctx->d_done.p); std::swap(kd.cap, ctx->d_done.cap);
+          std::swap(kt.p, ctx->d_total.p); std::swap(kt.cap, ctx->d_total.cap);
+          std::swap(ku.p, ctx->d_consumed.p); std::swap(ku.cap, ctx->d_consumed.cap);
+          std::swap(ctx->d_stat.p, ctx->d_stat2.p);
+          std::swap(ctx->d_stat.cap, ctx->d_stat2.cap);
         }
-        CK(ctx->d_perm.ensure(tab.size()));
-        CK(h2d(ctx, ctx->d_perm.p, tab.data(), tab.size() * sizeof(unsigned short)));
-        CK(cudaStreamSynchronize(ctx->stream));
-        // rows of this sub-batch are contiguous in a scratch region, then scattered to their items
-        CK(ctx->d_stat2.ensure(bg.size() * (size_t)P));
-        std::swap(ctx->d_stat.p, ctx->d_stat2.p);
-        std::swap(ctx->d_stat.cap, ctx->d_stat2.cap);
-        // evaluate into scratch rows [0, bg.size())
-        DevBuf<double> keep_true;
-        DevBuf<long long> kc, kd, kt, ku;
-        std::swap(keep_true.p, ctx->d_true.p); std::swap(keep_true.cap, ctx->d_true.cap);
-        std::swap(kc.p, ctx->d_count.p); std::swap(kc.cap, ctx->d_count.cap);
-        std::swap(kd.p, ctx->d_done.p); std::swap(kd.cap, ctx->d_done.cap);
-        std::swap(kt.p, ctx->d_total.p); std::swap(kt.cap, ctx->d_total.cap);
-        std::swap(ku.p, ctx->d_consumed.p); std::swap(ku.cap, ctx->d_consumed.cap);
-        CK(ctx->d_true.ensure(bg.size()));
-        CK(ctx->d_count.ensure(bg.size()));
-        CK(ctx->d_done.ensure(bg.size()));
-        CK(ctx->d_total.ensure(bg.size()));
-        CK(ctx->d_consumed.ensure(bg.size()));
-        int rc = eval_perm_items(ctx, bg, bt, pc, kind, 0);
-        if (rc) return rc;
-        // scatter to the final rows
-        for (size_t b = 0; b < bg.size(); ++b) {
-          const size_t r = (size_t)bidx[b];
-          CK(cudaMemcpyAsync(ctx->d_stat2.p + r * (size_t)P, ctx->d_stat.p + b * (size_t)P, (size_t)P * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-          CK(cudaMemcpyAsync(keep_true.p + r, ctx->d_true.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-          CK(cudaMemcpyAsync(kc.p + r, ctx->d_count.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-          CK(cudaMemcpyAsync(kd.p + r, ctx->d_done.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-          CK(cudaMemcpyAsync(kt.p + r, ctx->d_total.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-          CK(cudaMemcpyAsync(ku.p + r, ctx->d_consumed.p + b, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        }
-        h_consumed.resize(bg.size());
-        CK(cudaMemcpyAsync(h_consumed.data(), ctx->d_consumed.p, bg.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        for (size_t b = 0; b < bg.size(); ++b) group_off[group_of[bidx[b]]] += h_consumed[b];
-        // restore the full-size buffers
-        ctx->d_true.release(); ctx->d_count.release(); ctx->d_done.release(); ctx->d_total.release(); ctx->d_consumed.release();
-        std::swap(keep_true.p, ctx->d_true.p); std::swap(keep_true.cap, ctx->d_true.cap);
-        std::swap(kc.p, ctx->d_count.p); std::swap(kc.cap, ctx->d_count.cap);
-        std::swap(kd.p, ctx->d_done.p); std::swap(kd.cap, ctx->d_done.cap);
-        std::swap(kt.p, ctx->d_total.p); std::swap(kt.cap, ctx->d_total.cap);
-        std::swap(ku.p, ctx->d_consumed.p); std::swap(ku.cap, ctx->d_consumed.cap);
-        std::swap(ctx->d_stat.p, ctx->d_stat2.p);
-        std::swap(ctx->d_stat.cap, ctx->d_stat2.cap);
       }
     }
   }

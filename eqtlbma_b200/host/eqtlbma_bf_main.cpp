@@ -24,8 +24,11 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <dirent.h>
 #include <sys/time.h>
+#include <sys/wait.h>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/eqtlbma_b200.h"
@@ -223,6 +226,9 @@ struct Options {
   vector<string> sbgrp;
   int device = 0;
   int shard_k = 0, shard_n = 1; // --shard k/N (extension): this process handles the k-th of N gene shards
+  int gpus = 1;                 // --gpus N (extension): launcher, one shard process per GPU + merge of the outputs
+  bool shard_child = false;     // (internal) process started by the --gpus launcher
+  bool no_header = false;       // (internal) shards after the first one write no header lines
 };
 
 void help(char **argv)
@@ -239,7 +245,10 @@ void help(char **argv)
        << "      --device\tCUDA device ordinal (extension)" << endl
        << "      --shard\tk/N: handle the k-th of N contiguous, cost-balanced gene shards (extension;\n"
        << "\t\tone process per GPU, outputs concatenate in shard order like the batches of\n"
-       << "\t\teqtlbma_bf_parallel.bash)" << endl;
+       << "\t\teqtlbma_bf_parallel.bash)" << endl
+       << "      --gpus\tN: run the N shards on GPUs 0..N-1 of this machine, one process each, and\n"
+       << "\t\tconcatenate their outputs in shard order (extension; replaces the launcher +\n"
+       << "\t\t`zcat | sed 1d` merge of eqtlbma_bf_parallel.bash; same files as a single run)" << endl;
 }
 
 void die_usage(int argc, char **argv, const string &msg)
@@ -272,7 +281,7 @@ void parse_cmdline(int argc, char **argv, Options &o)
       {"maxbf", no_argument, 0, 0},           {"thread", required_argument, 0, 0},
       {"snp", required_argument, 0, 0},       {"sbgrp", required_argument, 0, 0},
       {"wrtsize", required_argument, 0, 0},   {"device", required_argument, 0, 0},
-      {"shard", required_argument, 0, 0},
+      {"shard", required_argument, 0, 0},     {"gpus", required_argument, 0, 0},
       {0, 0, 0, 0}};
   while (true) {
     int idx = 0;
@@ -328,6 +337,10 @@ void parse_cmdline(int argc, char **argv, Options &o)
     else if (n == "sbgrp") split(optarg, "+", o.sbgrp);
     else if (n == "wrtsize") o.wrtsize = atoi(optarg);
     else if (n == "device") o.device = atoi(optarg);
+    else if (n == "gpus") {
+      o.gpus = atoi(optarg);
+      if (o.gpus < 1 || o.gpus > 64) die_usage(argc, argv, "--gpus should be between 1 and 64");
+    }
     else if (n == "shard") {
       if (sscanf(optarg, "%d/%d", &o.shard_k, &o.shard_n) != 2 || o.shard_n < 1 || o.shard_k < 0 || o.shard_k >= o.shard_n)
         die_usage(argc, argv, "--shard should be k/N with 0 <= k < N");
@@ -924,6 +937,107 @@ vector<string> config_names(int S, const string &bfs)
   return names;
 }
 
+// --gpus N: the reference spreads gene batches over OS processes with scripts/eqtlbma_bf_parallel.bash:248-345 and
+// merges with `zcat | sed 1d` (doc/manual_eqtlbma.texi:1211-1218).  Here: one child per GPU with --shard k/N (contiguous
+// cost-balanced ranges of whole write-groups, eqb_partition_by_cost), each writing <out>.shard<k>_*; shard 0 writes the
+// header members, the others none, so the byte-wise concatenation in shard order IS the output of a single run
+// (gzip members concatenate; same lines, same order).  Returns the exit status for main(), or -1 in a child.
+int launch_shards(int argc, char **argv, Options &o, time_t t_start)
+{
+  const string out = o.out;
+  vector<pid_t> pids(o.gpus);
+  fflush(stdout);
+  fflush(stderr);
+  for (int k = 0; k < o.gpus; ++k) {
+    const pid_t pid = fork(); // (before any CUDA call: every child creates its own context on its own device)
+    if (pid < 0) {
+      cerr << "ERROR: fork failed" << endl;
+      return EXIT_FAILURE;
+    }
+    if (pid == 0) {
+      o.shard_k = k;
+      o.shard_n = o.gpus;
+      o.device = k;
+      o.out = out + ".shard" + to_string(k);
+      o.shard_child = true;
+      o.no_header = k > 0;
+      if (k > 0) o.verbose = 0;
+      return -1;
+    }
+    pids[k] = pid;
+  }
+  bool ok = true;
+  for (int k = 0; k < o.gpus; ++k) {
+    int status = 0;
+    if (waitpid(pids[k], &status, 0) < 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) ok = false;
+  }
+  if (!ok) {
+    cerr << "ERROR: a shard process failed" << endl;
+    return EXIT_FAILURE;
+  }
+  // merge: every file <out>.shard0<suffix> with its counterparts of the other shards
+  string dir = ".", base = out;
+  const size_t slash = out.find_last_of('/');
+  if (slash != string::npos) {
+    dir = out.substr(0, slash);
+    base = out.substr(slash + 1);
+  }
+  const string pre0 = base + ".shard0";
+  vector<string> suffixes;
+  if (DIR *dp = opendir(dir.c_str())) {
+    while (struct dirent *e = readdir(dp)) {
+      const string fn = e->d_name;
+      if (fn.compare(0, pre0.size(), pre0) == 0 && fn.size() > pre0.size() && fn[pre0.size()] == '_')
+        suffixes.push_back(fn.substr(pre0.size()));
+    }
+    closedir(dp);
+  }
+  sort(suffixes.begin(), suffixes.end());
+  vector<char> buf(1 << 22);
+  for (const string &suf : suffixes) {
+    FILE *fo = fopen((out + suf).c_str(), "wb");
+    if (fo == NULL) {
+      cerr << "ERROR: can't open file " << out + suf << " with mode wb" << endl;
+      return EXIT_FAILURE;
+    }
+    for (int k = 0; k < o.gpus; ++k) {
+      const string part = out + ".shard" + to_string(k) + suf;
+      FILE *fi = fopen(part.c_str(), "rb");
+      if (fi == NULL) continue;
+      size_t n;
+      while ((n = fread(buf.data(), 1, buf.size(), fi)) > 0)
+        if (fwrite(buf.data(), 1, n, fo) != n) {
+          cerr << "ERROR: can't write to file " << out + suf << endl;
+          return EXIT_FAILURE;
+        }
+      fclose(fi);
+      remove(part.c_str());
+    }
+    fclose(fo);
+  }
+  size_t pairs = 0, genes = 0;
+  for (int k = 0; k < o.gpus; ++k) {
+    const string cf = out + ".shard" + to_string(k) + ".count";
+    if (FILE *f = fopen(cf.c_str(), "r")) {
+      size_t a = 0, b = 0;
+      if (fscanf(f, "%zu %zu", &a, &b) == 2) {
+        pairs += a;
+        genes += b;
+      }
+      fclose(f);
+      remove(cf.c_str());
+    }
+  }
+  if (o.verbose > 0) {
+    cout << "nb of analyzed gene-SNP pairs: " << pairs << " (" << genes << " genes)" << endl;
+    time_t t_end;
+    time(&t_end);
+    cout << "END " << argv[0] << " " << ctime(&t_end) << "elapsed -> " << difftime(t_end, t_start) << " sec" << endl;
+  }
+  (void)argc;
+  return EXIT_SUCCESS;
+}
+
 } // namespace
 
 int main(int argc, char **argv)
@@ -937,6 +1051,12 @@ int main(int argc, char **argv)
          << "cmd-line:";
     for (int i = 0; i < argc; ++i) cout << " " << argv[i];
     cout << endl << flush;
+  }
+  if (o.gpus > 1 && o.shard_n == 1) {
+    const int rc = launch_shards(argc, argv, o, t_start);
+    if (rc >= 0) return rc; // launcher (parent); children fall through with their shard options
+    const int ndev = eqb_device_count(); // (first CUDA call of the child: after the fork)
+    if (ndev > 0) o.device = o.shard_k % ndev; // fewer GPUs than shards: the shards share them
   }
   Loaded d;
   load_all(o, d);
@@ -1116,35 +1236,47 @@ int main(int argc, char **argv)
   const bool write_ss = !join || (o.outss && o.error != "mvlr");
   const bool is_perm = o.nb_permutations > 0 && (o.perm_sep != 0 || o.pbf != "none");
   const string sep = "\t";
+  // (shards after the first one start their files empty: the launcher concatenates the shards' gzip members in order)
+  auto gz_header = [&](const string &path, const string &txt) {
+    if (o.no_header) {
+      FILE *f = fopen(path.c_str(), "wb");
+      if (f == NULL) {
+        cerr << "ERROR: can't open file " << path << " with mode wb" << endl;
+        exit(EXIT_FAILURE);
+      }
+      fclose(f);
+    } else
+      gz_write(path, "wb", txt);
+  };
   if (write_ss)
     for (int s = 0; s < S; ++s)
-      gz_write(o.out + "_sumstats_" + d.subgroups[s] + ".txt.gz", "wb",
-               "gene\tsnp\tmaf\tn\tpve\tsigmahat\tbetahat.geno\tsebetahat.geno\tbetapval.geno\n");
+      gz_header(o.out + "_sumstats_" + d.subgroups[s] + ".txt.gz",
+                "gene\tsnp\tmaf\tn\tpve\tsigmahat\tbetahat.geno\tsebetahat.geno\tbetapval.geno\n");
   if (join) {
     string h = "gene\tsnp\tconfig";
     for (int i = 0; i < L; ++i) h += "\tl10abf.grid" + to_string(i + 1);
-    gz_write(o.out + "_l10abfs_raw.txt.gz", "wb", h + "\n");
+    gz_header(o.out + "_l10abfs_raw.txt.gz", h + "\n");
     if (o.outw) {
       h = "gene\tsnp\tnb.subgroups\tl10abf.gen\tl10abf.gen.fix\tl10abf.gen.maxh";
       if (o.bfs != "gen") h += "\tl10abf.gen.sin";
       if (o.bfs == "all") h += "\tl10abf.all";
       for (size_t c = 0; c < cnames.size(); ++c) h += "\tl10abf." + cnames[c];
-      gz_write(o.out + "_l10abfs_avg-grids.txt.gz", "wb", h + "\n");
+      gz_header(o.out + "_l10abfs_avg-grids.txt.gz", h + "\n");
     }
     if (o.nb_permutations > 0) {
       stringstream ss;
       ss << "# perm.bf=" << o.pbf << " seed=" << o.seed << "\n"
          << "gene\tnb.snps\tjoin.perm.pval\tnb.permutations\ttrue.l10abf\tmed.perm.l10abf\n";
-      gz_write(o.out + "_joinPermPvals.txt.gz", "wb", ss.str());
+      gz_header(o.out + "_joinPermPvals.txt.gz", ss.str());
     }
   } else if (o.nb_permutations > 0 && o.perm_sep != 0) {
     stringstream ss;
     ss << "# seed=" << o.seed << "\n"
        << "gene\tnb.snps\tsep.perm.pval\tnb.permutations\ttrue.min.pval\n";
     if (o.perm_sep == 1)
-      gz_write(o.out + "_sepPermPvals.txt.gz", "wb", ss.str());
+      gz_header(o.out + "_sepPermPvals.txt.gz", ss.str());
     else
-      for (int s = 0; s < S; ++s) gz_write(o.out + "_sepPermPvals_" + d.subgroups[s] + ".txt.gz", "wb", ss.str());
+      for (int s = 0; s < S; ++s) gz_header(o.out + "_sepPermPvals_" + d.subgroups[s] + ".txt.gz", ss.str());
   }
 
   if (o.verbose > 0)
@@ -1351,10 +1483,16 @@ int main(int argc, char **argv)
       }
     g0 = g1;
   }
-  if (o.verbose > 0)
+  if (o.shard_child) { // the launcher adds the shards' counts up
+    FILE *f = fopen((o.out + ".count").c_str(), "w");
+    if (f != NULL) {
+      fprintf(f, "%zu %zu\n", nbAnalyzedPairs, nbAnalyzedGenes);
+      fclose(f);
+    }
+  } else if (o.verbose > 0)
     cout << "nb of analyzed gene-SNP pairs: " << nbAnalyzedPairs << " (" << nbAnalyzedGenes << " genes)" << endl;
   eqb_destroy(ctx);
-  if (o.verbose > 0) {
+  if (o.verbose > 0 && !o.shard_child) {
     time_t t_end;
     time(&t_end);
     cout << "END " << argv[0] << " " << ctime(&t_end) << "elapsed -> " << difftime(t_end, t_start) << " sec" << endl;

@@ -203,7 +203,7 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
                  dosage=False, maf=0.3, gridL=None, gridS=None, radius=None, anchor="TSS",
                  null_frac=0.3, separate_geno_files=False, missing_geno_frac=0.0,
                  pad_names=False, monomorphic_frac=0.0, gene_spacing=1000, far_snp=True,
-                 geno_format="custom", layout_only=False) -> Dataset:
+                 geno_format="custom", layout_only=False, perfect_frac=0.0) -> Dataset:
     """Generate a dataset. One SNP stream per chromosome at uniform spacing; each gene's +-radius
     TSS window holds ~snps_per_gene SNPs; expression y = mu_s + b_s*g + N(0,1) with ES-model
     effects from the first cis SNP of the gene (simul_flutre_et_al.cpp:682-743)."""
@@ -339,6 +339,9 @@ def make_dataset(seed=1859, n_subgroups=3, n_inds=200, n_genes=10, snps_per_gene
                 y = y + b * np.nan_to_num(G[m])
             if n_cov > 0:
                 y = y + 0.5 * Cfull[0]
+            if perfect_frac > 0 and end[g] > beg[g] and rng.random() < perfect_frac:
+                # almost deterministic eQTL: |t| of several hundreds, the Student tail underflows
+                y = mus[s] + np.nan_to_num(G[int(beg[g])]) + rng.normal(0, 0.004, n_inds)
             Y[g] = y[cols]
         Y = _round(Y, 6)
         if nan_frac > 0:

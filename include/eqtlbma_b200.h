@@ -117,6 +117,8 @@ typedef struct {
   double *perm_stats; /* optional [genes][nperm] (x S for permsep 2): every permuted statistic, NaN if not evaluated */
 } eqb_perm_results;
 
+/* Number of usable CUDA devices (0 if none); lets a launcher place one shard process per GPU. */
+int eqb_device_count(void);
 int eqb_create(eqb_ctx **ctx, const eqb_config *cfg);
 void eqb_destroy(eqb_ctx *ctx);
 const char *eqb_last_error(const eqb_ctx *ctx);

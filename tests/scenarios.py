@@ -41,6 +41,21 @@ SCENARIOS = {
                          perm=dict(nperm=80, permsep=1, seed=13)),
     "sep_permsep2_trick2": dict(data=dict(BASE, seed=52, absent_gene_frac=0.2), analysis="sep", bfs="gen",
                                 wrtsize=4, perm=dict(nperm=80, permsep=2, seed=14, trick=2, tricut=3)),
+    # --trick 1 with --permsep 2: the generator is re-seeded per subgroup and a gene's stopping point is its own in
+    # every subgroup (eqtlbma_bf.cpp:806-822, gene.cpp:380-450)
+    "sep_permsep2_trick1": dict(data=dict(BASE, seed=53, n_genes=12, null_frac=0.7, absent_gene_frac=0.1), analysis="sep",
+                                bfs="gen", wrtsize=4, perm=dict(nperm=120, permsep=2, seed=15, trick=1, tricut=3)),
+    # c4 slices at the permutation count of the GTEx target (10^4): 9 ragged tissues, exceedance counts exact
+    "c4_slice_gensin_10k_trick2": dict(data=dict(seed=1901, n_subgroups=9, n_inds=60, n_genes=3, snps_per_gene=5, ragged=True,
+                                                 ragged_min_frac=0.5, null_frac=0.5), analysis="join", bfs="sin",
+                                       wrtsize=10, perm=dict(nperm=10000, pbf="gen-sin", seed=1859, trick=2, tricut=10)),
+    "c4_slice_all_10k": dict(data=dict(seed=1902, n_subgroups=9, n_inds=60, n_genes=2, snps_per_gene=3, ragged=True,
+                                       ragged_min_frac=0.5, null_frac=0.5), analysis="join", bfs="all", wrtsize=10,
+                             perm=dict(nperm=10000, pbf="all", seed=1859)),
+    # almost deterministic eQTLs: Student tail below the double range -> Phi^-1(0) = -inf -> NaN / infinite standardised
+    # statistics -> ABF 0 through the reference's own guards
+    "huge_t": dict(data=dict(BASE, seed=91, n_genes=8, perfect_frac=0.5), analysis="join", bfs="all", wrtsize=4,
+                   perm=dict(nperm=20, pbf="all", seed=4)),
     # --qnorm
     "qnorm": dict(data=dict(BASE, seed=61, n_inds=60, ragged=True), analysis="join", bfs="sin", wrtsize=10,
                   qnorm=True, perm=dict(nperm=30, pbf="gen-sin", seed=21)),

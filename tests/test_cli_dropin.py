@@ -80,3 +80,47 @@ def _run_and_compare(tmp_path, name, threads):
                 n_cells += 1
                 n_exact += exact
     assert n_exact >= 0.995 * n_cells, (n_exact, n_cells)
+
+
+def _read_outputs(prefix):
+    out = {}
+    d, base = os.path.dirname(prefix), os.path.basename(prefix)
+    for fn in sorted(os.listdir(d)):
+        if fn.startswith(base + "_") and fn.endswith(".txt.gz"):
+            out[fn[len(base) + 1:]] = gzip.open(os.path.join(d, fn), "rt").read()
+    return out
+
+
+@pytest.mark.parametrize("name", ["basic_all_perm", "sep_permsep2_trick2", "ragged5"])
+def test_cli_shards_concatenate_to_the_unsharded_outputs(tmp_path, name):
+    """--shard k/N (contiguous cost-balanced ranges of whole write-groups, eqb_partition_by_cost): the shards' outputs,
+    concatenated in shard order without the later headers (the `zcat | sed 1d` merge of the reference's recipe,
+    doc/manual_eqtlbma.texi:1211-1218), are identical to the outputs of one run -- permutation p-values included, since
+    the generator is re-seeded per write-group.  --gpus N does the same through the launcher (one process per shard,
+    gzip members concatenated byte-wise)."""
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "eqtlbma_b200", "host")])
+    sc = SCENARIOS[name]
+    ds = build_dataset(sc)
+    d = str(tmp_path / "in")
+    ds.write_files(d)
+
+    def run(out, extra):
+        cmd = [EXE] + ds.ref_args(d, out) + ref_flags(sc) + cli_extra(sc, ds, d) + ["-v", "0"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return _read_outputs(out)
+
+    full = run(str(tmp_path / "full"), [])
+    assert full
+    n = 3
+    parts = [run(str(tmp_path / f"part{k}"), ["--shard", f"{k}/{n}"]) for k in range(n)]
+    for fn, txt in full.items():
+        n_head = 2 if "PermPvals" in fn else 1  # the permutation files carry a comment line above the column names
+        merged = parts[0][fn]
+        for k in range(1, n):
+            merged += "".join(parts[k][fn].splitlines(keepends=True)[n_head:])
+        assert merged == txt, fn
+    launched = run(str(tmp_path / "launched"), ["--gpus", "3"])
+    assert launched == full
+    assert not [f for f in os.listdir(tmp_path) if ".shard" in f]  # the launcher removed its intermediate files

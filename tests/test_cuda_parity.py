@@ -18,6 +18,9 @@ pytestmark = pytest.mark.gpu
 NOT_YET = set()
 # degenerate rank-deficient designs: documented tie, checked separately
 DEGENERATE = {"monomorphic"}
+# 10^4-permutation slices: checked against the reference dumps only (the CPU oracle needs minutes for them and is itself
+# pinned to the same dumps by the CPU suite)
+DUMP_ONLY = {"c4_slice_gensin_10k_trick2", "c4_slice_all_10k"}
 
 
 @pytest.mark.parametrize("name", sorted(set(SCENARIOS) - NOT_YET - DEGENERATE))
@@ -35,7 +38,7 @@ def test_cuda_matches_reference_dump(cuda_lib, name):
     eng.close()
 
 
-@pytest.mark.parametrize("name", sorted(set(SCENARIOS) - NOT_YET))
+@pytest.mark.parametrize("name", sorted(set(SCENARIOS) - NOT_YET - DUMP_ONLY))
 def test_cuda_matches_oracle(cuda_lib, oracle_lib, name):
     import eqtlbma_b200
     sc = SCENARIOS[name]
