@@ -21,6 +21,7 @@
 
 #include <chrono>
 
+#include "fast_all_kernel.cuh"
 #include "fast_kernels.cuh"
 #include "mvlr_kernel.cuh"
 #include "perm_gemm.h"
@@ -1888,9 +1889,12 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         fa.which = ctx->cfg.bfs + 1;
         fa.out_n = o_n ? ctx->d_out_n.p : nullptr;
         fa.out_ss = o_ss ? ctx->d_ss.p : nullptr;
-        fa.out_gen = join ? ctx->d_gen.p : nullptr; // also the staging area of phase C
+        fa.out_gen = join ? ctx->d_gen.p : nullptr; // also the staging area of phase C of fast_pair_kernel
         fa.out_cfg = (join && C > 0) ? ctx->d_cfg.p : nullptr;
         fa.out_w = join ? ctx->d_w.p : nullptr;
+        // --bfs all on the warp-autonomous kernel (fast_all_kernel.cuh) when its tables fit: S <= 10, K <= 16
+        const bool all_warp = fa.which == 3 && S <= FA_MAXS && K >= 1 && K <= FA_MAXK && ctx->gc_ok &&
+                              fast_all_smem_bytes(S, K, L, ctx->gt.UL) <= (size_t)100 * 1024 && tuning_env("EQB_FAST_TILE") == nullptr;
         int T = 64;
         if (const char *e = tuning_env("EQB_FAST_T")) T = std::max(4, atoi(e)); // tuning knob (power of two)
         size_t tile_budget = 72 * 1024;
@@ -1898,10 +1902,23 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         while (T > 4 && ((T & (T - 1)) || fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which) > tile_budget)) T /= 2;
         // --bfs gen|sin and --analys sep: warp-autonomous tiles of 32 pairs (no CTA barriers); --bfs all keeps the
         // CTA-synchronous tile kernel (its per-pair term table lives in shared memory)
-        const bool warp_tiles = fa.which != 3 && tuning_env("EQB_FAST_TILE") == nullptr;
+        const bool warp_tiles = (fa.which != 3 || all_warp) && tuning_env("EQB_FAST_TILE") == nullptr;
         int nwarp = WARPS;
         size_t smem;
-        if (warp_tiles) {
+        if (all_warp) {
+          T = 32;
+          nwarp = 1; // (one CTA per tile: the grid below is n_tiles / nwarp)
+          smem = fast_all_smem_bytes(S, K, L, ctx->gt.UL);
+          fa.use_dmma = 1;
+          for (int s0 = 0; s0 < S; s0 += 8)
+            for (int a = s0 + 1; a < std::min(S, s0 + 8); ++a)
+              if (ctx->hp.sub[a].X != ctx->hp.sub[s0].X) fa.use_dmma = 0;
+          CK(cudaFuncSetAttribute(fast_pair_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CK(cudaFuncSetAttribute(fast_pair_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          // raw values are only produced on request (device-only timing: want_raw; otherwise: the caller passed the arrays)
+          if (!o_gen) fa.out_gen = nullptr;
+          if (!o_cfg) fa.out_cfg = nullptr;
+        } else if (warp_tiles) {
           T = 32;
           if (const char *e = tuning_env("EQB_FASTW_WARPS")) nwarp = std::min(WARPS, std::max(1, atoi(e)));
           while (nwarp > 1 && nwarp * fast_warp_smem_bytes(S) > tile_budget) nwarp /= 2;
@@ -1926,6 +1943,8 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          if (!o_gen) fa.out_gen = nullptr; // raw values only on request (the kernel skips the stores)
+          if (!o_cfg) fa.out_cfg = nullptr;
         } else {
           smem = fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which);
           if (smem > 200 * 1024) return fail(ctx, "configuration table does not fit in shared memory");
@@ -2075,7 +2094,11 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           if (pipelined) CK(cudaStreamWaitEvent(ctx->stream, ctx->xready[seg_chunk[sgi]], 0));
           if (fa.n_pairs > fa.q_begin) {
             const long long tiles = (fa.n_pairs - fa.q_begin + T - 1) / T;
-            if (warp_tiles) {
+            if (all_warp) {
+              const unsigned grid = (unsigned)((fa.n_tiles + nwarp - 1) / nwarp);
+              if (fa.use_dmma) fast_pair_all_kernel<true><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->gc);
+              else fast_pair_all_kernel<false><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->gc);
+            } else if (warp_tiles) {
               const bool tp = ctx->gc_ok && tuning_env("EQB_FASTW_NO_CONST") == nullptr;
               const unsigned grid = (unsigned)((fa.n_tiles + nwarp - 1) / nwarp);
 #define EQB_FASTW_LAUNCH(TPV, DMV)                                                                                    \

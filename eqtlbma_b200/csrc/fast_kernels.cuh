@@ -19,6 +19,7 @@
 #pragma once
 
 #include "pair_kernel.cuh"
+#include "table_math.cuh"
 
 namespace eqb {
 
@@ -779,6 +780,52 @@ __device__ __forceinline__ void consistent_sums(const double *__restrict__ st, i
   sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log_fast(prod)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
 }
 
+// the same three helpers on the table-driven elementary functions (table_math.cuh: absolute error of a log10 ABF
+// < 1e-12, four orders of magnitude inside the 1e-8 budget), used by the warp-autonomous kernel whose phase C is bound
+// by instruction issue: log / exp10 / division of the CUDA library were two thirds of its instructions
+__device__ __forceinline__ double abf_from_sums_t(double den, double num, double sing, double oma2, const TabRef T)
+{
+  if (num != 0.0 && den != 0.0 && den == den) {
+    if (oma2 == 0.0) return sing;
+    const double z = fma(oma2, den, 1.0);
+    return fma(fma(-0.5, log_tab16(z, T), 0.5 * num * num * oma2 * rcp_n(z)), EQB_INV_LN10, sing);
+  }
+  return 0.0;
+}
+__device__ __forceinline__ void consistent_sums_t(const double *__restrict__ st, int S, unsigned long long mask, double phi2,
+                                                  double &den, double &num, double &sing, const TabRef T)
+{
+  double tsum = 0.0, prod = 1.0, slog = 0.0;
+  den = 0.0;
+  num = 0.0;
+  while (mask) {
+    const int s = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    const double b = st[s], v = st[S + s], tt = st[2 * S + s];
+    if (!(fabs(tt) < 1e-8)) { // (gene_snp_pair.cpp:314: |t| < 1e-8 contributes nothing)
+      const double inv = rcp_n(v + phi2);
+      den += inv;
+      num = fma(b, inv, num);
+      tsum = fma(tt * tt, inv, tsum);
+      prod *= v * inv;
+      if (prod < 1e-200) {
+        slog += log(prod);
+        prod = 1.0;
+      }
+    }
+  }
+  sing = (phi2 == 0.0) ? 0.0 : (0.5 * (slog + log_tab16(prod, T)) + 0.5 * phi2 * tsum) * EQB_INV_LN10;
+}
+__device__ __forceinline__ double singleton_value_t(double b, double vv, double tt, double phi2, double oma2, const TabRef T)
+{
+  // (vv is +inf for |t| <= 1e-8: the guard comes first, the reciprocal seed is not defined there)
+  if (!(fabs(tt) < 1e-8) && b != 0.0 && vv == vv && vv < INFINITY) {
+    const double inv = rcp_n(vv + phi2), w = rcp_n(vv + phi2 + oma2);
+    return (0.5 * log_tab16(vv * w, T) + 0.5 * inv * fma(tt * tt, phi2, b * b * oma2 * w)) * EQB_INV_LN10;
+  }
+  return 0.0;
+}
+
 // singleton configuration: term + ABF of one subgroup merged,
 // 0.5 log10(v/(v+phi2)) - 0.5 log10(1 + oma2/(v+phi2)) = 0.5 log10(v / (v + phi2 + oma2))  (one logarithm);
 // guards of CalcLog10AbfUvlr as in abf_from_sums
@@ -1307,6 +1354,11 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
   extern __shared__ double fsm[];
   const int S = prm.S, ldn = prm.ldn, L = prm.L, K = prm.K, UL = gt.UL;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  __shared__ BfTabs Tsm; // exp / log tables of phase C: the only CTA-wide step of the kernel
+  bf_tabs_init(Tsm);
+  __syncthreads();
+  TabRef T;
+  T.base = smem_u32(&Tsm);
   const long long tile = (long long)blockIdx.x * nwarp + warp;
   if (tile >= fa.n_tiles) return; // (no barrier anywhere below)
 #ifdef EQB_TUNING
@@ -1416,34 +1468,34 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
   }
   __syncwarp();
   if (!join || lane >= tn || (dbg & 4)) return;
-  const bool st_raw = !(dbg & 1);
+  const bool st_raw = !(dbg & 1) && fa.out_gen != nullptr; // raw values only on request
   // ---------------- phase C: lane per pair
   const double *stj = st + (size_t)lane * sst;
   const unsigned long long mask = hasm[lane];
   double *og = fa.out_gen + my_pair * 3 * L;
   double *ow = fa.out_w + my_pair * (5 + C);
-  LseOnline r0, r1, r2;
+  LseTab r0, r1, r2;
   r0.init();
   r1.init();
   r2.init();
   const double wL = 1.0 / (double)L;
   for (int u = 0; u < UL; ++u) {
     double den, num, sing;
-    consistent_sums(stj, S, mask, TP ? gc.uphi[u] : gt.uphi[u], den, num, sing); // ONE logarithm per (pair, phi2)
+    consistent_sums_t(stj, S, mask, TP ? gc.uphi[u] : gt.uphi[u], den, num, sing, T); // ONE logarithm per (pair, phi2)
     const int i0 = TP ? (int)gc.ustart[u] : go.ustart[u], i1 = TP ? (int)gc.ustart[u + 1] : go.ustart[u + 1];
     for (int i = i0; i < i1; ++i) {
       const int e = TP ? (int)gc.ent[i] : go.uent[i]; // warp-uniform
-      const double v = abf_from_sums(den, num, sing, TP ? gc.oma[i] : gt.omaL[e]);
+      const double v = abf_from_sums_t(den, num, sing, TP ? gc.oma[i] : gt.omaL[e], T);
       if (st_raw) og[e] = v;
-      if (e < L) r0.add(v, wL, e == 0);
-      else if (e < 2 * L) r1.add(v, wL, e == L);
-      else r2.add(v, wL, e == 2 * L);
+      if (e < L) r0.add(v, wL, e == 0, T);
+      else if (e < 2 * L) r1.add(v, wL, e == L, T);
+      else r2.add(v, wL, e == 2 * L, T);
     }
   }
-  const double wgen = r0.result();
+  const double wgen = r0.result(T);
   ow[0] = wgen;
-  ow[1] = r1.result();
-  ow[2] = r2.result();
+  ow[1] = r1.result(T);
+  ow[2] = r2.result(T);
   if (fa.which == 1) {
     ow[3] = nan("");
     ow[4] = nan("");
@@ -1451,25 +1503,25 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
   }
   // singleton configurations (CalcAbfsUvlrForSingletons, gene_snp_pair.cpp:422-463) + BMAlite (:552-570)
   double *oc = fa.out_cfg + my_pair * C * K;
-  LseOnline lite;
+  LseTab lite;
   lite.init();
   const double wK = 1.0 / (double)K, wS = 0.5 / (double)S;
   for (int c = 0; c < S; ++c) {
-    LseOnline rc;
+    LseTab rc;
     rc.init();
     const bool has = (mask >> c) & 1ull;
     const double b = stj[c], vv = stj[S + c], tt = stj[2 * S + c];
     for (int k = 0; k < K; ++k) {
-      const double v = has ? singleton_value(b, vv, tt, TP ? gc.phiS[k] : prm.phi2S[k], TP ? gc.omaS[k] : prm.oma2S[k]) : 0.0;
+      const double v = has ? singleton_value_t(b, vv, tt, TP ? gc.phiS[k] : prm.phi2S[k], TP ? gc.omaS[k] : prm.oma2S[k], T) : 0.0;
       if (st_raw) oc[c * K + k] = v;
-      rc.add(v, wK, k == 0);
+      rc.add(v, wK, k == 0, T);
     }
-    const double wc = rc.result();
+    const double wc = (K > 0) ? rc.result(T) : nan("");
     ow[5 + c] = wc;
-    lite.add(wc, wS, c == 0);
+    lite.add(wc, wS, c == 0, T);
   }
-  lite.add(wgen, 0.5, false);
-  ow[3] = lite.result();
+  lite.add(wgen, 0.5, false, T);
+  ow[3] = lite.result(T);
   ow[4] = nan("");
 }
 
