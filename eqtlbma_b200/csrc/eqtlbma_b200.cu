@@ -21,7 +21,7 @@
 
 #include <chrono>
 
-#include "fast_all_kernel.cuh"
+#include "fast_all.h"
 #include "fast_kernels.cuh"
 #include "mvlr_kernel.cuh"
 #include "perm_gemm.h"
@@ -376,6 +376,8 @@ struct eqb_ctx {
   std::vector<uint8_t> gene_fast;
   std::vector<int> dup_of;
   DevBuf<int> d_genes2, d_tile_gene;
+  DevBuf<double> d_fa_st;                 // --bfs all: b, v, t of every fast-path (pair, subgroup) between the two passes
+  DevBuf<unsigned long long> d_fa_has;
   DevBuf<long long> d_tile_q0;
   DevBuf<long long> d_pair_off2, d_fast_base;
   struct XChunk { // one prep_x_dmma launch: subgroups sharing a genotype variant, their basis / mask columns
@@ -1245,6 +1247,8 @@ void eqb_destroy(eqb_ctx *ctx)
   ctx->xchunks.clear();
   ctx->d_fix.release();
   ctx->d_tile_gene.release();
+  ctx->d_fa_st.release();
+  ctx->d_fa_has.release();
   ctx->d_tile_q0.release();
   if (ctx->d_prm) dfree(ctx->d_prm);
   if (ctx->d_grids) dfree(ctx->d_grids);
@@ -1892,33 +1896,21 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         fa.out_gen = join ? ctx->d_gen.p : nullptr; // also the staging area of phase C of fast_pair_kernel
         fa.out_cfg = (join && C > 0) ? ctx->d_cfg.p : nullptr;
         fa.out_w = join ? ctx->d_w.p : nullptr;
-        // --bfs all on the warp-autonomous kernel (fast_all_kernel.cuh) when its tables fit: S <= 10, K <= 16
-        const bool all_warp = fa.which == 3 && S <= FA_MAXS && K >= 1 && K <= FA_MAXK && ctx->gc_ok &&
-                              fast_all_smem_bytes(S, K, L, ctx->gt.UL) <= (size_t)100 * 1024 && tuning_env("EQB_FAST_TILE") == nullptr;
+        // --bfs all on fast_pair_all_kernel (fast_all_kernel.cuh: lane = (pair, grid point), lane-private subset-sum tables)
+        // when its tables fit: S <= 10, K <= 16
+        const bool all_warp = fa.which == 3 && S <= FA_MAXS && K >= 1 && K <= FA_MAXK && ctx->gc_ok && C >= 1 && C < 65536 &&
+                              tuning_env("EQB_FAST_TILE") == nullptr;
         int T = 64;
         if (const char *e = tuning_env("EQB_FAST_T")) T = std::max(4, atoi(e)); // tuning knob (power of two)
         size_t tile_budget = 72 * 1024;
         if (const char *e = tuning_env("EQB_FAST_SMEM_KB")) tile_budget = (size_t)std::max(8, atoi(e)) * 1024;
         while (T > 4 && ((T & (T - 1)) || fast_smem_bytes(T, S, L, K, ctx->gt.UL, fa.which) > tile_budget)) T /= 2;
-        // --bfs gen|sin and --analys sep: warp-autonomous tiles of 32 pairs (no CTA barriers); --bfs all keeps the
-        // CTA-synchronous tile kernel (its per-pair term table lives in shared memory)
+        // --bfs gen|sin and --analys sep: warp-autonomous tiles of 32 pairs (no CTA barriers); --bfs all: the same kernel as
+        // the first pass, then fast_pair_all_kernel; shapes outside its limits keep the CTA-synchronous tile kernel
         const bool warp_tiles = (fa.which != 3 || all_warp) && tuning_env("EQB_FAST_TILE") == nullptr;
         int nwarp = WARPS;
         size_t smem;
-        if (all_warp) {
-          T = 32;
-          nwarp = 1; // (one CTA per tile: the grid below is n_tiles / nwarp)
-          smem = fast_all_smem_bytes(S, K, L, ctx->gt.UL);
-          fa.use_dmma = 1;
-          for (int s0 = 0; s0 < S; s0 += 8)
-            for (int a = s0 + 1; a < std::min(S, s0 + 8); ++a)
-              if (ctx->hp.sub[a].X != ctx->hp.sub[s0].X) fa.use_dmma = 0;
-          CK(cudaFuncSetAttribute(fast_pair_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CK(cudaFuncSetAttribute(fast_pair_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          // raw values are only produced on request (device-only timing: want_raw; otherwise: the caller passed the arrays)
-          if (!o_gen) fa.out_gen = nullptr;
-          if (!o_cfg) fa.out_cfg = nullptr;
-        } else if (warp_tiles) {
+        if (warp_tiles) {
           T = 32;
           if (const char *e = tuning_env("EQB_FASTW_WARPS")) nwarp = std::min(WARPS, std::max(1, atoi(e)));
           while (nwarp > 1 && nwarp * fast_warp_smem_bytes(S) > tile_budget) nwarp /= 2;
@@ -2029,6 +2021,12 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
         }
         CK(ctx->d_fast_base.ensure(gf.size()));
         CK(h2d(ctx, ctx->d_fast_base.p, fbase.data(), gf.size() * 8));
+        if (all_warp) {
+          CK(ctx->d_fa_st.ensure(std::max<size_t>((size_t)nfp * 3 * S, 1)));
+          CK(ctx->d_fa_has.ensure(std::max<size_t>((size_t)nfp, 1)));
+          fa.st_all = ctx->d_fa_st.p;
+          fa.has_all = ctx->d_fa_has.p;
+        }
         fa.genes = ctx->d_genes2.p;
         fa.fast_base = ctx->d_fast_base.p;
         fa.pair_off = ctx->d_pair_off2.p;
@@ -2094,11 +2092,7 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           if (pipelined) CK(cudaStreamWaitEvent(ctx->stream, ctx->xready[seg_chunk[sgi]], 0));
           if (fa.n_pairs > fa.q_begin) {
             const long long tiles = (fa.n_pairs - fa.q_begin + T - 1) / T;
-            if (all_warp) {
-              const unsigned grid = (unsigned)((fa.n_tiles + nwarp - 1) / nwarp);
-              if (fa.use_dmma) fast_pair_all_kernel<true><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->gc);
-              else fast_pair_all_kernel<false><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->gc);
-            } else if (warp_tiles) {
+            if (warp_tiles) {
               const bool tp = ctx->gc_ok && tuning_env("EQB_FASTW_NO_CONST") == nullptr;
               const unsigned grid = (unsigned)((fa.n_tiles + nwarp - 1) / nwarp);
 #define EQB_FASTW_LAUNCH(TPV, DMV)                                                                                    \
@@ -2108,6 +2102,14 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
               else if (fa.use_dmma) EQB_FASTW_LAUNCH(false, true);
               else EQB_FASTW_LAUNCH(false, false);
 #undef EQB_FASTW_LAUNCH
+              if (all_warp) {
+                // second pass of --bfs all: every configuration on gridS, BMAlite, BMA (persistent CTAs, 4 per SM)
+                const int ppw = fa_pairs_per_warp(K);
+                const long long want = (fa.n_pairs - fa.q_begin + ppw - 1) / ppw;
+                const unsigned grid2 = (unsigned)std::min<long long>(want, (long long)ctx->n_sm * 4);
+                CK(launch_fast_pair_all(K, grid2, fast_all_smem_bytes(S, C), ctx->stream, ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->gc));
+                ctx->launches++;
+              }
             }
             else
               fast_pair_kernel<<<(unsigned)tiles, THREADS, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt);

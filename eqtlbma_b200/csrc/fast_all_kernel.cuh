@@ -2,49 +2,42 @@
 //
 // Reference: GeneSnpPair::CalcAbfsUvlrForEachConfiguration + CalcBMAlite + CalcBMA (gene_snp_pair.cpp:504-602): for every
 // pair, the closed-form ABF of each of the 2^S - 1 configurations on every gridS point (raw values), their grid averages,
-// and the two model averages.  One CTA of 8 warps owns a tile of 32 pairs:
-//   A  mma.sync.m8n8k4 (DMMA) tile product xy[pairs][S] = X_tile . Ytil_gene^T, one 8-row block per warp (4 warps)
-//   B  thread per (pair, subgroup): summary statistics + standardisation
-//   C  pair after pair, the whole CTA on one pair; LANE = CONFIGURATION in the reference's order (gsl_combination order),
-//      every warp takes every 8th group of 32 consecutive configurations.  A configuration's sums over its subgroups
-//      cost O(1): the subgroups are split into a low part (<= 5) and a high part, the sums of every subset of either
-//      part are tabulated per grid point in shared memory ONCE PER PAIR for the whole CTA (component-major: the 16 high
-//      entries sit in distinct banks, and 32 consecutive configurations share a handful of low entries).  The K raw
-//      values of a configuration go to the warp's staging tile and leave as contiguous runs (the output rows of 32
-//      consecutive configurations are contiguous); their grid average is accumulated in the linear domain against the
-//      likelihood-ratio bound (online log-sum-exp as the fallback: NaN rules of utils::log10_weighted_sum).
-//      (First version: one warp per tile with private tables -- 27 KB of shared memory per warp, 7 warps per SM,
-//      2.4 ms per tile: latency-bound at 0.37 instructions per clock per SM and no faster than the kernel it replaced.)
-// want_raw = 0 (fa.out_cfg == nullptr) skips the emission: compute and emission can be timed separately.
+// and the two model averages.  Two passes:
+//   1  fast_pair_warp_kernel (fast_kernels.cuh, which = 3): warp per tile of 32 pairs -- DMMA contraction, summary statistics
+//      and standardisation, the 3L values of the consistent configuration and their grid averages; leaves b, v, t of every
+//      (pair, subgroup) in fa.st_all (216 bytes per pair at S = 9).  HBM-bound, a few per cent of the step.
+//   2  fast_pair_all_kernel (this file): persistent CTAs of 4 warps, four of them per SM; a CTA takes tiles of
+//      PPW = min(4, 32 / K) consecutive pairs:
+//   T  LANE = (pair, grid point k): the lane's per-subgroup terms { 1/(v+phi2_k), b/(v+phi2_k), ln ABF_s } depend on nothing
+//      else, so the sums over a configuration's subgroups cost O(1): the subgroups are split into three parts and the sums
+//      of every subset of a part are tabulated ONCE per (pair, k) in lane-private columns of shared memory (<= 8 + 8 + 8
+//      entries for S = 9; one warp per part).  The four warps of the CTA share the tables.
+//   C  the configurations in the reference's order (gsl_combination order, masks staged in shared memory: warp-uniform),
+//      chunks of 32 dealt round-robin to the warps:
+//      C1  lane = (pair, k): 9 conflict-free LDS + 6 DADD per value, then the ES-model ABF; the value goes straight to its
+//          raw output slot (the K lanes of a pair write one contiguous run) and into the warp's staging tile [32][33]
+//      C2  lane = configuration: for each pair the reference's two-pass log10_weighted_sum over the K staged values
+//          (utils_math.cpp:100-131), coalesced store of the grid averages, online accumulation of the BMA (CalcBMA); the
+//          first chunk holds the S singletons: BMAlite right there
+//   M  the warps' partial BMA states merged through shared memory.
+// History (c3 slice, 9 ragged tissues, 511 configurations x 10 grid points): (1) CTA per pair, lane = configuration, tables
+// shared by the CTA, four barriers per pair: 174 thread instructions per value, a third of the issue slots at barriers,
+// 19 M pairs/s.  (2) this mapping with one CTA of 8 warps per SM, private tables per warp (27 KB each): 17 M pairs/s --
+// 8 warps per SM cannot hide the FP64 latency even with four evaluations in flight per warp (issue slots 35 % used, 19 % of
+// the time spent by 5 of 8 warps waiting for the contraction).  (3) the tables shared by the 4 warps of a small CTA, 16 warps
+// per SM, contraction still inside: 18.7 M pairs/s, 28 % of the time in the 3-row contraction (58 dependent round trips to
+// HBM per tile) and at the barriers around it.  (4) contraction and statistics as a first pass over 32-pair tiles.
+// fa.out_cfg == nullptr / fa.out_gen == nullptr skip the raw-value emission: compute and emission are timed separately.
 #pragma once
 
+#include "fast_all.h"
 #include "fast_kernels.cuh"
 
 namespace eqb {
 
-constexpr int FA_SL = 5;      // subgroups of the low part
-constexpr int FA_MAXS = 10;   // S <= 10 (high part <= 5 subgroups), K <= 16
-constexpr int FA_MAXK = 16;
-constexpr int FA_MAXG = 4;    // configuration groups per warp: ceil((2^10 - 1) / 32 / 8)
-
-__host__ __device__ inline int fa_low(int S) { return S < FA_SL ? S : FA_SL; }
-// doubles of the CTA's phase-C scratch: A[K][3][2^SL] | B[K][3][2^SH] | MA[2^SL] | MB[2^SH] | te[K][S][3] | usum[UL][3] |
-// gv[3L] | w0[32] | part[WARPS][3] | stg[WARPS][32][K+1]
-__host__ __device__ inline size_t fa_scratch_doubles(int S, int K, int L, int UL)
-{
-  const int SL = fa_low(S), SH = S - SL;
-  return (size_t)K * 3 * (1 << SL) + (size_t)K * 3 * (1 << SH) + (1 << SL) + (1 << SH) + (size_t)K * S * 3 + (size_t)UL * 3 +
-         (size_t)3 * L + 32 + (size_t)WARPS * 3 + (size_t)WARPS * 32 * (K + 1);
-}
-__host__ __device__ inline size_t fast_all_smem_bytes(int S, int K, int L, int UL)
-{
-  return fast_warp_smem_bytes(S) + fa_scratch_doubles(S, K, L, UL) * 8;
-}
-
 // utils::log10_weighted_sum (utils_math.cpp:100-131) of n <= 32 values held one per lane (lanes >= n pass anything),
 // by the whole warp: maximum seeded with element 0 (a NaN there poisons the result), NaN elements skipped, weighted sum
-// of 10^(x - max), |result| <= DBL_EPSILON snapped to 0.  A serial loop over the values is a chain of ~40 dependent
-// instructions per element on ONE thread while the rest of the CTA waits at the next barrier.
+// of 10^(x - max), |result| <= DBL_EPSILON snapped to 0.
 __device__ __forceinline__ double warp_lws(double x, double w, int n, int lane, const TabRef T)
 {
   const bool in = lane < n;
@@ -56,15 +49,28 @@ __device__ __forceinline__ double warp_lws(double x, double w, int n, int lane, 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
   if (x0 != x0) return nan("");
-  double r = fma(log_tab16(e, T), EQB_INV_LN10, mx);
+  const double d1 = e - 1.0; // (weights summing to 1 on equal values: ln(1 + d) = d, not the table's 1e-13)
+  double r = fma((fabs(d1) < 1e-8) ? d1 : log_tab16(e, T), EQB_INV_LN10, mx);
   if (fabs(r) <= DBL_EPSILON) r = 0.0;
   return r;
 }
 
-template <bool DM>
-__global__ void __launch_bounds__(THREADS, 2) fast_pair_all_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
-                                                                   const FastArgs fa, const GridTab gt,
-                                                                   const __grid_constant__ GridConst gc)
+__device__ __forceinline__ void lse_merge(LseTab &a, double m2, double acc2, const TabRef T)
+{
+  const double mx = fmax(a.m, m2);
+  double r = 0.0;
+  if (a.m > -INFINITY) r = fma(a.acc, exp10_tab16<true>(a.m - mx, T), r);
+  if (m2 > -INFINITY) r = fma(acc2, exp10_tab16<true>(m2 - mx, T), r);
+  a.m = mx;
+  a.acc = r;
+}
+
+// PPW: pairs per tile = min(4, 32 / K) (compile-time: the per-pair chains of phase C2 are unrolled side by side).
+// fa.use_dmma: every group of 8 subgroups shares one genotype matrix and phase A runs on the tensor cores (the common case).
+template <int PPW>
+__global__ void __launch_bounds__(FA_THREADS, 4) fast_pair_all_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
+                                                                      const FastArgs fa, const GridTab gt,
+                                                                      const __grid_constant__ GridConst gc)
 {
   const DevParams &prm = *prm_;
   extern __shared__ double fsm[];
@@ -74,287 +80,196 @@ __global__ void __launch_bounds__(THREADS, 2) fast_pair_all_kernel(const DevPara
   bf_tabs_init(Tsm);
   TabRef T;
   T.base = smem_u32(&Tsm);
-  const long long tile = blockIdx.x;
-  const long long q0 = fa.tile_q0[tile];
-  const int tn = (int)(fa.tile_q0[tile + 1] - q0); // 1 .. 32
   const long long C = prm.C;
   const int sst = (3 * S) | 1;
-  char *wbase = reinterpret_cast<char *>(fsm);
-  double *xy = reinterpret_cast<double *>(wbase);            // [32][S]
-  double *st = xy + (size_t)32 * S;                          // [32][sst]  b, v, t per subgroup
-  unsigned long long *hasm = (unsigned long long *)(st + (size_t)32 * sst); // [32]
-  long long *s_pair = (long long *)(hasm + 32);
-  long long *s_m = s_pair + 32;
-  int *s_gene = (int *)(s_m + 32);
-  double *scr = reinterpret_cast<double *>(wbase + fast_warp_smem_bytes(S));
-  const int SL = fa_low(S), SH = S - SL, NA = 1 << SL, NB = 1 << SH;
-  double *tA = scr;                                // [K][3][NA]
-  double *tB = tA + (size_t)K * 3 * NA;            // [K][3][NB]
-  double *mA = tB + (size_t)K * 3 * NB;            // [NA] bound of the low subset: sum t^2 / 2
-  double *mB = mA + NA;                            // [NB]
-  double *te = mB + NB;                            // [K][S][3] per-(grid point, subgroup) terms (natural-log units)
-  double *usum = te + (size_t)K * S * 3;           // [UL][3]
-  double *gv = usum + (size_t)UL * 3;              // [3L]
-  double *w0 = gv + (size_t)3 * L;                 // [32] grid averages of the first 32 configurations (singletons first)
-  double *part = w0 + 32;                          // [WARPS][3] partial model averages (m, acc, poisoned)
-  double *stg = part + (size_t)WARPS * 3 + (size_t)warp * 32 * (K + 1); // this warp's [32][K+1] staging tile
+  double *st = fsm;                                          // [4][sst]  b, v, t per subgroup
+  unsigned long long *hasm = (unsigned long long *)(st + (size_t)4 * sst); // [4]
+  long long *s_pair = (long long *)(hasm + 4);               // [4] output pair index
+  double *genavg = (double *)(s_pair + 4);                   // [4] grid average of the consistent configuration
+  double *part = genavg + 4;                                 // [FA_WARPS][4][3] partial BMA states (m, acc, poisoned)
+  char *after = reinterpret_cast<char *>(fsm) + fa_tile_doubles(S) * 8;
+  unsigned short *s_mask = reinterpret_cast<unsigned short *>(after); // [C] + zero padding
+  double *tab = reinterpret_cast<double *>(after + fa_mask_bytes(C)); // [ne][3][32]
+  const FaParts P = fa_parts(S);
+  double *stg = tab + (size_t)P.ne * 3 * 32 + (size_t)warp * FA_CH * FA_SROW; // this warp's [FA_CH][FA_SROW] staging tile
 
-  if (threadIdx.x < tn) {
-    const long long q = q0 + threadIdx.x;
-    int lo = fa.tile_gene[tile];
-    while (lo + 1 < fa.n_genes && fa.fast_base[lo + 1] <= q) ++lo;
-    const int g = fa.genes[lo];
-    const long long off = q - fa.fast_base[lo];
-    s_gene[threadIdx.x] = g;
-    s_m[threadIdx.x] = prm.cis_begin[g] + off;
-    s_pair[threadIdx.x] = fa.pair_off[lo] + off;
-    hasm[threadIdx.x] = 0ull;
-  }
-  // the configurations of this lane (the same for every pair): masks and BMA weights stay in registers
-  unsigned long long cmask[FA_MAXG];
-  double cwt[FA_MAXG];
-#pragma unroll
-  for (int jj = 0; jj < FA_MAXG; ++jj) {
-    const long long c = ((long long)(warp + jj * WARPS)) * 32 + lane;
-    cmask[jj] = (c < C) ? prm.cfg_mask[c] : 0ull;
-    cwt[jj] = (c < C) ? prm.cfg_weight[c] : 0.0;
-  }
-  __syncthreads();
-  // ---------------- phase A: contraction, one block of 8 pairs per warp
-  if (warp < 4 && warp * 8 < tn) {
-    const int r0 = warp * 8, tw = min(8, tn - r0);
-    for (int s0 = 0; s0 < S; s0 += 8) {
-      const int sn = min(8, S - s0);
-      const FastSub *fsub = fp_->sub + s0;
-      if (DM)
-        contract_tile_dmma(prm.sub[s0].X, fsub, sn, s_m + r0, s_gene + r0, tw, S, ldn, lane, xy + (size_t)r0 * S + s0);
-      else
-        for (int a = 0; a < sn; ++a)
-          contract_tile<1>(prm.sub[s0 + a].X, fsub + a, s_m + r0, s_gene + r0, tw, S, ldn, lane, xy + (size_t)r0 * S + s0 + a);
-    }
-  }
-  __syncthreads();
-  // ---------------- phase B: thread per (pair, subgroup)
-  for (int it = threadIdx.x; it < tn * S; it += THREADS) {
-    const int j = it / S, s = it - j * S;
-    const long long m = s_m[j];
-    const int g = s_gene[j];
-    const SubDev &sb = prm.sub[s];
-    const FastSub &fs = fp_->sub[s];
-    const double *ys = fs.ystat + (size_t)g * 4;
-    const bool have = sb.gene_has[g] && sb.snp_has[m] && fs.n > 0;
-    PairStat ps;
-    ps.pve = ps.sigmahat = ps.betahat = ps.se = ps.pval = nan("");
-    ps.b = ps.v = ps.t = nan("");
-    if (have) {
-      const double *xs = fs.xstat + (size_t)m * 3;
-      stats_from_dots(xy[(size_t)j * S + s], xs[0], xs[1], xs[2], ys[0], ys[1], ys[2], fs.n, sb.Q, fs.rankz, fs.tz, fs.tz_nu,
-                      fs.tz_wmax, ps);
-      atomicOr(&hasm[j], 1ull << s);
-    }
-    st[(size_t)j * sst + s] = ps.b;
-    st[(size_t)j * sst + S + s] = ps.v;
-    st[(size_t)j * sst + 2 * S + s] = ps.t;
-    const long long pair = s_pair[j];
-    if (fa.out_n) fa.out_n[pair * S + s] = have ? fs.n : 0;
-    if (fa.out_ss) {
-      double *o = fa.out_ss + (pair * S + s) * 5;
-      o[0] = ps.pve;
-      o[1] = ps.sigmahat;
-      o[2] = ps.betahat;
-      o[3] = ps.se;
-      o[4] = ps.pval;
-    }
-  }
-  __syncthreads();
-  // ---------------- phase C: pair after pair, lane = configuration
-  const int rpi = 32 / K;                         // staged rows copied out per step (their K values are contiguous)
-  const int cr = lane / K, ck = lane - cr * K;    // this lane's (row, grid point) in a copy-out step
+  for (long long c = threadIdx.x; c < (long long)(fa_mask_bytes(C) / 2); c += FA_THREADS)
+    s_mask[c] = (c < C) ? (unsigned short)prm.cfg_mask[c] : (unsigned short)0; // (the padding is read by the last step)
+
+  // lane = (pair jl, grid point k) in the table and C1 phases
+  const int jl = lane / K, k = lane - jl * K;
+  const double oma2 = gc.omaS[k], phi2 = gc.phiS[k];
   const double invK = 1.0 / (double)K, wL = 1.0 / (double)L;
-  const int ngroups = (int)((C + 31) / 32);
-  for (int j = 0; j < tn; ++j) {
-    const double *stj = st + (size_t)j * sst;
-    const unsigned long long has = hasm[j];
-    const long long pair = s_pair[j];
-    double *ow = fa.out_w + pair * (5 + C);
-    // ---- step 1: sums of the consistent configuration per unique phi2; per-(grid point, subgroup) terms in
-    // natural-log units { 1/(v+phi2), b/(v+phi2), ln single-subgroup ABF }
-    for (int u = threadIdx.x; u < UL; u += THREADS) {
-      double den, num, sing;
-      consistent_sums_t(stj, S, has, gt.uphi[u], den, num, sing, T);
-      usum[u * 3] = den;
-      usum[u * 3 + 1] = num;
-      usum[u * 3 + 2] = sing;
-    }
-    for (int e = threadIdx.x; e < K * S; e += THREADS) {
-      const int k = e / S, s = e - k * S;
-      double d = 0.0, bd = 0.0, A = 0.0;
-      const double b = stj[s], v = stj[S + s], tt = stj[2 * S + s];
-      if (((has >> s) & 1ull) && !(fabs(tt) < 1e-8)) {
-        const double phi2 = gc.phiS[k];
-        const double inv = rcp_n(v + phi2);
-        d = inv;
-        bd = b * inv;
-        A = (phi2 == 0.0) ? 0.0 : fma(0.5, log_tab16(v * inv, T), 0.5 * tt * tt * phi2 * inv);
+  const int sh1 = P.np[0], sh2 = P.np[0] + P.np[1];
+  const int mk0 = (1 << P.np[0]) - 1, mk1 = (1 << P.np[1]) - 1;
+  const double *tb0 = tab + lane, *tb1 = tab + (size_t)P.off[1] * 96 + lane, *tb2 = tab + (size_t)P.off[2] * 96 + lane;
+  const int nchunk = (int)((C + FA_CH - 1) / FA_CH);
+  const long long n_tiles = (fa.n_pairs - fa.q_begin + PPW - 1) / PPW;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long q0 = fa.q_begin + tile * PPW;
+    const int tn = (int)min((long long)PPW, fa.n_pairs - q0); // 1 .. PPW
+    __syncthreads(); // the previous tile is finished (first pass: masks and math tables are in place)
+    if (threadIdx.x < tn) {
+      const long long q = q0 + threadIdx.x;
+      int lo = 0, hi = fa.n_genes - 1; // the last gene whose first compact pair index is <= q (empty genes share a base)
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (fa.fast_base[mid] <= q) lo = mid;
+        else hi = mid - 1;
       }
-      te[e * 3] = d;
-      te[e * 3 + 1] = bd;
-      te[e * 3 + 2] = A;
+      const long long pair = fa.pair_off[lo] + (q - fa.fast_base[lo]);
+      s_pair[threadIdx.x] = pair;
+      hasm[threadIdx.x] = fa.has_all[q];
+      genavg[threadIdx.x] = fa.out_w[pair * (5 + C)]; // (first pass)
+    }
+    for (int i = threadIdx.x; i < tn * 3 * S; i += FA_THREADS) {
+      const int j = i / (3 * S);
+      st[(size_t)j * sst + (i - j * 3 * S)] = fa.st_all[q0 * 3 * S + i];
     }
     __syncthreads();
-    // ---- step 2: the 3L consistent values (gene_snp_pair.cpp:364-416); subset sums of the low / high part for every
-    // grid point (component-major) and their likelihood-ratio bounds
-    for (int e = threadIdx.x; e < 3 * L; e += THREADS) {
-      const double *a = usum + 3 * gt.idxL[e];
-      const double v = abf_from_sums_t(a[0], a[1], a[2], gt.omaL[e], T);
-      gv[e] = v;
-      if (fa.out_gen) fa.out_gen[pair * 3 * L + e] = v;
-    }
-    for (int it = threadIdx.x; it < K * (NA + NB); it += THREADS) {
-      const bool low = it < K * NA;
-      const int i2 = low ? it : it - K * NA, sh = low ? SL : SH, nn = low ? NA : NB, s0 = low ? 0 : SL;
-      const int k = i2 >> sh, a = i2 & (nn - 1);
-      double d = 0.0, n_ = 0.0, A = 0.0;
-      for (int s = 0; s < sh; ++s)
-        if ((a >> s) & 1) {
-          const double *t3 = te + ((size_t)k * S + s0 + s) * 3;
-          d += t3[0];
-          n_ += t3[1];
-          A += t3[2];
+    // ---------------- T: subset-sum tables, one warp per part, lane-private columns
+    const bool active = jl < tn;
+    const int jme = active ? jl : 0;
+    for (int p = warp; p < 3; p += FA_WARPS) {
+      const double *stj = st + (size_t)jme * sst;
+      const unsigned long long has = active ? hasm[jme] : 0ull;
+      double *tp = tab + (size_t)P.off[p] * 96 + lane;
+      tp[0] = 0.0;
+      tp[32] = 0.0;
+      tp[64] = 0.0;
+      for (int i = 0; i < P.np[p]; ++i) {
+        const int s = P.start[p] + i;
+        double d = 0.0, bd = 0.0, A = 0.0;
+        const double b = stj[s], v = stj[S + s], tt = stj[2 * S + s];
+        if (((has >> s) & 1ull) && !(fabs(tt) < 1e-8)) { // (gene_snp_pair.cpp:314: |t| < 1e-8 contributes nothing)
+          const double inv = rcp_n(v + phi2);
+          d = inv;
+          bd = b * inv;
+          A = (phi2 == 0.0) ? 0.0 : fma(0.5, log_tab16(v * inv, T), 0.5 * tt * tt * phi2 * inv);
         }
-      double *tab = (low ? tA : tB) + (size_t)k * 3 * nn + a;
-      tab[0] = d;
-      tab[nn] = n_;
-      tab[2 * nn] = A;
-    }
-    for (int a = threadIdx.x; a < NA + NB; a += THREADS) {
-      const bool low = a < NA;
-      const int bits = low ? a : a - NA, s0 = low ? 0 : SL, ns = low ? SL : SH;
-      double m = 0.0;
-      for (int s = 0; s < ns; ++s)
-        if ((bits >> s) & 1) {
-          const double tt = stj[2 * S + s0 + s];
-          if (((has >> (s0 + s)) & 1ull) && !(fabs(tt) < 1e-8)) m = fma(0.5 * tt, tt, m);
-        }
-      (low ? mA : mB)[bits] = m;
+        double *te = tp + (size_t)(1 << i) * 96;
+        te[0] = d;
+        te[32] = bd;
+        te[64] = A;
+      }
+      for (int a = 3; a < (1 << P.np[p]); ++a) {
+        const int lo = a & (a - 1);
+        if (lo == 0) continue; // single subgroup: written above
+        const double *e0 = tp + (size_t)lo * 96, *e1 = tp + (size_t)(a & -a) * 96;
+        double *ea = tp + (size_t)a * 96;
+        ea[0] = e0[0] + e1[0];
+        ea[32] = e0[32] + e1[32];
+        ea[64] = e0[64] + e1[64];
+      }
     }
     __syncthreads();
-    // ---- step 3: every configuration on gridS, warp w takes the groups w, w + 8, ...
-    if (warp >= WARPS - 3) { // grid averages of gen / gen-fix / gen-maxh: one row per warp, the lanes share the row
-      const int r = warp - (WARPS - 3);
-      double wr;
-      if (L <= 32)
-        wr = warp_lws(lane < L ? gv[r * L + lane] : 0.0, wL, L, lane, T);
-      else {
-        LseTab q;
-        q.init();
-        for (int k = 0; k < L; ++k) q.add(gv[r * L + k], wL, k == 0, T);
-        wr = q.result(T);
-      }
-      if (lane == 0) {
-        ow[r] = wr;
-        if (r == 0) part[WARPS * 3 - 1] = wr; // (read back by warp 0 below; slot 3 of the last warp is unused)
-      }
-    }
-    LseTab bma;
-    bma.init();
+    // ---------------- C: chunks of 32 configurations, round-robin over the warps
+    double *oc = nullptr; // this lane's raw output column: out_cfg[pair][c][k]
+    if (fa.out_cfg && active) oc = fa.out_cfg + s_pair[jme] * C * K + k;
+    LseTab bma[PPW];
 #pragma unroll
-    for (int jj = 0; jj < FA_MAXG; ++jj) {
-      const int grp = warp + jj * WARPS;
-      if (grp >= ngroups) break; // warp-uniform
-      const long long c0 = (long long)grp * 32, c = c0 + lane;
-      const bool valid = c < C;
-      const unsigned long long mask = cmask[jj] & has;
-      const int ia = (int)(mask & (unsigned long long)(NA - 1)), ib = (int)(mask >> SL);
-      const double Mc = mA[ia] + mB[ib];
-      double acc = 0.0;
-      double *srow = stg + (size_t)lane * (K + 1);
-      const double *pa = tA + ia, *pb = tB + ib;
-#pragma unroll 2
-      for (int k = 0; k < K; ++k, pa += 3 * NA, pb += 3 * NB) {
-        const double den = pa[0] + pb[0], num = pa[NA] + pb[NB], sing = pa[2 * NA] + pb[2 * NB];
-        // natural-log ABF; CalcLog10AbfUvlr's guards (see abf_from_sums) as a select: z >= 1 is a normal number whenever
-        // den is one, a NaN den (NaN statistics) gives 0 like the reference's "V < +Inf" test
-        const double oma2 = gc.omaS[k];
-        const double z = fma(oma2, den, 1.0);
-        const bool ok = num != 0.0 && den != 0.0 && den == den && z < 1e300;
-        const double zz = ok ? z : 1.0;
-        double x = sing + fma(-0.5, log_tab16_pos(zz, T), 0.5 * num * num * oma2 * rcp_n(zz));
-        x = ok ? x : 0.0;
-        srow[k] = x * EQB_INV_LN10;
-        acc += exp_tab16<true>(x - Mc, T);
-      }
-      double w;
-      if (acc > 1e-280 && acc < INFINITY) {
-        w = (Mc + log_tab16(acc * invK, T)) * EQB_INV_LN10;
-        if (fabs(w) <= DBL_EPSILON) w = 0.0;
-      } else { // NaN values or a sum outside the representable window: online form on the staged values
-        LseTab r;
-        r.init();
-        for (int k = 0; k < K; ++k) r.add(srow[k], invK, k == 0, T);
-        w = r.result(T);
-      }
-      if (valid) {
-        ow[5 + c] = w;
-        bma.add(w, cwt[jj], c == 0, T); // CalcBMA (gene_snp_pair.cpp:572-602)
-      }
-      if (grp == 0) w0[lane] = w;
-      __syncwarp();
-      if (fa.out_cfg) {
-        // rows of 32 consecutive configurations are contiguous in the output: copy rpi rows (rpi * K lanes) per step
-        double *dst = fa.out_cfg + (pair * C + c0) * K;
-        const int nrow = (int)min((long long)32, C - c0);
-        if (cr < rpi)
-          for (int r0 = 0; r0 < nrow; r0 += rpi) {
-            const int r = r0 + cr;
-            if (r < nrow) dst[(size_t)r * K + ck] = stg[(size_t)r * (K + 1) + ck];
-          }
+    for (int jj = 0; jj < PPW; ++jj) bma[jj].init();
+    for (int ch = warp; ch < nchunk; ch += FA_WARPS) {
+      const long long c0 = (long long)ch * FA_CH;
+      const int nc = (int)min((long long)FA_CH, C - c0);
+      // ---- C1 (two configurations per step, independent straight-line chains)
+      const unsigned short *mk = s_mask + c0;
+      for (int cl0 = 0; cl0 < nc; cl0 += 2) {
+        const unsigned int mm = *reinterpret_cast<const unsigned int *>(mk + cl0);
+        double xv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int m = (int)(mm >> (u * 16)) & 0xffff;
+          const double *p0 = tb0 + (m & mk0) * 96, *p1 = tb1 + ((m >> sh1) & mk1) * 96, *p2 = tb2 + (m >> sh2) * 96;
+          const double den = p0[0] + p1[0] + p2[0], num = p0[32] + p1[32] + p2[32], sing = p0[64] + p1[64] + p2[64];
+          // natural-log ABF; CalcLog10AbfUvlr's guards (see abf_from_sums) as a select: z >= 1 is a normal number whenever
+          // den is one, a NaN den (NaN statistics) gives 0 like the reference's "V < +Inf" test
+          const double z = fma(oma2, den, 1.0);
+          const bool ok = num != 0.0 && den != 0.0 && den == den && z < 1e300;
+          const double zz = ok ? z : 1.0;
+          const double x = sing + fma(-0.5, log_tab16_pos(zz, T), 0.5 * num * num * oma2 * rcp_n(zz));
+          xv[u] = ok ? x * EQB_INV_LN10 : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int cl = cl0 + u;
+          stg[cl * FA_SROW + lane] = xv[u]; // (a row >= nc of the last chunk holds the value of a zero-padded mask: never used)
+          if (oc && cl < nc) oc[(c0 + cl) * K] = xv[u];
+        }
       }
       __syncwarp();
-    }
-    // merge the lanes' partial model averages (online log-sum-exp states), then the warps' through shared memory
+      // ---- C2: lane = configuration c0 + lane; the pairs side by side (PPW independent max / sum chains)
+      const long long c = c0 + lane;
+      const bool valid = lane < nc;
+      const double cwt = valid ? prm.cfg_weight[c] : 0.0;
+      const double *row = stg + lane * FA_SROW;
+      double x0[PPW], mx[PPW], sum[PPW];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double m2 = __shfl_xor_sync(0xffffffffu, bma.m, o), a2 = __shfl_xor_sync(0xffffffffu, bma.acc, o);
-      const int p2 = __shfl_xor_sync(0xffffffffu, (int)bma.poisoned, o);
-      const double mx = fmax(bma.m, m2);
-      double a = 0.0;
-      if (bma.m > -INFINITY) a = fma(bma.acc, exp10_tab16<true>(bma.m - mx, T), a);
-      if (m2 > -INFINITY) a = fma(a2, exp10_tab16<true>(m2 - mx, T), a);
-      bma.m = mx;
-      bma.acc = a;
-      bma.poisoned = bma.poisoned || p2;
-    }
-    if (lane == 0) {
-      part[warp * 3] = bma.m;
-      part[warp * 3 + 1] = bma.acc;
-      if (warp < WARPS - 1) part[warp * 3 + 2] = bma.poisoned ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      // the warps' partial model averages (lane w holds warp w's state), merged by the lanes together
-      const double pm = (lane < WARPS) ? part[lane * 3] : -INFINITY, pa2 = (lane < WARPS) ? part[lane * 3 + 1] : 0.0;
-      double mx = pm;
+      for (int jj = 0; jj < PPW; ++jj) {
+        x0[jj] = mx[jj] = row[jj * K];
+        sum[jj] = 0.0;
+      }
+      for (int kk = 1; kk < K; ++kk) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      double a = (pm > -INFINITY) ? pa2 * exp10_tab16<true>(pm - mx, T) : 0.0;
+        for (int jj = 0; jj < PPW; ++jj) mx[jj] = fmax(mx[jj], row[jj * K + kk]); // (fmax drops a NaN operand; mx is NaN only if x0 is)
+      }
+      for (int kk = 0; kk < K; ++kk) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      LseTab all;
-      all.m = mx;
-      all.acc = a;
-      all.poisoned = part[2] != 0.0; // (configuration 0 belongs to warp 0)
-      // CalcBMAlite (gene_snp_pair.cpp:552-570): the S singleton averages (0.5 / S each), then the consistent one (0.5)
-      const double term = (lane < S) ? w0[lane] : part[WARPS * 3 - 1];
-      const double lite = warp_lws(term, (lane < S) ? 0.5 / (double)S : 0.5, S + 1, lane, T);
+        for (int jj = 0; jj < PPW; ++jj) {
+          const double v = row[jj * K + kk];
+          const double e = exp10_tab16<true>(v - mx[jj], T);
+          sum[jj] += (v == v) ? e : 0.0;
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < PPW; ++jj) {
+        // the maximum contributes 1: 1/K <= mean <= 1; K equal values give exactly 1 and must give exactly 0 (the table
+        // logarithm is good to 1e-13 absolute, the reference's result is 0 after its DBL_EPSILON snap)
+        const double mean = sum[jj] * invK;
+        double wj = fma((mean == 1.0) ? 0.0 : log_tab16_pos(mean, T), EQB_INV_LN10, mx[jj]);
+        if (fabs(wj) <= DBL_EPSILON) wj = 0.0;
+        if (x0[jj] != x0[jj]) wj = nan("");
+        if (valid) bma[jj].add(wj, cwt, c == 0, T); // CalcBMA (gene_snp_pair.cpp:572-602)
+        double *ow = fa.out_w + s_pair[jj] * (5 + C);
+        if (valid && jj < tn) ow[5 + c] = wj;
+        if (ch == 0) { // warp-uniform (warp 0 only)
+          // CalcBMAlite (gene_snp_pair.cpp:552-570): the S singleton averages (0.5 / S each), then the consistent one (0.5)
+          const double lite = warp_lws(lane < S ? wj : genavg[jj], lane < S ? 0.5 / (double)S : 0.5, S + 1, lane, T);
+          if (lane == 0 && jj < tn) ow[3] = lite;
+        }
+      }
+      __syncwarp();
+    }
+    // ---------------- M: the lanes' partial model averages (online log-sum-exp states) merged across the warp, then
+    // across the warps through shared memory
+#pragma unroll
+    for (int jj = 0; jj < PPW; ++jj) {
+      LseTab b = bma[jj];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double m2 = __shfl_xor_sync(0xffffffffu, b.m, o), a2 = __shfl_xor_sync(0xffffffffu, b.acc, o);
+        const int p2 = __shfl_xor_sync(0xffffffffu, (int)b.poisoned, o);
+        lse_merge(b, m2, a2, T);
+        b.poisoned = b.poisoned || p2;
+      }
       if (lane == 0) {
-        ow[3] = lite;
-        ow[4] = all.result(T);
+        part[(warp * 4 + jj) * 3] = b.m;
+        part[(warp * 4 + jj) * 3 + 1] = b.acc;
+        part[(warp * 4 + jj) * 3 + 2] = b.poisoned ? 1.0 : 0.0;
       }
     }
-    // (the next pair's step 1 writes usum / te only after the barrier that ends its own step 1 ... the tables it replaces
-    // are no longer read: every warp passed the barrier above after its last table lookup; part / w0 are rewritten only
-    // in the next step 3, two barriers away)
+    __syncthreads();
+    if (threadIdx.x < tn) {
+      const int jj = threadIdx.x;
+      LseTab b;
+      b.init();
+      for (int w = 0; w < FA_WARPS; ++w) {
+        lse_merge(b, part[(w * 4 + jj) * 3], part[(w * 4 + jj) * 3 + 1], T);
+        b.poisoned = b.poisoned || part[(w * 4 + jj) * 3 + 2] != 0.0;
+      }
+      fa.out_w[s_pair[jj] * (5 + C) + 4] = b.result(T);
+    }
   }
 }
 

@@ -60,6 +60,10 @@ struct FastArgs {
   int debug;                   // timing experiments only (-DEQB_TUNING, EQB_FASTW_DEBUG): 1 no raw-value stores, 2 no phase A, 4 no phase C
   long long n_tiles;           // fast_pair_warp_kernel: tiles of this launch
   const long long *tile_q0;    // [n_tiles + 1] first compact pair index of each tile (variable size, <= 32 pairs)
+  // --bfs all (which == 3): fast_pair_warp_kernel is the first pass (contraction, summary statistics, the consistent
+  // configuration) and leaves b, v, t of every (pair, subgroup) here for fast_pair_all_kernel (fast_all_kernel.cuh)
+  double *st_all;              // [compact pair][3 S]
+  unsigned long long *has_all; // [compact pair] subgroups with a result
 };
 
 // ---------------------------------------------------------------- K1a
@@ -1373,7 +1377,7 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
 #endif
   const long long q0 = fa.tile_q0[tile];
   const int tn = (int)(fa.tile_q0[tile + 1] - q0); // 1 .. 32
-  const long long C = (fa.which == 1) ? 0 : S;
+  const long long C = (fa.which == 1) ? 0 : (fa.which == 3 ? prm.C : S); // configurations in a row of out_w
   const bool join = prm.analysis == 1;
   const int sst = (3 * S) | 1;
   // per-warp shared memory
@@ -1467,6 +1471,13 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
     }
   }
   __syncwarp();
+  if (fa.st_all) { // --bfs all: the standardised statistics of the tile for the second pass (coalesced)
+    for (int i = lane; i < tn * 3 * S; i += 32) {
+      const int j = i / (3 * S);
+      fa.st_all[q0 * 3 * S + i] = st[(size_t)j * sst + (i - j * 3 * S)];
+    }
+    if (lane < tn) fa.has_all[q0 + lane] = hasm[lane];
+  }
   if (!join || lane >= tn || (dbg & 4)) return;
   const bool st_raw = !(dbg & 1) && fa.out_gen != nullptr; // raw values only on request
   // ---------------- phase C: lane per pair
@@ -1501,6 +1512,7 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
     ow[4] = nan("");
     return;
   }
+  if (fa.which == 3) return; // (the configurations and both model averages: fast_pair_all_kernel)
   // singleton configurations (CalcAbfsUvlrForSingletons, gene_snp_pair.cpp:422-463) + BMAlite (:552-570)
   double *oc = fa.out_cfg + my_pair * C * K;
   LseTab lite;

@@ -151,7 +151,10 @@ struct LseTab {
   __device__ __forceinline__ double result(const TabRef T) const
   {
     if (poisoned) return nan("");
-    double r = fma(log_tab16(acc, T), PGK[11], m); // m + log10(acc)
+    // m + log10(acc); weights that sum to 1 on equal values give acc = 1 +- 1 ulp and the reference's result is exactly m
+    // (0 after its DBL_EPSILON snap): ln(1 + d) = d there, not the table's 1e-13
+    const double d1 = acc - 1.0;
+    double r = fma((fabs(d1) < 1e-8) ? d1 : log_tab16(acc, T), PGK[11], m);
     if (fabs(r) <= DBL_EPSILON) r = 0.0;
     return r;
   }
