@@ -183,19 +183,19 @@ __global__ void __launch_bounds__(FA_THREADS, 4) fast_pair_all_kernel(const DevP
           const int m = (int)(mm >> (u * 16)) & 0xffff;
           const double *p0 = tb0 + (m & mk0) * 96, *p1 = tb1 + ((m >> sh1) & mk1) * 96, *p2 = tb2 + (m >> sh2) * 96;
           const double den = p0[0] + p1[0] + p2[0], num = p0[32] + p1[32] + p2[32], sing = p0[64] + p1[64] + p2[64];
-          // natural-log ABF; CalcLog10AbfUvlr's guards (see abf_from_sums) as a select: z >= 1 is a normal number whenever
-          // den is one, a NaN den (NaN statistics) gives 0 like the reference's "V < +Inf" test
+          // natural-log ABF; CalcLog10AbfUvlr's guards (see abf_from_sums) as ONE select on the result: num != 0 implies
+          // den != 0 (sums of the same terms), a NaN or infinite den fails z < 1e300 like the reference's "V < +Inf"; the
+          // logarithm and the reciprocal of a rejected z are bit manipulations on garbage, never used
           const double z = fma(oma2, den, 1.0);
-          const bool ok = num != 0.0 && den != 0.0 && den == den && z < 1e300;
-          const double zz = ok ? z : 1.0;
-          const double x = sing + fma(-0.5, log_tab16_pos(zz, T), 0.5 * num * num * oma2 * rcp_n(zz));
-          xv[u] = ok ? x * EQB_INV_LN10 : 0.0;
+          const bool ok = num != 0.0 && z < 1e300;
+          const double x = sing + fma(-0.5, log_tab16_pos(z, T), 0.5 * num * num * oma2 * rcp_n(z));
+          xv[u] = ok ? x : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int cl = cl0 + u;
-          stg[cl * FA_SROW + lane] = xv[u]; // (a row >= nc of the last chunk holds the value of a zero-padded mask: never used)
-          if (oc && cl < nc) oc[(c0 + cl) * K] = xv[u];
+          stg[cl * FA_SROW + lane] = xv[u]; // natural-log units (a row >= nc of the last chunk belongs to a zero-padded mask: unused)
+          if (oc && cl < nc) oc[(c0 + cl) * K] = xv[u] * EQB_INV_LN10;
         }
       }
       __syncwarp();
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(FA_THREADS, 4) fast_pair_all_kernel(const DevP
 #pragma unroll
         for (int jj = 0; jj < PPW; ++jj) {
           const double v = row[jj * K + kk];
-          const double e = exp10_tab16<true>(v - mx[jj], T);
+          const double e = exp_tab16<true>(v - mx[jj], T);
           sum[jj] += (v == v) ? e : 0.0;
         }
       }
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(FA_THREADS, 4) fast_pair_all_kernel(const DevP
         // the maximum contributes 1: 1/K <= mean <= 1; K equal values give exactly 1 and must give exactly 0 (the table
         // logarithm is good to 1e-13 absolute, the reference's result is 0 after its DBL_EPSILON snap)
         const double mean = sum[jj] * invK;
-        double wj = fma((mean == 1.0) ? 0.0 : log_tab16_pos(mean, T), EQB_INV_LN10, mx[jj]);
+        double wj = (mx[jj] + ((mean == 1.0) ? 0.0 : log_tab16_pos(mean, T))) * EQB_INV_LN10;
         if (fabs(wj) <= DBL_EPSILON) wj = 0.0;
         if (x0[jj] != x0[jj]) wj = nan("");
         if (valid) bma[jj].add(wj, cwt, c == 0, T); // CalcBMA (gene_snp_pair.cpp:572-602)
