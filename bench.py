@@ -240,16 +240,34 @@ def perm_flop_model(S, n_all, Q, L, K, pbf):
     return contraction, bf
 
 
-def run_perm_block(eqtlbma_b200, rank, local_rank, fp64, with_cpu):
+def run_perm_block(eqtlbma_b200, rank, local_rank, fp64, with_cpu, n_genes=None, nperm=None):
     from eqtlbma_b200.synth import make_dataset, make_grid
-    pds = make_dataset(**dict(C4, seed=1860 + rank, gridL=make_grid("general")[:10]))
-    out = {"workload": C4_DESC, "nperm": C4_NPERM, "runs": {}}
+    C4_NPERM = nperm or globals()["C4_NPERM"]
+    n_genes = n_genes or C4["n_genes"]
+    pds = make_dataset(**dict(C4, n_genes=n_genes, seed=1860 + rank, gridL=make_grid("general")[:10]))
+    out = {"workload": C4_DESC.replace("8 genes", f"{n_genes} genes"), "nperm": C4_NPERM, "runs": {}}
+    # the c3 true pass on the same shape: --bfs all (511 configurations x 10 grid points), with and without the raw ABFs
+    eng = eqtlbma_b200.Engine(pds, analysis="join", bfs="all", device=local_rank)
+    pairs = int(eng.pair_offsets()[-1])
+    tp = {"pairs": pairs, "configurations": int(eng.n_configs), "kernels": "fast_pair_warp_kernel (first pass) + fast_pair_all_kernel"}
+    for raw in (False, True):
+        for _ in range(3):
+            ms = eng.run_device_only(raw=raw)
+        kms = eng.last_pair_kernel_ms()
+        key = "with_raw_abfs" if raw else "averaged_only"
+        tp[key] = {"pairs_per_s": pairs / (ms * 1e-3), "ms_per_step": ms, "pair_kernels_ms": kms}
+        if raw:
+            raw_bytes = pairs * (3 * eng.L + eng.n_configs * eng.K) * 8
+            tp[key]["raw_emission_gbs"] = raw_bytes / (kms * 1e-3) / 1e9
+    eng.close()
+    out["true_pass_bfs_all"] = tp
     for pbf in ("all", "gen-sin"):
         eng = eqtlbma_b200.Engine(pds, analysis="join", bfs="all" if pbf == "all" else "sin", device=local_rank)
         pairs = int(eng.pair_offsets()[-1])
         eng.set_perm_timing(False)
         eng.run_permutations_device_only(C4_NPERM, 1859, pbf=pbf, wrtsize=WRTSIZE)  # warm-up (also builds the shuffle tables)
-        ms = [eng.run_permutations_device_only(C4_NPERM, 1859, pbf=pbf, wrtsize=WRTSIZE) for _ in range(2)]
+        reps = 2 if pairs * C4_NPERM < 5e8 else 1
+        ms = [eng.run_permutations_device_only(C4_NPERM, 1859, pbf=pbf, wrtsize=WRTSIZE) for _ in range(reps)]
         eng.set_perm_timing(True)
         eng.run_permutations_device_only(C4_NPERM, 1859, pbf=pbf, wrtsize=WRTSIZE)
         tm = eng.last_perm_timing()
@@ -409,7 +427,8 @@ def run_ours(args, rank, world, local_rank):
         fp64 = obj[0]
     perm_info = None
     if not args.no_perm:
-        perm_info = run_perm_block(eqtlbma_b200, rank, local_rank, fp64, with_cpu=(world == 1 and not args.no_cpu))
+        perm_info = run_perm_block(eqtlbma_b200, rank, local_rank, fp64, with_cpu=(world == 1 and not args.no_cpu),
+                                   n_genes=args.perm_genes or None, nperm=args.perm_nperm or None)
 
     # ---- max over ranks, whole-job aggregate
     tot_pairs = pairs
@@ -427,6 +446,10 @@ def run_ours(args, rank, world, local_rank):
                 pp = torch.tensor([r["permuted_pairs_per_s"]], device="cuda", dtype=torch.float64)
                 dist.all_reduce(pp, op=dist.ReduceOp.SUM)
                 r["permuted_pairs_per_s"] = float(pp[0])
+            for key in ("averaged_only", "with_raw_abfs"):
+                pp = torch.tensor([perm_info["true_pass_bfs_all"][key]["pairs_per_s"]], device="cuda", dtype=torch.float64)
+                dist.all_reduce(pp, op=dist.ReduceOp.SUM)
+                perm_info["true_pass_bfs_all"][key]["pairs_per_s"] = float(pp[0])
         gathered = [None] * world
         dist.all_gather_object(gathered, (digest, shard_ok[0], shard_info["genes"], pairs))
         digests = [g[0] for g in gathered]
@@ -490,6 +513,9 @@ def run_ours(args, rank, world, local_rank):
         par = parity_vs_reference(ds, eng, full, args.cpu_genes)
         if par:
             out.update(par)
+        cli = cli_e2e(ds, args.cli_genes)
+        if cli:
+            out["cli_e2e"] = cli
     print(json.dumps(out))
     if dist:
         dist.destroy_process_group()
@@ -611,6 +637,55 @@ def cpu_baseline_reference(ds, sample_genes=60):
     return out
 
 
+def cli_e2e(ds, n_genes=500):
+    """Command-line drop-in, wall clock: eqtlbma_b200/eqtlbma_bf and the reference binary on the SAME input files (text
+    parsing, association pass, %.6e formatting and gzip output all inside both times)."""
+    exe = os.path.join(ROOT, "eqtlbma_b200", "eqtlbma_bf")
+    ref = os.path.join(ROOT, "oracle", "_ref", "eqtlbma_bf_ref")
+    if not os.path.exists(exe):
+        return None
+    sub = subset_dataset(ds, n_genes)
+    tmp = tempfile.mkdtemp(prefix="eqb_cli_")
+    try:
+        sub.write_files(tmp)
+        in_bytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp))
+        nthr = str(os.cpu_count() or 1)
+
+        def run(binary, tag, threads):
+            cmd = [binary] + sub.ref_args(tmp, os.path.join(tmp, tag)) + REF_FLAGS + ["--thread", threads, "-v", "1"]
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                return None
+            pairs = None
+            for line in r.stdout.splitlines():
+                if line.startswith("nb of analyzed gene-SNP pairs:"):
+                    pairs = int(line.split(":")[1].split("(")[0])
+            return {"pairs": pairs, "wall_s": wall, "pairs_per_s": (pairs or 0) / wall}
+
+        run(exe, "warm", nthr)  # first process on the device pays the driver / module load once
+        ours = run(exe, "ours", nthr)
+        out = {"workload": f"first {len(sub.gene_names)} genes of the bench workload written as the reference's input files "
+                           f"({in_bytes / 1e6:.1f} MB gzipped), --analys join --bfs sin --outss --outw", "ours": ours}
+        if os.path.exists(ref):
+            theirs = run(ref, "ref", "1")
+            out["reference"] = theirs
+            if ours and theirs and ours["pairs"] == theirs["pairs"]:
+                out["wall_ratio"] = theirs["wall_s"] / ours["wall_s"]
+                import gzip
+                same = True
+                for fn in sorted(os.listdir(tmp)):
+                    if fn.startswith("ours_") and fn.endswith(".gz"):
+                        a = gzip.open(os.path.join(tmp, fn), "rt").read().splitlines()
+                        b = gzip.open(os.path.join(tmp, "ref_" + fn[5:]), "rt").read().splitlines()
+                        same = same and len(a) == len(b) and all(x.split("\t")[:2] == y.split("\t")[:2] for x, y in zip(a, b))
+                out["same_rows"] = bool(same)
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def cpu_baseline_port(ds, sample_genes=60):
     from eqtlbma_b200._capi import Engine as AnyEngine
     path = os.path.join(ROOT, "oracle", "liboracle.so")
@@ -729,8 +804,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genes", type=int, default=0, help="override the number of genes per block / GPU (debug)")
     ap.add_argument("--cpu-genes", type=int, default=60, help="genes in the bounded CPU sample")
+    ap.add_argument("--cli-genes", type=int, default=500, help="genes in the command-line end-to-end comparison")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-perm", action="store_true")
+    ap.add_argument("--perm-genes", type=int, default=0, help="genes per GPU of the c3/c4-shape block (default 8)")
+    ap.add_argument("--perm-nperm", type=int, default=0, help="permutations of the c4-shape block (default 2047)")
     ap.add_argument("--no-check", action="store_true", help="skip the sharding-invariance check")
     ap.add_argument("--no-e2e", action="store_true", help="kernel A/B runs only: skip the end-to-end loop (e2e = null)")
     args = ap.parse_args()

@@ -1141,7 +1141,9 @@ int eqb_create(eqb_ctx **out, const eqb_config *cfg)
   *out = ctx; // returned even on failure so that eqb_last_error() can be read
   if (cfg->abi_version != EQB_ABI_VERSION) return fail(ctx, "ABI version mismatch");
   if (cfg->n_subgroups < 1 || cfg->n_subgroups > MAXS) return fail(ctx, "1..64 subgroups are supported");
-  if (cfg->n_samples_all < 1 || cfg->n_samples_all > 65535) return fail(ctx, "1..65535 samples are supported");
+  // (a sample row is register-resident in the projection and general kernels: 64 doubles per lane)
+  if (cfg->n_samples_all < 1 || cfg->n_samples_all > 2048)
+    return fail(ctx, "1..2048 samples (sorted union over the subgroups) are supported");
   if (cfg->bfs == EQB_BFS_ALL && cfg->analysis == EQB_ANALYSIS_JOIN && cfg->n_subgroups > 20)
     return fail(ctx, "--bfs all supports at most 20 subgroups");
   int ndev = 0;

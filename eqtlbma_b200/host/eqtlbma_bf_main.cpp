@@ -16,11 +16,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
 #include <ctime>
+#include <deque>
 #include <iostream>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <set>
 #include <sstream>
 #include <string>
@@ -59,9 +62,91 @@ void split(const string &s, const char *delim, vector<string> &tokens)
   }
 }
 
+// The two big matrices (custom-format genotypes, expression levels) are tokenised in place -- no std::string per cell --
+// and their cells go through a decimal fast path: a literal [-]ddd[.ddd] with <= 15 significant digits is m / 10^d with m
+// and 10^d exactly representable, and the IEEE quotient of two exact doubles is the correctly rounded value of the
+// decimal, i.e. the very double strtod / atof returns (Clinger's fast path).  Everything else (exponents, inf, nan, long
+// mantissas) goes through strtod.  data_loader.cpp:437-527, 878-1010 parse the same cells with utils::split + atof.
+struct Span {
+  const char *p;
+  size_t n;
+  bool eq(const char *s) const { return strlen(s) == n && memcmp(p, s, n) == 0; }
+  string str() const { return string(p, n); }
+};
+
+void split_spans(const string &s, vector<Span> &tok) // delimiters: space and tab (strtok semantics)
+{
+  tok.clear();
+  const char *b = s.data(), *e = b + s.size();
+  while (b < e) {
+    while (b < e && (*b == ' ' || *b == '\t')) ++b;
+    if (b >= e) break;
+    const char *t = b;
+    while (b < e && *b != ' ' && *b != '\t') ++b;
+    Span sp;
+    sp.p = t;
+    sp.n = (size_t)(b - t);
+    tok.push_back(sp);
+  }
+}
+
+bool is_na(const Span &t)
+{
+  if (t.n < 2 || t.n > 3 || (t.p[0] != 'N' && t.p[0] != 'n')) return false; // (a number never starts with n)
+  return t.eq("NA") || t.eq("na") || t.eq("NaN") || t.eq("nan");
+}
+
+double fast_atof(const Span &t)
+{
+  static const double p10[] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                               1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const char *b = t.p, *e = t.p + t.n;
+  bool neg = false;
+  if (b < e && (*b == '-' || *b == '+')) neg = (*b++ == '-');
+  unsigned long long m = 0;
+  int nd = 0, dec = 0;
+  bool any = false, ok = true;
+  while (b < e && *b >= '0' && *b <= '9') {
+    if (m || *b != '0') ++nd;
+    m = m * 10 + (unsigned long long)(*b++ - '0');
+    any = true;
+    if (nd > 15) { ok = false; break; }
+  }
+  if (ok && b < e && *b == '.') {
+    ++b;
+    while (b < e && *b >= '0' && *b <= '9') {
+      if (m || *b != '0') ++nd;
+      m = m * 10 + (unsigned long long)(*b++ - '0');
+      ++dec;
+      any = true;
+      if (nd > 15 || dec > 22) { ok = false; break; }
+    }
+  }
+  if (ok && any && b == e) {
+    const double v = (double)m / p10[dec];
+    return neg ? -v : v;
+  }
+  char buf[64];
+  if (t.n < sizeof(buf)) {
+    memcpy(buf, t.p, t.n);
+    buf[t.n] = 0;
+    return atof(buf);
+  }
+  return atof(t.str().c_str());
+}
+
+// Line reader over a gzip (or plain) file.  zlib inflates on a background thread into 1 MiB blocks (a bounded queue), the
+// caller's thread cuts lines out of them: decompression -- half the loading time of a dosage matrix -- overlaps the parsing.
 struct GzReader {
   gzFile f;
   string path;
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<string> q;
+  bool done = false, stop = false, started = false;
+  string cur;
+  size_t pos = 0;
   explicit GzReader(const string &p) : path(p)
   {
     f = gzopen(p.c_str(), "rb");
@@ -71,23 +156,71 @@ struct GzReader {
     }
     gzbuffer(f, 1 << 20);
   }
+  void producer()
+  {
+    const size_t BLOCK = 1 << 20, MAXQ = 6;
+    while (true) {
+      string b(BLOCK, '\0');
+      const int n = gzread(f, &b[0], (unsigned)BLOCK);
+      std::unique_lock<std::mutex> lk(mu);
+      if (n <= 0) {
+        done = true;
+        cv.notify_all();
+        return;
+      }
+      b.resize((size_t)n);
+      cv.wait(lk, [&] { return q.size() < MAXQ || stop; });
+      if (stop) return;
+      q.push_back(std::move(b));
+      cv.notify_all();
+    }
+  }
+  bool next_block()
+  {
+    if (!started) {
+      started = true;
+      th = std::thread(&GzReader::producer, this);
+    }
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return !q.empty() || done; });
+    if (q.empty()) return false;
+    cur = std::move(q.front());
+    q.pop_front();
+    pos = 0;
+    cv.notify_all();
+    return true;
+  }
+  // true for every line ended by a newline (possibly empty) and for a non-empty last line without one
   bool getline(string &line)
   {
     line.clear();
-    char buf[1 << 16];
     bool got = false;
-    while (gzgets(f, buf, sizeof(buf)) != NULL) {
-      got = true;
-      size_t len = strlen(buf);
-      if (len > 0 && buf[len - 1] == '\n') {
-        line.append(buf, len - 1);
+    while (true) {
+      if (pos >= cur.size() && !next_block()) return got && !line.empty();
+      const char *b = cur.data() + pos;
+      const char *nl = (const char *)memchr(b, '\n', cur.size() - pos);
+      if (nl) {
+        line.append(b, (size_t)(nl - b));
+        pos += (size_t)(nl - b) + 1;
         return true;
       }
-      line.append(buf, len);
+      line.append(b, cur.size() - pos);
+      pos = cur.size();
+      got = true;
     }
-    return got && !line.empty();
   }
-  ~GzReader() { gzclose(f); }
+  ~GzReader()
+  {
+    if (started) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        stop = true;
+        cv.notify_all();
+      }
+      th.join();
+    }
+    gzclose(f);
+  }
 };
 
 bool file_exists(const string &p)
@@ -248,7 +381,11 @@ void help(char **argv)
        << "\t\teqtlbma_bf_parallel.bash)" << endl
        << "      --gpus\tN: run the N shards on GPUs 0..N-1 of this machine, one process each, and\n"
        << "\t\tconcatenate their outputs in shard order (extension; replaces the launcher +\n"
-       << "\t\t`zcat | sed 1d` merge of eqtlbma_bf_parallel.bash; same files as a single run)" << endl;
+       << "\t\t`zcat | sed 1d` merge of eqtlbma_bf_parallel.bash; same files as a single run)" << endl
+       << endl
+       << "Limits of the device path: at most 2048 samples in the union over the subgroups, 64 subgroups\n"
+       << "(20 with --bfs all, 16 with --error mvlr); not built: --error hybrid, --inss, --lik other than\n"
+       << "normal, tabix-indexed --scoord." << endl;
 }
 
 void die_usage(int argc, char **argv, const string &msg)
@@ -697,20 +834,21 @@ void load_all(const Options &o, Loaded &d)
     r.getline(line);
     const size_t ns = d.exp_samples[sg].size();
     size_t nb = 1, kept = 0;
+    vector<Span> sp;
     while (r.getline(line)) {
       ++nb;
-      split(line, " \t", tok);
-      if (tok.size() != ns + 1) {
-        cerr << "ERROR: not enough columns on line " << nb << " of file " << d.expfile[sg] << " (" << tok.size()
+      split_spans(line, sp);
+      if (sp.size() != ns + 1) {
+        cerr << "ERROR: not enough columns on line " << nb << " of file " << d.expfile[sg] << " (" << sp.size()
              << " != " << ns + 1 << ")" << endl;
         exit(EXIT_FAILURE);
       }
-      map<string, GeneRec>::iterator g = d.genes.find(tok[0]);
+      map<string, GeneRec>::iterator g = d.genes.find(sp[0].str());
       if (g == d.genes.end()) continue;
       if (g->second.exp.find(sg) != g->second.exp.end()) continue; // map::insert keeps the first
       vector<double> v(ns, kNaN);
       for (size_t i = 0; i < ns; ++i)
-        if (!is_na(tok[i + 1])) v[i] = atof(tok[i + 1].c_str());
+        if (!is_na(sp[i + 1])) v[i] = fast_atof(sp[i + 1]);
       g->second.exp[sg] = v;
       ++kept;
     }
@@ -797,20 +935,50 @@ void load_all(const Options &o, Loaded &d)
         if (line.find("#CHROM") != string::npos) break;
     const size_t ns = d.geno_samples[sg].size();
     size_t nb = 1, kept = 0;
+    vector<Span> sp;
     while (r.getline(line)) {
       ++nb;
-      split(line, " \t", tok);
       string name, chr, pos;
       size_t first = 1, idx_gt = 0;
       if (fmt == FMT_DOSE) {
-        if (tok.size() != ns + 1) {
-          cerr << "ERROR: not enough columns on line " << nb << " of file " << it->second << " (" << tok.size()
+        // custom format: in-place tokens, decimal fast path (Snp::AddSubgroupFromDoseLine, snp.cpp:88-113)
+        split_spans(line, sp);
+        if (sp.size() != ns + 1) {
+          cerr << "ERROR: not enough columns on line " << nb << " of file " << it->second << " (" << sp.size()
                << " != " << ns + 1 << ")" << endl;
           exit(EXIT_FAILURE);
         }
-        name = tok[0];
-        if (d.snps.find(name) == d.snps.end()) continue;
-        if (find(tok.begin(), tok.end(), "NA") != tok.end()) continue; // data_loader.cpp:937-938
+        name = sp[0].str();
+        map<string, SnpRec>::iterator si = d.snps.find(name);
+        if (si == d.snps.end()) continue;
+        bool has_NA = false;
+        for (size_t i = 0; i < sp.size() && !has_NA; ++i)
+          has_NA = sp[i].n == 2 && sp[i].p[0] == 'N' && sp[i].p[1] == 'A'; // data_loader.cpp:937-938
+        if (has_NA) continue;
+        SnpRec &sr = si->second;
+        vector<double> &g = sr.geno[sg];
+        if (!g.empty()) {
+          cerr << "ERROR: SNP " << name << " is duplicated in file " << it->second << endl;
+          exit(EXIT_FAILURE);
+        }
+        g.assign(ns, kNaN);
+        double maf = 0.0;
+        for (size_t i = 0; i < ns; ++i) {
+          if (is_na(sp[i + 1]))
+            maf = kNaN;
+          else {
+            g[i] = fast_atof(sp[i + 1]);
+            if (maf == maf) maf += g[i];
+          }
+        }
+        if (maf == maf) maf /= (2 * ns);
+        if (maf == maf) maf = (maf <= 0.5 ? maf : 1 - maf);
+        sr.maf[sg] = maf;
+        ++kept;
+        continue;
+      }
+      split(line, " \t", tok);
+      if (false) {
       } else if (fmt == FMT_VCF) {
         if (tok.size() != ns + 9) {
           cerr << "ERROR: not enough columns on line " << nb << " of file " << it->second << endl;
