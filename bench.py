@@ -290,13 +290,15 @@ def run_perm_block(eqtlbma_b200, rank, local_rank, fp64, with_cpu, n_genes=None,
                                           "(prep + GEMM + BF + merge) against the measured DFMA peak"}
         out["runs"][pbf] = r
     if with_cpu:
-        out["cpu_baseline"] = cpu_baseline_perm()
+        out["cpu_baseline"] = cpu_baseline_perm(eqtlbma_b200, local_rank)
     return out
 
 
-def cpu_baseline_perm():
+def cpu_baseline_perm(eqtlbma_b200=None, device=0):
     """The reference's permutation loop (gene.cpp:598-717; OpenMP over SNPs, --thread = host cores) on a bounded slice
-    of the c4 shape: run with permutations minus the same run without."""
+    of the c4 shape: run with permutations minus the same run without.  The same slices go through
+    oracle/_ref/eqtlbma_bf_ref_dump and through the CUDA path: true statistic, number of permutations and p-value (i.e. the
+    exceedance count) of every gene must agree ('parity' of each entry)."""
     from eqtlbma_b200.synth import make_dataset, make_grid
     threads = os.cpu_count() or 1
     res = {}
@@ -305,7 +307,8 @@ def cpu_baseline_perm():
                                  gridL=make_grid("general")[:10]))
         bfs = "all" if pbf == "all" else "sin"
         base = ["--analys", "join", "--bfs", bfs, "--outw"]
-        t1 = time_reference_binary(ds, base + ["--nperm", str(nperm), "--seed", "1859", "--pbf", pbf], threads=threads, raw_wall=True)
+        pflags = ["--nperm", str(nperm), "--seed", "1859", "--pbf", pbf]
+        t1 = time_reference_binary(ds, base + pflags, threads=threads, raw_wall=True)
         t0 = time_reference_binary(ds, base, threads=threads, raw_wall=True)
         if not t1 or not t0:
             return None
@@ -314,6 +317,35 @@ def cpu_baseline_perm():
                     "sample": f"{n_genes} genes x ~{spg} cis SNPs of the c4 shape ({t1['pairs']} pairs), --nperm {nperm} --pbf {pbf} "
                               f"--thread {threads} through oracle/_ref/eqtlbma_bf_ref: {t1['t_full']:.1f} s with permutations - "
                               f"{t0['t_full']:.1f} s without"}
+        exe = os.path.join(ROOT, "oracle", "_ref", "eqtlbma_bf_ref_dump")
+        if eqtlbma_b200 is not None and os.path.exists(exe):
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from refdump import parse_dump
+            tmp = tempfile.mkdtemp(prefix="eqb_ppar_")
+            try:
+                ds.write_files(tmp)
+                dump = os.path.join(tmp, "dump.txt")
+                cmd = [exe] + ds.ref_args(tmp, os.path.join(tmp, "obs")) + base + pflags + ["--thread", str(threads), "-v", "0"]
+                r = subprocess.run(cmd, env=dict(os.environ, EQTLBMA_DUMP=dump), capture_output=True, text=True)
+                d = parse_dump(dump) if r.returncode == 0 else None
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+            if d:
+                eng = eqtlbma_b200.Engine(ds, analysis="join", bfs=bfs, device=device)
+                eng.run()
+                pr = eng.run_permutations(nperm=nperm, seed=1859, pbf=pbf, wrtsize=10)
+                eng.close()
+                ok, worst = True, 0.0
+                for g, name in enumerate(ds.gene_names):
+                    e = d["permjoin"].get(name)
+                    if e is None:
+                        ok = ok and pr.nperm_done[g] == 0
+                        continue
+                    ok = ok and int(pr.nperm_done[g]) == e["nperm"] and int(pr.count[g]) == round(e["pval"] * (e["total"] + 1))
+                    worst = max(worst, abs(float(pr.true_stat[g]) - e["true"]))
+                res[pbf]["parity"] = {"ok": bool(ok and worst <= 1e-8), "genes": len(d["permjoin"]), "exceedance_counts_exact": bool(ok),
+                                      "max_abs_err_true_statistic": worst,
+                                      "against": "oracle/_ref/eqtlbma_bf_ref_dump on the same slice, seed and write-group size"}
     return res
 
 

@@ -1066,6 +1066,11 @@ void load_all(const Options &o, Loaded &d)
   // subgroups that were not loaded themselves carry the first file's genotypes (and sample list)
   for (map<string, string>::iterator sgi = d.genofile.begin(); sgi != d.genofile.end(); ++sgi)
     if (d.loaded_from.find(sgi->first) == d.loaded_from.end()) {
+      if (sgi->second != d.genofile.begin()->second)
+        // (the reference stops reading genotype files at the first repeat of the first one, data_loader.cpp:733-740, and
+        // pairs the duplicated vectors with this file's own sample list; the listed file is ignored by both programs)
+        cerr << "WARNING: genotype file " << sgi->second << " of subgroup " << sgi->first << " is not read: the list repeats "
+             << d.genofile.begin()->second << " before it, and its genotypes and samples are used instead" << endl;
       d.loaded_from[sgi->first] = d.genofile.begin()->second;
       d.geno_samples[sgi->first] = d.geno_samples[first_sg];
     }
@@ -1456,6 +1461,10 @@ int main(int argc, char **argv)
   // ---- batches of whole write-groups, sized by a host-memory budget for the raw ABFs
   const size_t per_pair = (size_t)S * 44 + (join ? ((size_t)3 * L + (size_t)C * K + 5 + C) * 8 : 0);
   const size_t budget = (size_t)1 << 30;
+  // permutation statistics kept per gene of a batch (device + host copy for the median): [per][nperm] doubles
+  const size_t per_gene = o.nb_permutations > 0
+                              ? (size_t)((o.analys == "sep" && o.perm_sep == 2) ? S : 1) * (size_t)o.nb_permutations * 16
+                              : 0;
   size_t nbAnalyzedGenes = 0, nbAnalyzedPairs = 0;
   int64_t g0 = 0, g_end = G;
   if (o.shard_n > 1) { // gene sharding over GPUs: contiguous cost-balanced ranges of whole write-groups
@@ -1475,7 +1484,7 @@ int main(int argc, char **argv)
       int64_t gn = min<int64_t>(g_end, g1 + o.wrtsize);
       size_t add = 0;
       for (int64_t g = g1; g < gn; ++g) add += (size_t)(ce[g] - cb[g]);
-      if (g1 > g0 && (pairs_est + add) * per_pair > budget) break;
+      if (g1 > g0 && (pairs_est + add) * per_pair + (size_t)(gn - g0) * per_gene > budget) break;
       pairs_est += add;
       g1 = gn;
     }
