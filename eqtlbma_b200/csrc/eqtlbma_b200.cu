@@ -2178,6 +2178,168 @@ int eqb_run(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_results *res)
   return run_true_impl(ctx, gene_lo, gene_hi, res, true, false, nullptr);
 }
 
+// --inss (eqtlbma_bf.cpp:1496-1503, data_loader.cpp:1251-1343, gene.cpp:293-311): Bayes factors of pairs whose summary
+// statistics are given.  Needs only eqb_create + eqb_set_grids (no samples, genotypes or windows; not finalized); join
+// analysis, --error uvlr.  Same kernels as the true pass from the standardisation on.
+int eqb_bf_from_sstats(eqb_ctx *ctx, int64_t n_pairs, const int32_t *n, const double *sigmahat, const double *betahat,
+                       const double *sebetahat, eqb_results *res)
+{
+  if (!ctx || !ctx->stream) return 1;
+  if (!res || !n || !sigmahat || !betahat || !sebetahat) return fail(ctx, "null argument");
+  if (ctx->cfg.analysis != EQB_ANALYSIS_JOIN || ctx->cfg.error_model != EQB_ERROR_UVLR)
+    return fail(ctx, "--inss requires --analys join and --error uvlr");
+  if (ctx->phi2L.empty()) return fail(ctx, "grids not set");
+  if (n_pairs <= 0) return 0;
+  AllocScope alloc_scope(ctx->stream);
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int S = ctx->cfg.n_subgroups, L = (int)ctx->phi2L.size(), K = (int)ctx->phi2S.size();
+  const int which = ctx->cfg.bfs + 1;
+  if (which != 1 && K < 1) return fail(ctx, "--gridS is required by --bfs sin|all");
+  // grid tables by value (constant bank): unique phi2 values of the three consistent rows, entries grouped by them
+  GridConst gc;
+  memset(&gc, 0, sizeof(gc));
+  std::vector<double> uphi;
+  std::vector<int> idx(3 * L);
+  std::vector<double> oma(3 * L);
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < L; ++k) {
+      const double ph = ctx->phi2L[k], om = ctx->oma2L[k];
+      const double phi2 = (r == 0) ? ph : ((r == 1) ? 0.0 : ph + om);
+      int u = -1;
+      for (size_t i = 0; i < uphi.size(); ++i)
+        if (uphi[i] == phi2) u = (int)i;
+      if (u < 0) {
+        u = (int)uphi.size();
+        uphi.push_back(phi2);
+      }
+      idx[r * L + k] = u;
+      oma[r * L + k] = (r == 0) ? om : ((r == 1) ? ph + om : 0.0);
+    }
+  const int UL = (int)uphi.size();
+  if (UL > GC_UL || 3 * L > GC_3L || K > GC_K) return fail(ctx, "--inss: at most 64 grid points in --gridL and 32 in --gridS");
+  {
+    int cnt = 0;
+    for (int u = 0; u < UL; ++u) {
+      gc.uphi[u] = uphi[u];
+      gc.ustart[u] = (short)cnt;
+      for (int e = 0; e < 3 * L; ++e)
+        if (idx[e] == u) {
+          gc.ent[cnt] = (unsigned char)e;
+          gc.oma[cnt] = oma[e];
+          ++cnt;
+        }
+    }
+    gc.ustart[UL] = (short)cnt;
+    for (int k = 0; k < K; ++k) {
+      gc.phiS[k] = ctx->phi2S[k];
+      gc.omaS[k] = ctx->oma2S[k];
+    }
+  }
+  GridTab gt;
+  memset(&gt, 0, sizeof(gt));
+  gt.UL = UL;
+  GridOrder go;
+  memset(&go, 0, sizeof(go));
+  // configurations and the parameter block (only the fields the Bayes-factor phases read)
+  std::vector<unsigned long long> masks;
+  std::vector<double> weights;
+  if (which == 3) enumerate_configs(S, masks, weights);
+  const long long C = (which == 1) ? 0 : ((which == 2) ? S : (long long)masks.size());
+  if (which == 3 && !(S <= FA_MAXS && K <= FA_MAXK && C < 65536)) return fail(ctx, "--inss --bfs all: at most 10 subgroups and 16 points in --gridS");
+  unsigned long long *d_mask = nullptr;
+  double *d_wt = nullptr;
+  DevParams *d_prm = nullptr;
+  CK(dmalloc(&d_mask, std::max<size_t>(masks.size(), 1) * 8));
+  CK(dmalloc(&d_wt, std::max<size_t>(masks.size(), 1) * 8));
+  CK(dmalloc(&d_prm, sizeof(DevParams)));
+  CK(h2d(ctx, d_mask, masks.data(), masks.size() * 8));
+  CK(h2d(ctx, d_wt, weights.data(), weights.size() * 8));
+  DevParams hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.S = S;
+  hp.analysis = ctx->cfg.analysis;
+  hp.bfs = ctx->cfg.bfs;
+  hp.L = L;
+  hp.K = K;
+  hp.C = (which == 3) ? (long long)masks.size() : 0;
+  hp.cfg_mask = d_mask;
+  hp.cfg_weight = d_wt;
+  CK(h2d(ctx, d_prm, &hp, sizeof(DevParams)));
+  // inputs, standardisation
+  const size_t items = (size_t)n_pairs * S;
+  int *d_n = nullptr;
+  double *d_in = nullptr;
+  CK(dmalloc(&d_n, items * sizeof(int)));
+  CK(dmalloc(&d_in, items * 3 * sizeof(double)));
+  CK(cudaMemcpyAsync(d_n, n, items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_in, sigmahat, items * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_in + items, betahat, items * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_in + 2 * items, sebetahat, items * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->d_fa_st.ensure(items * 3));
+  CK(ctx->d_fa_has.ensure((size_t)n_pairs));
+  CK(cudaMemsetAsync(ctx->d_fa_has.p, 0, (size_t)n_pairs * 8, ctx->stream));
+  sstats_std_kernel<<<(unsigned)((items + 255) / 256), 256, 0, ctx->stream>>>((long long)items, S, d_n, d_in, d_in + items,
+                                                                            d_in + 2 * items, ctx->d_fa_st.p, ctx->d_fa_has.p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  // outputs
+  const bool o_gen = res->abf_gen != nullptr, o_cfg = res->abf_cfg != nullptr && C > 0;
+  CK(ctx->d_gen.ensure((size_t)n_pairs * 3 * L));
+  CK(ctx->d_cfg.ensure(std::max<size_t>((size_t)n_pairs * C * K, 1)));
+  CK(ctx->d_w.ensure((size_t)n_pairs * (5 + C)));
+  // tiles of 32 consecutive pairs
+  const long long n_tiles = (n_pairs + 31) / 32;
+  std::vector<long long> tq(n_tiles + 1);
+  for (long long t = 0; t <= n_tiles; ++t) tq[t] = std::min<long long>(t * 32, n_pairs);
+  CK(ctx->d_tile_q0.ensure(tq.size()));
+  CK(h2d(ctx, ctx->d_tile_q0.p, tq.data(), tq.size() * 8));
+  CK(ctx->d_fast_base.ensure(1));
+  CK(ctx->d_pair_off2.ensure(1));
+  const long long zero = 0;
+  CK(h2d(ctx, ctx->d_fast_base.p, &zero, 8));
+  CK(h2d(ctx, ctx->d_pair_off2.p, &zero, 8));
+  FastArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.n_genes = 1;
+  fa.T = 32;
+  fa.which = which;
+  fa.n_pairs = n_pairs;
+  fa.q_begin = 0;
+  fa.fast_base = ctx->d_fast_base.p;
+  fa.pair_off = ctx->d_pair_off2.p;
+  fa.out_gen = o_gen ? ctx->d_gen.p : nullptr;
+  fa.out_cfg = o_cfg ? ctx->d_cfg.p : nullptr;
+  fa.out_w = ctx->d_w.p;
+  fa.n_tiles = n_tiles;
+  fa.tile_q0 = ctx->d_tile_q0.p;
+  fa.st_all = ctx->d_fa_st.p;
+  fa.has_all = ctx->d_fa_has.p;
+  fa.from_st = 1;
+  const int nwarp = WARPS;
+  const size_t smem = (size_t)nwarp * fast_warp_smem_bytes(S);
+  if (smem > 200 * 1024) return fail(ctx, "too many subgroups for the shared memory of one warp tile");
+  CK(cudaFuncSetAttribute(fast_pair_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fast_pair_warp_kernel<true, true><<<(unsigned)((n_tiles + nwarp - 1) / nwarp), nwarp * 32, smem, ctx->stream>>>(d_prm, nullptr, fa, gt, go, gc);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (which == 3) {
+    const int ppw = fa_pairs_per_warp(K);
+    const unsigned grid2 = (unsigned)std::min<long long>((n_pairs + ppw - 1) / ppw, (long long)ctx->n_sm * 4);
+    CK(launch_fast_pair_all(K, grid2, fast_all_smem_bytes(S, C), ctx->stream, d_prm, nullptr, fa, gt, gc));
+    ctx->launches++;
+  }
+  if (res->abf_gen) CK(cudaMemcpyAsync(res->abf_gen, ctx->d_gen.p, (size_t)n_pairs * 3 * L * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (o_cfg) CK(cudaMemcpyAsync(res->abf_cfg, ctx->d_cfg.p, (size_t)n_pairs * C * K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (res->abf_w) CK(cudaMemcpyAsync(res->abf_w, ctx->d_w.p, (size_t)n_pairs * (5 + C) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  dfree(d_mask);
+  dfree(d_wt);
+  dfree(d_prm);
+  dfree(d_n);
+  dfree(d_in);
+  return 0;
+}
+
 int eqb_run_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int32_t want_raw, float *ms)
 {
   return run_true_impl(ctx, gene_lo, gene_hi, nullptr, want_raw != 0, true, ms);

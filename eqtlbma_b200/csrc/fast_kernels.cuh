@@ -64,6 +64,9 @@ struct FastArgs {
   // configuration) and leaves b, v, t of every (pair, subgroup) here for fast_pair_all_kernel (fast_all_kernel.cuh)
   double *st_all;              // [compact pair][3 S]
   unsigned long long *has_all; // [compact pair] subgroups with a result
+  // --inss (eqb_bf_from_sstats): the standardised statistics are INPUT (st_all / has_all filled by sstats_std_kernel), the
+  // contraction and the summary statistics are skipped, output pair = compact pair
+  int from_st;
 };
 
 // ---------------------------------------------------------------- K1a
@@ -710,6 +713,44 @@ static __device__ __noinline__ void stats_from_dots(double xy, double xx, double
   o.b = bhat;
   o.v = sebhat * sebhat;
   o.t = t;
+}
+
+// --inss: GeneSnpPair::SetSstats + StandardizeSstatsAndCorrectSmallSampleSize (gene_snp_pair.cpp:241-290) for summary
+// statistics read from files: thread per (pair, subgroup); n <= 0 = no entry for that subgroup.  The number of covariates
+// is unknown to the reference on this path (its map lookup default-constructs 0): nu = n - 2.
+static __global__ void sstats_std_kernel(long long n_items, int S, const int *__restrict__ nn, const double *__restrict__ sigmahat,
+                                         const double *__restrict__ betahat, const double *__restrict__ sebetahat,
+                                         double *__restrict__ st_all, unsigned long long *__restrict__ has_all)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  const long long pair = i / S;
+  const int s = (int)(i - pair * S);
+  double b = nan(""), v = nan(""), t = nan("");
+  const int n = nn[i];
+  if (n > 0) {
+    atomicOr(&has_all[pair], 1ull << s);
+    double bhat = betahat[i] / sigmahat[i], sebhat = sebetahat[i] / sigmahat[i];
+    t = bhat / sebhat;
+    if (!isnan(t)) {
+      const double nu = (double)n - 2.0;
+      t = ugaussian_Pinv(tdist_P(-fabs(bhat / sebhat), nu));
+      if (fabs(t) > 1e-8) {
+        const double sg2 = fabs(betahat[i]) / (fabs(t) * sebhat);
+        bhat = betahat[i] / sg2;
+        sebhat = fabs(bhat / t);
+      } else {
+        bhat = 0.0;
+        sebhat = INFINITY;
+      }
+      b = bhat;
+      v = sebhat * sebhat;
+    }
+  }
+  double *o = st_all + pair * 3 * S;
+  o[s] = b;
+  o[S + s] = v;
+  o[2 * S + s] = t;
 }
 
 // unique phi2 values of the consistent-configuration rows (gen / gen-fix / gen-maxh on gridL):
@@ -1390,6 +1431,18 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
   int *s_gene = (int *)(s_m + 32);                           // [32] gene id
 
   long long my_pair = 0;
+  if (fa.from_st) {
+    if (lane < tn) {
+      my_pair = q0 + lane;
+      s_pair[lane] = my_pair;
+      hasm[lane] = fa.has_all[q0 + lane];
+    }
+    for (int i = lane; i < tn * 3 * S; i += 32) {
+      const int j = i / (3 * S);
+      st[(size_t)j * sst + (i - j * 3 * S)] = fa.st_all[q0 * 3 * S + i];
+    }
+    __syncwarp();
+  } else {
   if (lane < tn) {
     const long long q = q0 + lane;
     int lo = fa.tile_gene[tile]; // gene of the tile's first pair (host-computed); walk forward from it
@@ -1478,6 +1531,7 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
     }
     if (lane < tn) fa.has_all[q0 + lane] = hasm[lane];
   }
+  } // (!fa.from_st)
   if (!join || lane >= tn || (dbg & 4)) return;
   const bool st_raw = !(dbg & 1) && fa.out_gen != nullptr; // raw values only on request
   // ---------------- phase C: lane per pair

@@ -6,7 +6,7 @@
 // (SURVEY.md App. B #1), hands the hot path -- testForAssociations / makePermutations,
 // eqtlbma_bf.cpp:1546-1574 -- to libeqtlbma_b200.so through its C ABI, and serialises the results
 // with the reference's text conventions (writeRes*, eqtlbma_bf.cpp:919-1447).  No statistics are
-// computed on the host.  Out of scope here (reported as errors): --inss, --lik poisson /
+// computed on the host.  Out of scope here (reported as errors): --lik poisson /
 // quasipoisson, --error hybrid, tabix-indexed --scoord (an index is ignored: every SNP of the BED
 // file is loaded, which gives the same cis sets).
 #include <getopt.h>
@@ -384,7 +384,7 @@ void help(char **argv)
        << "\t\t`zcat | sed 1d` merge of eqtlbma_bf_parallel.bash; same files as a single run)" << endl
        << endl
        << "Limits of the device path: at most 2048 samples in the union over the subgroups, 64 subgroups\n"
-       << "(20 with --bfs all, 16 with --error mvlr); not built: --error hybrid, --inss, --lik other than\n"
+       << "(20 with --bfs all, 16 with --error mvlr; --inss: 10 with --bfs all); not built: --error hybrid, --lik other than\n"
        << "normal, tabix-indexed --scoord." << endl;
 }
 
@@ -484,14 +484,23 @@ void parse_cmdline(int argc, char **argv, Options &o)
     }
   }
   // validation: same conditions and messages as eqtlbma_bf.cpp:463-692
-  if (!o.inss.empty()) die_usage(argc, argv, "--inss is not supported by the B200 front-end (out of scope)");
-  if (o.geno.empty()) die_usage(argc, argv, "missing compulsory option --geno");
-  if (!file_exists(o.geno)) die_usage(argc, argv, "can't find " + o.geno);
+  if (o.inss.empty()) {
+    if (o.geno.empty()) die_usage(argc, argv, "missing compulsory option --geno");
+    if (!file_exists(o.geno)) die_usage(argc, argv, "can't find " + o.geno);
+  } else { // eqtlbma_bf.cpp:518-537
+    if (!file_exists(o.inss)) die_usage(argc, argv, "can't find " + o.inss);
+    if (o.analys != "join") die_usage(argc, argv, "--inss requires --analys join");
+    if (o.error != "uvlr") die_usage(argc, argv, "--inss requires --error uvlr");
+    if (o.nb_permutations > 0) die_usage(argc, argv, "--inss cannot be combined with --nperm (permutations need the raw data)");
+    if (o.gpus > 1 || o.shard_n > 1) die_usage(argc, argv, "--inss runs on one GPU");
+  }
   if (!o.scoord.empty() && !file_exists(o.scoord)) die_usage(argc, argv, "can't find " + o.scoord);
-  if (o.exp.empty()) die_usage(argc, argv, "missing compulsory option --exp");
-  if (!file_exists(o.exp)) die_usage(argc, argv, "can't find " + o.exp);
-  if (o.gcoord.empty()) die_usage(argc, argv, "missing compulsory option --gcoord");
-  if (!file_exists(o.gcoord)) die_usage(argc, argv, "can't find " + o.gcoord);
+  if (o.inss.empty()) {
+    if (o.exp.empty()) die_usage(argc, argv, "missing compulsory option --exp");
+    if (!file_exists(o.exp)) die_usage(argc, argv, "can't find " + o.exp);
+    if (o.gcoord.empty()) die_usage(argc, argv, "missing compulsory option --gcoord");
+    if (!file_exists(o.gcoord)) die_usage(argc, argv, "can't find " + o.gcoord);
+  }
   if (o.anchor != "TSS" && o.anchor != "TSS+TES") die_usage(argc, argv, "--anchor should be TSS or TSS+TES");
   if (o.out.empty()) die_usage(argc, argv, "missing compulsory option --out");
   if (o.wrtsize < 1) die_usage(argc, argv, "--wrtsize should be greater than 1");
@@ -1213,6 +1222,212 @@ int launch_shards(int argc, char **argv, Options &o, time_t t_start)
 
 } // namespace
 
+// --inss: Bayes factors from per-subgroup summary-statistics files (the `_sumstats_<subgroup>.txt.gz` files --outss writes)
+// instead of raw data: loadSummaryStats / fillGeneSnpPairsWithSstats (data_loader.cpp:1212-1343), then the write-group loop
+// of run() with hasDataNotSstats = false (eqtlbma_bf.cpp:1546-1574).  Genes in name order; the SNPs of a gene in the order
+// of their first appearance (subgroups in name order, file order inside a subgroup); a (pair, subgroup) listed twice keeps
+// its first line (map::insert).
+int run_inss(const Options &o, char **argv, time_t t_start)
+{
+  map<string, string> files = load_two_column_file(o.inss, o.verbose);
+  vector<string> subgroups;
+  for (map<string, string>::iterator it = files.begin(); it != files.end(); ++it) subgroups.push_back(it->first);
+  const int S = (int)subgroups.size();
+  struct PairIn {
+    string snp;
+    vector<int32_t> n;
+    vector<double> sig, beta, se;
+  };
+  map<string, vector<PairIn> > genes;
+  map<string, map<string, size_t> > snp_idx; // gene -> snp -> index in its vector
+  static const char *cols[6] = {"gene", "snp", "n", "sigmahat", "betahat.geno", "sebetahat.geno"};
+  for (int s = 0; s < S; ++s) {
+    if (o.verbose > 0) cout << "load summary statistics for subgroup " << subgroups[s] << " ..." << endl;
+    GzReader r(files[subgroups[s]]);
+    string line;
+    vector<string> tok;
+    if (!r.getline(line)) continue;
+    split(line, "\t", tok);
+    size_t ci[6];
+    for (int c = 0; c < 6; ++c) {
+      ci[c] = string::npos;
+      for (size_t i = 0; i < tok.size(); ++i)
+        if (tok[i] == cols[c]) ci[c] = i;
+      if (ci[c] == string::npos) {
+        cerr << "ERROR: missing " << cols[c] << " in header of " << files[subgroups[s]] << endl;
+        exit(EXIT_FAILURE);
+      }
+    }
+    while (r.getline(line)) {
+      split(line, "\t", tok);
+      size_t need = 0;
+      for (int c = 0; c < 6; ++c) need = max(need, ci[c] + 1);
+      if (tok.size() < need) continue;
+      vector<PairIn> &v = genes[tok[ci[0]]];
+      map<string, size_t> &ix = snp_idx[tok[ci[0]]];
+      map<string, size_t>::iterator f = ix.find(tok[ci[1]]);
+      size_t j;
+      if (f == ix.end()) {
+        j = v.size();
+        ix[tok[ci[1]]] = j;
+        PairIn pi;
+        pi.snp = tok[ci[1]];
+        pi.n.assign(S, 0);
+        pi.sig.assign(S, kNaN);
+        pi.beta.assign(S, kNaN);
+        pi.se.assign(S, kNaN);
+        v.push_back(pi);
+      } else
+        j = f->second;
+      if (v[j].n[s] > 0) continue; // insert() keeps the first
+      v[j].n[s] = (int32_t)atol(tok[ci[2]].c_str());
+      v[j].sig[s] = atof(tok[ci[3]].c_str());
+      v[j].beta[s] = atof(tok[ci[4]].c_str());
+      v[j].se[s] = atof(tok[ci[5]].c_str());
+    }
+  }
+  if (genes.empty()) return EXIT_SUCCESS;
+  vector<double> phi2L, oma2L, phi2S, oma2S;
+  load_grid(o.gridL, phi2L, oma2L, o.verbose);
+  load_grid(o.gridS, phi2S, oma2S, o.verbose);
+  const int L = (int)phi2L.size(), K = (int)phi2S.size();
+  const vector<string> cnames = config_names(S, o.bfs);
+  const int64_t C = (int64_t)cnames.size();
+  // headers (writeRes(..., "only"))
+  const string sep = "\t";
+  {
+    string h = "gene\tsnp\tconfig";
+    for (int i = 0; i < L; ++i) h += "\tl10abf.grid" + to_string(i + 1);
+    gz_write(o.out + "_l10abfs_raw.txt.gz", "wb", h + "\n");
+    if (o.outw) {
+      h = "gene\tsnp\tnb.subgroups\tl10abf.gen\tl10abf.gen.fix\tl10abf.gen.maxh";
+      if (o.bfs != "gen") h += "\tl10abf.gen.sin";
+      if (o.bfs == "all") h += "\tl10abf.all";
+      for (size_t c = 0; c < cnames.size(); ++c) h += "\tl10abf." + cnames[c];
+      gz_write(o.out + "_l10abfs_avg-grids.txt.gz", "wb", h + "\n");
+    }
+  }
+  if (o.verbose > 0)
+    cout << "test for association between each pair gene-SNP ..." << endl
+         << "analysis=" << o.analys << " likelihood=" << o.lik << " error_model=" << o.error << endl
+         << flush;
+  eqb_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.abi_version = EQB_ABI_VERSION;
+  cfg.n_subgroups = S;
+  cfg.n_samples_all = 1;
+  cfg.analysis = EQB_ANALYSIS_JOIN;
+  cfg.bfs = o.bfs == "gen" ? EQB_BFS_GEN : (o.bfs == "sin" ? EQB_BFS_SIN : EQB_BFS_ALL);
+  cfg.error_model = EQB_ERROR_UVLR;
+  cfg.device = o.device;
+  cfg.fiterr = o.fiterr;
+  eqb_ctx *ctx = NULL;
+  check(ctx, eqb_create(&ctx, &cfg), "eqb_create");
+  check(ctx, eqb_set_grids(ctx, phi2L.data(), oma2L.data(), L, phi2S.data(), oma2S.data(), K), "eqb_set_grids");
+  // batches of whole genes sized by the raw-ABF budget
+  vector<const string *> gname;
+  vector<const vector<PairIn> *> gpairs;
+  for (map<string, vector<PairIn> >::iterator it = genes.begin(); it != genes.end(); ++it) {
+    gname.push_back(&it->first);
+    gpairs.push_back(&it->second);
+  }
+  const int64_t G = (int64_t)gname.size();
+  const size_t per_pair = ((size_t)3 * L + (size_t)C * K + 5 + C) * 8 + (size_t)S * 28;
+  const size_t budget = (size_t)1 << 30;
+  const int nthr = max(1, o.nb_threads);
+  static const char *rows[3] = {"gen", "gen-fix", "gen-maxh"};
+  size_t nbPairs = 0;
+  for (int64_t g0 = 0; g0 < G;) {
+    int64_t g1 = g0;
+    size_t np = 0;
+    while (g1 < G && (g1 == g0 || (np + gpairs[g1]->size()) * per_pair <= budget)) np += gpairs[g1++]->size();
+    vector<int64_t> off(g1 - g0 + 1, 0);
+    for (int64_t g = g0; g < g1; ++g) off[g - g0 + 1] = off[g - g0] + (int64_t)gpairs[g]->size();
+    const int64_t P = off[g1 - g0];
+    vector<int32_t> n((size_t)P * S);
+    vector<double> sig((size_t)P * S), beta((size_t)P * S), se((size_t)P * S);
+    for (int64_t g = g0; g < g1; ++g)
+      for (size_t j = 0; j < gpairs[g]->size(); ++j) {
+        const PairIn &pi = (*gpairs[g])[j];
+        const size_t p = (size_t)off[g - g0] + j;
+        for (int s = 0; s < S; ++s) {
+          n[p * S + s] = pi.n[s];
+          sig[p * S + s] = pi.sig[s];
+          beta[p * S + s] = pi.beta[s];
+          se[p * S + s] = pi.se[s];
+        }
+      }
+    vector<double> agen((size_t)P * 3 * L), acfg((size_t)P * C * K), aw((size_t)P * (5 + C));
+    eqb_results res;
+    memset(&res, 0, sizeof(res));
+    res.abf_gen = agen.data();
+    res.abf_cfg = acfg.data();
+    res.abf_w = aw.data();
+    check(ctx, eqb_bf_from_sstats(ctx, P, n.data(), sig.data(), beta.data(), se.data(), &res), "eqb_bf_from_sstats");
+    parallel_emit(o.out + "_l10abfs_raw.txt.gz", nthr, g0, g1, off, [&](int64_t ga, int64_t gb, string &raw) {
+      for (int64_t g = ga; g < gb; ++g)
+        for (size_t j = 0; j < gpairs[g]->size(); ++j) {
+          const int64_t p = off[g - g0] + (int64_t)j;
+          const string &gn = *gname[g], &sn = (*gpairs[g])[j].snp;
+          for (int r = 0; r < 3; ++r) {
+            raw += gn + sep + sn + sep + rows[r];
+            for (int k = 0; k < L; ++k) {
+              raw += sep;
+              put_sci(raw, agen[(p * 3 + r) * L + k]);
+            }
+            raw += "\n";
+          }
+          for (int64_t c = 0; c < C; ++c) {
+            raw += gn + sep + sn + sep + cnames[c];
+            for (int k = 0; k < L; ++k) { // padded / truncated to |gridL| columns (eqtlbma_bf.cpp:1207-1212)
+              raw += sep;
+              put_sci(raw, k < K ? acfg[(p * C + c) * K + k] : kNaN);
+            }
+            raw += "\n";
+          }
+        }
+    });
+    if (o.outw)
+      parallel_emit(o.out + "_l10abfs_avg-grids.txt.gz", nthr, g0, g1, off, [&](int64_t ga, int64_t gb, string &avg) {
+        for (int64_t g = ga; g < gb; ++g)
+          for (size_t j = 0; j < gpairs[g]->size(); ++j) {
+            const int64_t p = off[g - g0] + (int64_t)j;
+            int nsub = 0;
+            for (int s = 0; s < S; ++s) nsub += n[p * S + s] > 0 ? 1 : 0;
+            avg += *gname[g] + sep + (*gpairs[g])[j].snp + sep + to_string(nsub);
+            const double *w = &aw[p * (5 + C)];
+            for (int k = 0; k < 3; ++k) {
+              avg += sep;
+              put_sci(avg, w[k]);
+            }
+            if (o.bfs != "gen") {
+              avg += sep;
+              put_sci(avg, w[3]);
+            }
+            if (o.bfs == "all") {
+              avg += sep;
+              put_sci(avg, w[4]);
+            }
+            for (int64_t c = 0; c < C; ++c) {
+              avg += sep;
+              put_sci(avg, w[5 + c]);
+            }
+            avg += "\n";
+          }
+      });
+    nbPairs += (size_t)P;
+    g0 = g1;
+  }
+  eqb_destroy(ctx);
+  if (o.verbose > 0) {
+    cout << "nb of analyzed gene-SNP pairs: " << nbPairs << " (" << G << " genes)" << endl;
+    time_t t_end;
+    time(&t_end);
+    cout << "END " << argv[0] << " " << ctime(&t_end) << "elapsed -> " << difftime(t_end, t_start) << " sec" << endl;
+  }
+  return EXIT_SUCCESS;
+}
+
 int main(int argc, char **argv)
 {
   Options o;
@@ -1231,6 +1446,7 @@ int main(int argc, char **argv)
     const int ndev = eqb_device_count(); // (first CUDA call of the child: after the fork)
     if (ndev > 0) o.device = o.shard_k % ndev; // fewer GPUs than shards: the shards share them
   }
+  if (!o.inss.empty()) return run_inss(o, argv, t_start);
   Loaded d;
   load_all(o, d);
   if (d.genes.empty() || d.snps.empty()) return EXIT_SUCCESS;

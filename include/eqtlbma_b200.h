@@ -174,6 +174,14 @@ int eqb_run_permutations(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, const e
 int eqb_run_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, int32_t want_raw, float *ms);
 int eqb_run_permutations_device_only(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi,
                                      const eqb_perm_config *pc, float *ms);
+/* --inss: Bayes factors from summary statistics instead of raw data -- what loadSummaryStats +
+ * fillGeneSnpPairsWithSstats (data_loader.cpp:1251-1343, GeneSnpPair::SetSstats gene_snp_pair.cpp:241-254) feed into
+ * TestForAssociations(hasDataNotSstats = false) (gene.cpp:293-311): standardisation with nu = n - 2
+ * (gene_snp_pair.cpp:256-290; the covariate count is unknown on this path) and CalcAbfsUvlr.  Inputs are pair-major
+ * [pairs][S]; n <= 0 marks a subgroup without an entry for the pair.  Needs eqb_create (join analysis, uvlr) and
+ * eqb_set_grids only; fills res->abf_gen / abf_cfg / abf_w (NULL pointers are skipped). */
+int eqb_bf_from_sstats(eqb_ctx *ctx, int64_t n_pairs, const int32_t *n, const double *sigmahat, const double *betahat,
+                       const double *sebetahat, eqb_results *res);
 /* Multi-GPU sharding (replaces scripts/eqtlbma_bf_parallel.bash:248-262, one OS process per gene batch):
  * genes are independent, so the G genes are cut into n_shards CONTIGUOUS ranges of whole write-groups
  * (the generator is re-seeded per write-group, eqtlbma_bf.cpp:847, so a group never straddles two
