@@ -251,3 +251,40 @@ def test_warp_kernel_variants_match_oracle(cuda_lib, oracle_lib, case):
         assert np.allclose(a.abf_gen, b.abf_gen, rtol=0, atol=1e-8, equal_nan=True)
         assert np.allclose(a.abf_cfg, b.abf_cfg, rtol=0, atol=1e-8, equal_nan=True)
         assert np.allclose(a.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_sub,K,n_genes,spg,absent", [
+    (9, 10, 30, 70, 0.0),   # c3 shape, 3 pairs per tile, > 592 tiles: every persistent CTA loops over several tiles
+    (10, 16, 6, 9, 0.2),    # 4 + 3 + 3 subgroups, 1,023 configurations, 2 pairs per tile, genes absent from subgroups
+    (6, 5, 10, 7, 0.2),     # 2 + 2 + 2, 4 pairs per tile (32 / 5 capped), ragged last tile
+    (4, 11, 9, 5, 0.0),     # 2 + 1 + 1, 2 pairs per tile, one chunk of 15 configurations
+    (2, 3, 7, 3, 0.3),      # 1 + 1 + 0
+    (1, 10, 5, 4, 0.0),     # a single subgroup: one configuration
+])
+def test_bfs_all_kernel_shapes_match_oracle(cuda_lib, oracle_lib, n_sub, K, n_genes, spg, absent):
+    """fast_pair_all_kernel (fast_all_kernel.cuh) over its shape space -- parts of the subset-sum tables, pairs per tile, chunk
+    counts, tiles per CTA, absent subgroups -- against the CPU oracle: raw ABFs of every configuration, their grid averages,
+    BMAlite and BMA (gene_snp_pair.cpp:504-602)."""
+    import eqtlbma_b200
+    from eqtlbma_b200._capi import Engine as AnyEngine
+    from eqtlbma_b200.synth import make_dataset, make_grid
+    rng = np.random.default_rng(5 + n_sub)
+    gridS = np.column_stack([rng.choice([0.0, 0.01, 0.04, 0.16, 0.64], size=K), rng.choice([0.0, 0.0025, 0.04, 0.3, 2.56], size=K)])
+    ds = make_dataset(seed=300 + n_sub, n_subgroups=n_sub, n_inds=90, n_genes=n_genes, snps_per_gene=spg, ragged=True,
+                      ragged_min_frac=0.5, absent_gene_frac=absent, gridL=make_grid("general")[:7], gridS=gridS, n_chr=2,
+                      radius=100, gene_spacing=201, far_snp=False)
+    eng = eqtlbma_b200.Engine(ds, analysis="join", bfs="all")
+    ora = AnyEngine(oracle_lib, "eqo_", ds, analysis="join", bfs="all")
+    a, b = eng.run(), ora.run()
+    assert eng.n_configs == 2 ** n_sub - 1
+    assert np.array_equal(a.offsets, b.offsets) and np.array_equal(a.n, b.n)
+    assert np.allclose(a.sstats[..., 1:], b.sstats[..., 1:], rtol=1e-9, atol=0, equal_nan=True)
+    assert np.allclose(a.abf_gen, b.abf_gen, rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(a.abf_cfg, b.abf_cfg, rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(a.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
+    # the averaged-only call (no raw arrays) returns the same averages, bit for bit
+    c = eng.run(raw=False)
+    assert np.array_equal(a.abf_w, c.abf_w, equal_nan=True)
+    eng.close()
+    ora.close()
