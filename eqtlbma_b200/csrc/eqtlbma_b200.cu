@@ -153,7 +153,8 @@ struct Mt19937 {
 template <class T>
 __global__ void expand_rows_kernel(const T *__restrict__ in, int n_cols, const int *__restrict__ map,
                                    const uint8_t *__restrict__ row_ok, double *__restrict__ out, int N, int ldn,
-                                   long long n_rows, double fill, double fill_bad_row, double denom = 1.0)
+                                   long long n_rows, double fill, double fill_bad_row, double denom = 1.0,
+                                   unsigned short *__restrict__ out16 = nullptr)
 {
   const long long r = blockIdx.x;
   if (r >= n_rows) return;
@@ -162,16 +163,29 @@ __global__ void expand_rows_kernel(const T *__restrict__ in, int n_cols, const i
   double *dst = out + (size_t)r * ldn;
   for (int i = threadIdx.x; i < ldn; i += blockDim.x) {
     double v = fill;
+    unsigned short k = 0;
     if (i < N) {
       const int c = map[i];
       if (!ok)
         v = fill_bad_row;
-      else if (c >= 0)
+      else if (c >= 0) {
         v = sizeof(T) == 8 ? (double)src[c] : __ddiv_rn((double)src[c], denom);
+        if (sizeof(T) < 8) k = (unsigned short)src[c];
+      }
     } else
       v = (fill != fill) ? fill : 0.0; // padding: NaN for expression rows, 0 otherwise
     dst[i] = v;
+    // the integer numerators stay resident next to the doubles (fixed-point transport only): the contraction of the
+    // true pass reads them (4x fewer HBM bytes) and looks the exact quotient up in k2v (absent sample / padding: k = 0 -> 0.0)
+    if (out16) out16[(size_t)r * ldn + i] = k;
   }
+}
+
+// k2v[k] = k / denom, the correctly rounded double of the decimal the numerator stands for (see expand_rows_kernel)
+__global__ void k2v_kernel(double *__restrict__ tab, int n, double denom)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) tab[k] = __ddiv_rn((double)k, denom);
 }
 
 __global__ void mask_from_basis_kernel(const double *__restrict__ q0, double *__restrict__ mask, int ldn)
@@ -354,6 +368,8 @@ struct eqb_ctx {
   std::vector<long long> cb, ce;
   std::vector<uint8_t> analyzed;
   std::vector<double *> d_X; // all-sample-space genotype variants
+  std::vector<unsigned short *> d_X16; // [variant] integer numerators of the same rows (fixed-point transport), else nullptr
+  std::vector<double *> d_k2v;         // [variant] 65536 exact quotients k / denom
   DevParams hp;
   DevParams *d_prm = nullptr;
   double *d_grids = nullptr;
@@ -828,10 +844,12 @@ int enqueue_x_pipeline(eqb_ctx *ctx, bool with_prep)
         const int *dmap = ctx->xvars[v].dmap;
         if (gh.elem_bytes == 1)
           expand_rows_kernel<uint8_t><<<(unsigned)(r1 - r0), 128, 0, ctx->xcomp>>>((const uint8_t *)gh.d_raw + roff, gh.n_cols, dmap,
-                                                                                   nullptr, dst, N, ldn, r1 - r0, 0.0, 0.0, gh.denom);
+                                                                                   nullptr, dst, N, ldn, r1 - r0, 0.0, 0.0, gh.denom,
+                                                                                   ctx->d_X16[v] ? ctx->d_X16[v] + (size_t)r0 * ldn : nullptr);
         else if (gh.elem_bytes == 2)
           expand_rows_kernel<uint16_t><<<(unsigned)(r1 - r0), 128, 0, ctx->xcomp>>>((const uint16_t *)gh.d_raw + roff, gh.n_cols, dmap,
-                                                                                    nullptr, dst, N, ldn, r1 - r0, 0.0, 0.0, gh.denom);
+                                                                                    nullptr, dst, N, ldn, r1 - r0, 0.0, 0.0, gh.denom,
+                                                                                    ctx->d_X16[v] ? ctx->d_X16[v] + (size_t)r0 * ldn : nullptr);
         else
           expand_rows_kernel<double><<<(unsigned)(r1 - r0), 128, 0, ctx->xcomp>>>((const double *)gh.d_raw + roff, gh.n_cols, dmap,
                                                                                   nullptr, dst, N, ldn, r1 - r0, 0.0, 0.0);
@@ -1229,6 +1247,10 @@ void eqb_destroy(eqb_ctx *ctx)
   }
   for (auto p : ctx->d_X)
     if (p) dfree(p);
+  for (auto p : ctx->d_X16)
+    if (p) dfree(p);
+  for (auto p : ctx->d_k2v)
+    if (p) dfree(p);
   for (auto p : ctx->d_Bs) if (p) dfree(p);
   for (auto p : ctx->d_Ytil) if (p) dfree(p);
   for (auto p : ctx->d_ystat) if (p) dfree(p);
@@ -1520,6 +1542,16 @@ int eqb_finalize(eqb_ctx *ctx)
       int *dmap = nullptr;
       CK(dmalloc(&dX, std::max<size_t>((size_t)M * ldn, 1) * sizeof(double)));
       CK(dmalloc(&dmap, N * sizeof(int)));
+      unsigned short *dX16 = nullptr;
+      double *dk2v = nullptr;
+      if (ctx->genos[sb.geno_id].elem_bytes < 8 && M > 0) {
+        CK(dmalloc(&dX16, (size_t)M * ldn * sizeof(unsigned short)));
+        CK(dmalloc(&dk2v, (size_t)65536 * sizeof(double)));
+        k2v_kernel<<<256, 256, 0, ctx->stream>>>(dk2v, 65536, ctx->genos[sb.geno_id].denom);
+        ctx->launches++;
+      }
+      ctx->d_X16.push_back(dX16);
+      ctx->d_k2v.push_back(dk2v);
       CK(h2d(ctx, dmap, sb.all2geno.data(), N * sizeof(int)));
       if ((size_t)N * sizeof(int) > STAGE_MAX) CK(cudaStreamSynchronize(ctx->stream)); // (not staged: pageable source)
       ctx->xvars.push_back({sb.geno_id, dmap}); // re-indexed chunk by chunk by enqueue_x_pipeline()
@@ -1933,6 +1965,16 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
           for (int s0 = 0; s0 < S; s0 += 8)
             for (int a = s0 + 1; a < std::min(S, s0 + 8); ++a)
               if (ctx->hp.sub[a].X != ctx->hp.sub[s0].X) fa.use_dmma = 0;
+          // one genotype matrix for every subgroup, uploaded as integer numerators: the contraction reads the resident u16 copy
+          if (fa.use_dmma && tuning_env("EQB_FASTW_NO_X16") == nullptr) {
+            bool one = true;
+            for (int a = 1; a < S; ++a) one = one && ctx->subs[a].xvar == ctx->subs[0].xvar;
+            const int v0 = ctx->subs[0].xvar;
+            if (one && v0 >= 0 && (size_t)v0 < ctx->d_X16.size() && ctx->d_X16[v0]) {
+              fa.x16 = ctx->d_X16[v0];
+              fa.k2v = ctx->d_k2v[v0];
+            }
+          }
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

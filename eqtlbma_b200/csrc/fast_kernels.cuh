@@ -67,6 +67,10 @@ struct FastArgs {
   // --inss (eqb_bf_from_sstats): the standardised statistics are INPUT (st_all / has_all filled by sstats_std_kernel), the
   // contraction and the summary statistics are skipped, output pair = compact pair
   int from_st;
+  // fixed-point genotype transport, one matrix for all subgroups: the resident integer numerators [M][ldn] and the table of
+  // exact quotients k2v[k] = k / denom; phase A of fast_pair_warp_kernel reads these instead of the doubles (same values)
+  const unsigned short *x16;
+  const double *k2v;
 };
 
 // ---------------------------------------------------------------- K1a
@@ -1376,6 +1380,58 @@ __device__ __forceinline__ void contract_tile_dmma(const double *__restrict__ X,
   }
 }
 
+// The same product with the A fragments taken from the resident integer numerators: a lane loads the two u16 of its
+// k-steps (4 bytes instead of 16) and looks the doubles up in k2v (512 KB, the handful of entries a dosage file uses stay in
+// L1): the HBM bytes of the contraction drop 4x, the fragment VALUES are the doubles of the f64 matrix, bit for bit.
+__device__ __forceinline__ void contract_tile_dmma_u16(const unsigned short *__restrict__ X16, const double *__restrict__ k2v,
+                                                       const FastSub *__restrict__ fsub, int sn, const long long *s_m,
+                                                       const int *s_gene, int tn, int S, int ldn, int lane,
+                                                       double *__restrict__ xy)
+{
+  const int r = lane >> 2, kq = lane & 3;
+  const unsigned short *xp[4];
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb) {
+    const int j = min(mb * 8 + r, tn - 1); // rows past the end of the tile repeat the last one (results dropped)
+    xp[mb] = X16 + (size_t)s_m[j] * ldn + 2 * kq;
+  }
+  const int col = min(r, sn - 1);
+  const int nchunk = ldn >> 3;
+  int j0 = 0;
+  while (j0 < tn) {
+    const int g = s_gene[j0];
+    const unsigned same = __ballot_sync(0xffffffffu, lane < tn && s_gene[lane < tn ? lane : 0] == g);
+    const int j1 = j0 + __popc(same >> j0 << j0); // rows of a gene are consecutive
+    const double *yp = fsub[col].Ytil + (size_t)g * ldn + 2 * kq;
+    double acc[4][2];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) acc[mb][0] = acc[mb][1] = 0.0;
+    const int mb0 = j0 >> 3, mb1 = (j1 - 1) >> 3; // only the row blocks that hold rows of this run (warp-uniform)
+#pragma unroll 4
+    for (int c = 0; c < nchunk; ++c) {
+      const double2 b2 = *reinterpret_cast<const double2 *>(yp + 8 * c);
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {
+        if (mb >= mb0 && mb <= mb1) {
+          const unsigned int w = *reinterpret_cast<const unsigned int *>(xp[mb] + 8 * c);
+          const double ax = __ldg(k2v + (w & 0xffffu)), ay = __ldg(k2v + (w >> 16));
+          dmma_m8n8k4(acc[mb][0], acc[mb][1], ax, b2.x);
+          dmma_m8n8k4(acc[mb][0], acc[mb][1], ay, b2.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const int j = mb * 8 + r;
+      if (j >= j0 && j < j1) {
+        if (2 * kq < sn) xy[(size_t)j * S + 2 * kq] = acc[mb][0];
+        if (2 * kq + 1 < sn) xy[(size_t)j * S + 2 * kq + 1] = acc[mb][1];
+      }
+    }
+    j0 = j1;
+  }
+}
+
 // shared memory of fast_pair_warp_kernel: one region per warp
 __host__ __device__ inline size_t fast_warp_smem_bytes(int S)
 {
@@ -1458,6 +1514,12 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
   __syncwarp();
   // ---------------- phase A: contraction x . ytil_s
   // the genotype rows of the tile are requested from HBM up front (one L2 prefetch per 128-byte line)
+  if (DM && fa.x16) {
+    for (int j = 0; j < tn; ++j) {
+      const unsigned short *row = fa.x16 + (size_t)s_m[j] * ldn;
+      for (int l = lane; l < ((ldn + 63) >> 6); l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 64 * l));
+    }
+  } else
   for (int s0 = 0; s0 < S; s0 += 8) {
     if (s0 > 0 && prm.sub[s0].X == prm.sub[0].X) continue;
     for (int j = 0; j < tn; ++j) {
@@ -1473,7 +1535,8 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
     if (dbg & 2) {
       for (int i = lane; i < tn * sn; i += 32) xy[(size_t)(i / sn) * S + s0 + i % sn] = 0.1;
     } else if (DM) {
-      contract_tile_dmma(prm.sub[s0].X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0);
+      if (fa.x16) contract_tile_dmma_u16(fa.x16, fa.k2v, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0);
+      else contract_tile_dmma(prm.sub[s0].X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0);
     } else if (same) {
       const double *X = prm.sub[s0].X;
       switch (sn) {
