@@ -1150,6 +1150,16 @@ int eqb_device_count(void)
   return n;
 }
 
+// Creates the device's primary CUDA context (0.5 - 1.5 s of driver work per process) so that a host can overlap it with
+// its own start-up, e.g. the front-end parses its input files meanwhile.  Optional: eqb_create does the same when needed.
+int eqb_warmup(int32_t device)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return 1;
+  if (cudaSetDevice(device) != cudaSuccess) return 2;
+  return cudaFree(0) == cudaSuccess ? 0 : 3;
+}
+
 int eqb_create(eqb_ctx **out, const eqb_config *cfg)
 {
   if (!out || !cfg) return 1;
@@ -1970,12 +1980,13 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
             bool one = true;
             for (int a = 1; a < S; ++a) one = one && ctx->subs[a].xvar == ctx->subs[0].xvar;
             const int v0 = ctx->subs[0].xvar;
-            if (one && v0 >= 0 && (size_t)v0 < ctx->d_X16.size() && ctx->d_X16[v0]) {
+            if (one && ctx->gc_ok && v0 >= 0 && (size_t)v0 < ctx->d_X16.size() && ctx->d_X16[v0]) {
               fa.x16 = ctx->d_X16[v0];
               fa.k2v = ctx->d_k2v[v0];
             }
           }
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CK(cudaFuncSetAttribute(fast_pair_warp_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CK(cudaFuncSetAttribute(fast_pair_warp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2141,7 +2152,9 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
               const unsigned grid = (unsigned)((fa.n_tiles + nwarp - 1) / nwarp);
 #define EQB_FASTW_LAUNCH(TPV, DMV)                                                                                    \
   fast_pair_warp_kernel<TPV, DMV><<<grid, nwarp * 32, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->go, ctx->gc)
-              if (tp && fa.use_dmma) EQB_FASTW_LAUNCH(true, true);
+              if (tp && fa.use_dmma && fa.x16)
+                fast_pair_warp_kernel<true, true, true><<<grid, nwarp * 32, smem, ctx->stream>>>(ctx->d_prm, ctx->d_fp, fa, ctx->gt, ctx->go, ctx->gc);
+              else if (tp && fa.use_dmma) EQB_FASTW_LAUNCH(true, true);
               else if (tp) EQB_FASTW_LAUNCH(true, false);
               else if (fa.use_dmma) EQB_FASTW_LAUNCH(false, true);
               else EQB_FASTW_LAUNCH(false, false);

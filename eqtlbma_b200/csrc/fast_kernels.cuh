@@ -1445,7 +1445,9 @@ __host__ __device__ inline size_t fast_warp_smem_bytes(int S)
 // DM: every group of 8 subgroups shares one genotype matrix and phase A runs on the tensor cores (the common case);
 //     the instantiation without DM carries the shuffle-reduced fallbacks, whose register needs would otherwise
 //     set the allocation (and the occupancy) of the common case too.
-template <bool TP, bool DM>
+// X16: the contraction reads the resident u16 numerators (fa.x16 / fa.k2v); its own instantiation so that the f64 kernel keeps
+//      its register allocation and schedule (with both loops in one kernel the f64 path ran 4 % slower).
+template <bool TP, bool DM, bool X16 = false>
 __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_warp_kernel(const DevParams *__restrict__ prm_,
                                                                  const FastParams *__restrict__ fp_, const FastArgs fa,
                                                                  const GridTab gt, const GridOrder go,
@@ -1514,7 +1516,7 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
   __syncwarp();
   // ---------------- phase A: contraction x . ytil_s
   // the genotype rows of the tile are requested from HBM up front (one L2 prefetch per 128-byte line)
-  if (DM && fa.x16) {
+  if (DM && X16) {
     for (int j = 0; j < tn; ++j) {
       const unsigned short *row = fa.x16 + (size_t)s_m[j] * ldn;
       for (int l = lane; l < ((ldn + 63) >> 6); l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 64 * l));
@@ -1535,7 +1537,7 @@ __global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_wa
     if (dbg & 2) {
       for (int i = lane; i < tn * sn; i += 32) xy[(size_t)(i / sn) * S + s0 + i % sn] = 0.1;
     } else if (DM) {
-      if (fa.x16) contract_tile_dmma_u16(fa.x16, fa.k2v, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0);
+      if (X16) contract_tile_dmma_u16(fa.x16, fa.k2v, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0);
       else contract_tile_dmma(prm.sub[s0].X, fsub, sn, s_m, s_gene, tn, S, ldn, lane, xy + s0);
     } else if (same) {
       const double *X = prm.sub[s0].X;

@@ -46,6 +46,15 @@ namespace {
 
 const double kNaN = numeric_limits<double>::quiet_NaN();
 
+// The CUDA context is created on a thread while the input files are parsed; every exit path waits for that thread first
+// (the CUDA runtime must not be torn down by exit() while another thread is still inside its initialisation).
+std::thread *g_warm = NULL;
+[[noreturn]] void eqb_exit(int code)
+{
+  if (g_warm && g_warm->joinable()) g_warm->join();
+  exit(code);
+}
+
 // ------------------------------------------------------------------ small text / gz helpers
 // utils::split with strtok semantics: consecutive delimiters collapse (utils_io.cpp:48-62)
 void split(const string &s, const char *delim, vector<string> &tokens)
@@ -152,7 +161,7 @@ struct GzReader {
     f = gzopen(p.c_str(), "rb");
     if (f == NULL) {
       cerr << "ERROR: can't open file " << p << " with mode rb" << endl;
-      exit(EXIT_FAILURE);
+      eqb_exit(EXIT_FAILURE);
     }
     gzbuffer(f, 1 << 20);
   }
@@ -253,7 +262,7 @@ void gz_write(const string &path, const char *mode, const string &txt)
   gzFile f = gzopen(path.c_str(), mode);
   if (f == NULL) {
     cerr << "ERROR: can't open file " << path << " with mode " << mode << endl;
-    exit(EXIT_FAILURE);
+    eqb_exit(EXIT_FAILURE);
   }
   gzbuffer(f, 1 << 20);
   size_t off = 0;
@@ -261,7 +270,7 @@ void gz_write(const string &path, const char *mode, const string &txt)
     const unsigned chunk = (unsigned)min<size_t>(txt.size() - off, 1u << 30);
     if (gzwrite(f, txt.data() + off, chunk) <= 0) {
       cerr << "ERROR: can't write to file " << path << endl;
-      exit(EXIT_FAILURE);
+      eqb_exit(EXIT_FAILURE);
     }
     off += chunk;
   }
@@ -279,7 +288,7 @@ void deflate_member(const string &txt, vector<unsigned char> &out)
   memset(&zs, 0, sizeof(zs));
   if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) {
     cerr << "ERROR: deflateInit2 failed" << endl;
-    exit(EXIT_FAILURE);
+    eqb_exit(EXIT_FAILURE);
   }
   out.resize(deflateBound(&zs, txt.size()) + 64);
   zs.next_in = (Bytef *)txt.data();
@@ -288,7 +297,7 @@ void deflate_member(const string &txt, vector<unsigned char> &out)
   zs.avail_out = (uInt)out.size();
   if (deflate(&zs, Z_FINISH) != Z_STREAM_END) {
     cerr << "ERROR: deflate failed" << endl;
-    exit(EXIT_FAILURE);
+    eqb_exit(EXIT_FAILURE);
   }
   out.resize(zs.total_out);
   deflateEnd(&zs);
@@ -338,12 +347,12 @@ void parallel_emit(const string &path, int nthreads, int64_t g0, int64_t g1, con
   FILE *f = fopen(path.c_str(), "ab");
   if (f == NULL) {
     cerr << "ERROR: can't open file " << path << " with mode ab" << endl;
-    exit(EXIT_FAILURE);
+    eqb_exit(EXIT_FAILURE);
   }
   for (int t = 0; t < nthreads; ++t)
     if (!members[t].empty() && fwrite(members[t].data(), 1, members[t].size(), f) != members[t].size()) {
       cerr << "ERROR: can't write to file " << path << endl;
-      exit(EXIT_FAILURE);
+      eqb_exit(EXIT_FAILURE);
     }
   fclose(f);
 }
@@ -394,7 +403,7 @@ void die_usage(int argc, char **argv, const string &msg)
   for (int i = 0; i < argc; ++i) cerr << " " << argv[i];
   cerr << endl << endl << "ERROR: " << msg << endl << endl;
   help(argv);
-  exit(EXIT_FAILURE);
+  eqb_exit(EXIT_FAILURE);
 }
 
 void parse_cmdline(int argc, char **argv, Options &o)
@@ -426,11 +435,11 @@ void parse_cmdline(int argc, char **argv, Options &o)
     if (c == -1) break;
     if (c == 'h') {
       help(argv);
-      exit(0);
+      eqb_exit(0);
     }
     if (c == 'V') {
       cout << argv[0] << " " << EQB_VERSION << endl;
-      exit(0);
+      eqb_exit(0);
     }
     if (c == 'v') {
       o.verbose = atoi(optarg);
@@ -554,7 +563,7 @@ map<string, string> load_two_column_file(const string &file, int verbose)
     split(line, " \t,", tok);
     if (tok.size() != 2) {
       cerr << "ERROR: file " << file << " should have only two columns at line " << nb << endl;
-      exit(EXIT_FAILURE);
+      eqb_exit(EXIT_FAILURE);
     }
     if (tok[0][0] == '#') continue;
     if (m.find(tok[0]) == m.end()) m.insert(make_pair(tok[0], tok[1]));
@@ -569,7 +578,7 @@ vector<string> header_samples(const string &file)
   string line;
   if (!r.getline(line) || line.empty()) {
     cerr << "ERROR: problem with the header of file " << file << endl;
-    exit(EXIT_FAILURE);
+    eqb_exit(EXIT_FAILURE);
   }
   vector<string> tok;
   split(line, " \t", tok);
@@ -577,7 +586,7 @@ vector<string> header_samples(const string &file)
   set<string> uniq(tok.begin(), tok.end());
   if (uniq.size() != tok.size()) {
     cerr << "ERROR: file " << file << " has redundant samples in its header";
-    exit(EXIT_FAILURE);
+    eqb_exit(EXIT_FAILURE);
   }
   return tok;
 }
@@ -592,7 +601,7 @@ vector<string> genotype_samples(const string &file, GenoFormat &fmt)
   vector<string> tok;
   if (!r.getline(line) || line.empty()) {
     cerr << "ERROR: problem with the header of file " << file << endl;
-    exit(EXIT_FAILURE);
+    eqb_exit(EXIT_FAILURE);
   }
   if (line.find("##fileformat=VCF") != string::npos) {
     fmt = FMT_VCF;
@@ -609,7 +618,7 @@ vector<string> genotype_samples(const string &file, GenoFormat &fmt)
     fmt = FMT_IMPUTE;
     if ((tok.size() - 5) % 3 != 0) {
       cerr << "ERROR: the header of IMPUTE file " << file << " is badly formatted" << endl;
-      exit(EXIT_FAILURE);
+      eqb_exit(EXIT_FAILURE);
     }
     vector<string> s;
     for (size_t i = 5; i < tok.size(); i += 3) {
@@ -711,7 +720,7 @@ void load_grid(const string &file, vector<double> &phi2, vector<double> &oma2, i
     split(line, " \t", tok);
     if (tok.size() != 2) {
       cerr << "ERROR: format of file " << file << " should be phi2<space/tab>oma2" << endl;
-      exit(1);
+      eqb_exit(1);
     }
     phi2.push_back(atof(tok[0].c_str()));
     oma2.push_back(atof(tok[1].c_str()));
@@ -740,7 +749,7 @@ void load_all(const Options &o, Loaded &d)
     for (map<string, string>::iterator it = d.genofile.begin(); it != d.genofile.end(); ++it)
       if (it->second != d.genofile.begin()->second) {
         cerr << "ERROR: --error mvlr/hybrid requires the same genotypes in a single file for all subgroups" << endl;
-        exit(EXIT_FAILURE);
+        eqb_exit(EXIT_FAILURE);
       }
   for (map<string, string>::iterator it = d.expfile.begin(); it != d.expfile.end(); ++it) d.subgroups.push_back(it->first);
   d.covfile = load_two_column_file(o.covar, verbose);
@@ -774,7 +783,7 @@ void load_all(const Options &o, Loaded &d)
       if (all.find(d.cov_samples[it->first][i]) == all.end()) {
         cerr << "ERROR: sample " << d.cov_samples[it->first][i]
              << " has covariates but neither expression levels nor genotypes" << endl;
-        exit(EXIT_FAILURE);
+        eqb_exit(EXIT_FAILURE);
       }
   }
 
@@ -792,14 +801,14 @@ void load_all(const Options &o, Loaded &d)
       if (tok.size() != ns + 1) {
         cerr << "ERROR: not enough columns on line " << nb << " of file " << it->second << " (" << tok.size()
              << " != " << ns + 1 << ")" << endl;
-        exit(EXIT_FAILURE);
+        eqb_exit(EXIT_FAILURE);
       }
       if (d.covars[it->first].find(tok[0]) != d.covars[it->first].end()) continue;
       vector<double> v(ns);
       for (size_t i = 0; i < ns; ++i) {
         if (is_na(tok[i + 1])) {
           cerr << "ERROR: no missing value allowed, see covariate " << tok[0] << " in subgroup " << it->first << endl;
-          exit(EXIT_FAILURE);
+          eqb_exit(EXIT_FAILURE);
         }
         v[i] = atof(tok[i + 1].c_str());
       }
@@ -820,7 +829,7 @@ void load_all(const Options &o, Loaded &d)
       if (d.genes.find(tok[3]) != d.genes.end()) continue;
       if (tok[1] == tok[2]) {
         cerr << "ERROR: start and end coordinates of " << tok[3] << " should be different (at least 1 bp)" << endl;
-        exit(1);
+        eqb_exit(1);
       }
       GeneRec g;
       g.name = tok[3];
@@ -850,7 +859,7 @@ void load_all(const Options &o, Loaded &d)
       if (sp.size() != ns + 1) {
         cerr << "ERROR: not enough columns on line " << nb << " of file " << d.expfile[sg] << " (" << sp.size()
              << " != " << ns + 1 << ")" << endl;
-        exit(EXIT_FAILURE);
+        eqb_exit(EXIT_FAILURE);
       }
       map<string, GeneRec>::iterator g = d.genes.find(sp[0].str());
       if (g == d.genes.end()) continue;
@@ -883,7 +892,7 @@ void load_all(const Options &o, Loaded &d)
       split(line, " \t,", tok);
       if (tok.size() != 1) {
         cerr << "ERROR: file " << o.snp << " should have only one column" << endl;
-        exit(EXIT_FAILURE);
+        eqb_exit(EXIT_FAILURE);
       }
       if (tok[0][0] == '#') continue;
       snps_to_keep.insert(tok[0]);
@@ -905,7 +914,7 @@ void load_all(const Options &o, Loaded &d)
       if (d.snps.find(tok[3]) != d.snps.end()) continue;
       if (tok[1] == tok[2]) {
         cerr << "ERROR: start and end coordinates of " << tok[3] << " should be different (at least 1 bp)" << endl;
-        exit(1);
+        eqb_exit(1);
       }
       SnpRec s;
       s.name = tok[3];
@@ -929,11 +938,11 @@ void load_all(const Options &o, Loaded &d)
     GenoFormat fmt = gfmt[sg];
     if (custom && fmt != FMT_DOSE) {
       cerr << "ERROR: don't use --scoord if genotypes in IMPUTE or VCF format" << endl;
-      exit(1);
+      eqb_exit(1);
     }
     if (!custom && fmt == FMT_DOSE) {
       cerr << "ERROR: file " << it->second << " seems to be in the custom format but --scoord is missing" << endl;
-      exit(EXIT_FAILURE);
+      eqb_exit(EXIT_FAILURE);
     }
     GzReader r(it->second);
     string line;
@@ -955,7 +964,7 @@ void load_all(const Options &o, Loaded &d)
         if (sp.size() != ns + 1) {
           cerr << "ERROR: not enough columns on line " << nb << " of file " << it->second << " (" << sp.size()
                << " != " << ns + 1 << ")" << endl;
-          exit(EXIT_FAILURE);
+          eqb_exit(EXIT_FAILURE);
         }
         name = sp[0].str();
         map<string, SnpRec>::iterator si = d.snps.find(name);
@@ -968,7 +977,7 @@ void load_all(const Options &o, Loaded &d)
         vector<double> &g = sr.geno[sg];
         if (!g.empty()) {
           cerr << "ERROR: SNP " << name << " is duplicated in file " << it->second << endl;
-          exit(EXIT_FAILURE);
+          eqb_exit(EXIT_FAILURE);
         }
         g.assign(ns, kNaN);
         double maf = 0.0;
@@ -991,11 +1000,11 @@ void load_all(const Options &o, Loaded &d)
       } else if (fmt == FMT_VCF) {
         if (tok.size() != ns + 9) {
           cerr << "ERROR: not enough columns on line " << nb << " of file " << it->second << endl;
-          exit(EXIT_FAILURE);
+          eqb_exit(EXIT_FAILURE);
         }
         if (tok[8].find("GT") == string::npos) {
           cerr << "ERROR: missing GT in 9-th field on line " << nb << " of file " << it->second << endl;
-          exit(EXIT_FAILURE);
+          eqb_exit(EXIT_FAILURE);
         }
         chr = tok[0];
         pos = tok[1];
@@ -1008,7 +1017,7 @@ void load_all(const Options &o, Loaded &d)
       } else {
         if (tok.size() != 3 * ns + 5) {
           cerr << "ERROR: not enough columns on line " << nb << " of file " << it->second << endl;
-          exit(EXIT_FAILURE);
+          eqb_exit(EXIT_FAILURE);
         }
         chr = tok[0];
         name = tok[1];
@@ -1027,7 +1036,7 @@ void load_all(const Options &o, Loaded &d)
       SnpRec &sr = d.snps[name];
       if (sr.geno.find(sg) != sr.geno.end() && !sr.geno[sg].empty()) {
         cerr << "ERROR: SNP " << name << " is duplicated in file " << it->second << endl;
-        exit(EXIT_FAILURE);
+        eqb_exit(EXIT_FAILURE);
       }
       vector<double> g;
       double maf;
@@ -1088,11 +1097,42 @@ void load_all(const Options &o, Loaded &d)
   load_grid(o.gridS, d.phi2S, d.oma2S, verbose);
 }
 
+// wall-clock phases of a run, printed with -v 2 and above (extension; the reference only reports the total)
+struct PhaseClock {
+  double t0, last;
+  vector<pair<string, double> > ph;
+  static double now()
+  {
+    timeval tv;
+    gettimeofday(&tv, NULL);
+    return (double)tv.tv_sec + 1e-6 * (double)tv.tv_usec;
+  }
+  PhaseClock() : t0(now()), last(t0) {}
+  void mark(const string &name)
+  {
+    const double t = now();
+    for (size_t i = 0; i < ph.size(); ++i)
+      if (ph[i].first == name) {
+        ph[i].second += t - last;
+        last = t;
+        return;
+      }
+    ph.push_back(make_pair(name, t - last));
+    last = t;
+  }
+  void print() const
+  {
+    cout << "phases (wall clock, s):";
+    for (size_t i = 0; i < ph.size(); ++i) cout << " " << ph[i].first << "=" << ph[i].second;
+    cout << " total=" << now() - t0 << endl;
+  }
+};
+
 void check(eqb_ctx *ctx, int rc, const char *what)
 {
   if (rc != 0) {
     cerr << "ERROR: " << what << ": " << eqb_last_error(ctx) << endl;
-    exit(EXIT_FAILURE);
+    eqb_exit(EXIT_FAILURE);
   }
 }
 
@@ -1255,7 +1295,7 @@ int run_inss(const Options &o, char **argv, time_t t_start)
         if (tok[i] == cols[c]) ci[c] = i;
       if (ci[c] == string::npos) {
         cerr << "ERROR: missing " << cols[c] << " in header of " << files[subgroups[s]] << endl;
-        exit(EXIT_FAILURE);
+        eqb_exit(EXIT_FAILURE);
       }
     }
     while (r.getline(line)) {
@@ -1447,8 +1487,16 @@ int main(int argc, char **argv)
     if (ndev > 0) o.device = o.shard_k % ndev; // fewer GPUs than shards: the shards share them
   }
   if (!o.inss.empty()) return run_inss(o, argv, t_start);
+  PhaseClock pc;
+  // the CUDA context is created while the input files are parsed (after the --gpus fork: one context per shard process)
+  std::thread warm([&o] { eqb_warmup(o.device); });
+  g_warm = &warm;
   Loaded d;
   load_all(o, d);
+  pc.mark("load");
+  warm.join();
+  g_warm = NULL;
+  pc.mark("cuda-start");
   if (d.genes.empty() || d.snps.empty()) return EXIT_SUCCESS;
 
   const int S = (int)d.subgroups.size(), N = (int)d.samples.size();
@@ -1492,7 +1540,9 @@ int main(int argc, char **argv)
   cfg.device = o.device;
   cfg.fiterr = o.fiterr;
   eqb_ctx *ctx = NULL;
+  pc.mark("index");
   check(ctx, eqb_create(&ctx, &cfg), "eqb_create");
+  pc.mark("create");
 
   // genotype matrices: one per genotype file actually loaded (subgroups that share a file share it)
   map<string, int> path2gid;
@@ -1616,7 +1666,9 @@ int main(int argc, char **argv)
     } else
       check(ctx, eqb_set_genotypes(ctx, (int)j, Gmats[j].data(), M, Gcols[j]), "eqb_set_genotypes");
   }
+  pc.mark("matrices+upload");
   check(ctx, eqb_finalize(ctx), "eqb_finalize");
+  pc.mark("finalize");
 
   // ---- headers (writeRes(..., "only"), eqtlbma_bf.cpp:1510-1513)
   const int L = (int)d.phi2L.size(), K = (int)d.phi2S.size();
@@ -1631,7 +1683,7 @@ int main(int argc, char **argv)
       FILE *f = fopen(path.c_str(), "wb");
       if (f == NULL) {
         cerr << "ERROR: can't open file " << path << " with mode wb" << endl;
-        exit(EXIT_FAILURE);
+        eqb_exit(EXIT_FAILURE);
       }
       fclose(f);
     } else
@@ -1688,7 +1740,7 @@ int main(int argc, char **argv)
     for (int64_t g = 0; g < G; ++g) cost[g] = (ce[g] - cb[g]) * (int64_t)(1 + o.nb_permutations);
     if (eqb_partition_by_cost(cost.data(), G, o.wrtsize, o.shard_n, sb.data()) != 0) {
       cerr << "ERROR: eqb_partition_by_cost failed" << endl;
-      exit(EXIT_FAILURE);
+      eqb_exit(EXIT_FAILURE);
     }
     g0 = sb[o.shard_k];
     g_end = sb[o.shard_k + 1];
@@ -1723,7 +1775,9 @@ int main(int argc, char **argv)
       res.abf_cfg = acfg.data();
       res.abf_w = aw.data();
     }
+    pc.mark("other");
     check(ctx, eqb_run(ctx, g0, g1, &res), "eqb_run");
+    pc.mark("run");
     const int per = (!join && o.perm_sep == 2) ? S : 1;
     vector<double> pv, ptrue, pmed;
     vector<int64_t> pdone, pcount;
@@ -1884,7 +1938,10 @@ int main(int argc, char **argv)
     }
   } else if (o.verbose > 0)
     cout << "nb of analyzed gene-SNP pairs: " << nbAnalyzedPairs << " (" << nbAnalyzedGenes << " genes)" << endl;
+  pc.mark("write");
   eqb_destroy(ctx);
+  pc.mark("destroy");
+  if (o.verbose > 1) pc.print();
   if (o.verbose > 0 && !o.shard_child) {
     time_t t_end;
     time(&t_end);

@@ -119,6 +119,9 @@ typedef struct {
 
 /* Number of usable CUDA devices (0 if none); lets a launcher place one shard process per GPU. */
 int eqb_device_count(void);
+/* Optional: create the device's primary CUDA context ahead of eqb_create (driver start-up, 0.5 - 1.5 s per process), e.g. on
+ * a thread while the host parses its input files (loadRawInputData, eqtlbma_bf.cpp:1496-1501, has no device work). */
+int eqb_warmup(int32_t device);
 int eqb_create(eqb_ctx **ctx, const eqb_config *cfg);
 void eqb_destroy(eqb_ctx *ctx);
 const char *eqb_last_error(const eqb_ctx *ctx);
