@@ -67,8 +67,17 @@ __device__ __forceinline__ void lse_merge(LseTab &a, double m2, double acc2, con
 
 // PPW: pairs per tile = min(4, 32 / K) (compile-time: the per-pair chains of phase C2 are unrolled side by side).
 // fa.use_dmma: every group of 8 subgroups shares one genotype matrix and phase A runs on the tensor cores (the common case).
+#ifndef FA_U
+#define FA_U 2 // configurations per C1 step (independent chains in flight per warp)
+#endif
+#ifndef FA_MINB
+#define FA_MINB 4
+#endif
+#ifndef FA_CLAMP
+#define FA_CLAMP true
+#endif
 template <int PPW>
-__global__ void __launch_bounds__(FA_THREADS, 4) fast_pair_all_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
+__global__ void __launch_bounds__(FA_THREADS, FA_MINB) fast_pair_all_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
                                                                       const FastArgs fa, const GridTab gt,
                                                                       const __grid_constant__ GridConst gc)
 {
@@ -173,14 +182,13 @@ __global__ void __launch_bounds__(FA_THREADS, 4) fast_pair_all_kernel(const DevP
     for (int ch = warp; ch < nchunk; ch += FA_WARPS) {
       const long long c0 = (long long)ch * FA_CH;
       const int nc = (int)min((long long)FA_CH, C - c0);
-      // ---- C1 (two configurations per step, independent straight-line chains)
+      // ---- C1 (FA_U configurations per step, independent straight-line chains)
       const unsigned short *mk = s_mask + c0;
-      for (int cl0 = 0; cl0 < nc; cl0 += 2) {
-        const unsigned int mm = *reinterpret_cast<const unsigned int *>(mk + cl0);
-        double xv[2];
+      for (int cl0 = 0; cl0 < nc; cl0 += FA_U) {
+        double xv[FA_U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int m = (int)(mm >> (u * 16)) & 0xffff;
+        for (int u = 0; u < FA_U; ++u) {
+          const int m = mk[cl0 + u]; // (zero-padded past C)
           const double *p0 = tb0 + (m & mk0) * 96, *p1 = tb1 + ((m >> sh1) & mk1) * 96, *p2 = tb2 + (m >> sh2) * 96;
           const double den = p0[0] + p1[0] + p2[0], num = p0[32] + p1[32] + p2[32], sing = p0[64] + p1[64] + p2[64];
           // natural-log ABF; CalcLog10AbfUvlr's guards (see abf_from_sums) as ONE select on the result: num != 0 implies
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(FA_THREADS, 4) fast_pair_all_kernel(const DevP
           xv[u] = ok ? x : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < FA_U; ++u) {
           const int cl = cl0 + u;
           stg[cl * FA_SROW + lane] = xv[u]; // natural-log units (a row >= nc of the last chunk belongs to a zero-padded mask: unused)
           if (oc && cl < nc) oc[(c0 + cl) * K] = xv[u] * EQB_INV_LN10;
@@ -218,7 +226,7 @@ __global__ void __launch_bounds__(FA_THREADS, 4) fast_pair_all_kernel(const DevP
 #pragma unroll
         for (int jj = 0; jj < PPW; ++jj) {
           const double v = row[jj * K + kk];
-          const double e = exp_tab16<true>(v - mx[jj], T);
+          const double e = exp_tab16<FA_CLAMP>(v - mx[jj], T);
           sum[jj] += (v == v) ? e : 0.0;
         }
       }
