@@ -702,21 +702,33 @@ def cli_e2e(ds, n_genes=500):
         in_bytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in os.listdir(tmp))
         nthr = str(os.cpu_count() or 1)
 
-        def run(binary, tag, threads):
-            cmd = [binary] + sub.ref_args(tmp, os.path.join(tmp, tag)) + REF_FLAGS + ["--thread", threads, "-v", "1"]
+        def run(binary, tag, threads, verbose="1"):
+            cmd = [binary] + sub.ref_args(tmp, os.path.join(tmp, tag)) + REF_FLAGS + ["--thread", threads, "-v", verbose]
             t0 = time.perf_counter()
             r = subprocess.run(cmd, capture_output=True, text=True)
             wall = time.perf_counter() - t0
             if r.returncode != 0:
                 return None
-            pairs = None
+            pairs, phases = None, None
             for line in r.stdout.splitlines():
                 if line.startswith("nb of analyzed gene-SNP pairs:"):
                     pairs = int(line.split(":")[1].split("(")[0])
-            return {"pairs": pairs, "wall_s": wall, "pairs_per_s": (pairs or 0) / wall}
+                if line.startswith("phases (wall clock, s):"):
+                    phases = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in line.split(":", 1)[1].split()}
+            out_ = {"pairs": pairs, "wall_s": wall, "pairs_per_s": (pairs or 0) / wall}
+            if phases:
+                import gzip
+                text = sum(len(gzip.open(os.path.join(tmp, f), "rb").read()) for f in os.listdir(tmp)
+                           if f.startswith(tag + "_") and f.endswith(".gz"))
+                out_["phases_s"] = phases
+                out_["output_encoder"] = {"text_bytes": text, "threads": int(threads),
+                                          "MB_per_s": text / 1e6 / max(phases.get("write", 0.0), 1e-9),
+                                          "what": "%.6e formatting + one gzip member per thread slice (parallel_emit), "
+                                                  "the 'write' phase of the run"}
+            return out_
 
         run(exe, "warm", nthr)  # first process on the device pays the driver / module load once
-        ours = run(exe, "ours", nthr)
+        ours = run(exe, "ours", nthr, verbose="2")
         out = {"workload": f"first {len(sub.gene_names)} genes of the bench workload written as the reference's input files "
                            f"({in_bytes / 1e6:.1f} MB gzipped), --analys join --bfs sin --outss --outw", "ours": ours}
         if os.path.exists(ref):
