@@ -1447,8 +1447,11 @@ __host__ __device__ inline size_t fast_warp_smem_bytes(int S)
 //     set the allocation (and the occupancy) of the common case too.
 // X16: the contraction reads the resident u16 numerators (fa.x16 / fa.k2v); its own instantiation so that the f64 kernel keeps
 //      its register allocation and schedule (with both loops in one kernel the f64 path ran 4 % slower).
+#ifndef EQB_FASTW_MINB_X16
+#define EQB_FASTW_MINB_X16 EQB_FASTW_MINB
+#endif
 template <bool TP, bool DM, bool X16 = false>
-__global__ void __launch_bounds__(THREADS, DM ? EQB_FASTW_MINB : 2) fast_pair_warp_kernel(const DevParams *__restrict__ prm_,
+__global__ void __launch_bounds__(THREADS, X16 ? EQB_FASTW_MINB_X16 : (DM ? EQB_FASTW_MINB : 2)) fast_pair_warp_kernel(const DevParams *__restrict__ prm_,
                                                                  const FastParams *__restrict__ fp_, const FastArgs fa,
                                                                  const GridTab gt, const GridOrder go,
                                                                  const __grid_constant__ GridConst gc)
