@@ -743,14 +743,17 @@ __global__ void __launch_bounds__(256, 2) perm_bf_kernel(const DevParams *__rest
   const DevParams &prm = *prm_;
   extern __shared__ double bf_smem[];
   __shared__ BfTabs Tsm;
+  __shared__ double Exp64[64];
   if (threadIdx.x < 16) {
     const double mj = 1.0 + ((double)threadIdx.x + 0.5) / 16.0;
     Tsm.exp16[threadIdx.x] = exp2((double)threadIdx.x / 16.0);
     Tsm.log16[threadIdx.x] = make_double2(1.0 / mj, log(mj));
   }
+  if (ALLCFG && threadIdx.x < 64) Exp64[threadIdx.x] = exp2((double)threadIdx.x / 64.0);
   __syncthreads();
   TabRef T;
   T.base = smem_u32(&Tsm);
+  const uint32_t base64 = smem_u32(Exp64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= warps_per_cta) return;
   const int S = prm.S, ldn = prm.ldn;
@@ -1031,9 +1034,9 @@ __global__ void __launch_bounds__(256, 2) perm_bf_kernel(const DevParams *__rest
 #pragma unroll
               for (int a = 0; a < (1 << PBF_SA); ++a) {
                 if (a >= (1 << SA)) break; // (S < 3)
-                const double num = hn + ln_[a];
                 const double r = rsqrt_newton1(hz + lz[a]);
-                const double e = exp_tab16<false>(fma(num * num * (r * r), hom2, hA + lA[a]), T);
+                const double q = (hn + ln_[a]) * r; // num / sqrt(1 + oma2 den)
+                const double e = exp_tab64(fma(q * q, hom2, hA + lA[a]), base64);
                 ksum = fma(wq[__popc(a)], r * e, ksum);
               }
             }
