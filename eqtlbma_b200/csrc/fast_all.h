@@ -35,9 +35,9 @@ __host__ __device__ inline FaParts fa_parts(int S)
   return p;
 }
 __host__ __device__ inline int fa_pairs_per_warp(int K) { return (32 / K) < FA_MAXPPW ? (32 / K) : FA_MAXPPW; }
-// shared memory of a CTA: tile arrays (doubles: st[4][sst] hasm[4] s_pair[4] genavg[4] part[FA_WARPS][4][3]) |
+// shared memory of a CTA: tile arrays (doubles: st[4][sst] hasm[4] s_pair[4] genavg[4] part[FA_WARPS][4][3] mcT[4][32]) |
 // configuration masks u16[C] (zero-padded to 16 bytes) | tab[ne][3][32] | stg[FA_WARPS][FA_CH][FA_SROW]
-__host__ __device__ inline size_t fa_tile_doubles(int S) { return (size_t)4 * ((3 * S) | 1) + 12 + (size_t)FA_WARPS * 12; }
+__host__ __device__ inline size_t fa_tile_doubles(int S) { return (size_t)4 * ((3 * S) | 1) + 12 + (size_t)FA_WARPS * 12 + 4 * 32; }
 __host__ __device__ inline size_t fa_mask_bytes(long long C) { return (size_t)((C * 2 + 15) / 16) * 16; }
 __host__ __device__ inline size_t fast_all_smem_bytes(int S, long long C)
 {

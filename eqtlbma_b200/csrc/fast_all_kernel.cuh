@@ -76,7 +76,12 @@ __device__ __forceinline__ void lse_merge(LseTab &a, double m2, double acc2, con
 #ifndef FA_CLAMP
 #define FA_CLAMP true
 #endif
-template <int PPW>
+// LIN (no raw values requested): C1 works in the LINEAR domain against the likelihood-ratio bound Mc = sum_{s in c} t_s^2 / 2 (a
+//      Bayes factor cannot exceed the maximised likelihood ratio): the per-subgroup term is tabulated as ln ABF_s - t_s^2 / 2, so
+//      the table sum is x - Mc + ln(z) / 2 and the staged value e = exp(.) / sqrt(z) lies in (0, 1] -- no logarithm per value in
+//      C1, no maximum pass and no exponential in C2 (K loads and adds, one logarithm per configuration).  A sum that underflows,
+//      a NaN and the reference's "b-bar = 0" corner fall back to the log-domain evaluation of that (configuration, pair).
+template <int PPW, bool LIN>
 __global__ void __launch_bounds__(FA_THREADS, FA_MINB) fast_pair_all_kernel(const DevParams *__restrict__ prm_, const FastParams *__restrict__ fp_,
                                                                       const FastArgs fa, const GridTab gt,
                                                                       const __grid_constant__ GridConst gc)
@@ -96,6 +101,7 @@ __global__ void __launch_bounds__(FA_THREADS, FA_MINB) fast_pair_all_kernel(cons
   long long *s_pair = (long long *)(hasm + 4);               // [4] output pair index
   double *genavg = (double *)(s_pair + 4);                   // [4] grid average of the consistent configuration
   double *part = genavg + 4;                                 // [FA_WARPS][4][3] partial BMA states (m, acc, poisoned)
+  double *mcT = part + FA_WARPS * 12;                        // [4][32] LIN: sum of t^2 / 2 over every subset of every part
   char *after = reinterpret_cast<char *>(fsm) + fa_tile_doubles(S) * 8;
   unsigned short *s_mask = reinterpret_cast<unsigned short *>(after); // [C] + zero padding
   double *tab = reinterpret_cast<double *>(after + fa_mask_bytes(C)); // [ne][3][32]
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(FA_THREADS, FA_MINB) fast_pair_all_kernel(cons
 
   // lane = (pair jl, grid point k) in the table and C1 phases
   const int jl = lane / K, k = lane - jl * K;
-  const double oma2 = gc.omaS[k], phi2 = gc.phiS[k];
+  const double oma2 = gc.omaS[k], phi2 = gc.phiS[k], hom2 = 0.5 * oma2;
   const double invK = 1.0 / (double)K, wL = 1.0 / (double)L;
   const int sh1 = P.np[0], sh2 = P.np[0] + P.np[1];
   const int mk0 = (1 << P.np[0]) - 1, mk1 = (1 << P.np[1]) - 1;
@@ -155,7 +161,10 @@ __global__ void __launch_bounds__(FA_THREADS, FA_MINB) fast_pair_all_kernel(cons
           const double inv = rcp_n(v + phi2);
           d = inv;
           bd = b * inv;
-          A = (phi2 == 0.0) ? 0.0 : fma(0.5, log_tab16(v * inv, T), 0.5 * tt * tt * phi2 * inv);
+          if (LIN) // ln ABF_s - t^2 / 2 = ln(v / (v + phi2)) / 2 - t^2 v / (2 (v + phi2)), formed without cancellation
+            A = (phi2 == 0.0) ? -0.5 * tt * tt : fma(0.5, log_tab16(v * inv, T), -0.5 * tt * tt * v * inv);
+          else
+            A = (phi2 == 0.0) ? 0.0 : fma(0.5, log_tab16(v * inv, T), 0.5 * tt * tt * phi2 * inv);
         }
         double *te = tp + (size_t)(1 << i) * 96;
         te[0] = d;
@@ -170,6 +179,20 @@ __global__ void __launch_bounds__(FA_THREADS, FA_MINB) fast_pair_all_kernel(cons
         ea[0] = e0[0] + e1[0];
         ea[32] = e0[32] + e1[32];
         ea[64] = e0[64] + e1[64];
+      }
+    }
+    if (LIN && warp == FA_WARPS - 1 && lane < 3 * PPW) {
+      // bounds of the subsets: lane = (pair, part), 2^np entries each (warp 3 has no table part to build)
+      const int jj = lane / 3, p = lane - jj * 3;
+      double *mc = mcT + jj * 32 + P.off[p];
+      const double *stj = st + (size_t)min(jj, tn - 1) * sst;
+      const unsigned long long has = (jj < tn) ? hasm[jj] : 0ull;
+      mc[0] = 0.0;
+      for (int a = 1; a < (1 << P.np[p]); ++a) {
+        const int i = __ffs(a) - 1, s = P.start[p] + i;
+        const double tt = stj[2 * S + s];
+        const bool on = ((has >> s) & 1ull) && !(fabs(tt) < 1e-8);
+        mc[a] = mc[a & (a - 1)] + (on ? 0.5 * tt * tt : 0.0);
       }
     }
     __syncthreads();
@@ -195,15 +218,25 @@ __global__ void __launch_bounds__(FA_THREADS, FA_MINB) fast_pair_all_kernel(cons
           // den != 0 (sums of the same terms), a NaN or infinite den fails z < 1e300 like the reference's "V < +Inf"; the
           // logarithm and the reciprocal of a rejected z are bit manipulations on garbage, never used
           const double z = fma(oma2, den, 1.0);
-          const bool ok = num != 0.0 && z < 1e300;
-          const double x = sing + fma(-0.5, log_tab16_pos(z, T), 0.5 * num * num * oma2 * rcp_n(z));
-          xv[u] = ok ? x : 0.0;
+          if (LIN) {
+            // e = exp(x - Mc): a configuration without any active subgroup gives exp(0) / sqrt(1) = 1 by itself; the corners the
+            // reference maps to x = 0 although subgroups are active (b-bar = 0, V not finite) and NaN statistics are marked NaN
+            const double r = rsqrt_newton1(z);
+            const double q = num * r;
+            const double e = exp_tab16<true>(fma(q * q, hom2, sing), T) * r;
+            const bool plain = (num != 0.0 || den == 0.0) && z < 1e300 && sing == sing;
+            xv[u] = plain ? e : nan("");
+          } else {
+            const bool ok = num != 0.0 && z < 1e300;
+            const double x = sing + fma(-0.5, log_tab16_pos(z, T), num * num * (hom2 * rcp_n(z)));
+            xv[u] = ok ? x : 0.0;
+          }
         }
 #pragma unroll
         for (int u = 0; u < FA_U; ++u) {
           const int cl = cl0 + u;
           stg[cl * FA_SROW + lane] = xv[u]; // natural-log units (a row >= nc of the last chunk belongs to a zero-padded mask: unused)
-          if (oc && cl < nc) oc[(c0 + cl) * K] = xv[u] * EQB_INV_LN10;
+          if (!LIN && oc && cl < nc) oc[(c0 + cl) * K] = xv[u] * EQB_INV_LN10;
         }
       }
       __syncwarp();
@@ -213,6 +246,51 @@ __global__ void __launch_bounds__(FA_THREADS, FA_MINB) fast_pair_all_kernel(cons
       const double cwt = valid ? prm.cfg_weight[c] : 0.0;
       const double *row = stg + lane * FA_SROW;
       double x0[PPW], mx[PPW], sum[PPW];
+      if (LIN) {
+        // the bound of this lane's configuration for every pair, then K loads and adds per pair
+        const int m = s_mask[valid ? c : 0];
+        const int i0 = m & mk0, i1 = P.off[1] + ((m >> sh1) & mk1), i2 = P.off[2] + (m >> sh2);
+#pragma unroll
+        for (int jj = 0; jj < PPW; ++jj) {
+          const double *mc = mcT + jj * 32;
+          mx[jj] = mc[i0] + mc[i1] + mc[i2];
+          x0[jj] = 0.0;
+          sum[jj] = 0.0;
+        }
+        for (int kk = 0; kk < K; ++kk) {
+#pragma unroll
+          for (int jj = 0; jj < PPW; ++jj) sum[jj] += row[jj * K + kk];
+        }
+#pragma unroll
+        for (int jj = 0; jj < PPW; ++jj) {
+          if (!(sum[jj] > 1e-280)) { // NaN marker or underflow (rare): the log-domain evaluation of the configuration, as below
+            double xm = 0.0, x00 = 0.0;
+            for (int pass = 0; pass < 2; ++pass) {
+              double acc = 0.0;
+              for (int kk = 0; kk < K; ++kk) {
+                const int col = jj * K + kk;
+                const double *p0 = tab + (size_t)i0 * 96 + col, *p1 = tab + (size_t)i1 * 96 + col, *p2 = tab + (size_t)i2 * 96 + col;
+                const double den = p0[0] + p1[0] + p2[0], num = p0[32] + p1[32] + p2[32];
+                const double sing = p0[64] + p1[64] + p2[64] + mx[jj]; // (the tabulated terms carry - t^2 / 2)
+                const double oma2k = gc.omaS[kk];
+                const double z = fma(oma2k, den, 1.0);
+                const bool ok = num != 0.0 && z < 1e300;
+                double x = sing + fma(-0.5, log_tab16(ok ? z : 1.0, T), 0.5 * num * num * oma2k * rcp_n(ok ? z : 1.0));
+                x = ok ? x : 0.0;
+                if (pass == 0) {
+                  if (kk == 0) x00 = xm = x;
+                  else xm = fmax(xm, x);
+                } else
+                  acc += (x == x) ? exp_tab16<true>(x - xm, T) : 0.0;
+              }
+              if (pass == 1) sum[jj] = acc;
+            }
+            // (from here on as in the log-domain kernel: maximum xm instead of the bound, poisoned by a NaN first value)
+            mx[jj] = xm;
+            x0[jj] = x00;
+          }
+        }
+      } else {
 #pragma unroll
       for (int jj = 0; jj < PPW; ++jj) {
         x0[jj] = mx[jj] = row[jj * K];
@@ -230,12 +308,13 @@ __global__ void __launch_bounds__(FA_THREADS, FA_MINB) fast_pair_all_kernel(cons
           sum[jj] += (v == v) ? e : 0.0;
         }
       }
+      }
 #pragma unroll
       for (int jj = 0; jj < PPW; ++jj) {
-        // the maximum contributes 1: 1/K <= mean <= 1; K equal values give exactly 1 and must give exactly 0 (the table
-        // logarithm is good to 1e-13 absolute, the reference's result is 0 after its DBL_EPSILON snap)
-        const double mean = sum[jj] * invK;
-        double wj = (mx[jj] + ((mean == 1.0) ? 0.0 : log_tab16_pos(mean, T))) * EQB_INV_LN10;
+        // 0 < mean <= 1 (log domain: the maximum contributes 1, so 1/K <= mean); K equal values give 1 and must give exactly the
+        // common value (the table logarithm is good to 1e-13 absolute, the reference prints 0 after its DBL_EPSILON snap)
+        const double mean = sum[jj] * invK, d1 = mean - 1.0; // (ln(1 + d) = d next to 1)
+        double wj = (mx[jj] + ((fabs(d1) < 1e-8) ? d1 : log_tab16_pos(mean, T))) * EQB_INV_LN10;
         if (fabs(wj) <= DBL_EPSILON) wj = 0.0;
         if (x0[jj] != x0[jj]) wj = nan("");
         if (valid) bma[jj].add(wj, cwt, c == 0, T); // CalcBMA (gene_snp_pair.cpp:572-602)

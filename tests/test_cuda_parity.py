@@ -56,6 +56,10 @@ def test_cuda_matches_oracle(cuda_lib, oracle_lib, name):
         assert np.allclose(a.abf_gen, b.abf_gen, rtol=0, atol=1e-8, equal_nan=True)
         assert np.allclose(a.abf_cfg, b.abf_cfg, rtol=0, atol=1e-8, equal_nan=True)
         assert np.allclose(a.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
+        # without the raw arrays (--bfs all: the linear-domain kernel with its log-domain fall-backs): same averages
+        c = eng.run(raw=False)
+        assert np.allclose(c.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
+        assert np.array_equal(np.isnan(c.abf_w), np.isnan(b.abf_w))
     pk = perm_kwargs(sc)
     if pk:
         pa, pb = eng.run_permutations(**pk), ora.run_permutations(**pk)

@@ -283,8 +283,9 @@ def test_bfs_all_kernel_shapes_match_oracle(cuda_lib, oracle_lib, n_sub, K, n_ge
     assert np.allclose(a.abf_gen, b.abf_gen, rtol=0, atol=1e-8, equal_nan=True)
     assert np.allclose(a.abf_cfg, b.abf_cfg, rtol=0, atol=1e-8, equal_nan=True)
     assert np.allclose(a.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
-    # the averaged-only call (no raw arrays) returns the same averages, bit for bit
+    # the averaged-only call (no raw arrays) takes the linear-domain instantiation of the kernel: same averages
     c = eng.run(raw=False)
-    assert np.array_equal(a.abf_w, c.abf_w, equal_nan=True)
+    assert np.allclose(c.abf_w, b.abf_w, rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(c.abf_w, a.abf_w, rtol=0, atol=1e-9, equal_nan=True)
     eng.close()
     ora.close()
