@@ -294,6 +294,80 @@ def run_perm_block(eqtlbma_b200, rank, local_rank, fp64, with_cpu, n_genes=None,
     return out
 
 
+def run_hm_block(eqtlbma_b200, local_rank, hbm_gbs, with_cpu, n_genes=10000, snps=(50, 150)):
+    """the EM of the hierarchical model (eqtlbma_hm --model configs) on raw ABFs resident in HBM.
+    Dominant kernel hm_estep_kernel: one streaming pass over B[pairs][7][10] per fixed-point iteration (algorithmic bytes =
+    8 * pairs * dim * grid, read once), HBM-bound.  CPU arm: the unmodified reference eqtlbma_hm (oracle/_ref) with
+    --thread = host cores on the first genes of the same data written as `_l10abfs_raw.txt.gz`, its own `EM ran for`
+    clock (whole seconds) falling back to wall clock minus a --maxit 2 run of the same files."""
+    import time
+    from eqtlbma_b200.hm import HmEngine, HmFit
+    from eqtlbma_b200.hm_synth import make_hm_dataset
+    ds = make_hm_dataset(seed=1861, n_genes=n_genes, snps_lo=snps[0], snps_hi=snps[1], n_subgroups=3, grid=10, round_text=False)
+    t0 = time.perf_counter()
+    hm = HmEngine(ds.dim, ds.grid, device=local_rank)
+    hm.append(ds.B, ds.gene_off)
+    hm.finalize()
+    t_load = time.perf_counter() - t0
+    gw, cp = np.full(ds.grid, 1.0 / ds.grid), np.full(ds.dim, 1.0 / ds.dim)
+    hm.estep_device_only(gw, cp, reps=3)
+    ms = hm.estep_device_only(gw, cp, reps=20)
+    alg = 8.0 * ds.n_pairs * ds.dim * ds.grid
+    out = {"workload": f"eqtlbma_hm --model configs: {ds.n_genes} genes, {ds.n_pairs} pairs, dim {ds.dim}, grid {ds.grid} "
+                       f"({alg / 1e6:.0f} MB of raw log10 ABFs, larger than L2)",
+           "pairs": int(ds.n_pairs), "h2d_s": t_load,
+           "roofline": {"bound": "hbm", "kernel": "hm_estep_kernel", "kernel_ms": ms, "algorithmic_bytes_per_launch": alg,
+                        "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) / 1e9 / hbm_gbs, "traffic": None}}
+    for label, msl in (("classic", 1.0), ("squarem", 3.0)):
+        l0 = hm.launch_count
+        t0 = time.perf_counter()
+        fit = hm.em(HmFit(0.5, gw, cp), thresh=0.05, stepmax=msl)
+        dt = time.perf_counter() - t0
+        n_lines = len([ln for ln in fit.log_lines if ln.startswith("iter ")])
+        out[label] = {"em_s": dt, "likelihood_evaluations": n_lines, "pairs_iterations_per_s": ds.n_pairs * n_lines / dt,
+                      "loglik": fit.loglik, "pi0": fit.pi0, "gpu_launches": hm.launch_count - l0}
+    hm.close()
+    if with_cpu:
+        out["cpu_baseline"] = cpu_baseline_hm(ds)
+    return out
+
+
+def cpu_baseline_hm(ds, sample_genes=1000):
+    import re
+    import shutil
+    import tempfile
+    import time
+    ref = os.path.join(ROOT, "oracle", "_ref", "eqtlbma_hm_ref")
+    if not os.path.exists(ref):
+        return {"unavailable": "oracle/_ref/eqtlbma_hm_ref is not built"}
+    cores = os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="hm_cpu_")
+    try:
+        # the text precision of the file is the reference's own input format; names are needed only here
+        ds.write_raw_file(os.path.join(tmp, "s_l10abfs_raw.txt.gz"), 0, sample_genes)
+        pairs = int(ds.gene_off[sample_genes])
+        base = [ref, "--data", os.path.join(tmp, "s_l10abfs_raw.txt.gz"), "--nsubgrp", "3", "--dim", str(ds.dim), "--ngrid",
+                str(ds.grid), "--out", os.path.join(tmp, "o.txt.gz"), "--thread", str(cores), "-v", "1"]
+        t0 = time.perf_counter()
+        r = subprocess.run(base, capture_output=True, text=True, cwd=tmp)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"unavailable": "reference eqtlbma_hm failed: " + r.stderr[-200:]}
+        n_lines = len([ln for ln in r.stdout.splitlines() if ln.startswith("iter ")])
+        t0 = time.perf_counter()
+        subprocess.run(base + ["--maxit", "2"], capture_output=True, text=True, cwd=tmp)
+        wall1 = time.perf_counter() - t0
+        r1_lines = 3  # iteration 0, one fixed point, the closing fixed point
+        em_s = max(wall - wall1, 1e-3)
+        return {"value": pairs * (n_lines - r1_lines) / em_s, "unit": "pairs x likelihood evaluations/s", "cores": cores,
+                "kind": "reference", "sample": f"first {sample_genes} genes ({pairs} pairs), classical EM to --thresh 0.05, "
+                f"{n_lines} likelihood evaluations, wall {wall:.2f} s minus {wall1:.2f} s of a --maxit 2 run (file parsing + 3 evaluations)",
+                "wall_s": wall, "load_s": wall1}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def cpu_baseline_perm(eqtlbma_b200=None, device=0):
     """The reference's permutation loop (gene.cpp:598-717; OpenMP over SNPs, --thread = host cores) on a bounded slice
     of the c4 shape: run with permutations minus the same run without.  The same slices go through
@@ -559,6 +633,8 @@ def run_ours(args, rank, world, local_rank):
         out["value_u16_resident"] = fx_info
     if perm_info:
         out["perm"] = perm_info
+    if world == 1 and not args.no_hm:
+        out["hm"] = run_hm_block(eqtlbma_b200, local_rank, pk["hbm_gbs"], not args.no_cpu)
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_reference(ds, sample_genes=args.cpu_genes)
         par = parity_vs_reference(ds, eng, full, args.cpu_genes)
@@ -870,6 +946,7 @@ def main():
     ap.add_argument("--cli-genes", type=int, default=500, help="genes in the command-line end-to-end comparison")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-perm", action="store_true")
+    ap.add_argument("--no-hm", action="store_true", help="skip the hierarchical-model (eqtlbma_hm) block")
     ap.add_argument("--perm-genes", type=int, default=0, help="genes per GPU of the c3/c4-shape block (default 8)")
     ap.add_argument("--perm-nperm", type=int, default=0, help="permutations of the c4-shape block (default 2047)")
     ap.add_argument("--no-check", action="store_true", help="skip the sharding-invariance check")

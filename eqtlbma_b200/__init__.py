@@ -46,7 +46,7 @@ def build_library(force: bool = False) -> str:
     names = sorted(os.listdir(src_dir))
     units = [os.path.join(src_dir, f) for f in names if f.endswith(".cu")]
     headers = [os.path.join(src_dir, f) for f in names if f.endswith((".cuh", ".h"))] + \
-              [os.path.join(ROOT, "include", "eqtlbma_b200.h")]
+              [os.path.join(ROOT, "include", f) for f in sorted(os.listdir(os.path.join(ROOT, "include"))) if f.endswith(".h")]
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = NVCC_FLAGS + (["-DEQB_TUNING"] if os.environ.get("EQB_BUILD_TUNING") else [])
     todo, objs = [], []
@@ -94,6 +94,17 @@ class Engine(_Engine):
 
     def __init__(self, ds, **kw):
         super().__init__(load_library(), "eqb_", ds, **kw)
+
+    def raw_abfs_device(self):
+        """(device address, n_pairs, gene ids, gene offsets) of the raw ABFs of the last chunk of the true pass
+        (eqb_raw_abfs_device): what HmEngine.append_device takes."""
+        import numpy as np
+        ptr, n_pairs, n_genes = ctypes.c_void_p(), ctypes.c_int64(0), ctypes.c_int64(0)
+        self._call("raw_abfs_device", ctypes.byref(ptr), ctypes.byref(n_pairs), ctypes.byref(n_genes))
+        ids = np.zeros(n_genes.value, dtype=np.int64)
+        off = np.zeros(n_genes.value + 1, dtype=np.int64)
+        self._call("raw_abfs_layout", ids.ctypes.data_as(ctypes.c_void_p), off.ctypes.data_as(ctypes.c_void_p))
+        return ptr.value, n_pairs.value, ids, off
 
     def launch_count(self) -> int:
         f = self.lib.eqb_launch_count

@@ -379,6 +379,11 @@ struct eqb_ctx {
   int *d_err = nullptr;
   long long n_cfg_all = 0;
   long long launches = 0;
+  // raw ABFs of the last chunk of the true pass, still resident in d_cfg (eqb_raw_abfs_device)
+  std::vector<int> last_genes;
+  std::vector<long long> last_pair_off;
+  long long last_pairs = 0;
+  bool last_cfg_valid = false;
   // work buffers (grow-only)
   DevBuf<int> d_genes, d_slots, d_out_n;
   DevBuf<long long> d_pair_off, d_count, d_done, d_total, d_consumed;
@@ -2210,6 +2215,12 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
       }
       pt.mark("run.wait_results");
     }
+    ctx->last_cfg_valid = o_cfg && !genes.empty();
+    if (ctx->last_cfg_valid) {
+      ctx->last_genes = genes;
+      ctx->last_pair_off = pair_off;
+      ctx->last_pairs = n_pairs;
+    }
     pair_base += n_pairs;
     g0 = g1;
   }
@@ -2225,6 +2236,38 @@ static int run_true_impl(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_res
     ctx->x_complete = true;
   }
   return check_device_errors(ctx);
+}
+
+int eqb_raw_abfs_device(eqb_ctx *ctx, const double **d_B, int64_t *n_pairs, int64_t *n_genes)
+{
+  if (!ctx || !d_B || !n_pairs || !n_genes) return 1;
+  if (!ctx->last_cfg_valid) return fail(ctx, "eqb_raw_abfs_device: no raw ABFs are resident (join analysis with abf_cfg / want_raw needed)");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  long long ng = 0;
+  for (size_t i = 0; i < ctx->last_genes.size(); ++i) {
+    const long long e = (i + 1 < ctx->last_pair_off.size()) ? ctx->last_pair_off[i + 1] : ctx->last_pairs;
+    if (e > ctx->last_pair_off[i]) ++ng;
+  }
+  *d_B = ctx->d_cfg.p;
+  *n_pairs = ctx->last_pairs;
+  *n_genes = ng;
+  return 0;
+}
+
+int eqb_raw_abfs_layout(eqb_ctx *ctx, int64_t *gene_ids, int64_t *gene_off)
+{
+  if (!ctx || !gene_off) return 1;
+  if (!ctx->last_cfg_valid) return fail(ctx, "eqb_raw_abfs_layout: no raw ABFs are resident");
+  long long ng = 0;
+  for (size_t i = 0; i < ctx->last_genes.size(); ++i) {
+    const long long e = (i + 1 < ctx->last_pair_off.size()) ? ctx->last_pair_off[i + 1] : ctx->last_pairs;
+    if (e <= ctx->last_pair_off[i]) continue;
+    if (gene_ids) gene_ids[ng] = ctx->last_genes[i];
+    gene_off[ng++] = ctx->last_pair_off[i];
+  }
+  gene_off[ng] = ctx->last_pairs;
+  return 0;
 }
 
 int eqb_run(eqb_ctx *ctx, int64_t gene_lo, int64_t gene_hi, eqb_results *res)

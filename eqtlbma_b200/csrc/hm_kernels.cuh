@@ -1,0 +1,426 @@
+// hm_kernels.cuh -- kernels of the EM of the hierarchical model (eqtlbma_hm --model configs; include/eqtlbma_hm_b200.h).
+//
+// What the reference computes per EM iteration (src/eqtlbma_hm.cpp:659-868, src/hm_methods.cpp:391-672), with
+// B[p][k][l] the raw log10 BF of pair p, configuration k, grid point l, eta the configuration prior, lambda the grid
+// weights and uniform SNP priors 1/m_g:
+//     a[p][k]   = log10 sum_l lambda_l 10^B[p][k][l]                       snp_eQTL::em_update_config
+//     A[g][k]   = log10 (1/m_g) sum_p 10^a[p][k]                           gene_eQTL::em_update_config
+//     Gd[g][l]  = log10 (1/m_g) sum_p sum_k eta_k 10^B[p][k][l]            gene_eQTL::em_update_grid
+//     BF[g]     = log10 (1/m_g) sum_p sum_k eta_k sum_l lambda_l 10^B      gene_eQTL::compute_log10_BF
+//               = log10 sum_l lambda_l 10^Gd[g][l]
+// i.e. three groupings of ONE pass over the rows (p, k) of the data.  The reference makes that pass 2 + dim + grid times
+// per iteration through nested log10_weighted_sum calls (utils_math.cpp:135-159); hm_estep_kernel makes it once:
+//
+//   hm_estep_kernel   CTA = one work unit (a run of whole pairs of one gene, ~4096 rows), 4 warps; a warp takes rounds of 32
+//                     consecutive rows (contiguous 32 x grid doubles), staged in shared memory by 1-D TMA bulk copies
+//                     (cp.async.bulk + mbarrier, HM_STAGES deep per warp, issued by lane 0); lane = row: row maximum, one
+//                     table exponential per element, the row average a (optionally stored), an online log-sum-exp state per
+//                     configuration in shared memory, and lane-private linear-domain column sums against a running reference
+//                     (the largest row maximum seen), merged over the CTA at the end -> U[unit][dim + grid] (log10 domain).
+//                     HBM-bound by design (8 bytes per element read once) with (grid + 2) exponentials per row on the FP64
+//                     pipe: the two limits are within 2x of each other at grid = 10.
+//   hm_gene_kernel    per gene: log-sum-exp of its units, - log10 m_g, BF[g]           -> PA[j][g], BF[g]
+//   hm_lik_kernel     per-gene log10(pi0 + (1 - pi0) BF), fixed-order sum, optional keep
+//   hm_sums_kernel    one CTA per output: log-sum-exp over genes of PA[j][g] - lik_g (kept), and sum_g pi0 / 10^lik_g
+//   hm_snp_kernel     warp per pair: log10 sum_k eta_k 10^a[p][k] (posterior pass)
+//   hm_check_kernel   counts non-finite values at load time
+// All reductions have a fixed order (no atomics on data): results do not depend on scheduling.
+#pragma once
+
+#include "table_math.cuh"
+
+namespace eqb {
+
+constexpr int HM_WARPS = 4;
+constexpr int HM_THREADS = HM_WARPS * 32;
+constexpr int HM_MAXGRID = 32;
+constexpr int HM_MAXDIM = 4096;
+
+struct HmArgs {
+  const char *B;              // first byte of the data; 16-byte aligned, 16 readable bytes before and after the array
+  const long long *unit_row0; // [n_units] first row (pair * dim) of the unit
+  const int *unit_rows;       // [n_units] rows of the unit (whole pairs)
+  double *U;                  // [n_units][dim + grid] partial log-sum-exps
+  const double *cfg;          // [dim] configuration prior
+  double *rowA;               // [rows] a[p][k] (posterior pass) or nullptr
+  int dim, grid;
+  int rpr;         // rows per round: 32 (dim >= 32) or (32 / dim) * dim
+  int nslot;       // configuration-state slots per warp: dim (dim >= 32) or rpr
+  int stages;      // TMA stages per warp
+  int stage_bytes; // bytes of one stage (rpr rows + 16, multiple of 16)
+  double gw[HM_MAXGRID]; // grid weights: constant-bank operands
+};
+
+__device__ __forceinline__ void hm_mbar_init(uint32_t bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void hm_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hm_mbar_wait(uint32_t bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "HM_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra HM_DONE;\n"
+      "bra HM_WAIT;\n"
+      "HM_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA: `bytes` (multiple of 16) from global `src` (16-byte aligned) to shared `dst`, completion on `bar`
+__device__ __forceinline__ void hm_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ double hm_warp_max(double v)
+{
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double hm_warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__host__ __device__ inline size_t hm_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+// shared memory of hm_estep_kernel: tables | barriers | configuration states | column partials | stages
+__host__ __device__ inline size_t hm_smem_bytes(int nslot, int stages, int stage_bytes)
+{
+  return hm_align16(sizeof(BfTabs)) + hm_align16((size_t)HM_WARPS * stages * 8) + (size_t)HM_WARPS * nslot * 16 +
+         (size_t)HM_WARPS * (HM_MAXGRID + 2) * 8 + (size_t)HM_WARPS * stages * stage_bytes;
+}
+
+// G: compile-time number of grid points (EXACT) or their upper bound (the loops are predicated on l < grid)
+template <int G, bool EXACT>
+__global__ void __launch_bounds__(HM_THREADS) hm_estep_kernel(const __grid_constant__ HmArgs a)
+{
+  extern __shared__ __align__(16) unsigned char hm_smem[];
+  const int grid = EXACT ? G : a.grid;
+  const int dim = a.dim, rpr = a.rpr, nslot = a.nslot, stages = a.stages, stage_bytes = a.stage_bytes;
+  BfTabs *tabs = reinterpret_cast<BfTabs *>(hm_smem);
+  unsigned char *p_bar = hm_smem + hm_align16(sizeof(BfTabs));
+  double2 *kst_all = reinterpret_cast<double2 *>(p_bar + hm_align16((size_t)HM_WARPS * stages * 8));
+  double *colp_all = reinterpret_cast<double *>(kst_all + (size_t)HM_WARPS * nslot);
+  unsigned char *stage_all = reinterpret_cast<unsigned char *>(colp_all + HM_WARPS * (HM_MAXGRID + 2));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bf_tabs_init(*tabs);
+  const TabRef T{smem_u32(tabs)};
+  const uint32_t bars = smem_u32(p_bar) + (uint32_t)(warp * stages * 8);
+  double2 *kst = kst_all + (size_t)warp * nslot;
+  unsigned char *stg = stage_all + (size_t)warp * stages * stage_bytes;
+  const uint32_t stg_u32 = smem_u32(stg);
+  for (int i = lane; i < nslot; i += 32) kst[i] = make_double2(-INFINITY, 0.0);
+  if (lane == 0) {
+    for (int s = 0; s < stages; ++s) hm_mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long row0 = a.unit_row0[blockIdx.x];
+  const int nrows = a.unit_rows[blockIdx.x];
+  const int n_rounds = (nrows + rpr - 1) / rpr;
+  const int n_my = (n_rounds > warp) ? (n_rounds - warp + HM_WARPS - 1) / HM_WARPS : 0;
+  const long long row_bytes = (long long)grid * 8;
+
+  auto issue = [&](int i) { // lane 0: round i of this warp into stage i % stages
+    const int r_first = (warp + i * HM_WARPS) * rpr;
+    const int nr = min(rpr, nrows - r_first);
+    const long long off = (row0 + r_first) * row_bytes;
+    const int shift = (int)(off & 15);
+    const uint32_t bytes = (uint32_t)((shift + nr * (int)row_bytes + 15) & ~15);
+    const int st = i % stages;
+    hm_mbar_expect_tx(bars + 8 * st, bytes);
+    hm_bulk_load(stg_u32 + (uint32_t)(st * stage_bytes), a.B + (off - shift), bytes, bars + 8 * st);
+  };
+  if (lane == 0)
+    for (int i = 0; i < stages && i < n_my; ++i) issue(i);
+
+  // lane-private column sums against the running reference mref
+  double cs[G];
+#pragma unroll
+  for (int l = 0; l < G; ++l) cs[l] = 0.0;
+  double mref = -INFINITY;
+  const bool small_dim = dim < 32;
+  const double cfg_fixed = small_dim ? ((lane < rpr) ? __ldg(a.cfg + lane % dim) : 0.0) : 0.0;
+
+  for (int i = 0; i < n_my; ++i) {
+    const int st = i % stages;
+    hm_mbar_wait(bars + 8 * st, (uint32_t)((i / stages) & 1));
+    const int r_first = (warp + i * HM_WARPS) * rpr;
+    const int nr = min(rpr, nrows - r_first);
+    if (lane < nr) {
+      const long long off = (row0 + r_first) * row_bytes;
+      const double *x = reinterpret_cast<const double *>(stg + (size_t)st * stage_bytes + (int)(off & 15)) + (size_t)lane * grid;
+      double m = x[0];
+#pragma unroll
+      for (int l = 1; l < G; ++l)
+        if (EXACT || l < grid) m = fmax(m, x[l]);
+      const int k = small_dim ? 0 : (int)((r_first + lane) % dim);
+      const double cfgk = small_dim ? cfg_fixed : __ldg(a.cfg + k);
+      // column reference: rescale the sums when this row raises it
+      const double d = m - mref; // +inf for the first row
+      double wc;
+      if (d > 0.0) {
+        const double sc = exp10_tab16<true>(-d, T);
+#pragma unroll
+        for (int l = 0; l < G; ++l) cs[l] *= sc;
+        mref = m;
+        wc = cfgk;
+      } else
+        wc = cfgk * exp10_tab16<true>(d, T);
+      double rs = 0.0;
+#pragma unroll
+      for (int l = 0; l < G; ++l)
+        if (EXACT || l < grid) {
+          const double e = exp10_tab16<true>(x[l] - m, T);
+          rs = fma(a.gw[l], e, rs);
+          cs[l] = fma(wc, e, cs[l]);
+        }
+      const double ar = fma(log_tab16(rs, T), PGK[11], m); // a[p][k]; -inf for a zero sum, NaN for a negative one
+      if (a.rowA) a.rowA[row0 + r_first + lane] = ar;
+      // online log-sum-exp of a over the rows with this configuration
+      const int slot = small_dim ? lane : k;
+      double2 s = kst[slot];
+      if (ar != ar)
+        s = make_double2(ar, ar); // (negative weights of a SQUAREM proposal: the likelihood is NaN, as in the reference)
+      else if (ar > -INFINITY) {
+        const double dd = ar - s.x;
+        const bool up = dd > 0.0;
+        const double e = exp10_tab16<true>(up ? -dd : dd, T);
+        s.y = up ? fma(s.y, e, 1.0) : s.y + e;
+        s.x = up ? ar : s.x;
+      }
+      kst[slot] = s;
+    }
+    __syncwarp();
+    if (lane == 0 && i + stages < n_my) issue(i + stages);
+  }
+
+  // ---- merge: columns
+  double *colp = colp_all + warp * (HM_MAXGRID + 2);
+  {
+    const double M = hm_warp_max(mref);
+    const double fac = (mref > -INFINITY) ? exp10_tab16<true>(mref - M, T) : 0.0;
+#pragma unroll
+    for (int l = 0; l < G; ++l)
+      if (EXACT || l < grid) {
+        const double v = hm_warp_sum(cs[l] * fac);
+        if (lane == 0) colp[1 + l] = v;
+      }
+    if (lane == 0) colp[0] = M;
+  }
+  __syncthreads();
+  double *Uu = a.U + (size_t)blockIdx.x * (dim + grid);
+  if ((int)threadIdx.x < grid) {
+    double MM = -INFINITY;
+    for (int w = 0; w < HM_WARPS; ++w) MM = fmax(MM, colp_all[w * (HM_MAXGRID + 2)]);
+    double sum = 0.0;
+    for (int w = 0; w < HM_WARPS; ++w) {
+      const double mw = colp_all[w * (HM_MAXGRID + 2)];
+      if (mw > -INFINITY) sum += colp_all[w * (HM_MAXGRID + 2) + 1 + threadIdx.x] * exp10(mw - MM);
+    }
+    Uu[dim + threadIdx.x] = (sum == 0.0) ? -INFINITY : MM + log10(sum); // (NaN sums stay NaN)
+  }
+  // ---- merge: configurations
+  const int q = small_dim ? rpr / dim : 1;
+  for (int k = threadIdx.x; k < dim; k += HM_THREADS) {
+    double MM = -INFINITY;
+    bool bad = false;
+    for (int w = 0; w < HM_WARPS; ++w)
+      for (int j = 0; j < q; ++j) {
+        const double2 s = kst_all[(size_t)w * nslot + j * dim + k];
+        bad = bad || (s.x != s.x);
+        MM = fmax(MM, s.x);
+      }
+    double sum = 0.0;
+    for (int w = 0; w < HM_WARPS; ++w)
+      for (int j = 0; j < q; ++j) {
+        const double2 s = kst_all[(size_t)w * nslot + j * dim + k];
+        if (s.x > -INFINITY) sum += s.y * exp10(s.x - MM);
+      }
+    Uu[k] = bad ? nan("") : ((sum == 0.0) ? -INFINITY : MM + log10(sum));
+  }
+}
+
+// per gene: merge its units, subtract log10 m_g; PA is output-major [dim + grid][n_genes]
+__global__ void __launch_bounds__(128) hm_gene_kernel(const double *__restrict__ U, const long long *__restrict__ gene_unit0,
+                                                     const long long *__restrict__ gene_off, int dim, int grid, long long n_genes,
+                                                     const double *__restrict__ gw, double *__restrict__ PA, double *__restrict__ BF)
+{
+  __shared__ double gd[HM_MAXGRID];
+  const long long g = blockIdx.x;
+  const long long u0 = gene_unit0[g], u1 = gene_unit0[g + 1];
+  const double l10m = log10((double)(gene_off[g + 1] - gene_off[g]));
+  const int nout = dim + grid;
+  for (int j = threadIdx.x; j < nout; j += blockDim.x) {
+    double MM = -INFINITY;
+    bool bad = false;
+    for (long long u = u0; u < u1; ++u) {
+      const double v = U[(size_t)u * nout + j];
+      bad = bad || (v != v);
+      MM = fmax(MM, v);
+    }
+    double val;
+    if (bad)
+      val = nan("");
+    else if (!(MM > -INFINITY))
+      val = -INFINITY;
+    else if (u1 - u0 == 1)
+      val = MM - l10m;
+    else {
+      double sum = 0.0;
+      for (long long u = u0; u < u1; ++u) sum += exp10(U[(size_t)u * nout + j] - MM);
+      val = MM + log10(sum) - l10m;
+    }
+    PA[(size_t)j * n_genes + g] = val;
+    if (j >= dim) gd[j - dim] = val;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // BF_g = log10 sum_l lambda_l 10^Gd[l]
+    double MM = -INFINITY;
+    bool bad = false;
+    for (int l = 0; l < grid; ++l) {
+      bad = bad || (gd[l] != gd[l]);
+      MM = fmax(MM, gd[l]);
+    }
+    double sum = 0.0;
+    for (int l = 0; l < grid; ++l)
+      if (gd[l] > -INFINITY) sum += gw[l] * exp10(gd[l] - MM);
+    BF[g] = bad ? nan("") : MM + log10(sum);
+  }
+}
+
+// fixed-order block reductions (blockDim.x a power of two <= 1024)
+__device__ __forceinline__ double hm_block_sum(double v, double *sh)
+{
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double hm_block_max(double v, double *sh)
+{
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const double b = sh[threadIdx.x + o];
+      // NaN-propagating maximum
+      sh[threadIdx.x] = (b != b || sh[threadIdx.x] != sh[threadIdx.x]) ? nan("") : fmax(sh[threadIdx.x], b);
+    }
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// gene_eQTL::compute_log10_obs_lik (hm_methods.cpp:476-497) for every gene and their sum (one CTA)
+__global__ void __launch_bounds__(1024) hm_lik_kernel(const double *__restrict__ BF, long long n_genes, double pi0, int keep,
+                                                      double *__restrict__ kept_lik, double *__restrict__ kept_bf, double *__restrict__ out)
+{
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (long long g = threadIdx.x; g < n_genes; g += blockDim.x) {
+    const double bf = BF[g];
+    const double mx = (bf > 0.0) ? bf : 0.0; // max of {0, BF} starting from vec[0] = 0; NaN BF: the sum below is NaN-skipped
+    double lik;
+    if (bf != bf)
+      lik = log10(pi0); // log10_weighted_sum skips a NaN entry that is not the first one (utils_math.cpp:146-150)
+    else
+      lik = mx + log10(pi0 * exp10(0.0 - mx) + (1.0 - pi0) * exp10(bf - mx));
+    if (fabs(lik) <= DBL_EPSILON) lik = 0.0;
+    if (keep) {
+      kept_lik[g] = lik;
+      kept_bf[g] = bf;
+    }
+    acc += lik;
+  }
+  const double tot = hm_block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = tot;
+}
+
+// CTA j < dim + grid: log10 sum_g 10^(PA[j][g] - lik_g); CTA dim + grid: sum_g 10^(log10 pi0 - lik_g)
+__global__ void __launch_bounds__(256) hm_sums_kernel(const double *__restrict__ PA, const double *__restrict__ kept_lik, long long n_genes,
+                                                     int nout, double pi0, double *__restrict__ out)
+{
+  __shared__ double sh[256];
+  const int j = blockIdx.x;
+  if (j == nout) {
+    const double l10pi0 = log10(pi0);
+    double acc = 0.0;
+    for (long long g = threadIdx.x; g < n_genes; g += blockDim.x) acc += exp10(l10pi0 - kept_lik[g]);
+    const double tot = hm_block_sum(acc, sh);
+    if (threadIdx.x == 0) out[1] = tot;
+    return;
+  }
+  const double *row = PA + (size_t)j * n_genes;
+  double mx = -INFINITY;
+  for (long long g = threadIdx.x; g < n_genes; g += blockDim.x) {
+    const double v = row[g] - kept_lik[g];
+    mx = (v != v || mx != mx) ? nan("") : fmax(mx, v);
+  }
+  const double MM = hm_block_max(mx, sh);
+  double acc = 0.0;
+  if (MM > -INFINITY)
+    for (long long g = threadIdx.x; g < n_genes; g += blockDim.x) {
+      const double v = row[g] - kept_lik[g];
+      if (v > -INFINITY) acc += exp10(v - MM);
+    }
+  const double tot = hm_block_sum(acc, sh);
+  if (threadIdx.x == 0) out[2 + j] = (MM != MM) ? nan("") : ((MM > -INFINITY) ? MM + log10(tot) : -INFINITY);
+}
+
+// warp per pair: snp_eQTL::compute_log10_BF (hm_methods.cpp:75-128) from the stored row averages
+__global__ void __launch_bounds__(128) hm_snp_kernel(const double *__restrict__ rowA, const double *__restrict__ cfg, int dim,
+                                                    long long n_pairs, double *__restrict__ snp_bf)
+{
+  const long long p = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= n_pairs) return;
+  const double *ar = rowA + (size_t)p * dim;
+  double mx = -INFINITY;
+  for (int k = lane; k < dim; k += 32) mx = fmax(mx, ar[k]);
+  mx = hm_warp_max(mx);
+  double acc = 0.0;
+  for (int k = lane; k < dim; k += 32)
+    if (ar[k] > -INFINITY) acc += cfg[k] * exp10(ar[k] - mx);
+  acc = hm_warp_sum(acc);
+  if (lane == 0) {
+    double r = mx + log10(acc);
+    if (fabs(r) <= DBL_EPSILON) r = 0.0;
+    snp_bf[p] = r;
+  }
+}
+
+__global__ void hm_check_kernel(const double *__restrict__ x, long long n, unsigned long long *__restrict__ bad)
+{
+  unsigned long long c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    if (!(fabs(v) <= DBL_MAX)) ++c;
+  }
+  if (c) atomicAdd(bad, c);
+}
+
+} // namespace eqb

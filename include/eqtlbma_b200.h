@@ -202,6 +202,14 @@ int64_t eqb_fast_gene_count(const eqb_ctx *ctx);
 float eqb_last_pair_kernel_ms(const eqb_ctx *ctx);
 /* Number of kernel launches issued by this context so far. */
 int64_t eqb_launch_count(const eqb_ctx *ctx);
+/* Raw per-configuration log10 ABFs of the LAST chunk computed by eqb_run (with results->abf_cfg) or
+ * eqb_run_device_only(want_raw = 1), still resident in device memory as [pair][config][small-grid point] doubles -- the
+ * layout eqb_hm_append_device (include/eqtlbma_hm_b200.h) takes, so that the hierarchical model can be fitted without the
+ * `_l10abfs_raw.txt.gz` round trip (eqtlbma_bf.cpp:1083-1229 writes it, eqtlbma_hm.cpp:287-371 parses it back).  The
+ * pointer stays valid until the next eqb_run* call on this context.  A run that fits the device budget is one chunk.
+ * eqb_raw_abfs_layout: ids of the genes with at least one pair (or NULL) and their pair offsets [n_genes + 1]. */
+int eqb_raw_abfs_device(eqb_ctx *ctx, const double **d_B, int64_t *n_pairs, int64_t *n_genes);
+int eqb_raw_abfs_layout(eqb_ctx *ctx, int64_t *gene_ids, int64_t *gene_off);
 /* diagnostics: worst deviation of the table-driven rcp / log / rsqrt / exp of the permutation BF kernel (perm_gemm.cuh)
  * from the CUDA library versions over n pseudo-random arguments:
  * out5 = { rcp rel, log abs, rsqrt rel, exp rel, special-value mismatches }. */

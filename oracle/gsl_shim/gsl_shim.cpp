@@ -1044,4 +1044,11 @@ double gsl_ran_flat(const gsl_rng *r, double a, double b)
   return a * (1.0 - u) + b * u;
 }
 
+/* GSL 2.x randist/exponential.c: -mu * log1p(-u), u from gsl_rng_uniform (eqtlbma_hm --rand, eqtlbma_hm.cpp:545-568) */
+double gsl_ran_exponential(const gsl_rng *r, double mu)
+{
+  const double u = gsl_rng_uniform(r);
+  return -mu * log1p(-u);
+}
+
 } /* extern "C" */

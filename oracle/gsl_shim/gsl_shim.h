@@ -181,6 +181,7 @@ double gsl_rng_uniform(const gsl_rng *r);
 unsigned long int gsl_rng_uniform_int(const gsl_rng *r, unsigned long int n);
 void gsl_ran_shuffle(const gsl_rng *r, void *base, size_t nmembm, size_t size);
 double gsl_ran_flat(const gsl_rng *r, double a, double b);
+double gsl_ran_exponential(const gsl_rng *r, double mu);
 
 #ifdef __cplusplus
 }
