@@ -45,15 +45,24 @@ def build_library(force: bool = False) -> str:
     os.makedirs(obj_dir, exist_ok=True)
     names = sorted(os.listdir(src_dir))
     units = [os.path.join(src_dir, f) for f in names if f.endswith(".cu")]
-    headers = [os.path.join(src_dir, f) for f in names if f.endswith((".cuh", ".h"))] + \
-              [os.path.join(ROOT, "include", f) for f in sorted(os.listdir(os.path.join(ROOT, "include"))) if f.endswith(".h")]
+
+    def deps(path, seen):
+        """Project headers a translation unit includes (quoted includes, followed recursively)."""
+        import re
+        for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(path).read(), flags=re.M):
+            h = os.path.normpath(os.path.join(os.path.dirname(path), inc))
+            if os.path.exists(h) and h not in seen:
+                seen.append(h)
+                deps(h, seen)
+        return seen
+
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = NVCC_FLAGS + (["-DEQB_TUNING"] if os.environ.get("EQB_BUILD_TUNING") else [])
     todo, objs = [], []
     for u in units:
         obj = os.path.join(obj_dir, os.path.basename(u)[:-3] + ".o")
         objs.append(obj)
-        want = _digest([u] + headers, " ".join(flags))
+        want = _digest([u] + sorted(deps(u, [])), " ".join(flags))
         stamp = obj + ".sha256"
         have = open(stamp).read().strip() if os.path.exists(stamp) and os.path.exists(obj) else ""
         if force or have != want:

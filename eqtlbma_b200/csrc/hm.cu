@@ -48,6 +48,9 @@ struct eqb_hm_ctx {
   double sums_pi0 = 0;
   bool sums_valid = false;
   long long launches = 0, heavy_passes = 0;
+  int estep_ctas = 0; // resident CTAs of hm_estep_kernel on this device (persistent grid)
+  int *d_counter = nullptr;
+  bool ranged = false; // every value within +-1e6 (hm_check_kernel): unclamped exponentials of differences
 };
 
 static int fail(eqb_hm_ctx *hm, int code, const char *fmt, ...)
@@ -66,13 +69,29 @@ static int fail(eqb_hm_ctx *hm, int code, const char *fmt, ...)
     if (e_ != cudaSuccess) return fail(hm, 100, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+template <int G, bool EXACT, bool RANGED>
+static cudaError_t launch_estep_t2(eqb_hm_ctx *hm)
+{
+  cudaError_t e = cudaFuncSetAttribute(hm_estep_kernel<G, EXACT, RANGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hm->smem);
+  if (e != cudaSuccess) return e;
+  if (hm->estep_ctas <= 0) { // persistent CTAs: as many as are resident at once
+    int per_sm = 0, n_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hm_estep_kernel<G, EXACT, RANGED>, HM_THREADS, hm->smem);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, hm->device);
+    if (e != cudaSuccess) return e;
+    hm->estep_ctas = std::max(1, per_sm) * std::max(1, n_sm);
+  }
+  const unsigned ctas = (unsigned)std::min<long long>((hm->n_units + HM_WARPS - 1) / HM_WARPS, hm->estep_ctas);
+  e = cudaMemsetAsync(hm->d_counter, 0, sizeof(int), hm->stream);
+  if (e != cudaSuccess) return e;
+  hm_estep_kernel<G, EXACT, RANGED><<<ctas, HM_THREADS, hm->smem, hm->stream>>>(hm->args);
+  return cudaGetLastError();
+}
 template <int G, bool EXACT>
 static cudaError_t launch_estep_t(eqb_hm_ctx *hm)
 {
-  cudaError_t e = cudaFuncSetAttribute(hm_estep_kernel<G, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hm->smem);
-  if (e != cudaSuccess) return e;
-  hm_estep_kernel<G, EXACT><<<(unsigned)hm->n_units, HM_THREADS, hm->smem, hm->stream>>>(hm->args);
-  return cudaGetLastError();
+  return hm->ranged ? launch_estep_t2<G, EXACT, true>(hm) : launch_estep_t2<G, EXACT, false>(hm);
 }
 static cudaError_t launch_estep(eqb_hm_ctx *hm)
 {
@@ -123,7 +142,7 @@ void eqb_hm_destroy(eqb_hm_ctx *hm)
     cudaSetDevice(hm->device);
     cudaStreamSynchronize(hm->stream);
   }
-  void *ptrs[] = {hm->d_alloc, hm->d_unit_row0, hm->d_gene_unit0, hm->d_gene_off, hm->d_unit_rows, hm->d_U, hm->d_PA, hm->d_BF,
+  void *ptrs[] = {hm->d_alloc, hm->d_counter, hm->d_unit_row0, hm->d_gene_unit0, hm->d_gene_off, hm->d_unit_rows, hm->d_U, hm->d_PA, hm->d_BF,
                   hm->d_kept_lik, hm->d_kept_bf, hm->d_cfg, hm->d_gw, hm->d_out, hm->d_rowA, hm->d_snp};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -193,19 +212,20 @@ int eqb_hm_finalize(eqb_hm_ctx *hm)
   HCK(cudaMemsetAsync(hm->d_alloc + 16 + (size_t)hm->n_pairs * pair_bytes, 0, 16, hm->stream));
   // non-finite values: the reference's likelihood is NaN / infinite and it stops (eqtlbma_hm.cpp:640-647)
   {
-    unsigned long long *d_bad = nullptr, bad = 0;
-    HCK(cudaMalloc(&d_bad, 8));
-    HCK(cudaMemsetAsync(d_bad, 0, 8, hm->stream));
+    unsigned long long *d_bad = nullptr, bad[2] = {0, 0};
+    HCK(cudaMalloc(&d_bad, 16));
+    HCK(cudaMemsetAsync(d_bad, 0, 16, hm->stream));
     hm_check_kernel<<<592, 256, 0, hm->stream>>>(reinterpret_cast<const double *>(hm->d_alloc + 16), hm->n_pairs * dim * grid, d_bad);
     ++hm->launches;
     HCK(cudaGetLastError());
-    HCK(cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, hm->stream));
+    HCK(cudaMemcpyAsync(bad, d_bad, 16, cudaMemcpyDeviceToHost, hm->stream));
     HCK(cudaStreamSynchronize(hm->stream));
     cudaFree(d_bad);
-    if (bad) return fail(hm, 4, "ERROR: %llu raw log10(BF) values are NaN or +-Inf", bad);
+    hm->ranged = bad[1] == 0;
+    if (bad[0]) return fail(hm, 4, "ERROR: %llu raw log10(BF) values are NaN or +-Inf", bad[0]);
   }
-  // work units: runs of whole pairs of one gene, about 4096 rows each
-  const int pairs_per_unit = std::max(1, 4096 / dim);
+  // work units: runs of whole pairs of one gene, about 1024 rows each (one warp per unit)
+  const int pairs_per_unit = std::max(1, 1024 / dim);
   std::vector<long long> unit_row0, gene_unit0(G + 1);
   std::vector<int> unit_rows;
   for (long long g = 0; g < G; ++g) {
@@ -220,6 +240,7 @@ int eqb_hm_finalize(eqb_hm_ctx *hm)
   hm->n_units = (long long)unit_row0.size();
   const int nout = dim + grid;
   HCK(cudaMalloc(&hm->d_unit_row0, hm->n_units * 8));
+  HCK(cudaMalloc(&hm->d_counter, sizeof(int)));
   HCK(cudaMalloc(&hm->d_unit_rows, hm->n_units * 4));
   HCK(cudaMalloc(&hm->d_gene_unit0, (G + 1) * 8));
   HCK(cudaMalloc(&hm->d_gene_off, (G + 1) * 8));
@@ -243,11 +264,17 @@ int eqb_hm_finalize(eqb_hm_ctx *hm)
   a.U = hm->d_U;
   a.cfg = hm->d_cfg;
   a.rowA = nullptr;
+  a.counter = hm->d_counter;
   a.dim = dim;
   a.grid = grid;
+  if (hm->n_units > 0x7fffffffLL) return fail(hm, 2, "eqb_hm_finalize: too many work units");
+  a.n_units = (int)hm->n_units;
   a.rpr = (dim >= 32) ? 32 : (32 / dim) * dim;
   a.nslot = (dim >= 32) ? dim : a.rpr;
-  a.stages = (grid <= 16) ? 4 : 2;
+#ifndef HM_STAGES_SMALL
+#define HM_STAGES_SMALL 3
+#endif
+  a.stages = (grid <= 16) ? HM_STAGES_SMALL : 2;
   a.stage_bytes = (int)hm_align16((size_t)a.rpr * grid * 8 + 16);
   hm->smem = hm_smem_bytes(a.nslot, a.stages, a.stage_bytes);
   if (hm->smem > 200 * 1024) return fail(hm, 2, "eqb_hm_finalize: dim %d x grid %d needs %zu bytes of shared memory", dim, grid, hm->smem);

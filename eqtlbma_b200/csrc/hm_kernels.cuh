@@ -11,12 +11,14 @@
 // i.e. three groupings of ONE pass over the rows (p, k) of the data.  The reference makes that pass 2 + dim + grid times
 // per iteration through nested log10_weighted_sum calls (utils_math.cpp:135-159); hm_estep_kernel makes it once:
 //
-//   hm_estep_kernel   CTA = one work unit (a run of whole pairs of one gene, ~4096 rows), 4 warps; a warp takes rounds of 32
+//   hm_estep_kernel   persistent WARPS (as many CTAs of 4 warps as are resident; the warps of a CTA share only the tables), each
+//                     claiming work units from a counter (a unit = a run of whole pairs of one gene, ~1024 rows; the first
+//                     rounds of the next unit are in flight while the current one is merged).  A warp takes rounds of 32
 //                     consecutive rows (contiguous 32 x grid doubles), staged in shared memory by 1-D TMA bulk copies
-//                     (cp.async.bulk + mbarrier, HM_STAGES deep per warp, issued by lane 0); lane = row: row maximum, one
+//                     (cp.async.bulk + mbarrier, `stages` deep per warp, issued by lane 0); lane = row: row maximum, one
 //                     table exponential per element, the row average a (optionally stored), an online log-sum-exp state per
 //                     configuration in shared memory, and lane-private linear-domain column sums against a running reference
-//                     (the largest row maximum seen), merged over the CTA at the end -> U[unit][dim + grid] (log10 domain).
+//                     (the largest row maximum seen), merged over the lanes at the end -> U[unit][dim + grid] (log10 domain).
 //                     HBM-bound by design (8 bytes per element read once) with (grid + 2) exponentials per row on the FP64
 //                     pipe: the two limits are within 2x of each other at grid = 10.
 //   hm_gene_kernel    per gene: log-sum-exp of its units, - log10 m_g, BF[g]           -> PA[j][g], BF[g]
@@ -33,6 +35,9 @@ namespace eqb {
 
 constexpr int HM_WARPS = 4;
 constexpr int HM_THREADS = HM_WARPS * 32;
+#ifndef HM_MIN_CTAS
+#define HM_MIN_CTAS 5
+#endif
 constexpr int HM_MAXGRID = 32;
 constexpr int HM_MAXDIM = 4096;
 
@@ -44,12 +49,44 @@ struct HmArgs {
   const double *cfg;          // [dim] configuration prior
   double *rowA;               // [rows] a[p][k] (posterior pass) or nullptr
   int dim, grid;
+  int n_units;   // work units, claimed one at a time by the persistent warps
+  int *counter;  // next unclaimed unit (zeroed before every launch)
   int rpr;         // rows per round: 32 (dim >= 32) or (32 / dim) * dim
   int nslot;       // configuration-state slots per warp: dim (dim >= 32) or rpr
   int stages;      // TMA stages per warp
   int stage_bytes; // bytes of one stage (rpr rows + 16, multiple of 16)
   double gw[HM_MAXGRID]; // grid weights: constant-bank operands
 };
+
+// 10^y with the base folded into the constants (no y * ln 10 first): 2^(k/16) from the table times 10^g - 1 to g^4,
+// |g| <= log10(2)/32, relative error < 4e-11 + 7e-14 |y|/300 like exp10_tab16.  FPCLAMP: any y (-inf, NaN -> ~1e-300);
+// otherwise y must be finite with |y| < 1e7 (integer clamp of the binary exponent: results below 2^-1000 come out as ~1e-301)
+static __constant__ double HMK[6] = {
+    53.150849518197795,    // 0  16 log2(10)
+    -0.018814374728998825, // 1  -log10(2) / 16
+    2.302585092994046,     // 2  ln 10
+    2.650949055239199,     // 3  ln^2 10 / 2
+    2.034678592293476,     // 4  ln^3 10 / 6
+    1.171255148912267};    // 5  ln^4 10 / 24
+template <bool FPCLAMP>
+__device__ __forceinline__ double hm_exp10(double y, const TabRef T)
+{
+  if (FPCLAMP) {
+    const unsigned int hy = (unsigned int)__double2hiint(y);
+    if (hy > 0xC072C000u) y = -300.0; // max(y, -300) on the bit pattern (NaN and -inf are larger)
+  }
+  const double tm = fma(y, HMK[0], PGK[1]);
+  const int k = __double2loint(tm);
+  const double kd = tm - PGK[1];
+  const double g = fma(kd, HMK[1], y);
+  double s = fma(g, HMK[5], HMK[4]);
+  s = fma(g, s, HMK[3]);
+  s = fma(g, s, HMK[2]);
+  const double tj = T.exp16(k & 15);
+  const double v = fma(tj * g, s, tj);
+  const int e2 = FPCLAMP ? (k >> 4) : max(k >> 4, -1000);
+  return __hiloint2double(__double2hiint(v) + (e2 << 20), __double2loint(v));
+}
 
 __device__ __forceinline__ void hm_mbar_init(uint32_t bar, uint32_t count)
 {
@@ -95,16 +132,18 @@ __device__ __forceinline__ double hm_warp_sum(double v)
 }
 
 __host__ __device__ inline size_t hm_align16(size_t x) { return (x + 15) & ~(size_t)15; }
-// shared memory of hm_estep_kernel: tables | barriers | configuration states | column partials | stages
+// shared memory of hm_estep_kernel: tables | barriers | configuration states | stages
 __host__ __device__ inline size_t hm_smem_bytes(int nslot, int stages, int stage_bytes)
 {
   return hm_align16(sizeof(BfTabs)) + hm_align16((size_t)HM_WARPS * stages * 8) + (size_t)HM_WARPS * nslot * 16 +
-         (size_t)HM_WARPS * (HM_MAXGRID + 2) * 8 + (size_t)HM_WARPS * stages * stage_bytes;
+         (size_t)HM_WARPS * stages * stage_bytes;
 }
 
 // G: compile-time number of grid points (EXACT) or their upper bound (the loops are predicated on l < grid)
-template <int G, bool EXACT>
-__global__ void __launch_bounds__(HM_THREADS) hm_estep_kernel(const __grid_constant__ HmArgs a)
+// RANGED: every value of the data set is within +-1e6 (checked at load time), so differences of two values can take the
+// exponential without the floating-point clamp
+template <int G, bool EXACT, bool RANGED>
+__global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_estep_kernel(const __grid_constant__ HmArgs a)
 {
   extern __shared__ __align__(16) unsigned char hm_smem[];
   const int grid = EXACT ? G : a.grid;
@@ -112,8 +151,7 @@ __global__ void __launch_bounds__(HM_THREADS) hm_estep_kernel(const __grid_const
   BfTabs *tabs = reinterpret_cast<BfTabs *>(hm_smem);
   unsigned char *p_bar = hm_smem + hm_align16(sizeof(BfTabs));
   double2 *kst_all = reinterpret_cast<double2 *>(p_bar + hm_align16((size_t)HM_WARPS * stages * 8));
-  double *colp_all = reinterpret_cast<double *>(kst_all + (size_t)HM_WARPS * nslot);
-  unsigned char *stage_all = reinterpret_cast<unsigned char *>(colp_all + HM_WARPS * (HM_MAXGRID + 2));
+  unsigned char *stage_all = reinterpret_cast<unsigned char *>(kst_all + (size_t)HM_WARPS * nslot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bf_tabs_init(*tabs);
@@ -128,131 +166,149 @@ __global__ void __launch_bounds__(HM_THREADS) hm_estep_kernel(const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __syncthreads();
+  __syncthreads(); // the only CTA-wide barrier: the warps share nothing but the tables from here on
 
-  const long long row0 = a.unit_row0[blockIdx.x];
-  const int nrows = a.unit_rows[blockIdx.x];
-  const int n_rounds = (nrows + rpr - 1) / rpr;
-  const int n_my = (n_rounds > warp) ? (n_rounds - warp + HM_WARPS - 1) / HM_WARPS : 0;
+  // lane-private column sums against the running reference mref
+  double cs[G];
+  const bool small_dim = dim < 32;
+  const double cfg_fixed = small_dim ? ((lane < rpr) ? __ldg(a.cfg + lane % dim) : 0.0) : 0.0;
   const long long row_bytes = (long long)grid * 8;
+  const int q = small_dim ? rpr / dim : 1;
 
-  auto issue = [&](int i) { // lane 0: round i of this warp into stage i % stages
-    const int r_first = (warp + i * HM_WARPS) * rpr;
+  // round i of the unit starting at row0 into the stage of pipeline slot `slot` (lane 0)
+  auto issue = [&](long long row0, int nrows, int i, uint32_t slot) {
+    const int r_first = i * rpr;
     const int nr = min(rpr, nrows - r_first);
     const long long off = (row0 + r_first) * row_bytes;
     const int shift = (int)(off & 15);
     const uint32_t bytes = (uint32_t)((shift + nr * (int)row_bytes + 15) & ~15);
-    const int st = i % stages;
+    const uint32_t st = slot % (uint32_t)stages;
     hm_mbar_expect_tx(bars + 8 * st, bytes);
-    hm_bulk_load(stg_u32 + (uint32_t)(st * stage_bytes), a.B + (off - shift), bytes, bars + 8 * st);
+    hm_bulk_load(stg_u32 + st * (uint32_t)stage_bytes, a.B + (off - shift), bytes, bars + 8 * st);
   };
-  if (lane == 0)
-    for (int i = 0; i < stages && i < n_my; ++i) issue(i);
+  auto next_unit = [&]() { // dynamic assignment: one counter per launch, claimed by lane 0
+    int u = 0;
+    if (lane == 0) u = atomicAdd(a.counter, 1);
+    return __shfl_sync(0xffffffffu, u, 0);
+  };
 
-  // lane-private column sums against the running reference mref
-  double cs[G];
+  // persistent warps: the pipeline slots of a warp are numbered consecutively across its units (cnt), so stage = cnt % stages
+  // and the mbarrier parity = (cnt / stages) & 1 throughout; the first rounds of the next unit are issued before the current
+  // one is merged
+  uint32_t cnt = 0;
+  int unit = next_unit();
+  long long row0 = 0;
+  int nrows = 0, n_rounds = 0;
+  if (unit < a.n_units) {
+    row0 = a.unit_row0[unit];
+    nrows = a.unit_rows[unit];
+    n_rounds = (nrows + rpr - 1) / rpr;
+    if (lane == 0)
+      for (int i = 0; i < stages && i < n_rounds; ++i) issue(row0, nrows, i, cnt + i);
+  }
+  while (unit < a.n_units) {
+    const int nxt = next_unit();
 #pragma unroll
-  for (int l = 0; l < G; ++l) cs[l] = 0.0;
-  double mref = -INFINITY;
-  const bool small_dim = dim < 32;
-  const double cfg_fixed = small_dim ? ((lane < rpr) ? __ldg(a.cfg + lane % dim) : 0.0) : 0.0;
+    for (int l = 0; l < G; ++l) cs[l] = 0.0;
+    double mref = -INFINITY;
 
-  for (int i = 0; i < n_my; ++i) {
-    const int st = i % stages;
-    hm_mbar_wait(bars + 8 * st, (uint32_t)((i / stages) & 1));
-    const int r_first = (warp + i * HM_WARPS) * rpr;
-    const int nr = min(rpr, nrows - r_first);
-    if (lane < nr) {
-      const long long off = (row0 + r_first) * row_bytes;
-      const double *x = reinterpret_cast<const double *>(stg + (size_t)st * stage_bytes + (int)(off & 15)) + (size_t)lane * grid;
-      double m = x[0];
+    for (int i = 0; i < n_rounds; ++i, ++cnt) {
+      const uint32_t st = cnt % (uint32_t)stages;
+      hm_mbar_wait(bars + 8 * st, (cnt / (uint32_t)stages) & 1u);
+      const int r_first = i * rpr;
+      const int nr = min(rpr, nrows - r_first);
+      if (lane < nr) {
+        const long long off = (row0 + r_first) * row_bytes;
+        const double *x = reinterpret_cast<const double *>(stg + (size_t)st * stage_bytes + (int)(off & 15)) + (size_t)lane * grid;
+        double m = x[0];
 #pragma unroll
-      for (int l = 1; l < G; ++l)
-        if (EXACT || l < grid) m = fmax(m, x[l]);
-      const int k = small_dim ? 0 : (int)((r_first + lane) % dim);
-      const double cfgk = small_dim ? cfg_fixed : __ldg(a.cfg + k);
-      // column reference: rescale the sums when this row raises it
-      const double d = m - mref; // +inf for the first row
-      double wc;
-      if (d > 0.0) {
-        const double sc = exp10_tab16<true>(-d, T);
+        for (int l = 1; l < G; ++l)
+          if (EXACT || l < grid) m = fmax(m, x[l]);
+        const int k = small_dim ? 0 : (int)((r_first + lane) % dim);
+        const double cfgk = small_dim ? cfg_fixed : __ldg(a.cfg + k);
+        // column reference: rescale the sums when this row raises it
+        const double d = m - mref; // +inf for the first row
+        double wc;
+        if (d > 0.0) {
+          const double sc = hm_exp10<true>(-d, T);
 #pragma unroll
-        for (int l = 0; l < G; ++l) cs[l] *= sc;
-        mref = m;
-        wc = cfgk;
-      } else
-        wc = cfgk * exp10_tab16<true>(d, T);
-      double rs = 0.0;
+          for (int l = 0; l < G; ++l) cs[l] *= sc;
+          mref = m;
+          wc = cfgk;
+        } else
+          wc = cfgk * hm_exp10<!RANGED>(d, T);
+        double rs = 0.0;
+#pragma unroll
+        for (int l = 0; l < G; ++l)
+          if (EXACT || l < grid) {
+            const double e = hm_exp10<!RANGED>(x[l] - m, T);
+            rs = fma(a.gw[l], e, rs);
+            cs[l] = fma(wc, e, cs[l]);
+          }
+        const double ar = fma(log_tab16(rs, T), PGK[11], m); // a[p][k]; -inf for a zero sum, NaN for a negative one
+        if (a.rowA) a.rowA[row0 + r_first + lane] = ar;
+        // online log-sum-exp of a over the rows with this configuration
+        const int slot = small_dim ? lane : k;
+        double2 s = kst[slot];
+        if (ar != ar)
+          s = make_double2(ar, ar); // (negative weights of a SQUAREM proposal: the likelihood is NaN, as in the reference)
+        else if (ar > -INFINITY) {
+          const double dd = ar - s.x;
+          const bool up = dd > 0.0;
+          const double e = hm_exp10<true>(up ? -dd : dd, T);
+          s.y = up ? fma(s.y, e, 1.0) : s.y + e;
+          s.x = up ? ar : s.x;
+        }
+        kst[slot] = s;
+      }
+      __syncwarp();
+      if (lane == 0 && i + stages < n_rounds) issue(row0, nrows, i + stages, cnt + (uint32_t)stages);
+    }
+
+    // ---- next unit: its first rounds travel while this one is merged (every stage of the warp is free here)
+    const int cur = unit;
+    unit = nxt;
+    if (unit < a.n_units) {
+      row0 = a.unit_row0[unit];
+      nrows = a.unit_rows[unit];
+      n_rounds = (nrows + rpr - 1) / rpr;
+      if (lane == 0)
+        for (int i = 0; i < stages && i < n_rounds; ++i) issue(row0, nrows, i, cnt + (uint32_t)i);
+    }
+
+    // ---- merge over the lanes: columns (lane l keeps column l) ...
+    double *Uu = a.U + (size_t)cur * (dim + grid);
+    {
+      const double M = hm_warp_max(mref);
+      const double fac = (mref > -INFINITY) ? exp10_tab16<true>(mref - M, T) : 0.0;
+      double mine = 0.0;
 #pragma unroll
       for (int l = 0; l < G; ++l)
         if (EXACT || l < grid) {
-          const double e = exp10_tab16<true>(x[l] - m, T);
-          rs = fma(a.gw[l], e, rs);
-          cs[l] = fma(wc, e, cs[l]);
+          const double v = hm_warp_sum(cs[l] * fac);
+          if (lane == l) mine = v;
         }
-      const double ar = fma(log_tab16(rs, T), PGK[11], m); // a[p][k]; -inf for a zero sum, NaN for a negative one
-      if (a.rowA) a.rowA[row0 + r_first + lane] = ar;
-      // online log-sum-exp of a over the rows with this configuration
-      const int slot = small_dim ? lane : k;
-      double2 s = kst[slot];
-      if (ar != ar)
-        s = make_double2(ar, ar); // (negative weights of a SQUAREM proposal: the likelihood is NaN, as in the reference)
-      else if (ar > -INFINITY) {
-        const double dd = ar - s.x;
-        const bool up = dd > 0.0;
-        const double e = exp10_tab16<true>(up ? -dd : dd, T);
-        s.y = up ? fma(s.y, e, 1.0) : s.y + e;
-        s.x = up ? ar : s.x;
-      }
-      kst[slot] = s;
+      if (lane < grid) Uu[dim + lane] = (mine == 0.0) ? -INFINITY : M + log10(mine); // (NaN sums stay NaN)
     }
-    __syncwarp();
-    if (lane == 0 && i + stages < n_my) issue(i + stages);
-  }
-
-  // ---- merge: columns
-  double *colp = colp_all + warp * (HM_MAXGRID + 2);
-  {
-    const double M = hm_warp_max(mref);
-    const double fac = (mref > -INFINITY) ? exp10_tab16<true>(mref - M, T) : 0.0;
-#pragma unroll
-    for (int l = 0; l < G; ++l)
-      if (EXACT || l < grid) {
-        const double v = hm_warp_sum(cs[l] * fac);
-        if (lane == 0) colp[1 + l] = v;
-      }
-    if (lane == 0) colp[0] = M;
-  }
-  __syncthreads();
-  double *Uu = a.U + (size_t)blockIdx.x * (dim + grid);
-  if ((int)threadIdx.x < grid) {
-    double MM = -INFINITY;
-    for (int w = 0; w < HM_WARPS; ++w) MM = fmax(MM, colp_all[w * (HM_MAXGRID + 2)]);
-    double sum = 0.0;
-    for (int w = 0; w < HM_WARPS; ++w) {
-      const double mw = colp_all[w * (HM_MAXGRID + 2)];
-      if (mw > -INFINITY) sum += colp_all[w * (HM_MAXGRID + 2) + 1 + threadIdx.x] * exp10(mw - MM);
-    }
-    Uu[dim + threadIdx.x] = (sum == 0.0) ? -INFINITY : MM + log10(sum); // (NaN sums stay NaN)
-  }
-  // ---- merge: configurations
-  const int q = small_dim ? rpr / dim : 1;
-  for (int k = threadIdx.x; k < dim; k += HM_THREADS) {
-    double MM = -INFINITY;
-    bool bad = false;
-    for (int w = 0; w < HM_WARPS; ++w)
+    // ... and configurations (the q states of a configuration, written by q lanes of this warp)
+    for (int k = lane; k < dim; k += 32) {
+      double MM = -INFINITY;
+      bool bad = false;
       for (int j = 0; j < q; ++j) {
-        const double2 s = kst_all[(size_t)w * nslot + j * dim + k];
+        const double2 s = kst[j * dim + k];
         bad = bad || (s.x != s.x);
         MM = fmax(MM, s.x);
       }
-    double sum = 0.0;
-    for (int w = 0; w < HM_WARPS; ++w)
+      double sum = 0.0;
       for (int j = 0; j < q; ++j) {
-        const double2 s = kst_all[(size_t)w * nslot + j * dim + k];
+        const double2 s = kst[j * dim + k];
         if (s.x > -INFINITY) sum += s.y * exp10(s.x - MM);
       }
-    Uu[k] = bad ? nan("") : ((sum == 0.0) ? -INFINITY : MM + log10(sum));
+      Uu[k] = bad ? nan("") : ((sum == 0.0) ? -INFINITY : MM + log10(sum));
+    }
+    __syncwarp();
+    for (int i = lane; i < nslot; i += 32) kst[i] = make_double2(-INFINITY, 0.0);
+    __syncwarp();
   }
 }
 
@@ -413,14 +469,19 @@ __global__ void __launch_bounds__(128) hm_snp_kernel(const double *__restrict__ 
   }
 }
 
+// bad[0]: non-finite values; bad[1]: finite values outside +-1e6 (the data set then takes the clamped exponentials)
 __global__ void hm_check_kernel(const double *__restrict__ x, long long n, unsigned long long *__restrict__ bad)
 {
-  unsigned long long c = 0;
+  unsigned long long c = 0, w = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double v = x[i];
-    if (!(fabs(v) <= DBL_MAX)) ++c;
+    if (!(fabs(v) <= DBL_MAX))
+      ++c;
+    else if (fabs(v) > 1e6)
+      ++w;
   }
   if (c) atomicAdd(bad, c);
+  if (w) atomicAdd(bad + 1, w);
 }
 
 } // namespace eqb

@@ -109,6 +109,31 @@ def test_hm_likelihood_and_esums_match_oracle(cuda_lib, shape):
     hm.close()
 
 
+def test_hm_extreme_values_take_the_clamped_path(cuda_lib):
+    """Values outside +-1e6 (finite): the data set is not `ranged` and every exponential is clamped; same results as
+    the restatement (10^(x - max) underflows to zero there)."""
+    from eqtlbma_b200.hm_synth import make_hm_dataset
+    ds = make_hm_dataset(seed=78, n_genes=300, snps_lo=1, snps_hi=30, round_text=False)
+    B = ds.B.copy()
+    rs = np.random.RandomState(9)
+    idx = rs.choice(B.size, 200, replace=False)
+    B.ravel()[idx[:100]] = -5e6 * rs.uniform(1, 1e3, 100)
+    B.ravel()[idx[100:150]] = -1e300
+    B.ravel()[idx[150:]] = 3e7 * rs.uniform(1, 5, 50)
+    o = HmOracle(B, ds.gene_off)
+    hm = _engine(B, ds.gene_off)
+    gw = rs.dirichlet(np.ones(ds.grid))
+    cp = rs.dirichlet(np.ones(ds.dim))
+    lik, ref = hm.loglik(0.3, gw, cp, keep=True), o.loglik(0.3, gw, cp)
+    assert abs(lik - ref) <= 1e-10 * abs(ref)
+    sums = hm.esums(0.3, gw, cp)
+    n_pi0, n_gw, n_cp = o.fixedpoint(0.3, gw, cp, dict(pi0=False, grid=False, configs=False))
+    assert abs(sums[0] / ds.n_genes - n_pi0) <= 1e-10
+    t = sums[1 + ds.dim:] + np.log10(gw)
+    np.testing.assert_allclose(10.0 ** (t - np.log10(np.sum(10.0 ** (t - t.max()))) - t.max()), n_gw, rtol=1e-9, atol=1e-15)
+    hm.close()
+
+
 def test_hm_em_monotone_and_append_in_pieces(cuda_lib):
     """Size-independent properties on a larger input: the likelihood never decreases along the EM (the reference aborts
     otherwise, eqtlbma_hm.cpp:1091-1095), weights stay on the simplex, and loading the genes file by file
