@@ -360,10 +360,30 @@ def cpu_baseline_hm(ds, sample_genes=1000):
         wall1 = time.perf_counter() - t0
         r1_lines = 3  # iteration 0, one fixed point, the closing fixed point
         em_s = max(wall - wall1, 1e-3)
+        # the drop-in front-end on the same file (wall clock, CUDA context creation included)
+        cli = None
+        ours = os.path.join(ROOT, "eqtlbma_b200", "eqtlbma_hm")
+        if os.path.exists(ours):
+            cmd = [ours] + base[1:]
+            cmd[cmd.index(os.path.join(tmp, "o.txt.gz"))] = os.path.join(tmp, "o2.txt.gz")
+            t0 = time.perf_counter()
+            r2 = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp)
+            wall2 = time.perf_counter() - t0
+            if r2.returncode == 0:
+                import gzip
+                a = gzip.open(os.path.join(tmp, "o.txt.gz"), "rt").read().splitlines()
+                b = gzip.open(os.path.join(tmp, "o2.txt.gz"), "rt").read().splitlines()
+                em2 = [ln for ln in r2.stdout.splitlines() if ln.startswith("EM ran for")]
+                cli = {"ours_wall_s": wall2, "reference_wall_s": wall, "wall_ratio": wall / wall2, "same_parameter_lines": a == b,
+                       "ours_em": em2[0] if em2 else None,
+                       "what": "eqtlbma_b200/eqtlbma_hm vs oracle/_ref/eqtlbma_hm_ref on the same `_l10abfs_raw.txt.gz` file, "
+                               "classical EM, parameter lines of the two output files compared as text"}
+            else:
+                cli = {"error": r2.stderr[-300:]}
         return {"value": pairs * (n_lines - r1_lines) / em_s, "unit": "pairs x likelihood evaluations/s", "cores": cores,
                 "kind": "reference", "sample": f"first {sample_genes} genes ({pairs} pairs), classical EM to --thresh 0.05, "
                 f"{n_lines} likelihood evaluations, wall {wall:.2f} s minus {wall1:.2f} s of a --maxit 2 run (file parsing + 3 evaluations)",
-                "wall_s": wall, "load_s": wall1}
+                "wall_s": wall, "load_s": wall1, "cli_e2e": cli}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 

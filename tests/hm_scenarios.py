@@ -33,6 +33,8 @@ HM_SCENARIOS = {
     "maxit5": dict(data=dict(seed=17, n_genes=100, strength=2.0), maxit=5, thresh=1e-6),
     # profile-likelihood confidence intervals (single-threaded and slow in the reference: small case)
     "getci": dict(data=dict(seed=18, n_genes=60, n_subgroups=2, grid=3), getci=True, getbf=True),
+    # random initialisation (--seed: gsl_rng_mt19937 + gsl_ran_exponential, eqtlbma_hm.cpp:529-579)
+    "rand_seed": dict(data=dict(seed=20, n_genes=100), seed=1859, getbf=True),
     # SQUAREM with 4 subgroups (15 configurations) and strong effects
     "squarem_s4": dict(data=dict(seed=19, n_genes=120, n_subgroups=4, grid=6, strength=2.5), msl=4.0, getbf=True),
 }
@@ -89,6 +91,8 @@ def ref_cmdline(sc, ds, pattern, out, init_path):
         cmd += ["--getbf"]
     if sc.get("getci"):
         cmd += ["--getci"]
+    if "seed" in sc:
+        cmd += ["--seed", str(sc["seed"])]
     if init_path:
         cmd += ["--init", init_path]
     return cmd
@@ -103,6 +107,17 @@ def initial_params(sc, dim, grid):
     if "pi0" in sc:
         pi0 = sc["pi0"]
         fixed["pi0"] = True
+    if "seed" in sc:
+        # gsl_rng_mt19937 seeded by gsl_rng_set = numpy's MT19937 seeded with the same integer; gsl_rng_uniform = raw 32 bits / 2^32
+        rs = np.random.RandomState(sc["seed"])
+        u = lambda: float(rs.randint(0, 2 ** 32, dtype=np.uint64)) / 4294967296.0  # noqa: E731
+        if not fixed["pi0"]:
+            pi0 = u()
+        gw = np.array([-np.log1p(-u()) for _ in range(grid)])
+        gw = gw / gw.sum()
+        if dim > 1:
+            cp = np.array([-np.log1p(-u()) for _ in range(dim)])
+            cp = cp / cp.sum()
     if "init" in sc:
         ig = ic = 0
         for ln in sc["init"].splitlines():
