@@ -374,7 +374,12 @@ def cpu_baseline_hm(ds, sample_genes=1000):
                 a = gzip.open(os.path.join(tmp, "o.txt.gz"), "rt").read().splitlines()
                 b = gzip.open(os.path.join(tmp, "o2.txt.gz"), "rt").read().splitlines()
                 em2 = [ln for ln in r2.stdout.splitlines() if ln.startswith("EM ran for")]
+                worst = 0.0
+                for la, lb in zip(a[1:], b[1:]):
+                    for x, y in zip(la.split("\t")[1:2], lb.split("\t")[1:2]):
+                        worst = max(worst, abs(float(x) - float(y)) / max(abs(float(x)), 1e-300))
                 cli = {"ours_wall_s": wall2, "reference_wall_s": wall, "wall_ratio": wall / wall2, "same_parameter_lines": a == b,
+                       "worst_rel_diff_of_printed_estimates": worst if len(a) == len(b) else None,
                        "ours_em": em2[0] if em2 else None,
                        "what": "eqtlbma_b200/eqtlbma_hm vs oracle/_ref/eqtlbma_hm_ref on the same `_l10abfs_raw.txt.gz` file, "
                                "classical EM, parameter lines of the two output files compared as text"}
