@@ -294,21 +294,26 @@ def run_perm_block(eqtlbma_b200, rank, local_rank, fp64, with_cpu, n_genes=None,
     return out
 
 
-def run_hm_block(eqtlbma_b200, local_rank, hbm_gbs, with_cpu, n_genes=10000, snps=(50, 150)):
+def run_hm_block(eqtlbma_b200, local_rank, hbm_gbs, with_cpu, n_genes=10000, snps=(50, 150), rank=0, world=1, dist=None):
     """the EM of the hierarchical model (eqtlbma_hm --model configs) on raw ABFs resident in HBM.
     Dominant kernel hm_estep_kernel: one streaming pass over B[pairs][7][10] per fixed-point iteration (algorithmic bytes =
     8 * pairs * dim * grid, read once), HBM-bound.  CPU arm: the unmodified reference eqtlbma_hm (oracle/_ref) with
     --thread = host cores on the first genes of the same data written as `_l10abfs_raw.txt.gz`, its own `EM ran for`
-    clock (whole seconds) falling back to wall clock minus a --maxit 2 run of the same files."""
+    clock (whole seconds) falling back to wall clock minus a --maxit 2 run of the same files.
+    N > 1 (weak scaling): every rank holds its own 10,000 genes of ONE model; the sums over genes of every evaluation are
+    all-gathered over NCCL (eqb_hm_set_collective: 2 + dim + grid doubles per rank and evaluation) -- the one real exchange
+    step of this repo's paths."""
     import time
     from eqtlbma_b200.hm import HmEngine, HmFit
     from eqtlbma_b200.hm_synth import make_hm_dataset
-    ds = make_hm_dataset(seed=1861, n_genes=n_genes, snps_lo=snps[0], snps_hi=snps[1], n_subgroups=3, grid=10, round_text=False)
+    ds = make_hm_dataset(seed=1861 + rank, n_genes=n_genes, snps_lo=snps[0], snps_hi=snps[1], n_subgroups=3, grid=10, round_text=False)
     t0 = time.perf_counter()
     hm = HmEngine(ds.dim, ds.grid, device=local_rank)
     hm.append(ds.B, ds.gene_off)
     hm.finalize()
     t_load = time.perf_counter() - t0
+    if world > 1:
+        hm.set_collective()
     gw, cp = np.full(ds.grid, 1.0 / ds.grid), np.full(ds.dim, 1.0 / ds.dim)
     hm.estep_device_only(gw, cp, reps=3)
     ms = hm.estep_device_only(gw, cp, reps=20)
@@ -319,13 +324,27 @@ def run_hm_block(eqtlbma_b200, local_rank, hbm_gbs, with_cpu, n_genes=10000, snp
            "roofline": {"bound": "hbm", "kernel": "hm_estep_kernel", "kernel_ms": ms, "algorithmic_bytes_per_launch": alg,
                         "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                         "frac": alg / (ms * 1e-3) / 1e9 / hbm_gbs, "traffic": None}}
+    tot_pairs = float(ds.n_pairs)
+    if world > 1:
+        import torch
+        c = torch.tensor([tot_pairs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        tot_pairs = float(c[0])
+        out["n_gpus"], out["pairs_all_ranks"] = world, tot_pairs
+        out["collective"] = "all-gather of %d doubles per rank and evaluation (NCCL), combined in rank order" % (2 + ds.dim + ds.grid)
     for label, msl in (("classic", 1.0), ("squarem", 3.0)):
         l0 = hm.launch_count
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         fit = hm.em(HmFit(0.5, gw, cp), thresh=0.05, stepmax=msl)
         dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
         n_lines = len([ln for ln in fit.log_lines if ln.startswith("iter ")])
-        out[label] = {"em_s": dt, "likelihood_evaluations": n_lines, "pairs_iterations_per_s": ds.n_pairs * n_lines / dt,
+        out[label] = {"em_s": dt, "likelihood_evaluations": n_lines, "pairs_iterations_per_s": tot_pairs * n_lines / dt,
                       "loglik": fit.loglik, "pi0": fit.pi0, "gpu_launches": hm.launch_count - l0}
     hm.close()
     if with_cpu:
@@ -578,6 +597,11 @@ def run_ours(args, rank, world, local_rank):
         perm_info = run_perm_block(eqtlbma_b200, rank, local_rank, fp64, with_cpu=(world == 1 and not args.no_cpu),
                                    n_genes=args.perm_genes or None, nperm=args.perm_nperm or None)
 
+    hm_info = None
+    if not args.no_hm:
+        hm_info = run_hm_block(eqtlbma_b200, local_rank, peaks()[0]["hbm_gbs"], with_cpu=(world == 1 and not args.no_cpu),
+                               rank=rank, world=world, dist=dist)
+
     # ---- max over ranks, whole-job aggregate
     tot_pairs = pairs
     digests = [digest]
@@ -658,8 +682,8 @@ def run_ours(args, rank, world, local_rank):
         out["value_u16_resident"] = fx_info
     if perm_info:
         out["perm"] = perm_info
-    if world == 1 and not args.no_hm:
-        out["hm"] = run_hm_block(eqtlbma_b200, local_rank, pk["hbm_gbs"], not args.no_cpu)
+    if hm_info:
+        out["hm"] = hm_info
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_reference(ds, sample_genes=args.cpu_genes)
         par = parity_vs_reference(ds, eng, full, args.cpu_genes)

@@ -50,6 +50,12 @@ struct eqb_hm_ctx {
   long long launches = 0, heavy_passes = 0;
   int estep_ctas = 0; // resident CTAs of hm_estep_kernel on this device (persistent grid)
   int *d_counter = nullptr;
+  // multi-GPU: genes sharded over ranks, partial sums exchanged through the caller's all-gather (eqb_hm_set_collective)
+  int world = 1, rank = 0;
+  eqb_hm_allgather_fn gather = nullptr;
+  void *gather_user = nullptr;
+  double total_genes = 0; // over all ranks
+  std::vector<double> gather_buf;
   bool ranged = false; // every value within +-1e6 (hm_check_kernel): unclamped exponentials of differences
 };
 
@@ -314,6 +320,44 @@ static int heavy(eqb_hm_ctx *hm, const double *gw, const double *cfg, bool want_
 
 static bool same_vec(const std::vector<double> &a, const double *b, size_t n) { return a.size() == n && memcmp(a.data(), b, n * 8) == 0; }
 
+// partial results of the ranks -> totals, in rank order (deterministic): entries 0 and 1 are plain sums (log-likelihood, pi0
+// sum), the others log10 of sums (NaN propagates, -inf = empty)
+static void combine_partials(const double *gathered, int world, int n, double *out)
+{
+  for (int j = 0; j < n; ++j) {
+    if (j < 2) {
+      double acc = 0.0;
+      for (int r = 0; r < world; ++r) acc += gathered[(size_t)r * n + j];
+      out[j] = acc;
+      continue;
+    }
+    double mx = -INFINITY;
+    bool bad = false;
+    for (int r = 0; r < world; ++r) {
+      const double v = gathered[(size_t)r * n + j];
+      bad = bad || (v != v);
+      mx = fmax(mx, v);
+    }
+    if (bad)
+      out[j] = NAN;
+    else if (!(mx > -INFINITY) || std::isinf(mx))
+      out[j] = mx;
+    else {
+      double acc = 0.0;
+      for (int r = 0; r < world; ++r) acc += pow(10.0, gathered[(size_t)r * n + j] - mx);
+      out[j] = mx + log10(acc);
+    }
+  }
+}
+static int exchange(eqb_hm_ctx *hm, double *v, size_t n)
+{
+  if (hm->world <= 1 || !hm->gather) return 0;
+  hm->gather_buf.resize((size_t)hm->world * n);
+  if (hm->gather(hm->gather_user, v, hm->gather_buf.data(), (int32_t)n) != 0) return fail(hm, 7, "eqb_hm: the all-gather callback failed");
+  combine_partials(hm->gather_buf.data(), hm->world, (int)n, v);
+  return 0;
+}
+
 // compute_log10_obs_lik; with keep, the E-step sums of the same parameters are produced in the same breath and cached
 static int loglik(eqb_hm_ctx *hm, double pi0, const double *gw, const double *cfg, bool keep, double *out)
 {
@@ -333,6 +377,7 @@ static int loglik(eqb_hm_ctx *hm, double pi0, const double *gw, const double *cf
   HCK(cudaGetLastError());
   HCK(cudaMemcpyAsync(hm->h_out, hm->d_out, n_out * 8, cudaMemcpyDeviceToHost, hm->stream));
   HCK(cudaStreamSynchronize(hm->stream));
+  if ((rc = exchange(hm, hm->h_out, n_out))) return rc;
   *out = hm->h_out[0];
   if (keep) {
     hm->sums_pi0 = pi0;
@@ -363,6 +408,8 @@ static int esums(eqb_hm_ctx *hm, double pi0, const double *gw, const double *cfg
   HCK(cudaGetLastError());
   HCK(cudaMemcpyAsync(hm->h_out, hm->d_out, (n + 1) * 8, cudaMemcpyDeviceToHost, hm->stream));
   HCK(cudaStreamSynchronize(hm->stream));
+  hm->h_out[0] = 0.0; // (slot of the log-likelihood: not produced here)
+  if ((rc = exchange(hm, hm->h_out, n + 1))) return rc;
   memcpy(out, hm->h_out + 1, n * 8);
   return 0;
 }
@@ -396,7 +443,7 @@ struct Em {
   std::vector<double> gw, gw0, gw1, gw2, new_gw, cfg, cfg0, cfg1, cfg2, new_cfg, ones, sums;
   long long fixedpoints = 0;
 
-  Em(eqb_hm_ctx *h, const eqb_hm_options *opt) : hm(h), o(opt), dim(h->dim), grid(h->grid), G((double)(h->gene_off.size() - 1))
+  Em(eqb_hm_ctx *h, const eqb_hm_options *opt) : hm(h), o(opt), dim(h->dim), grid(h->grid), G(h->world > 1 ? h->total_genes : (double)(h->gene_off.size() - 1))
   {
     gw.assign(grid, NAN);
     gw0 = gw1 = gw2 = new_gw = gw;
@@ -659,6 +706,33 @@ bool usable_fit(eqb_hm_ctx *hm, const eqb_hm_fit *fit)
 } // namespace
 
 extern "C" {
+
+int eqb_hm_set_collective(eqb_hm_ctx *hm, int32_t world, int32_t rank, eqb_hm_allgather_fn fn, void *user)
+{
+  if (!hm) return 1;
+  if (!hm->finalized) return fail(hm, 2, "eqb_hm_set_collective: call eqb_hm_finalize() first");
+  if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return fail(hm, 2, "eqb_hm_set_collective: invalid arguments");
+  hm->world = world;
+  hm->rank = rank;
+  hm->gather = fn;
+  hm->gather_user = user;
+  hm->sums_valid = false;
+  hm->total_genes = (double)(hm->gene_off.size() - 1);
+  if (world > 1) {
+    double mine[2] = {hm->total_genes, 0.0};
+    int rc = exchange(hm, mine, 2); // (two plain sums)
+    if (rc) return rc;
+    hm->total_genes = mine[0];
+  }
+  return 0;
+}
+
+int eqb_hm_combine_partials(const double *gathered, int32_t world, int32_t n, double *out)
+{
+  if (!gathered || !out || world < 1 || n < 0) return 1;
+  combine_partials(gathered, world, n, out);
+  return 0;
+}
 
 int eqb_hm_loglik(eqb_hm_ctx *hm, double pi0, const double *grid_wts, const double *config_prior, int32_t keep, double *out)
 {

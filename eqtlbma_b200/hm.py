@@ -21,6 +21,7 @@ class _Fit(C.Structure):
 
 
 _LOGFN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
+_GATHERFN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32)
 
 
 def _dp(a):
@@ -90,6 +91,29 @@ class HmEngine:
 
     def finalize(self):
         self._check(self.lib.eqb_hm_finalize(self.ctx), "finalize")
+
+    def set_collective(self, group=None):
+        """Genes sharded over the ranks of a torch.distributed group: the partial sums of every likelihood / E-step
+        evaluation are all-gathered (NCCL on the context's device, or gloo on the host) and combined in rank order."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        on_gpu = dist.get_backend(group) == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+
+        def gather(user, send, recv, n):
+            try:
+                mine = torch.from_numpy(np.ctypeslib.as_array(send, shape=(n,)).copy()).to(dev)
+                parts = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(world)]
+                dist.all_gather(parts, mine, group=group)
+                np.ctypeslib.as_array(recv, shape=(world * n,))[:] = torch.stack(parts).cpu().numpy().ravel()
+                return 0
+            except Exception as exc:  # the C side reports the failure
+                print("eqb_hm all-gather failed:", exc)
+                return 1
+
+        self._gather_cb = _GATHERFN(gather)
+        self._check(self.lib.eqb_hm_set_collective(self.ctx, C.c_int32(world), C.c_int32(rank), self._gather_cb, None), "set_collective")
 
     n_genes = property(lambda self: int(self.lib.eqb_hm_n_genes(self.ctx)))
     n_pairs = property(lambda self: int(self.lib.eqb_hm_n_pairs(self.ctx)))

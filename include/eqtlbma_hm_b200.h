@@ -44,6 +44,16 @@ int eqb_hm_finalize(eqb_hm_ctx *hm);
 int64_t eqb_hm_n_genes(const eqb_hm_ctx *hm);
 int64_t eqb_hm_n_pairs(const eqb_hm_ctx *hm);
 
+/* Multi-GPU: the genes are sharded over `world` processes (one per GPU), every rank holding whole genes.  The one exchange
+ * step of the EM is the sum over genes (eqtlbma_hm.cpp:625-633, 659-868: the OpenMP reductions of the reference): each
+ * likelihood / E-step evaluation all-gathers 2 + dim + grid doubles per rank through `fn` (recv = [world][n] in rank order;
+ * e.g. torch.distributed.all_gather over NCCL) and combines them in rank order, so every rank takes identical decisions.
+ * Call after eqb_hm_finalize on every rank; eqb_hm_posteriors stays local (the genes of the rank).
+ * eqb_hm_combine_partials is the host-side combination itself (entries 0-1 sums, the others log10 of sums). */
+typedef int (*eqb_hm_allgather_fn)(void *user, const double *send, double *recv, int32_t n);
+int eqb_hm_set_collective(eqb_hm_ctx *hm, int32_t world, int32_t rank, eqb_hm_allgather_fn fn, void *user);
+int eqb_hm_combine_partials(const double *gathered, int32_t world, int32_t n, double *out);
+
 /* Controller::compute_log10_obs_lik (eqtlbma_hm.cpp:617-650): sum over genes of log10(pi0 + (1 - pi0) BF_g) with
  * BF_g the average over SNPs, configurations (config_prior[dim]) and grid points (grid_wts[grid]).  keep != 0 stores the
  * per-gene values the E-step and the posteriors read (the reference's `keep`). */
