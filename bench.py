@@ -375,7 +375,9 @@ def cpu_baseline_hm(ds, sample_genes=1000):
             return {"unavailable": "reference eqtlbma_hm failed: " + r.stderr[-200:]}
         n_lines = len([ln for ln in r.stdout.splitlines() if ln.startswith("iter ")])
         t0 = time.perf_counter()
-        subprocess.run(base + ["--maxit", "2"], capture_output=True, text=True, cwd=tmp)
+        short = list(base)
+        short[short.index(os.path.join(tmp, "o.txt.gz"))] = os.path.join(tmp, "o_short.txt.gz")
+        subprocess.run(short + ["--maxit", "2"], capture_output=True, text=True, cwd=tmp)
         wall1 = time.perf_counter() - t0
         r1_lines = 3  # iteration 0, one fixed point, the closing fixed point
         em_s = max(wall - wall1, 1e-3)
