@@ -331,7 +331,9 @@ def run_hm_block(eqtlbma_b200, local_rank, hbm_gbs, with_cpu, n_genes=10000, snp
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         tot_pairs = float(c[0])
         out["n_gpus"], out["pairs_all_ranks"] = world, tot_pairs
-        out["collective"] = "all-gather of %d doubles per rank and evaluation (NCCL), combined in rank order" % (2 + ds.dim + ds.grid)
+        out["collective"] = ("hm_xchg_kernel: %d doubles per rank and evaluation stored into every peer's buffer over NVLink (CUDA IPC "
+                             "peer memory), epoch flags, combined in rank order on the device; NCCL only carries the IPC handles and "
+                             "this block's timing reductions" % (2 + ds.dim + ds.grid))
     for label, msl in (("classic", 1.0), ("squarem", 3.0)):
         l0 = hm.launch_count
         if world > 1:

@@ -55,6 +55,14 @@ struct eqb_hm_ctx {
   eqb_hm_allgather_fn gather = nullptr;
   void *gather_user = nullptr;
   double total_genes = 0; // over all ranks
+  // native exchange over peer memory (eqb_hm_ipc_export / eqb_hm_ipc_connect): hm_xchg_kernel
+  bool native = false;
+  void *d_xchg = nullptr;
+  int xchg_cap = 0;
+  HmPeers peers{};
+  std::vector<void *> opened;
+  unsigned long long epoch = 0;
+  int *d_status = nullptr;
   std::vector<double> gather_buf;
   bool ranged = false; // every value within +-1e6 (hm_check_kernel): unclamped exponentials of differences
 };
@@ -148,7 +156,8 @@ void eqb_hm_destroy(eqb_hm_ctx *hm)
     cudaSetDevice(hm->device);
     cudaStreamSynchronize(hm->stream);
   }
-  void *ptrs[] = {hm->d_alloc, hm->d_counter, hm->d_unit_row0, hm->d_gene_unit0, hm->d_gene_off, hm->d_unit_rows, hm->d_U, hm->d_PA, hm->d_BF,
+  for (void *p : hm->opened) cudaIpcCloseMemHandle(p);
+  void *ptrs[] = {hm->d_xchg, hm->d_status, hm->d_alloc, hm->d_counter, hm->d_unit_row0, hm->d_gene_unit0, hm->d_gene_off, hm->d_unit_rows, hm->d_U, hm->d_PA, hm->d_BF,
                   hm->d_kept_lik, hm->d_kept_bf, hm->d_cfg, hm->d_gw, hm->d_out, hm->d_rowA, hm->d_snp};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -349,9 +358,30 @@ static void combine_partials(const double *gathered, int world, int n, double *o
     }
   }
 }
+// native mode: enqueue the peer-memory exchange of d_out[0..n) on the context's stream (before the read-back)
+static int exchange_device(eqb_hm_ctx *hm, size_t n)
+{
+  if (hm->world <= 1 || !hm->native) return 0;
+  if ((int)n > hm->xchg_cap) return fail(hm, 7, "eqb_hm: exchange of %zu values exceeds the buffer", n);
+  ++hm->epoch;
+  hm_xchg_kernel<<<1, 256, 0, hm->stream>>>(hm->peers, hm->world, hm->rank, (int)n, hm->xchg_cap, hm->epoch, hm->d_out, hm->d_status);
+  ++hm->launches;
+  HCK(cudaGetLastError());
+  return 0;
+}
+static int exchange_status(eqb_hm_ctx *hm)
+{
+  if (hm->world <= 1 || !hm->native) return 0;
+  int st = 0;
+  HCK(cudaMemcpyAsync(&st, hm->d_status, sizeof(int), cudaMemcpyDeviceToHost, hm->stream));
+  HCK(cudaStreamSynchronize(hm->stream));
+  if (st) return fail(hm, 7, "eqb_hm: a peer did not publish its partial sums within the time limit");
+  return 0;
+}
+
 static int exchange(eqb_hm_ctx *hm, double *v, size_t n)
 {
-  if (hm->world <= 1 || !hm->gather) return 0;
+  if (hm->world <= 1 || !hm->gather || hm->native) return 0;
   hm->gather_buf.resize((size_t)hm->world * n);
   if (hm->gather(hm->gather_user, v, hm->gather_buf.data(), (int32_t)n) != 0) return fail(hm, 7, "eqb_hm: the all-gather callback failed");
   combine_partials(hm->gather_buf.data(), hm->world, (int)n, v);
@@ -375,8 +405,10 @@ static int loglik(eqb_hm_ctx *hm, double pi0, const double *gw, const double *cf
     hm->sums_valid = false;
   }
   HCK(cudaGetLastError());
+  if ((rc = exchange_device(hm, n_out))) return rc;
   HCK(cudaMemcpyAsync(hm->h_out, hm->d_out, n_out * 8, cudaMemcpyDeviceToHost, hm->stream));
   HCK(cudaStreamSynchronize(hm->stream));
+  if ((rc = exchange_status(hm))) return rc;
   if ((rc = exchange(hm, hm->h_out, n_out))) return rc;
   *out = hm->h_out[0];
   if (keep) {
@@ -406,9 +438,12 @@ static int esums(eqb_hm_ctx *hm, double pi0, const double *gw, const double *cfg
   hm_sums_kernel<<<dim + grid + 1, 256, 0, hm->stream>>>(hm->d_PA, hm->d_kept_lik, G, dim + grid, pi0, hm->d_out);
   ++hm->launches;
   HCK(cudaGetLastError());
+  if (hm->native) HCK(cudaMemsetAsync(hm->d_out, 0, 8, hm->stream)); // (slot of the log-likelihood: not produced here)
+  if ((rc = exchange_device(hm, n + 1))) return rc;
   HCK(cudaMemcpyAsync(hm->h_out, hm->d_out, (n + 1) * 8, cudaMemcpyDeviceToHost, hm->stream));
   HCK(cudaStreamSynchronize(hm->stream));
-  hm->h_out[0] = 0.0; // (slot of the log-likelihood: not produced here)
+  if ((rc = exchange_status(hm))) return rc;
+  hm->h_out[0] = 0.0;
   if ((rc = exchange(hm, hm->h_out, n + 1))) return rc;
   memcpy(out, hm->h_out + 1, n * 8);
   return 0;
@@ -716,12 +751,71 @@ int eqb_hm_set_collective(eqb_hm_ctx *hm, int32_t world, int32_t rank, eqb_hm_al
   hm->rank = rank;
   hm->gather = fn;
   hm->gather_user = user;
+  hm->native = false;
   hm->sums_valid = false;
   hm->total_genes = (double)(hm->gene_off.size() - 1);
   if (world > 1) {
     double mine[2] = {hm->total_genes, 0.0};
     int rc = exchange(hm, mine, 2); // (two plain sums)
     if (rc) return rc;
+    hm->total_genes = mine[0];
+  }
+  return 0;
+}
+
+int eqb_hm_ipc_export(eqb_hm_ctx *hm, void *handle64)
+{
+  if (!hm || !handle64) return 1;
+  if (!hm->finalized) return fail(hm, 2, "eqb_hm_ipc_export: call eqb_hm_finalize() first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  HCK(cudaSetDevice(hm->device));
+  if (!hm->d_xchg) {
+    hm->xchg_cap = hm->dim + hm->grid + 2;
+    const size_t bytes = (size_t)HM_XCHG_DATA_OFF + (size_t)2 * HM_MAXWORLD * hm->xchg_cap * 8;
+    HCK(cudaMalloc(&hm->d_xchg, bytes));
+    HCK(cudaMemset(hm->d_xchg, 0, bytes));
+    HCK(cudaMalloc(&hm->d_status, sizeof(int)));
+    HCK(cudaMemset(hm->d_status, 0, sizeof(int)));
+    HCK(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  HCK(cudaIpcGetMemHandle(&h, hm->d_xchg));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int eqb_hm_ipc_connect(eqb_hm_ctx *hm, int32_t world, int32_t rank, const void *handles)
+{
+  if (!hm || !handles) return 1;
+  if (!hm->d_xchg) return fail(hm, 2, "eqb_hm_ipc_connect: call eqb_hm_ipc_export() first");
+  if (world < 1 || world > HM_MAXWORLD || rank < 0 || rank >= world) return fail(hm, 2, "eqb_hm_ipc_connect: world must be 1..%d", HM_MAXWORLD);
+  HCK(cudaSetDevice(hm->device));
+  const bool again = !hm->opened.empty() && hm->world == world && hm->rank == rank; // peers already mapped: switch back to native
+  for (int r = 0; r < world && !again; ++r) {
+    if (r == rank) {
+      hm->peers.base[r] = hm->d_xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char *>(handles) + (size_t)r * 64, 64);
+    void *p = nullptr;
+    HCK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    hm->opened.push_back(p);
+    hm->peers.base[r] = p;
+  }
+  hm->world = world;
+  hm->rank = rank;
+  hm->native = world > 1;
+  hm->sums_valid = false;
+  hm->total_genes = (double)(hm->gene_off.size() - 1);
+  if (world > 1) { // total number of genes: the first exchange (two plain sums)
+    double mine[2] = {hm->total_genes, 0.0};
+    HCK(cudaMemcpyAsync(hm->d_out, mine, 16, cudaMemcpyHostToDevice, hm->stream));
+    int rc = exchange_device(hm, 2);
+    if (rc) return rc;
+    HCK(cudaMemcpyAsync(mine, hm->d_out, 16, cudaMemcpyDeviceToHost, hm->stream));
+    HCK(cudaStreamSynchronize(hm->stream));
+    if ((rc = exchange_status(hm))) return rc;
     hm->total_genes = mine[0];
   }
   return 0;

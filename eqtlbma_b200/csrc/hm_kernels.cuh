@@ -470,6 +470,69 @@ __global__ void __launch_bounds__(128) hm_snp_kernel(const double *__restrict__ 
 }
 
 // bad[0]: non-finite values; bad[1]: finite values outside +-1e6 (the data set then takes the clamped exponentials)
+// ---- multi-GPU exchange over peer memory (NVLink / NVSwitch), one launch per evaluation, no host round trip:
+// every rank owns an exchange buffer  flags[2][HM_MAXWORLD] (u64 epochs) | data[2][world][cap] doubles  that its peers map
+// through CUDA IPC.  The kernel (one CTA) stores the rank's n partial results into slot [epoch & 1][rank] of EVERY rank's
+// buffer (remote stores), fences, publishes the epoch in every rank's flag (release, system scope), waits until all ranks
+// have published theirs here (acquire; bounded: ~20 s, then *status = 1), and combines the world x n values in rank order
+// into out[] -- every rank computes the same bits from the same values.  Double buffering by epoch parity is enough: a peer
+// reaches epoch e + 2 only after this rank has published e + 1, i.e. after it has finished reading e.
+constexpr int HM_MAXWORLD = 16;
+constexpr int HM_XCHG_DATA_OFF = 2 * HM_MAXWORLD * 8;
+struct HmPeers {
+  void *base[HM_MAXWORLD];
+};
+__device__ __forceinline__ double hm_combine_ranks(const double *src, int world, int cap, int j)
+{
+  if (j < 2) { // plain sums
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r) acc += __ldcg(src + (size_t)r * cap + j);
+    return acc;
+  }
+  double mx = -INFINITY;
+  bool bad = false;
+  for (int r = 0; r < world; ++r) {
+    const double v = __ldcg(src + (size_t)r * cap + j);
+    bad = bad || (v != v);
+    mx = fmax(mx, v);
+  }
+  if (bad) return nan("");
+  if (!(mx > -INFINITY) || isinf(mx)) return mx;
+  double acc = 0.0;
+  for (int r = 0; r < world; ++r) acc += exp10(__ldcg(src + (size_t)r * cap + j) - mx);
+  return mx + log10(acc);
+}
+__global__ void __launch_bounds__(256) hm_xchg_kernel(const HmPeers peers, int world, int rank, int n, int cap, unsigned long long epoch,
+                                                      double *__restrict__ out, int *__restrict__ status)
+{
+  const int par = (int)(epoch & 1ull);
+  for (int r = 0; r < world; ++r) {
+    double *dst = reinterpret_cast<double *>(static_cast<char *>(peers.base[r]) + HM_XCHG_DATA_OFF) + ((size_t)par * world + rank) * cap;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) dst[j] = out[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    unsigned long long *f = static_cast<unsigned long long *>(peers.base[threadIdx.x]) + par * HM_MAXWORLD + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+    const unsigned long long *mine = static_cast<const unsigned long long *>(peers.base[rank]) + par * HM_MAXWORLD + threadIdx.x;
+    const long long t0 = clock64();
+    while (true) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > 40000000000ll) { // about 20 s: a peer is gone
+        *status = 1;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  const double *src = reinterpret_cast<const double *>(static_cast<const char *>(peers.base[rank]) + HM_XCHG_DATA_OFF) + (size_t)par * world * cap;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) out[j] = hm_combine_ranks(src, world, cap, j);
+}
+
 __global__ void hm_check_kernel(const double *__restrict__ x, long long n, unsigned long long *__restrict__ bad)
 {
   unsigned long long c = 0, w = 0;

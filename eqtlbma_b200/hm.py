@@ -92,12 +92,24 @@ class HmEngine:
     def finalize(self):
         self._check(self.lib.eqb_hm_finalize(self.ctx), "finalize")
 
-    def set_collective(self, group=None):
-        """Genes sharded over the ranks of a torch.distributed group: the partial sums of every likelihood / E-step
-        evaluation are all-gathered (NCCL on the context's device, or gloo on the host) and combined in rank order."""
+    def set_collective(self, group=None, native=None):
+        """Genes sharded over the ranks of a torch.distributed group.  native (default on an NCCL group): the partial sums
+        of every evaluation are exchanged by hm_xchg_kernel over peer memory (eqb_hm_ipc_export / eqb_hm_ipc_connect; the
+        group only carries the 64-byte IPC handles once).  Otherwise they are all-gathered through the group (NCCL on the
+        context's device, or gloo on the host) and combined on the host in rank order."""
         import torch
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if native is None:
+            native = dist.get_backend(group) == "nccl"
+        if native:
+            mine = C.create_string_buffer(64)
+            self._check(self.lib.eqb_hm_ipc_export(self.ctx, mine), "ipc_export")
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(mine.raw), group=group)
+            blob = C.create_string_buffer(b"".join(handles), 64 * world)
+            self._check(self.lib.eqb_hm_ipc_connect(self.ctx, C.c_int32(world), C.c_int32(rank), blob), "ipc_connect")
+            return
         on_gpu = dist.get_backend(group) == "nccl"
         dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
 

@@ -53,6 +53,14 @@ int64_t eqb_hm_n_pairs(const eqb_hm_ctx *hm);
 typedef int (*eqb_hm_allgather_fn)(void *user, const double *send, double *recv, int32_t n);
 int eqb_hm_set_collective(eqb_hm_ctx *hm, int32_t world, int32_t rank, eqb_hm_allgather_fn fn, void *user);
 int eqb_hm_combine_partials(const double *gathered, int32_t world, int32_t n, double *out);
+/* The same exchange WITHOUT the host: every rank exports an exchange buffer (CUDA IPC handle, 64 bytes), the caller gathers
+ * the handles of all ranks (any transport: torch.distributed.all_gather_object, MPI, a file) and connects.  From then on
+ * each evaluation ends with one kernel (hm_xchg_kernel) that stores the rank's partial sums into every peer's buffer over
+ * NVLink / NVSwitch, publishes an epoch flag, waits for the peers' flags (bounded) and combines in rank order -- one
+ * launch instead of device -> host -> NCCL -> host.  One process per GPU on one node, world <= 16.  Call both after
+ * eqb_hm_finalize; every rank must have exported before any rank connects. */
+int eqb_hm_ipc_export(eqb_hm_ctx *hm, void *handle64);
+int eqb_hm_ipc_connect(eqb_hm_ctx *hm, int32_t world, int32_t rank, const void *handles /* [world][64] */);
 
 /* Controller::compute_log10_obs_lik (eqtlbma_hm.cpp:617-650): sum over genes of log10(pi0 + (1 - pi0) BF_g) with
  * BF_g the average over SNPs, configurations (config_prior[dim]) and grid points (grid_wts[grid]).  keep != 0 stores the

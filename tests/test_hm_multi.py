@@ -73,12 +73,25 @@ p0, p1 = int(ds.gene_off[lo]), int(ds.gene_off[hi])
 hm = HmEngine(ds.dim, ds.grid, device=rank)
 hm.append(ds.B[p0:p1], ds.gene_off[lo:hi + 1] - p0)
 hm.finalize()
-hm.set_collective()
 gw, cp = np.full(ds.grid, 1.0 / ds.grid), np.full(ds.dim, 1.0 / ds.dim)
-fits = {}
-for label, msl in (("classic", 1.0), ("squarem", 3.0)):
-    fits[label] = hm.em(HmFit(0.5, gw, cp), thresh=0.01, stepmax=msl)
-post = hm.posteriors(fits["classic"])
+fits, by_mode = {}, {}
+for native in (True, False):    # hm_xchg_kernel over peer memory, then the NCCL all-gather through the host callback
+    hm.set_collective(native=native)
+    for label, msl in (("classic", 1.0), ("squarem", 3.0)):
+        fits[label] = hm.em(HmFit(0.5, gw, cp), thresh=0.01, stepmax=msl)
+    by_mode[native] = dict(fits)
+for label in fits:   # the two transports combine the same values in the same order (device exp10/log10 vs host pow/log10)
+    a, b = by_mode[True][label], by_mode[False][label]
+    assert abs(a.loglik - b.loglik) <= 1e-12 * abs(a.loglik) and len(a.log_lines) == len(b.log_lines)
+    assert np.allclose(a.grid_wts, b.grid_wts, rtol=1e-10, atol=1e-15)
+hm.set_collective(native=True)
+fits = by_mode[True]
+post = hm.posteriors(hm.em(HmFit(0.5, gw, cp), thresh=0.01))
+# every rank holds bit-identical estimates (the combination runs in rank order on every rank)
+mine = torch.tensor([fits["squarem"].loglik, fits["squarem"].pi0] + list(fits["squarem"].grid_wts), dtype=torch.float64, device="cuda")
+both = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(both, mine)
+assert all(torch.equal(both[0], t) for t in both)
 if rank == 0:
     one = HmEngine(ds.dim, ds.grid, device=0)
     one.append(ds.B, ds.gene_off); one.finalize()
