@@ -61,13 +61,15 @@ struct HmArgs {
 // 10^y with the base folded into the constants (no y * ln 10 first): 2^(k/16) from the table times 10^g - 1 to g^4,
 // |g| <= log10(2)/32, relative error < 4e-11 + 7e-14 |y|/300 like exp10_tab16.  FPCLAMP: any y (-inf, NaN -> ~1e-300);
 // otherwise y must be finite with |y| < 1e7 (integer clamp of the binary exponent: results below 2^-1000 come out as ~1e-301)
-static __constant__ double HMK[6] = {
+static __constant__ double HMK[8] = {
     53.150849518197795,    // 0  16 log2(10)
     -0.018814374728998825, // 1  -log10(2) / 16
     2.302585092994046,     // 2  ln 10
     2.650949055239199,     // 3  ln^2 10 / 2
     2.034678592293476,     // 4  ln^3 10 / 6
-    1.171255148912267};    // 5  ln^4 10 / 24
+    1.171255148912267,     // 5  ln^4 10 / 24
+    3.321928094887362,     // 6  log2(10)
+    0.30102999566398120};  // 7  log10(2)
 template <bool FPCLAMP>
 __device__ __forceinline__ double hm_exp10(double y, const TabRef T)
 {
@@ -87,6 +89,11 @@ __device__ __forceinline__ double hm_exp10(double y, const TabRef T)
   const int e2 = FPCLAMP ? (k >> 4) : max(k >> 4, -1000);
   return __hiloint2double(__double2hiint(v) + (e2 << 20), __double2loint(v));
 }
+
+// 2^d for an integer d <= 0 (exact; 0 below the normal range)
+__device__ __forceinline__ double hm_pow2i(int d) { return (d < -1022) ? 0.0 : __hiloint2double((1023 + d) << 20, 0); }
+// the same for an integer-valued double d <= 0 (or -inf)
+__device__ __forceinline__ double hm_pow2d(double d) { return (d < -1022.0) ? 0.0 : __hiloint2double((1023 + (int)d) << 20, 0); }
 
 __device__ __forceinline__ void hm_mbar_init(uint32_t bar, uint32_t count)
 {
@@ -210,7 +217,8 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
     const int nxt = next_unit();
 #pragma unroll
     for (int l = 0; l < G; ++l) cs[l] = 0.0;
-    double mref = -INFINITY;
+    double mref = -INFINITY;   // (clamped variant) running reference of the column sums, log10 domain
+    int eref = -(1 << 28);     // (RANGED variant) the same as a binary exponent: sums are relative to 2^eref
 
     for (int i = 0; i < n_rounds; ++i, ++cnt) {
       const uint32_t st = cnt % (uint32_t)stages;
@@ -226,38 +234,76 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
           if (EXACT || l < grid) m = fmax(m, x[l]);
         const int k = small_dim ? 0 : (int)((r_first + lane) % dim);
         const double cfgk = small_dim ? cfg_fixed : __ldg(a.cfg + k);
-        // column reference: rescale the sums when this row raises it
-        const double d = m - mref; // +inf for the first row
-        double wc;
-        if (d > 0.0) {
-          const double sc = hm_exp10<true>(-d, T);
-#pragma unroll
-          for (int l = 0; l < G; ++l) cs[l] *= sc;
-          mref = m;
-          wc = cfgk;
-        } else
-          wc = cfgk * hm_exp10<!RANGED>(d, T);
-        double rs = 0.0;
-#pragma unroll
-        for (int l = 0; l < G; ++l)
-          if (EXACT || l < grid) {
-            const double e = hm_exp10<!RANGED>(x[l] - m, T);
-            rs = fma(a.gw[l], e, rs);
-            cs[l] = fma(wc, e, cs[l]);
-          }
-        const double ar = fma(log_tab16(rs, T), PGK[11], m); // a[p][k]; -inf for a zero sum, NaN for a negative one
-        if (a.rowA) a.rowA[row0 + r_first + lane] = ar;
-        // online log-sum-exp of a over the rows with this configuration
         const int slot = small_dim ? lane : k;
         double2 s = kst[slot];
-        if (ar != ar)
-          s = make_double2(ar, ar); // (negative weights of a SQUAREM proposal: the likelihood is NaN, as in the reference)
-        else if (ar > -INFINITY) {
-          const double dd = ar - s.x;
-          const bool up = dd > 0.0;
-          const double e = hm_exp10<true>(up ? -dd : dd, T);
-          s.y = up ? fma(s.y, e, 1.0) : s.y + e;
-          s.x = up ? ar : s.x;
+        if constexpr (RANGED) {
+          // Everything relative to a power of two: E = ceil(m log2 10), so 10^(x - mq) <= 1 with mq = E log10 2, and changes of
+          // reference (column sums, per-configuration sums) are exact exponent arithmetic -- no exponential for them and no
+          // logarithm per row (the row average a = mq + log10(rs) is only formed when the posterior pass stores it)
+          const int E = __double2int_ru(m * HMK[6]);
+          const double mq = (double)E * HMK[7];
+          const int dE = E - eref;
+          double wc;
+          if (dE > 0) {
+            const double sc = hm_pow2i(-dE);
+#pragma unroll
+            for (int l = 0; l < G; ++l) cs[l] *= sc;
+            eref = E;
+            wc = cfgk;
+          } else
+            wc = cfgk * hm_pow2i(dE);
+          double rs = 0.0;
+#pragma unroll
+          for (int l = 0; l < G; ++l)
+            if (EXACT || l < grid) {
+              const double e = hm_exp10<false>(x[l] - mq, T);
+              rs = fma(a.gw[l], e, rs);
+              cs[l] = fma(wc, e, cs[l]);
+            }
+          if (a.rowA) a.rowA[row0 + r_first + lane] = fma(log_tab16(rs, T), PGK[11], mq);
+          // sum over the rows of this configuration of rs 2^E: state = (exponent as a double, sum relative to it)
+          if (!(rs >= 0.0))
+            s = make_double2(nan(""), nan("")); // (negative weights of a SQUAREM proposal: the reference's log10 is NaN)
+          else if (rs > 0.0 && s.x == s.x) {
+            const double Ed = (double)E, dd = Ed - s.x; // +inf for the first row
+            if (dd > 0.0) {
+              s.y = fma(s.y, hm_pow2d(-dd), rs);
+              s.x = Ed;
+            } else
+              s.y = fma(rs, hm_pow2d(dd), s.y);
+          }
+        } else {
+          // column reference: rescale the sums when this row raises it
+          const double d = m - mref; // +inf for the first row
+          double wc;
+          if (d > 0.0) {
+            const double sc = hm_exp10<true>(-d, T);
+#pragma unroll
+            for (int l = 0; l < G; ++l) cs[l] *= sc;
+            mref = m;
+            wc = cfgk;
+          } else
+            wc = cfgk * hm_exp10<true>(d, T);
+          double rs = 0.0;
+#pragma unroll
+          for (int l = 0; l < G; ++l)
+            if (EXACT || l < grid) {
+              const double e = hm_exp10<true>(x[l] - m, T);
+              rs = fma(a.gw[l], e, rs);
+              cs[l] = fma(wc, e, cs[l]);
+            }
+          const double ar = fma(log_tab16(rs, T), PGK[11], m); // a[p][k]; -inf for a zero sum, NaN for a negative one
+          if (a.rowA) a.rowA[row0 + r_first + lane] = ar;
+          // online log-sum-exp of a over the rows with this configuration
+          if (ar != ar)
+            s = make_double2(ar, ar); // (negative weights of a SQUAREM proposal: the likelihood is NaN, as in the reference)
+          else if (ar > -INFINITY) {
+            const double dd = ar - s.x;
+            const bool up = dd > 0.0;
+            const double e = hm_exp10<true>(up ? -dd : dd, T);
+            s.y = up ? fma(s.y, e, 1.0) : s.y + e;
+            s.x = up ? ar : s.x;
+          }
         }
         kst[slot] = s;
       }
@@ -278,9 +324,22 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
 
     // ---- merge over the lanes: columns (lane l keeps column l) ...
     double *Uu = a.U + (size_t)cur * (dim + grid);
-    {
+    if constexpr (RANGED) {
+      int EM = eref;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) EM = max(EM, __shfl_xor_sync(0xffffffffu, EM, o));
+      const double fac = hm_pow2i(eref - EM); // (0 for a lane that saw no row)
+      double mine = 0.0;
+#pragma unroll
+      for (int l = 0; l < G; ++l)
+        if (EXACT || l < grid) {
+          const double v = hm_warp_sum(cs[l] * fac);
+          if (lane == l) mine = v;
+        }
+      if (lane < grid) Uu[dim + lane] = (mine == 0.0) ? -INFINITY : fma((double)EM, HMK[7], log10(mine)); // (NaN sums stay NaN)
+    } else {
       const double M = hm_warp_max(mref);
-      const double fac = (mref > -INFINITY) ? exp10_tab16<true>(mref - M, T) : 0.0;
+      const double fac = (mref > -INFINITY) ? hm_exp10<true>(mref - M, T) : 0.0;
       double mine = 0.0;
 #pragma unroll
       for (int l = 0; l < G; ++l)
@@ -302,9 +361,12 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
       double sum = 0.0;
       for (int j = 0; j < q; ++j) {
         const double2 s = kst[j * dim + k];
-        if (s.x > -INFINITY) sum += s.y * exp10(s.x - MM);
+        if (s.x > -INFINITY) sum += RANGED ? s.y * hm_pow2d(s.x - MM) : s.y * exp10(s.x - MM);
       }
-      Uu[k] = bad ? nan("") : ((sum == 0.0) ? -INFINITY : MM + log10(sum));
+      if (RANGED)
+        Uu[k] = bad ? nan("") : ((sum == 0.0) ? -INFINITY : fma(MM, HMK[7], log10(sum)));
+      else
+        Uu[k] = bad ? nan("") : ((sum == 0.0) ? -INFINITY : MM + log10(sum));
     }
     __syncwarp();
     for (int i = lane; i < nslot; i += 32) kst[i] = make_double2(-INFINITY, 0.0);
