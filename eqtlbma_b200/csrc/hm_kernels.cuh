@@ -87,7 +87,8 @@ __device__ __forceinline__ double hm_exp10(double y, const TabRef T)
   const double tj = T.exp16(k & 15);
   const double v = fma(tj * g, s, tj);
   const int e2 = FPCLAMP ? (k >> 4) : max(k >> 4, -1000);
-  return __hiloint2double(__double2hiint(v) + (e2 << 20), __double2loint(v));
+  // the binary exponent is added on the 64-bit pattern (one integer add on the high word, no register shuffling)
+  return __longlong_as_double(__double_as_longlong(v) + ((long long)e2 << 52));
 }
 
 // 2^d for an integer d <= 0 (exact; 0 below the normal range)
@@ -182,14 +183,13 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
   const long long row_bytes = (long long)grid * 8;
   const int q = small_dim ? rpr / dim : 1;
 
-  // round i of the unit starting at row0 into the stage of pipeline slot `slot` (lane 0)
-  auto issue = [&](long long row0, int nrows, int i, uint32_t slot) {
+  // round i of the unit starting at row0 into stage st (lane 0)
+  auto issue = [&](long long row0, int nrows, int i, uint32_t st) {
     const int r_first = i * rpr;
     const int nr = min(rpr, nrows - r_first);
     const long long off = (row0 + r_first) * row_bytes;
     const int shift = (int)(off & 15);
     const uint32_t bytes = (uint32_t)((shift + nr * (int)row_bytes + 15) & ~15);
-    const uint32_t st = slot % (uint32_t)stages;
     hm_mbar_expect_tx(bars + 8 * st, bytes);
     hm_bulk_load(stg_u32 + st * (uint32_t)stage_bytes, a.B + (off - shift), bytes, bars + 8 * st);
   };
@@ -199,10 +199,17 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
     return __shfl_sync(0xffffffffu, u, 0);
   };
 
-  // persistent warps: the pipeline slots of a warp are numbered consecutively across its units (cnt), so stage = cnt % stages
-  // and the mbarrier parity = (cnt / stages) & 1 throughout; the first rounds of the next unit are issued before the current
-  // one is merged
-  uint32_t cnt = 0;
+  // persistent warps: the pipeline slots of a warp are used consecutively across its units, so the stage index st_cur cycles
+  // through 0 .. stages - 1 and the mbarrier parity ph_cur flips at every wrap, throughout; the first rounds of the next unit
+  // are issued before the current one is merged
+  uint32_t st_cur = 0, ph_cur = 0;
+  auto issue_first = [&](long long row0, int nrows, int n_rounds) { // the first rounds of a unit, from the current stage on
+    uint32_t st = st_cur;
+    for (int i = 0; i < stages && i < n_rounds; ++i) {
+      issue(row0, nrows, i, st);
+      st = (st + 1 == (uint32_t)stages) ? 0u : st + 1;
+    }
+  };
   int unit = next_unit();
   long long row0 = 0;
   int nrows = 0, n_rounds = 0;
@@ -210,8 +217,7 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
     row0 = a.unit_row0[unit];
     nrows = a.unit_rows[unit];
     n_rounds = (nrows + rpr - 1) / rpr;
-    if (lane == 0)
-      for (int i = 0; i < stages && i < n_rounds; ++i) issue(row0, nrows, i, cnt + i);
+    if (lane == 0) issue_first(row0, nrows, n_rounds);
   }
   while (unit < a.n_units) {
     const int nxt = next_unit();
@@ -220,18 +226,40 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
     double mref = -INFINITY;   // (clamped variant) running reference of the column sums, log10 domain
     int eref = -(1 << 28);     // (RANGED variant) the same as a binary exponent: sums are relative to 2^eref
 
-    for (int i = 0; i < n_rounds; ++i, ++cnt) {
-      const uint32_t st = cnt % (uint32_t)stages;
-      hm_mbar_wait(bars + 8 * st, (cnt / (uint32_t)stages) & 1u);
+    for (int i = 0; i < n_rounds; ++i) {
+      const uint32_t st = st_cur;
+      hm_mbar_wait(bars + 8 * st, ph_cur);
+      if (++st_cur == (uint32_t)stages) {
+        st_cur = 0;
+        ph_cur ^= 1u;
+      }
       const int r_first = i * rpr;
       const int nr = min(rpr, nrows - r_first);
       if (lane < nr) {
         const long long off = (row0 + r_first) * row_bytes;
         const double *x = reinterpret_cast<const double *>(stg + (size_t)st * stage_bytes + (int)(off & 15)) + (size_t)lane * grid;
-        double m = x[0];
+        // even compile-time grids: a row starts on a 16-byte boundary (row_bytes is a multiple of 16) and is read ONCE with
+        // 128-bit loads (conflict-free at a lane stride of 80 bytes, where 64-bit loads conflict two ways); otherwise the two
+        // passes below read the row from shared memory
+        constexpr bool CACHE = EXACT && (G % 2 == 0) && G <= 16;
+        double xr[CACHE ? G : 1];
+        if constexpr (CACHE) {
+          const double2 *x2 = reinterpret_cast<const double2 *>(x);
+#pragma unroll
+          for (int l = 0; l < G / 2; ++l) {
+            const double2 v = x2[l];
+            xr[2 * l] = v.x;
+            xr[2 * l + 1] = v.y;
+          }
+        }
+#define HM_X(l) (CACHE ? xr[CACHE ? (l) : 0] : x[l])
+        double m = HM_X(0); // (the data are finite, checked at load: a compare-and-select maximum, without fmax()'s NaN handling)
 #pragma unroll
         for (int l = 1; l < G; ++l)
-          if (EXACT || l < grid) m = fmax(m, x[l]);
+          if (EXACT || l < grid) {
+            const double v = HM_X(l);
+            m = (v > m) ? v : m;
+          }
         const int k = small_dim ? 0 : (int)((r_first + lane) % dim);
         const double cfgk = small_dim ? cfg_fixed : __ldg(a.cfg + k);
         const int slot = small_dim ? lane : k;
@@ -256,7 +284,7 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
 #pragma unroll
           for (int l = 0; l < G; ++l)
             if (EXACT || l < grid) {
-              const double e = hm_exp10<false>(x[l] - mq, T);
+              const double e = hm_exp10<false>(HM_X(l) - mq, T);
               rs = fma(a.gw[l], e, rs);
               cs[l] = fma(wc, e, cs[l]);
             }
@@ -288,7 +316,7 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
 #pragma unroll
           for (int l = 0; l < G; ++l)
             if (EXACT || l < grid) {
-              const double e = hm_exp10<true>(x[l] - m, T);
+              const double e = hm_exp10<true>(HM_X(l) - m, T);
               rs = fma(a.gw[l], e, rs);
               cs[l] = fma(wc, e, cs[l]);
             }
@@ -306,9 +334,10 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
           }
         }
         kst[slot] = s;
+#undef HM_X
       }
       __syncwarp();
-      if (lane == 0 && i + stages < n_rounds) issue(row0, nrows, i + stages, cnt + (uint32_t)stages);
+      if (lane == 0 && i + stages < n_rounds) issue(row0, nrows, i + stages, st); // the stage just consumed
     }
 
     // ---- next unit: its first rounds travel while this one is merged (every stage of the warp is free here)
@@ -318,8 +347,7 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
       row0 = a.unit_row0[unit];
       nrows = a.unit_rows[unit];
       n_rounds = (nrows + rpr - 1) / rpr;
-      if (lane == 0)
-        for (int i = 0; i < stages && i < n_rounds; ++i) issue(row0, nrows, i, cnt + (uint32_t)i);
+      if (lane == 0) issue_first(row0, nrows, n_rounds);
     }
 
     // ---- merge over the lanes: columns (lane l keeps column l) ...
