@@ -50,6 +50,8 @@ struct eqb_hm_ctx {
   long long launches = 0, heavy_passes = 0;
   int estep_ctas = 0; // resident CTAs of hm_estep_kernel on this device (persistent grid)
   int *d_counter = nullptr;
+  double *d_lik_partial = nullptr; // per-CTA partial sums of hm_lik_kernel
+  unsigned int *d_ticket = nullptr;
   // multi-GPU: genes sharded over ranks, partial sums exchanged through the caller's all-gather (eqb_hm_set_collective)
   int world = 1, rank = 0;
   eqb_hm_allgather_fn gather = nullptr;
@@ -157,7 +159,7 @@ void eqb_hm_destroy(eqb_hm_ctx *hm)
     cudaStreamSynchronize(hm->stream);
   }
   for (void *p : hm->opened) cudaIpcCloseMemHandle(p);
-  void *ptrs[] = {hm->d_xchg, hm->d_status, hm->d_alloc, hm->d_counter, hm->d_unit_row0, hm->d_gene_unit0, hm->d_gene_off, hm->d_unit_rows, hm->d_U, hm->d_PA, hm->d_BF,
+  void *ptrs[] = {hm->d_xchg, hm->d_status, hm->d_alloc, hm->d_counter, hm->d_lik_partial, hm->d_ticket, hm->d_unit_row0, hm->d_gene_unit0, hm->d_gene_off, hm->d_unit_rows, hm->d_U, hm->d_PA, hm->d_BF,
                   hm->d_kept_lik, hm->d_kept_bf, hm->d_cfg, hm->d_gw, hm->d_out, hm->d_rowA, hm->d_snp};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -256,6 +258,9 @@ int eqb_hm_finalize(eqb_hm_ctx *hm)
   const int nout = dim + grid;
   HCK(cudaMalloc(&hm->d_unit_row0, hm->n_units * 8));
   HCK(cudaMalloc(&hm->d_counter, sizeof(int)));
+  HCK(cudaMalloc(&hm->d_lik_partial, (size_t)((G + HM_LIK_THREADS - 1) / HM_LIK_THREADS) * 8));
+  HCK(cudaMalloc(&hm->d_ticket, sizeof(unsigned int)));
+  HCK(cudaMemsetAsync(hm->d_ticket, 0, sizeof(unsigned int), hm->stream));
   HCK(cudaMalloc(&hm->d_unit_rows, hm->n_units * 4));
   HCK(cudaMalloc(&hm->d_gene_unit0, (G + 1) * 8));
   HCK(cudaMalloc(&hm->d_gene_off, (G + 1) * 8));
@@ -319,7 +324,7 @@ static int heavy(eqb_hm_ctx *hm, const double *gw, const double *cfg, bool want_
   hm->args.rowA = want_rows ? hm->d_rowA : nullptr;
   HCK(launch_estep(hm));
   hm->args.rowA = nullptr;
-  hm_gene_kernel<<<(unsigned)G, 128, 0, hm->stream>>>(hm->d_U, hm->d_gene_unit0, hm->d_gene_off, dim, grid, G, hm->d_gw, hm->d_PA, hm->d_BF);
+  hm_gene_kernel<<<(unsigned)((G + HM_GENE_WARPS - 1) / HM_GENE_WARPS), HM_GENE_WARPS * 32, 0, hm->stream>>>(hm->d_U, hm->d_gene_unit0, hm->d_gene_off, dim, grid, G, hm->d_gw, hm->d_PA, hm->d_BF);
   ++hm->launches;
   ++hm->heavy_passes;
   HCK(cudaGetLastError());
@@ -395,11 +400,12 @@ static int loglik(eqb_hm_ctx *hm, double pi0, const double *gw, const double *cf
   const long long G = (long long)hm->gene_off.size() - 1;
   int rc = heavy(hm, gw, cfg, false);
   if (rc) return rc;
-  hm_lik_kernel<<<1, 1024, 0, hm->stream>>>(hm->d_BF, G, pi0, keep ? 1 : 0, hm->d_kept_lik, hm->d_kept_bf, hm->d_out);
+  hm_lik_kernel<<<(unsigned)((G + HM_LIK_THREADS - 1) / HM_LIK_THREADS), HM_LIK_THREADS, 0, hm->stream>>>(hm->d_BF, G, pi0, keep ? 1 : 0, hm->d_kept_lik, hm->d_kept_bf,
+                                                                                                         hm->d_lik_partial, hm->d_ticket, hm->d_out);
   ++hm->launches;
   size_t n_out = 1;
   if (keep) {
-    hm_sums_kernel<<<dim + grid + 1, 256, 0, hm->stream>>>(hm->d_PA, hm->d_kept_lik, G, dim + grid, pi0, hm->d_out);
+    hm_sums_kernel<<<dim + grid + 1, HM_SUMS_THREADS, 0, hm->stream>>>(hm->d_PA, hm->d_kept_lik, G, dim + grid, pi0, hm->d_out);
     ++hm->launches;
     n_out = (size_t)dim + grid + 2;
     hm->sums_valid = false;
@@ -435,7 +441,7 @@ static int esums(eqb_hm_ctx *hm, double pi0, const double *gw, const double *cfg
   // SQUAREM extrapolation, eqtlbma_hm.cpp:1296-1307): heavy pass for these parameters, sums with the kept values
   int rc = heavy(hm, gw, cfg, false);
   if (rc) return rc;
-  hm_sums_kernel<<<dim + grid + 1, 256, 0, hm->stream>>>(hm->d_PA, hm->d_kept_lik, G, dim + grid, pi0, hm->d_out);
+  hm_sums_kernel<<<dim + grid + 1, HM_SUMS_THREADS, 0, hm->stream>>>(hm->d_PA, hm->d_kept_lik, G, dim + grid, pi0, hm->d_out);
   ++hm->launches;
   HCK(cudaGetLastError());
   if (hm->native) HCK(cudaMemsetAsync(hm->d_out, 0, 8, hm->stream)); // (slot of the log-likelihood: not produced here)

@@ -402,17 +402,23 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
   }
 }
 
-// per gene: merge its units, subtract log10 m_g; PA is output-major [dim + grid][n_genes]
-__global__ void __launch_bounds__(128) hm_gene_kernel(const double *__restrict__ U, const long long *__restrict__ gene_unit0,
-                                                     const long long *__restrict__ gene_off, int dim, int grid, long long n_genes,
-                                                     const double *__restrict__ gw, double *__restrict__ PA, double *__restrict__ BF)
+// per gene: merge its units, subtract log10 m_g; PA is output-major [dim + grid][n_genes].  One WARP per gene (lane = output
+// j, j + 32, ...), HM_GENE_WARPS genes per CTA: most genes have one or two units and dim + grid <= 32 outputs
+constexpr int HM_GENE_WARPS = 8;
+__global__ void __launch_bounds__(HM_GENE_WARPS * 32) hm_gene_kernel(const double *__restrict__ U, const long long *__restrict__ gene_unit0,
+                                                                    const long long *__restrict__ gene_off, int dim, int grid, long long n_genes,
+                                                                    const double *__restrict__ gw, double *__restrict__ PA, double *__restrict__ BF)
 {
-  __shared__ double gd[HM_MAXGRID];
-  const long long g = blockIdx.x;
+  const long long g = (long long)blockIdx.x * HM_GENE_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= n_genes) return;
   const long long u0 = gene_unit0[g], u1 = gene_unit0[g + 1];
   const double l10m = log10((double)(gene_off[g + 1] - gene_off[g]));
   const int nout = dim + grid;
-  for (int j = threadIdx.x; j < nout; j += blockDim.x) {
+  // BF_g = log10 sum_l lambda_l 10^Gd[l]
+  double bf_max = -INFINITY;
+  bool bf_bad = false;
+  for (int j = lane; j < nout; j += 32) {
     double MM = -INFINITY;
     bool bad = false;
     for (long long u = u0; u < u1; ++u) {
@@ -433,22 +439,22 @@ __global__ void __launch_bounds__(128) hm_gene_kernel(const double *__restrict__
       val = MM + log10(sum) - l10m;
     }
     PA[(size_t)j * n_genes + g] = val;
-    if (j >= dim) gd[j - dim] = val;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // BF_g = log10 sum_l lambda_l 10^Gd[l]
-    double MM = -INFINITY;
-    bool bad = false;
-    for (int l = 0; l < grid; ++l) {
-      bad = bad || (gd[l] != gd[l]);
-      MM = fmax(MM, gd[l]);
+    if (j >= dim) {
+      bf_bad = bf_bad || (val != val);
+      bf_max = fmax(bf_max, val);
     }
-    double sum = 0.0;
-    for (int l = 0; l < grid; ++l)
-      if (gd[l] > -INFINITY) sum += gw[l] * exp10(gd[l] - MM);
-    BF[g] = bad ? nan("") : MM + log10(sum);
   }
+  bf_max = hm_warp_max(bf_max);
+  bf_bad = __any_sync(0xffffffffu, bf_bad);
+  // every lane weighs the grid-point values it produced itself (re-read: its own writes), butterfly sum = fixed order
+  double part = 0.0;
+  for (int j = lane; j < nout; j += 32)
+    if (j >= dim) {
+      const double v = PA[(size_t)j * n_genes + g];
+      if (v > -INFINITY) part += gw[j - dim] * exp10(v - bf_max);
+    }
+  part = hm_warp_sum(part);
+  if (lane == 0) BF[g] = bf_bad ? nan("") : bf_max + log10(part);
 }
 
 // fixed-order block reductions (blockDim.x a power of two <= 1024)
@@ -481,16 +487,21 @@ __device__ __forceinline__ double hm_block_max(double v, double *sh)
   return r;
 }
 
-// gene_eQTL::compute_log10_obs_lik (hm_methods.cpp:476-497) for every gene and their sum (one CTA)
-__global__ void __launch_bounds__(1024) hm_lik_kernel(const double *__restrict__ BF, long long n_genes, double pi0, int keep,
-                                                      double *__restrict__ kept_lik, double *__restrict__ kept_bf, double *__restrict__ out)
+// gene_eQTL::compute_log10_obs_lik (hm_methods.cpp:476-497) for every gene and their sum: one gene per thread, one partial
+// sum per CTA; the CTA that takes the last ticket adds the partials in CTA order (fixed order: no data atomics)
+constexpr int HM_LIK_THREADS = 256;
+__global__ void __launch_bounds__(HM_LIK_THREADS) hm_lik_kernel(const double *__restrict__ BF, long long n_genes, double pi0, int keep,
+                                                                double *__restrict__ kept_lik, double *__restrict__ kept_bf,
+                                                                double *__restrict__ partial, unsigned int *__restrict__ ticket,
+                                                                double *__restrict__ out)
 {
-  __shared__ double sh[1024];
-  double acc = 0.0;
-  for (long long g = threadIdx.x; g < n_genes; g += blockDim.x) {
+  __shared__ double sh[HM_LIK_THREADS];
+  __shared__ bool last;
+  const long long g = (long long)blockIdx.x * HM_LIK_THREADS + threadIdx.x;
+  double lik = 0.0;
+  if (g < n_genes) {
     const double bf = BF[g];
     const double mx = (bf > 0.0) ? bf : 0.0; // max of {0, BF} starting from vec[0] = 0; NaN BF: the sum below is NaN-skipped
-    double lik;
     if (bf != bf)
       lik = log10(pi0); // log10_weighted_sum skips a NaN entry that is not the first one (utils_math.cpp:146-150)
     else
@@ -500,17 +511,31 @@ __global__ void __launch_bounds__(1024) hm_lik_kernel(const double *__restrict__
       kept_lik[g] = lik;
       kept_bf[g] = bf;
     }
-    acc += lik;
   }
-  const double tot = hm_block_sum(acc, sh);
-  if (threadIdx.x == 0) out[0] = tot;
+  double tot = hm_block_sum(lik, sh);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = tot;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += HM_LIK_THREADS) acc += __ldcg(partial + i);
+  tot = hm_block_sum(acc, sh);
+  if (threadIdx.x == 0) {
+    out[0] = tot;
+    *ticket = 0u; // ready for the next launch (stream order)
+  }
 }
 
 // CTA j < dim + grid: log10 sum_g 10^(PA[j][g] - lik_g); CTA dim + grid: sum_g 10^(log10 pi0 - lik_g)
-__global__ void __launch_bounds__(256) hm_sums_kernel(const double *__restrict__ PA, const double *__restrict__ kept_lik, long long n_genes,
+constexpr int HM_SUMS_THREADS = 1024;
+__global__ void __launch_bounds__(HM_SUMS_THREADS) hm_sums_kernel(const double *__restrict__ PA, const double *__restrict__ kept_lik, long long n_genes,
                                                      int nout, double pi0, double *__restrict__ out)
 {
-  __shared__ double sh[256];
+  __shared__ double sh[HM_SUMS_THREADS];
   const int j = blockIdx.x;
   if (j == nout) {
     const double l10pi0 = log10(pi0);
