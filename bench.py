@@ -603,8 +603,11 @@ def run_ours(args, rank, world, local_rank):
 
     hm_info = None
     if not args.no_hm:
-        hm_info = run_hm_block(eqtlbma_b200, local_rank, peaks()[0]["hbm_gbs"], with_cpu=(world == 1 and not args.no_cpu),
-                               rank=rank, world=world, dist=dist)
+        try:
+            hm_info = run_hm_block(eqtlbma_b200, local_rank, peaks()[0]["hbm_gbs"], with_cpu=(world == 1 and not args.no_cpu),
+                                   rank=rank, world=world, dist=dist)
+        except Exception as exc:  # the headline line must not depend on the widening block
+            hm_info = {"error": repr(exc)[:300]}
 
     # ---- max over ranks, whole-job aggregate
     tot_pairs = pairs
