@@ -36,7 +36,7 @@ namespace eqb {
 constexpr int HM_WARPS = 4;
 constexpr int HM_THREADS = HM_WARPS * 32;
 #ifndef HM_MIN_CTAS
-#define HM_MIN_CTAS 5
+#define HM_MIN_CTAS 4
 #endif
 constexpr int HM_MAXGRID = 32;
 constexpr int HM_MAXDIM = 4096;
@@ -89,6 +89,33 @@ __device__ __forceinline__ double hm_exp10(double y, const TabRef T)
   const int e2 = FPCLAMP ? (k >> 4) : max(k >> 4, -1000);
   // the binary exponent is added on the 64-bit pattern (one integer add on the high word, no register shuffling)
   return __longlong_as_double(__double_as_longlong(v) + ((long long)e2 << 52));
+}
+
+// N independent exponentials evaluated stage by stage (all N first FMAs, then all N subtractions, ...): the dependency
+// chain of one evaluation is eight FP64 operations long, and the instruction scheduler interleaves only about two of them
+// when they are written one after the other.  y finite, |y| < 1e7 (the unclamped form of hm_exp10)
+template <int N>
+__device__ __forceinline__ void hm_exp10_batch(const double (&y)[N], double (&e)[N], const TabRef T)
+{
+  double tm[N], g[N], s[N], tj[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) tm[i] = fma(y[i], HMK[0], PGK[1]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) g[i] = fma(tm[i] - PGK[1], HMK[1], y[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) tj[i] = T.exp16(__double2loint(tm[i]) & 15);
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = fma(g[i], HMK[5], HMK[4]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = fma(g[i], s[i], HMK[3]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = fma(g[i], s[i], HMK[2]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double v = fma(tj[i] * g[i], s[i], tj[i]);
+    const int e2 = max(__double2loint(tm[i]) >> 4, -1000);
+    e[i] = __longlong_as_double(__double_as_longlong(v) + ((long long)e2 << 52));
+  }
 }
 
 // 2^d for an integer d <= 0 (exact; 0 below the normal range)
@@ -281,13 +308,31 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
           } else
             wc = cfgk * hm_pow2i(dE);
           double rs = 0.0;
+#ifndef HM_EXP_BATCH
+#define HM_EXP_BATCH 5
+#endif
+          if constexpr (CACHE && HM_EXP_BATCH > 1 && (G % HM_EXP_BATCH) == 0) {
 #pragma unroll
-          for (int l = 0; l < G; ++l)
-            if (EXACT || l < grid) {
-              const double e = hm_exp10<false>(HM_X(l) - mq, T);
-              rs = fma(a.gw[l], e, rs);
-              cs[l] = fma(wc, e, cs[l]);
+            for (int l0 = 0; l0 < G; l0 += HM_EXP_BATCH) {
+              double yb[HM_EXP_BATCH], eb[HM_EXP_BATCH];
+#pragma unroll
+              for (int i = 0; i < HM_EXP_BATCH; ++i) yb[i] = xr[l0 + i] - mq;
+              hm_exp10_batch<HM_EXP_BATCH>(yb, eb, T);
+#pragma unroll
+              for (int i = 0; i < HM_EXP_BATCH; ++i) {
+                rs = fma(a.gw[l0 + i], eb[i], rs);
+                cs[l0 + i] = fma(wc, eb[i], cs[l0 + i]);
+              }
             }
+          } else {
+#pragma unroll
+            for (int l = 0; l < G; ++l)
+              if (EXACT || l < grid) {
+                const double e = hm_exp10<false>(HM_X(l) - mq, T);
+                rs = fma(a.gw[l], e, rs);
+                cs[l] = fma(wc, e, cs[l]);
+              }
+          }
           if (a.rowA) a.rowA[row0 + r_first + lane] = fma(log_tab16(rs, T), PGK[11], mq);
           // sum over the rows of this configuration of rs 2^E: state = (exponent as a double, sum relative to it)
           if (!(rs >= 0.0))
