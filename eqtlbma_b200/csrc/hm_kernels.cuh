@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(HM_THREADS, (G <= 16) ? HM_MIN_CTAS : 3) hm_es
         // passes below read the row from shared memory
         constexpr bool CACHE = EXACT && (G % 2 == 0) && G <= 16;
         double xr[CACHE ? G : 1];
+        if constexpr (!CACHE) xr[0] = 0.0; // (never read: HM_X selects x[l])
         if constexpr (CACHE) {
           const double2 *x2 = reinterpret_cast<const double2 *>(x);
 #pragma unroll
