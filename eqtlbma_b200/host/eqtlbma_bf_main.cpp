@@ -1805,6 +1805,19 @@ int main(int argc, char **argv)
       pr.true_stat = ptrue.data();
       pr.median_perm = pmed.data();
       check(ctx, eqb_run_permutations(ctx, g0, g1, &pc, &pr), "eqb_run_permutations");
+      // NaN permuted statistics shrink a gene's number of permutations.  The reference decrements the caller's counter by
+      // reference (gene.cpp:431,551,681,693), so that every LATER gene of the run also loses them; here the loss stays with
+      // the gene: say so when it happens, the p-values of later genes differ from the reference's then
+      if (o.trick == 0) {
+        static bool warned = false;
+        for (size_t i = 0; i < pdone.size() && !warned; ++i)
+          if (pdone[i] > 0 && pdone[i] < (int64_t)o.nb_permutations) {
+            cerr << "WARNING: gene " << genes[g0 + (int64_t)(i / per)]->name << ": " << (o.nb_permutations - pdone[i])
+                 << " permuted statistics are NaN; they are dropped for this gene only (the reference would also drop as many"
+                 << " permutations from every later gene)" << endl;
+            warned = true;
+          }
+      }
     }
 
     // ---- serialisation (writeRes*, eqtlbma_bf.cpp:919-1399)
