@@ -58,5 +58,30 @@ def main():
             shutil.rmtree(tmp, ignore_errors=True)
 
 
+def chain():
+    """The bf -> hm chain of the reference's functional test (tests/test_hm.bash:117-131): the reference eqtlbma_hm on the
+    `_l10abfs_raw.txt.gz` file the reference eqtlbma_bf wrote for a scenario of tests/scenarios.py (stored as text in
+    tests/golden/<scenario>.text.json.gz) -> tests/golden/hm/chain_<scenario>.out_hm.txt.gz."""
+    from hm_scenarios import CHAIN_SCENARIOS, chain_cmdline
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "eqtlbma_hm_ref")
+    for name in CHAIN_SCENARIOS:
+        gold = json.loads(gzip.open(os.path.join(ROOT, "tests", "golden", name + ".text.json.gz"), "rt").read())
+        tmp = tempfile.mkdtemp(prefix="hmchain_")
+        try:
+            raw = os.path.join(tmp, "ref_bf_l10abfs_raw.txt.gz")
+            with gzip.open(raw, "wt") as f:
+                f.write(gold["l10abfs_raw.txt.gz"])
+            out = os.path.join(tmp, "out_hm.txt.gz")
+            r = subprocess.run([ref_bin] + chain_cmdline(name, raw, out), capture_output=True, text=True, cwd=tmp)
+            if r.returncode != 0:
+                print(r.stdout[-2000:], r.stderr[-2000:])
+                raise SystemExit("reference failed on chain " + name)
+            shutil.copy(out, os.path.join(OUT, "chain_" + name + ".out_hm.txt.gz"))
+            print("chain", name, "ok", len([ln for ln in r.stdout.splitlines() if ln.startswith("iter ")]), "iteration lines")
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
     main()
+    chain()

@@ -40,6 +40,16 @@ HM_SCENARIOS = {
 }
 
 
+# bf -> hm chain (the reference's tests/test_hm.bash): scenarios of tests/scenarios.py whose raw ABFs are all finite
+CHAIN_SCENARIOS = {"basic_all_perm": dict(nsubgrp=3, dim=7, ngrid=10), "basic_all_trick1": dict(nsubgrp=3, dim=7, ngrid=10)}
+
+
+def chain_cmdline(name, raw_file, out):
+    c = CHAIN_SCENARIOS[name]
+    return ["--data", raw_file, "--nsubgrp", str(c["nsubgrp"]), "--dim", str(c["dim"]), "--ngrid", str(c["ngrid"]),
+            "--out", out, "--getbf", "--getci", "-v", "1"]
+
+
 def build_dataset(sc):
     return make_hm_dataset(**sc["data"])
 

@@ -95,6 +95,40 @@ def test_cli_ci_only_mode(cuda_lib):
             assert abs(float(a) - float(b)) <= 2.5e-3, (lg, lr)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["basic_all_perm", "basic_all_trick1"])
+def test_bf_to_hm_chain_matches_reference_chain(cuda_lib, tmp_path, name):
+    """The reference's functional test of the pair of programs (tests/test_hm.bash:117-131): eqtlbma_bf --bfs all writes
+    `_l10abfs_raw.txt.gz`, eqtlbma_hm --getbf --getci fits the model on it.  Both drop-in front-ends in a row against the
+    reference's two programs in a row (golden: oracle/make_golden_hm.py chain()).  The raw files agree up to the last
+    printed digit of some cells, so the 4-digit estimates may differ in their last digit too."""
+    from hm_scenarios import chain_cmdline
+    from scenarios import SCENARIOS, build_dataset as build_bf_dataset, cli_extra, ref_flags
+    sc = SCENARIOS[name]
+    ds = build_bf_dataset(sc)
+    d = str(tmp_path / "in")
+    ds.write_files(d)
+    out = str(tmp_path / "obs")
+    bf = os.path.join(ROOT, "eqtlbma_b200", "eqtlbma_bf")
+    r = subprocess.run([bf] + ds.ref_args(d, out) + ref_flags(sc) + cli_extra(sc, ds, d) + ["-v", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    hm_out = str(tmp_path / "obs_hm.txt.gz")
+    r = subprocess.run([BIN] + chain_cmdline(name, out + "_l10abfs_raw.txt.gz", hm_out), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = gzip.open(hm_out, "rt").read().splitlines()
+    ref = gzip.open(os.path.join(GOLDEN_HM, "chain_" + name + ".out_hm.txt.gz"), "rt").read().splitlines()
+    assert len(got) == len(ref)
+    for lg, lr in zip(got, ref):
+        cg, cr = lg.split("\t"), lr.split("\t")
+        assert len(cg) == len(cr), (lg, lr)
+        for a, b in zip(cg, cr):
+            if a == b:
+                continue
+            fa, fb = float(a), float(b)
+            # estimates and Bayes factors to 1e-3 relative; interval ends may move by one 0.001 tick
+            assert abs(fa - fb) <= 1e-3 * max(abs(fa), abs(fb)) + 1.001e-3, (lg, lr)
+
+
 def test_cli_option_checks_and_loud_failure_without_device():
     assert os.path.exists(BIN), "eqtlbma_b200/eqtlbma_hm is not built (python -c 'import __graft_entry__ as g; g.build()')"
     r = subprocess.run([BIN, "--help"], capture_output=True, text=True)
