@@ -9,6 +9,9 @@
 // Not covered (rejected with a message): --model types.
 #include <getopt.h>
 #include <glob.h>
+#include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -31,7 +34,7 @@ namespace {
 const double NaN = std::numeric_limits<double>::quiet_NaN();
 
 struct Options {
-  int verbose = 1, threads = 1;
+  int verbose = 1, threads = 1, gpus = 1;
   std::string data, model = "configs", out, init, ci;
   long nsubgrp = -1, dim = -1, ngrid = -1, maxit = -1;
   bool rand_init = false, has_seed = false, keepgen = false, getci = false, getbf = false;
@@ -68,7 +71,9 @@ void help(const char *argv0)
          "      --thread\tnumber of host threads of the loader (default=1; the EM itself runs on the GPU)\n"
          "      --configs\tsubset of configurations to keep (e.g. \"1|3|1-3\")\n      --keepgen\tkeep 'general' ABFs\n"
          "      --getci\tcompute the confidence intervals\n      --getbf\tcompute the Bayes Factors using the estimated weights\n"
-         "      --pi0\tfixed value for pi0\n      --ci\tfile with estimates of hyperparameters to only compute confidence intervals\n",
+         "      --pi0\tfixed value for pi0\n      --ci\tfile with estimates of hyperparameters to only compute confidence intervals\n"
+         "      --gpus\tnumber of GPUs (default=1): one process per GPU, the input files (or the genes) cut into contiguous shards,\n"
+         "\t\tthe sums over genes exchanged over NVLink peer memory; same output file\n",
          argv0, argv0);
 }
 
@@ -82,7 +87,7 @@ Options parse_cmdline(int argc, char **argv)
                                {"thresh", required_argument, 0, 0}, {"maxit", required_argument, 0, 0}, {"msl", required_argument, 0, 0},
                                {"thread", required_argument, 0, 0}, {"configs", required_argument, 0, 0}, {"keepgen", no_argument, 0, 0},
                                {"getci", no_argument, 0, 0},        {"getbf", no_argument, 0, 0},       {"pi0", required_argument, 0, 0},
-                               {"ci", required_argument, 0, 0},     {0, 0, 0, 0}};
+                               {"ci", required_argument, 0, 0},     {"gpus", required_argument, 0, 0},  {0, 0, 0, 0}};
   int c, idx = 0;
   while ((c = getopt_long(argc, argv, "hVv:", lo, &idx)) != -1) {
     if (c == 'h') {
@@ -125,6 +130,7 @@ Options parse_cmdline(int argc, char **argv)
       else if (n == "getbf") o.getbf = true;
       else if (n == "pi0") o.pi0 = atof(optarg);
       else if (n == "ci") o.ci = optarg;
+      else if (n == "gpus") o.gpus = std::max(1, atoi(optarg));
     } else
       exit(EXIT_FAILURE);
   }
@@ -433,12 +439,13 @@ double seconds_since(const std::chrono::steady_clock::time_point &t0)
 
 } // namespace
 
-int main(int argc, char **argv)
+// one process = one GPU: rank `rank` of `world`; xdir = directory through which the ranks exchange their IPC handles
+int run_one(Options o, int rank, int world, const std::string &xdir)
 {
-  const Options o = parse_cmdline(argc, argv);
   const auto t_start = std::chrono::steady_clock::now();
+  if (rank > 0) o.verbose = 0; // rank 0 speaks for all (the ranks hold identical estimates)
   // the CUDA context (0.5-1 s on a cold process) is created while the files are parsed
-  std::thread warm([] { eqb_warmup(0); });
+  std::thread warm([rank] { eqb_warmup(rank); });
   g_warm = &warm;
 
   // ---- load_data (eqtlbma_hm.cpp:373-450)
@@ -455,17 +462,37 @@ int main(int argc, char **argv)
   Data d;
   std::string cur_gene, cur_snp;
   int cfg_in_pair = 0;
-  for (size_t i = 0; i < gl.gl_pathc; ++i) {
+  // several GPUs: contiguous shards of the input files when there are enough of them (a file starts a gene, so any cut
+  // between files is a cut between genes), of the genes otherwise
+  const size_t F = gl.gl_pathc;
+  const bool by_file = world > 1 && F >= (size_t)world;
+  const size_t f0 = by_file ? F * (size_t)rank / (size_t)world : 0, f1 = by_file ? F * (size_t)(rank + 1) / (size_t)world : F;
+  for (size_t i = f0; i < f1; ++i) {
     if (o.verbose > 1) printf("file %zu %s\n", i + 1, gl.gl_pathv[i]);
     load_one_file(gl.gl_pathv[i], o, d, cur_gene, cur_snp, cfg_in_pair);
   }
   globfree(&gl);
   if (d.snp_names.empty()) die("no gene-snp pair was loaded");
   if (cfg_in_pair != (int)o.dim) die("snp " + d.snp_names.back() + " has " + std::to_string(cfg_in_pair) + " configurations instead of --dim " + std::to_string(o.dim));
+  if (world > 1 && !by_file) { // keep the genes of this rank
+    const int64_t Gall = (int64_t)d.gene_names.size();
+    if (Gall < world) die("--gpus " + std::to_string(world) + " needs at least as many genes");
+    const int64_t ga = Gall * rank / world, gb = Gall * (rank + 1) / world;
+    const int64_t pa = d.gene_off[(size_t)ga], pb = d.gene_off[(size_t)gb];
+    const size_t per_pair = (size_t)o.dim * (size_t)o.ngrid;
+    Data k;
+    k.config_names = d.config_names;
+    k.gene_names.assign(d.gene_names.begin() + ga, d.gene_names.begin() + gb);
+    k.snp_names.assign(d.snp_names.begin() + pa, d.snp_names.begin() + pb);
+    k.gene_off.clear();
+    for (int64_t g = ga; g <= gb; ++g) k.gene_off.push_back(d.gene_off[(size_t)g] - pa);
+    k.B.assign(d.B.begin() + (size_t)pa * per_pair, d.B.begin() + (size_t)pb * per_pair);
+    d = std::move(k);
+  }
   const int64_t G = (int64_t)d.gene_names.size(), P = (int64_t)d.snp_names.size();
   join_warmup();
   eqb_hm_ctx *hm = nullptr;
-  if (eqb_hm_create(&hm, 0, (int32_t)o.dim, (int32_t)o.ngrid) != 0) die(hm ? eqb_hm_last_error(hm) : "eqb_hm_create failed (no CUDA device? there is no CPU fallback)");
+  if (eqb_hm_create(&hm, rank, (int32_t)o.dim, (int32_t)o.ngrid) != 0) die(hm ? eqb_hm_last_error(hm) : "eqb_hm_create failed (no CUDA device? there is no CPU fallback)");
   auto ck = [&](int rc) {
     if (rc != 0) {
       fprintf(stderr, "%s\n", eqb_hm_last_error(hm));
@@ -475,6 +502,28 @@ int main(int argc, char **argv)
   };
   ck(eqb_hm_append(hm, d.B.data(), P, d.gene_off.data(), G));
   ck(eqb_hm_finalize(hm));
+  if (world > 1) { // exchange the IPC handles through files, then connect (include/eqtlbma_hm_b200.h)
+    char mine[64];
+    ck(eqb_hm_ipc_export(hm, mine));
+    const std::string tmp = xdir + "/t." + std::to_string(rank), fin = xdir + "/h." + std::to_string(rank);
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f || fwrite(mine, 1, 64, f) != 64) die("can't write " + tmp);
+    fclose(f);
+    if (rename(tmp.c_str(), fin.c_str()) != 0) die("can't rename " + tmp);
+    std::vector<char> all((size_t)world * 64);
+    for (int r = 0; r < world; ++r) {
+      const std::string path = xdir + "/h." + std::to_string(r);
+      const auto t0 = std::chrono::steady_clock::now();
+      FILE *g = nullptr;
+      while (!(g = fopen(path.c_str(), "rb"))) {
+        if (seconds_since(t0) > 600.0) die("rank " + std::to_string(r) + " did not publish its handle");
+        usleep(2000);
+      }
+      if (fread(all.data() + (size_t)r * 64, 1, 64, g) != 64) die("short read of " + path);
+      fclose(g);
+    }
+    ck(eqb_hm_ipc_connect(hm, world, rank, all.data()));
+  }
   if (o.verbose > 0) fprintf(stderr, "finish loading %lld genes and %lld gene-snp pairs (%f sec)\n", (long long)G, (long long)P, seconds_since(t_start));
 
   Params pr;
@@ -520,11 +569,11 @@ int main(int argc, char **argv)
     opt.fixed_grid = pr.fixed_grid;
     opt.fixed_configs = pr.fixed_configs;
     opt.verbose = o.verbose;
-    opt.log = hm_log;
+    opt.log = rank == 0 ? hm_log : nullptr;
     const auto t_em = std::chrono::steady_clock::now();
     ck(eqb_hm_em(hm, &opt, &fit));
     pr.pi0 = fit.pi0;
-    printf("EM ran for %.3f sec\n", seconds_since(t_em));
+    if (rank == 0) printf("EM ran for %.3f sec\n", seconds_since(t_em));
     if (o.getbf) {
       if (o.verbose > 0) printf("compute posteriors ...\n");
       gene_post.assign((size_t)G, NaN);
@@ -542,8 +591,9 @@ int main(int argc, char **argv)
 
   // ---- save_result (eqtlbma_hm.cpp:1612-1752)
   if (o.verbose > 0) printf("save the results in %s ...\n", o.out.c_str());
+  const std::string out_path = world > 1 ? o.out + ".shard" + std::to_string(rank) : o.out;
   {
-    GzOut w(o.out);
+    GzOut w(out_path);
     auto line = [&](const std::string &name, double mle, double l, double r, bool fixed) {
       w.put(name.c_str());
       w.put("\t");
@@ -554,20 +604,24 @@ int main(int argc, char **argv)
       w.num(r);
       w.put(fixed ? "\ttrue\n" : "\tfalse\n");
     };
-    w.put("#param\tmle\tleft.ci\tright.ci\tfixed\n");
-    line("#pi0", fit.pi0, fit.pi0_ci[0], fit.pi0_ci[1], pr.fixed_pi0);
-    for (long k = 0; k < o.dim; ++k)
-      line("#config." + (k < (long)d.config_names.size() ? d.config_names[(size_t)k] : std::string("?")), pr.config[(size_t)k],
-           config_ci[2 * (size_t)k], config_ci[2 * (size_t)k + 1], pr.fixed_configs);
-    for (long l = 0; l < o.ngrid; ++l)
-      line("#grid." + std::to_string(l + 1), pr.grid[(size_t)l], grid_ci[2 * (size_t)l], grid_ci[2 * (size_t)l + 1], pr.fixed_grid);
+    if (rank == 0) {
+      w.put("#param\tmle\tleft.ci\tright.ci\tfixed\n");
+      line("#pi0", fit.pi0, fit.pi0_ci[0], fit.pi0_ci[1], pr.fixed_pi0);
+      for (long k = 0; k < o.dim; ++k)
+        line("#config." + (k < (long)d.config_names.size() ? d.config_names[(size_t)k] : std::string("?")), pr.config[(size_t)k],
+             config_ci[2 * (size_t)k], config_ci[2 * (size_t)k + 1], pr.fixed_configs);
+      for (long l = 0; l < o.ngrid; ++l)
+        line("#grid." + std::to_string(l + 1), pr.grid[(size_t)l], grid_ci[2 * (size_t)l], grid_ci[2 * (size_t)l + 1], pr.fixed_grid);
+    }
     if (with_bf) {
-      w.put("gene\tgene.posterior.prob\tgene.log10.bf\tsnp\tsnp.log10.bf");
-      for (long k = 0; k < o.dim; ++k) {
-        w.put("\tlog10.bf.");
-        w.put(d.config_names[(size_t)k].c_str());
+      if (rank == 0) {
+        w.put("gene\tgene.posterior.prob\tgene.log10.bf\tsnp\tsnp.log10.bf");
+        for (long k = 0; k < o.dim; ++k) {
+          w.put("\tlog10.bf.");
+          w.put(d.config_names[(size_t)k].c_str());
+        }
+        w.put("\n");
       }
-      w.put("\n");
       for (int64_t g = 0; g < G; ++g)
         for (int64_t p = d.gene_off[(size_t)g]; p < d.gene_off[(size_t)g + 1]; ++p) {
           w.put(d.gene_names[(size_t)g].c_str());
@@ -589,5 +643,53 @@ int main(int argc, char **argv)
   }
   eqb_hm_destroy(hm);
   if (o.verbose > 0) printf("END (%.3f sec)\n", seconds_since(t_start));
+  return EXIT_SUCCESS;
+}
+
+int main(int argc, char **argv)
+{
+  const Options o = parse_cmdline(argc, argv);
+  if (o.gpus <= 1) return run_one(o, 0, 1, "");
+  // --gpus N: one child per GPU, forked before any CUDA call; the children write <out>.shard<k> (gzip members; rank 0 alone
+  // writes the parameter lines and the header), concatenated byte-wise in rank order = gene order into <out>
+  char tmpl[] = "/tmp/eqtlbma_hm_XXXXXX";
+  if (!mkdtemp(tmpl)) die("can't create a temporary directory");
+  const std::string xdir = tmpl;
+  std::vector<pid_t> kids;
+  for (int r = 0; r < o.gpus; ++r) {
+    fflush(stdout);
+    fflush(stderr);
+    const pid_t pid = fork();
+    if (pid < 0) die("fork failed");
+    if (pid == 0) _exit(run_one(o, r, o.gpus, xdir));
+    kids.push_back(pid);
+  }
+  bool ok = true;
+  for (pid_t pid : kids) {
+    int st = 0;
+    if (waitpid(pid, &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) ok = false;
+  }
+  for (int r = 0; r < o.gpus; ++r) {
+    unlink((xdir + "/h." + std::to_string(r)).c_str());
+    unlink((xdir + "/t." + std::to_string(r)).c_str());
+  }
+  rmdir(xdir.c_str());
+  if (ok) {
+    FILE *dst = fopen(o.out.c_str(), "wb");
+    if (!dst) die("can't open file " + o.out);
+    std::vector<char> buf(1 << 20);
+    for (int r = 0; r < o.gpus; ++r) {
+      const std::string path = o.out + ".shard" + std::to_string(r);
+      FILE *src = fopen(path.c_str(), "rb");
+      if (!src) die("missing shard output " + path);
+      size_t n;
+      while ((n = fread(buf.data(), 1, buf.size(), src)) > 0)
+        if (fwrite(buf.data(), 1, n, dst) != n) die("can't write " + o.out);
+      fclose(src);
+    }
+    fclose(dst);
+  }
+  for (int r = 0; r < o.gpus; ++r) unlink((o.out + ".shard" + std::to_string(r)).c_str());
+  if (!ok) die("a shard process failed");
   return EXIT_SUCCESS;
 }

@@ -133,3 +133,33 @@ def test_two_gpu_em_matches_single_gpu(tmp_path, cuda_lib):
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
     outs = _run(tmp_path, GPU_WORKER, 2, extra=("2",))
     assert "HM_MULTI_GPU_OK" in outs[0][0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["configs_subset", "classic_bf", "getci"])
+def test_cli_two_gpus_writes_the_reference_file(tmp_path, cuda_lib, name):
+    """eqtlbma_hm --gpus 2: one process per GPU on contiguous shards of the files (configs_subset: 3 files) or of the genes
+    (one file), hm_xchg_kernel between them, shard outputs merged byte-wise: the reference's output file."""
+    import gzip
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from hm_scenarios import GOLDEN_HM, HM_SCENARIOS, build_dataset, ref_cmdline
+    from test_hm_cli import BIN, _cells_match, _write_inputs
+    sc = HM_SCENARIOS[name]
+    ds = build_dataset(sc)
+    tmp = str(tmp_path)
+    init = _write_inputs(sc, ds, tmp)
+    out = os.path.join(tmp, "out_hm.txt.gz")
+    cmd = [BIN] + ref_cmdline(sc, ds, os.path.join(tmp, "in_*_l10abfs_raw.txt.gz"), out, init) + ["--gpus", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = gzip.open(out, "rt").read().splitlines()
+    ref = gzip.open(os.path.join(GOLDEN_HM, name + ".out_hm.txt.gz"), "rt").read().splitlines()
+    assert len(got) == len(ref)
+    for lg, lr in zip(got, ref):
+        cg, cr = lg.split("\t"), lr.split("\t")
+        assert len(cg) == len(cr), (lg, lr)
+        assert all(_cells_match(a, b) for a, b in zip(cg, cr)), (lg, lr)
+    assert not [f for f in os.listdir(tmp) if ".shard" in f]
