@@ -15,7 +15,7 @@ ABI_VERSION = 1
 ANALYSIS = {"sep": 0, "join": 1}
 BFS = {"gen": 0, "sin": 1, "all": 2}
 PBF = {"none": 0, "gen": 1, "gen-sin": 2, "all": 3}
-ERROR = {"uvlr": 0, "mvlr": 1}
+ERROR = {"uvlr": 0, "mvlr": 1, "hybrid": 2}
 ANCHOR = {"TSS": 0, "TSS+TES": 1}
 
 

@@ -41,8 +41,8 @@ enum { EQB_ANALYSIS_SEP = 0, EQB_ANALYSIS_JOIN = 1 };
 enum { EQB_BFS_GEN = 0, EQB_BFS_SIN = 1, EQB_BFS_ALL = 2 };
 /* --pbf (eqtlbma_bf.cpp:652-657) */
 enum { EQB_PBF_NONE = 0, EQB_PBF_GEN = 1, EQB_PBF_GEN_SIN = 2, EQB_PBF_ALL = 3 };
-/* --error (eqtlbma_bf.cpp:1596); hybrid is out of scope */
-enum { EQB_ERROR_UVLR = 0, EQB_ERROR_MVLR = 1 };
+/* --error (eqtlbma_bf.cpp:1596) */
+enum { EQB_ERROR_UVLR = 0, EQB_ERROR_MVLR = 1, EQB_ERROR_HYBRID = 2 };
 /* --anchor (snp.cpp:274-297) */
 enum { EQB_ANCHOR_TSS = 0, EQB_ANCHOR_TSS_TES = 1 };
 

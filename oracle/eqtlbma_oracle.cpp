@@ -652,6 +652,229 @@ void calc_abfs_mvlr(eqo_ctx *c, int64_t g, int64_t m, const size_t *perm, int wh
   if (which == 3) bma(pr, S, c->configs_all);
 }
 
+/* ------------------------------------------------------------------ hybrid (gene_snp_pair.cpp:760-1423) */
+
+/* utils::mygsl_linalg_pseudoinverse (utils_math.cpp:249-275) through the shim's gsl_linalg_SV_decomp;
+ * optionally returns V D^-2 V' and the singular values (CalcBetahatsAndDiagsPerSubgroup needs them) */
+Mat pinv_svd(const Mat &A, Mat *VD2Vt = NULL, std::vector<double> *sv = NULL)
+{
+  const int M = A.r, N = A.c;
+  gsl_matrix *U = gsl_matrix_alloc(M, N), *V = gsl_matrix_alloc(N, N);
+  gsl_vector *D = gsl_vector_alloc(N), *work = gsl_vector_alloc(N);
+  for (int i = 0; i < M; ++i)
+    for (int j = 0; j < N; ++j) gsl_matrix_set(U, i, j, A(i, j));
+  gsl_linalg_SV_decomp(U, V, D, work);
+  if (sv) {
+    sv->resize(N);
+    for (int j = 0; j < N; ++j) (*sv)[j] = gsl_vector_get(D, j);
+  }
+  Mat Vm(N, N), VDinv(N, N), Um(M, N);
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) {
+      Vm(i, j) = gsl_matrix_get(V, i, j);
+      VDinv(i, j) = Vm(i, j) * pow(gsl_vector_get(D, j), -1.0);
+    }
+  for (int i = 0; i < M; ++i)
+    for (int j = 0; j < N; ++j) Um(i, j) = gsl_matrix_get(U, i, j);
+  if (VD2Vt) {
+    Mat VD2(N, N);
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) VD2(i, j) = Vm(i, j) * pow(pow(gsl_vector_get(D, j), -1.0), 2.0);
+    *VD2Vt = mul(VD2, false, Vm, true);
+  }
+  gsl_matrix_free(U);
+  gsl_matrix_free(V);
+  gsl_vector_free(D);
+  gsl_vector_free(work);
+  return mul(VDinv, false, Um, true);
+}
+
+/* utils::CalcMleErrorCovariance (utils_math.cpp:306-348): Sigma = Y' (I - X (X'X)^+ X') Y / N */
+Mat mle_error_covariance(const Mat &Y, const Mat &X)
+{
+  const int N = X.r;
+  const Mat XtXinv = pinv_svd(mul(X, true, X, false));
+  const Mat H = mul(mul(X, false, XtXinv, false), false, X, true);
+  Mat T(N, N);
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) T(i, j) = -H(i, j) + (i == j ? 1.0 : 0.0);
+  Mat Sg = mul(Y, true, mul(T, false, Y, false), false);
+  for (size_t e = 0; e < Sg.a.size(); ++e) Sg.a[e] *= 1 / (double)N;
+  return Sg;
+}
+
+/* CalcLog10AbfMvlr of gene_snp_pair.cpp:1165-1255 (the hybrid model's own, not X. Wen's class) */
+double abf_hybrid(const std::vector<int> &gamma, const std::vector<double> &bhat, const Mat &Sigma, const Mat &Vg,
+                  double phi2, double oma2)
+{
+  const int S = (int)gamma.size();
+  Mat Wg(S, S);
+  for (int i = 0; i < S; ++i)
+    for (int j = 0; j < S; ++j) Wg(i, j) = ((i == j) ? phi2 + oma2 : oma2) * (double)(gamma[i] * gamma[j]);
+  const Mat Vinv = lu_inverse(Vg, NULL);
+  Mat b(S, 1);
+  for (int i = 0; i < S; ++i) b(i, 0) = bhat[i];
+  const Mat bVg = mul(b, true, Vinv, false); /* 1 x S */
+  Mat sd(S, S);
+  for (int i = 0; i < S; ++i) sd(i, i) = pow(Sigma(i, i), 0.5);
+  Wg = mul(mul(sd, false, Wg, false), false, sd, false);
+  Mat ivw = mul(Vinv, false, Wg, false);
+  for (int i = 0; i < S; ++i) ivw(i, i) += 1.0;
+  double lndet = 0.0;
+  const Mat ivw_inv = lu_inverse(ivw, &lndet);
+  double l10 = -0.5 * lndet;
+  const Mat t6 = mul(mul(mul(bVg, false, Wg, false), false, ivw_inv, false), false, bVg, true);
+  l10 += 0.5 * t6(0, 0);
+  return l10 / log(10);
+}
+
+/* GeneSnpPair::CalcAbfsHybrid (gene_snp_pair.cpp:1384-1418) with CalcSstatsHybrid (:1134-1163),
+ * CalcBetahatsAndDiagsPerSubgroup (:760-879), CalcOffDiagCovarsFromPairsOfSubgroups (:1059-1132) */
+void calc_abfs_hybrid(eqo_ctx *c, int64_t g, int64_t m, const size_t *perm, int which, Pair &pr)
+{
+  const int S = c->cfg.n_subgroups, N_all = c->cfg.n_samples_all;
+  const double f = c->cfg.fiterr;
+  std::vector<double> bhat(S, kNaN);
+  Mat Sigma(S, S), Vg(S, S);
+  /* diagonals: each subgroup on its own individuals, permuted / quantile-normalised like the uvlr statistics */
+  for (int s = 0; s < S; ++s) {
+    std::vector<double> y, x;
+    std::vector<std::vector<double> > cov;
+    if (!gather(c, g, m, s, perm, y, x, cov)) continue;
+    const int N = (int)y.size(), Q = (int)cov.size(), Q1 = Q + 1, Q2 = Q + 2;
+    pr.n[s] = N;
+    pr.ncov[s] = Q;
+    Mat X(N, Q2), Xc(N, Q1), yv(N, 1);
+    for (int i = 0; i < N; ++i) {
+      yv(i, 0) = y[i];
+      X(i, 0) = Xc(i, 0) = 1.0;
+      X(i, 1) = x[i];
+      for (int j = 0; j < Q; ++j) X(i, j + 2) = Xc(i, j + 1) = cov[j][i];
+    }
+    Mat VD2Vt;
+    std::vector<double> sv;
+    const Mat Xps = pinv_svd(X, &VD2Vt, &sv);
+    size_t rank = 0;
+    for (size_t j = 0; j < sv.size(); ++j)
+      if (sv[j] > GSL_DBL_EPSILON) rank += 1;
+    const Mat B = mul(Xps, false, yv, false);
+    const Mat XB = mul(X, false, B, false);
+    double rss_full = 0.0;
+    for (int i = 0; i < N; ++i) rss_full += (yv(i, 0) - XB(i, 0)) * (yv(i, 0) - XB(i, 0));
+    const double sigma2_full = rss_full / (double)N;
+    pr.pve[s] = 1 - rss_full / gsl_stats_tss(y.data(), 1, y.size());
+    pr.sigmahat[s] = sqrt(rss_full / (double)(N - rank));
+    pr.betahat[s] = B(1, 0);
+    pr.sebetahat[s] = pr.sigmahat[s] * sqrt(VD2Vt(1, 1));
+    pr.pval[s] = 2 * gsl_cdf_tdist_Q(fabs(pr.betahat[s] / pr.sebetahat[s]), N - rank);
+    const Mat Bn = mul(pinv_svd(Xc), false, yv, false);
+    const Mat XBn = mul(Xc, false, Bn, false);
+    double sigma2_null = 0.0;
+    for (int i = 0; i < N; ++i) sigma2_null += (yv(i, 0) - XBn(i, 0)) * (yv(i, 0) - XBn(i, 0));
+    sigma2_null /= (double)N;
+    bhat[s] = B(1, 0);
+    Sigma(s, s) = f * sigma2_full + (1 - f) * sigma2_null;
+    Vg(s, s) = Sigma(s, s) * VD2Vt(1, 1);
+  }
+  /* off-diagonals: pairs of subgroups on their common individuals -- never permuted, never quantile-normalised,
+   * genotype and covariates of the FIRST subgroup of the pair, covariates indexed by the all-sample index itself
+   * (gene_snp_pair.cpp:881-983; samples.cpp:148-192) */
+  for (int s1 = 0; s1 < S - 1; ++s1)
+    for (int s2 = s1 + 1; s2 < S; ++s2) {
+      const Sub &a = c->subs[s1], &b = c->subs[s2];
+      const double *Ya = &a.Y[(size_t)g * a.n_exp_cols], *Yb = &b.Y[(size_t)g * b.n_exp_cols];
+      const double *Gm = &c->genos[a.geno_id][(size_t)m * c->geno_cols[a.geno_id]];
+      std::vector<int> both, only1, only2;
+      for (int i = 0; i < N_all; ++i) {
+        const bool p1 = a.all2geno[i] >= 0 && a.all2exp[i] >= 0 && !is_nan(Ya[a.all2exp[i]]);
+        const bool p2 = b.all2geno[i] >= 0 && b.all2exp[i] >= 0 && !is_nan(Yb[b.all2exp[i]]);
+        if (p1 && p2) both.push_back(i);
+        else if (p1) only1.push_back(i);
+        else if (p2) only2.push_back(i);
+      }
+      if (both.empty()) {
+        c->fatal = true;
+        c->err = "ERROR: two subgroups have no individuals in common";
+        return;
+      }
+      const int Q = a.Q, Q2 = Q + 2;
+      struct Fill {
+        static Mat design(eqo_ctx *c, const Sub &a, const double *Gm, const std::vector<int> &inds, int Q)
+        {
+          Mat X((int)inds.size(), Q + 2);
+          for (size_t r = 0; r < inds.size(); ++r) {
+            X((int)r, 0) = 1.0;
+            if (a.all2geno[inds[r]] < 0) {
+              c->fatal = true;
+              c->err = "--error hybrid: an individual unique to the second subgroup has no genotype in the first";
+              X((int)r, 1) = kNaN;
+            } else
+              X((int)r, 1) = Gm[a.all2geno[inds[r]]];
+            for (int q = 0; q < Q; ++q) {
+              if (inds[r] >= a.n_cov_cols) {
+                c->fatal = true;
+                c->err = "--error hybrid: covariate index out of range";
+                X((int)r, 2 + q) = kNaN;
+              } else
+                X((int)r, 2 + q) = a.C[(size_t)q * a.n_cov_cols + inds[r]];
+            }
+          }
+          return X;
+        }
+      };
+      const Mat X12 = Fill::design(c, a, Gm, both, Q);
+      Mat Y12((int)both.size(), 2);
+      for (size_t r = 0; r < both.size(); ++r) {
+        Y12((int)r, 0) = Ya[a.all2exp[both[r]]];
+        Y12((int)r, 1) = Yb[b.all2exp[both[r]]];
+      }
+      const Mat tXX = mul(X12, true, X12, false);
+      Mat A[2];
+      for (int u = 0; u < 2; ++u) { /* GetMatrixA (:985-1014) */
+        const std::vector<int> &only = u == 0 ? only1 : only2;
+        Mat G = tXX;
+        if (!only.empty()) {
+          const Mat Xu = Fill::design(c, a, Gm, only, Q);
+          const Mat tXuXu = mul(Xu, true, Xu, false);
+          for (size_t e = 0; e < G.a.size(); ++e) G.a[e] += tXuXu.a[e];
+        }
+        A[u] = mul(pinv_svd(G), false, X12, true);
+      }
+      if (c->fatal) return;
+      const Mat Sfull = mle_error_covariance(Y12, X12);
+      Mat Xc12(X12.r, Q2 - 1);
+      for (int i = 0; i < X12.r; ++i) {
+        Xc12(i, 0) = 1.0;
+        for (int j = 2; j < Q2; ++j) Xc12(i, j - 1) = X12(i, j);
+      }
+      const Mat Snull = mle_error_covariance(Y12, Xc12);
+      Sigma(s1, s2) = Sigma(s2, s1) = f * Sfull(0, 1) + (1 - f) * Snull(0, 1);
+      const Mat cov12 = mul(A[0], false, A[1], true);
+      Vg(s1, s2) = Vg(s2, s1) = Sigma(s1, s2) * cov12(1, 1);
+    }
+  const size_t L = c->phi2L.size(), K = c->phi2S.size();
+  const std::vector<int> ones(S, 1);
+  pr.raw_gen.assign(3, std::vector<double>(L));
+  for (size_t k = 0; k < L; ++k) { /* CalcAbfsHybridForConsistentConfiguration (:1257-1308) */
+    const double ph = c->phi2L[k], om = c->oma2L[k];
+    pr.raw_gen[0][k] = abf_hybrid(ones, bhat, Sigma, Vg, ph, om);
+    pr.raw_gen[1][k] = abf_hybrid(ones, bhat, Sigma, Vg, 0.0, ph + om);
+    pr.raw_gen[2][k] = abf_hybrid(ones, bhat, Sigma, Vg, ph + om, 0.0);
+  }
+  for (int j = 0; j < 3; ++j) pr.w_gen[j] = log10_weighted_sum(pr.raw_gen[j].data(), L);
+  if (which == 1) return;
+  std::vector<std::vector<int> > configs;
+  enumerate_configs(S, which == 2, configs);
+  pr.raw_cfg.assign(configs.size(), std::vector<double>(K));
+  pr.w_cfg.assign(configs.size(), kNaN);
+  for (size_t ci = 0; ci < configs.size(); ++ci) {
+    for (size_t k = 0; k < K; ++k) pr.raw_cfg[ci][k] = abf_hybrid(configs[ci], bhat, Sigma, Vg, c->phi2S[k], c->oma2S[k]);
+    pr.w_cfg[ci] = log10_weighted_sum(pr.raw_cfg[ci].data(), K);
+  }
+  bma_lite(pr, S);
+  if (which == 3) bma(pr, S, c->configs_all);
+}
+
 /* ------------------------------------------------------------------ gene level */
 
 bool gene_has_all(const eqo_ctx *c, int64_t g)
@@ -696,7 +919,10 @@ void test_pair(eqo_ctx *c, int64_t g, int64_t m, const size_t *perm, int which, 
     if (join) calc_abfs_uvlr(c, pr, which);
   } else {
     if (!snp_has_all(c, m)) return; /* gene.cpp:315-321 */
-    calc_abfs_mvlr(c, g, m, perm, which, pr);
+    if (c->cfg.error_model == EQB_ERROR_HYBRID)
+      calc_abfs_hybrid(c, g, m, perm, which, pr);
+    else
+      calc_abfs_mvlr(c, g, m, perm, which, pr);
   }
 }
 

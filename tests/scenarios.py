@@ -64,6 +64,14 @@ SCENARIOS = {
                       error="mvlr", fiterr=0.0, perm=dict(nperm=20, pbf="all", seed=5)),
     "mvlr_fit05_cov": dict(data=dict(BASE, seed=72, n_inds=100, n_genes=6, n_cov=2), analysis="join", bfs="all",
                            wrtsize=3, error="mvlr", fiterr=0.5, perm=dict(nperm=20, pbf="gen-sin", seed=6)),
+    # --error hybrid (gene_snp_pair.cpp:760-1423; test_common-uniq-inds.bash: --fiterr 0.0): individuals common to /
+    # unique to each pair of subgroups, expression levels missing per gene, and the default --fiterr 0.5 with covariates
+    "hybrid_fit0": dict(data=dict(BASE, seed=73, n_inds=100, n_genes=6, ragged=True, ragged_min_frac=0.6, nan_frac=0.03),
+                        analysis="join", bfs="all", wrtsize=3, error="hybrid", fiterr=0.0,
+                        perm=dict(nperm=20, pbf="all", seed=7)),
+    "hybrid_fit05_cov": dict(data=dict(BASE, seed=74, n_inds=100, n_genes=6, n_cov=2, ragged=True, ragged_min_frac=0.6,
+                                       pad_names=True, n_subgroups=4), analysis="join", bfs="sin", wrtsize=3,
+                             error="hybrid", fiterr=0.5, perm=dict(nperm=20, pbf="gen-sin", seed=9)),
     # degenerate inputs: monomorphic SNPs (rank-deficient designs)
     "monomorphic": dict(data=dict(BASE, seed=81, monomorphic_frac=0.3, snps_per_gene=4), analysis="join",
                         bfs="all", wrtsize=3),
