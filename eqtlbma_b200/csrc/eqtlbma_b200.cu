@@ -24,6 +24,7 @@
 #include "fast_all.h"
 #include "fast_kernels.cuh"
 #include "mvlr_kernel.cuh"
+#include "hybrid_kernel.cuh"
 #include "perm_gemm.h"
 
 using namespace eqb;
@@ -590,10 +591,57 @@ int run_mvlr_kernel(eqb_ctx *ctx, const LaunchArgs &la, int ppg)
   return 0;
 }
 
+template <int NPL>
+cudaError_t launch_hybrid(eqb_ctx *ctx, const LaunchArgs &la, int grid, size_t smem)
+{
+  cudaError_t e = cudaFuncSetAttribute(hybrid_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  hybrid_kernel<NPL><<<grid, THREADS, smem, ctx->stream>>>(ctx->d_prm, la);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+// --error hybrid: per-subgroup bases in shared memory when they fit (else a global workspace, bounded grid)
+int run_hybrid_kernel(eqb_ctx *ctx, const LaunchArgs &la, int ppg)
+{
+  const int S = ctx->cfg.n_subgroups;
+  if (S > MV_MAXS) return fail(ctx, "--error hybrid supports at most 16 subgroups on the device");
+  if (ctx->Qmax + 2 > HY_MAXQ2) return fail(ctx, "--error hybrid supports at most 6 covariates on the device");
+  const size_t nb = basis_doubles(S, ctx->Qmax, ctx->ldn, ctx->cfg.qnorm);
+  const bool basis_smem = hybrid_smem_bytes(S, ctx->Qmax, ctx->ldn, ctx->cfg.qnorm, true) <= 200 * 1024;
+  const size_t smem = hybrid_smem_bytes(S, ctx->Qmax, ctx->ldn, ctx->cfg.qnorm, basis_smem);
+  const int npl_need = (ctx->ldn + 31) / 32;
+  const long long cap = basis_smem ? (1LL << 30) : std::max<long long>(1, (148 * 8) / std::max(1, ppg));
+  for (long long g0 = 0; g0 < la.n_genes; g0 += cap) {
+    const long long g1 = std::min<long long>(la.n_genes, g0 + cap);
+    LaunchArgs l2 = la;
+    l2.genes = la.genes + g0;
+    l2.gene_slot = la.gene_slot ? la.gene_slot + g0 : nullptr;
+    l2.pair_off = la.pair_off ? la.pair_off + g0 : nullptr;
+    l2.n_genes = (int)(g1 - g0);
+    if (la.out_stat) l2.out_stat = la.out_stat + (size_t)g0 * (la.perms_per_gene > 0 ? (size_t)la.P_total : 1);
+    const long long grid = (g1 - g0) * std::max(1, ppg);
+    if (!basis_smem) {
+      if (ctx->d_basis_ws.ensure((size_t)grid * nb) != cudaSuccess) return fail(ctx, "workspace alloc failed");
+      l2.basis_ws = ctx->d_basis_ws.p;
+    }
+    cudaError_t e;
+    if (npl_need <= 4) e = launch_hybrid<4>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 8) e = launch_hybrid<8>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 16) e = launch_hybrid<16>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 32) e = launch_hybrid<32>(ctx, l2, (int)grid, smem);
+    else if (npl_need <= 64) e = launch_hybrid<64>(ctx, l2, (int)grid, smem);
+    else return fail(ctx, "more than 2048 samples are not supported yet");
+    if (e != cudaSuccess) return fail(ctx, std::string("hybrid_kernel launch: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 // picks workspaces (shared memory when they fit, else global) and the row-register template
 int run_pair_kernel(eqb_ctx *ctx, LaunchArgs la, long long n_ctas_total, int ppg)
 {
   if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model == EQB_ERROR_MVLR) return run_mvlr_kernel(ctx, la, ppg);
+  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model == EQB_ERROR_HYBRID) return run_hybrid_kernel(ctx, la, ppg);
   const int S = ctx->cfg.n_subgroups;
   const size_t nb = basis_doubles(S, ctx->Qmax, ctx->ldn, ctx->cfg.qnorm) * sizeof(double);
   const size_t nt = table_doubles(S, (int)ctx->phi2S.size()) * sizeof(double) * WARPS;
@@ -647,12 +695,16 @@ int run_pair_kernel(eqb_ctx *ctx, LaunchArgs la, long long n_ctas_total, int ppg
 
 int check_device_errors(eqb_ctx *ctx)
 {
-  int h[4] = {0, 0, 0, 0};
+  int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cudaMemcpyAsync(h, ctx->d_err, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
       cudaStreamSynchronize(ctx->stream) != cudaSuccess)
     return fail(ctx, std::string("device error: ") + cudaGetErrorString(cudaGetLastError()));
   if (h[0]) return fail(ctx, "ERROR: missing covariate for a sample kept in the regression (gene_snp_pair.cpp:138-144)");
   if (h[3]) return fail(ctx, "ERROR: --error mvlr requires the same individuals in every subgroup");
+  if (h[4])
+    return fail(ctx, "ERROR: --error hybrid: an individual unique to the second subgroup of a pair has no genotype or "
+                     "covariates in the first (the reference indexes past its vectors there, gene_snp_pair.cpp:959-975)");
+  if (h[5]) return fail(ctx, "ERROR: two subgroups have no individuals in common (gene_snp_pair.cpp:897-901)");
   return 0;
 }
 
@@ -935,7 +987,7 @@ int prepare_fast_path(eqb_ctx *ctx)
   ctx->d_xstat.assign(S, nullptr);
   ctx->d_emask.assign(S, nullptr);
   if (ctx->ldn > 32 * 64) return 0; // general path only
-  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model == EQB_ERROR_MVLR) return 0; // MVLR kernel only
+  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model != EQB_ERROR_UVLR) return 0; // MVLR / hybrid kernels only
   for (int s = 0; s < S; ++s) {
     const SubHost &sb = ctx->subs[s];
     CK(dmalloc(&ctx->d_Bs[s], (size_t)(sb.Q + 1) * ldn * sizeof(double)));
@@ -1223,8 +1275,8 @@ int eqb_create(eqb_ctx **out, const eqb_config *cfg)
     if ((k16 & 1) == 0) ++k16;
     ctx->ldn = k16 * 16;
   }
-  CK(dmalloc(&ctx->d_err, 4 * sizeof(int)));
-  CK(cudaMemset(ctx->d_err, 0, 4 * sizeof(int)));
+  CK(dmalloc(&ctx->d_err, 8 * sizeof(int)));
+  CK(cudaMemset(ctx->d_err, 0, 8 * sizeof(int)));
   return 0;
 }
 
@@ -1540,6 +1592,18 @@ int eqb_finalize(eqb_ctx *ctx)
   for (int s = 0; s < S; ++s)
     if (!ctx->subs[s].set) return fail(ctx, "a subgroup was not set");
   if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->phi2L.empty()) return fail(ctx, "grids not set");
+  if (ctx->cfg.analysis == EQB_ANALYSIS_JOIN && ctx->cfg.error_model == EQB_ERROR_HYBRID) {
+    // the off-diagonal designs of the reference read the covariates of the first subgroup of a pair BY THE ALL-SAMPLE INDEX
+    // (gene_snp_pair.cpp:931-933, 953-955, 975-977): only a covariate file in all-sample order gives it the rows it means
+    for (int s = 0; s + 1 < S; ++s) {
+      const SubHost &sb = ctx->subs[s];
+      if (sb.Q == 0) continue;
+      for (int i = 0; i < N; ++i)
+        if (sb.all2cov[i] != i)
+          return fail(ctx, "--error hybrid with covariates needs the covariate files in the order of the sorted sample names "
+                           "(the reference indexes them by the all-sample index, gene_snp_pair.cpp:931-933)");
+    }
+  }
 
   // genotype variants: one all-sample-space copy per distinct (file, sample map)
   std::map<std::pair<int, std::vector<int> >, int> variants;

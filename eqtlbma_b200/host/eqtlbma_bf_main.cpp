@@ -7,7 +7,7 @@
 // eqtlbma_bf.cpp:1546-1574 -- to libeqtlbma_b200.so through its C ABI, and serialises the results
 // with the reference's text conventions (writeRes*, eqtlbma_bf.cpp:919-1447).  No statistics are
 // computed on the host.  Out of scope here (reported as errors): --lik poisson /
-// quasipoisson, --error hybrid, tabix-indexed --scoord (an index is ignored: every SNP of the BED
+// quasipoisson, tabix-indexed --scoord (an index is ignored: every SNP of the BED
 // file is loaded, which gives the same cis sets).
 #include <getopt.h>
 #include <zlib.h>
@@ -393,7 +393,8 @@ void help(char **argv)
        << "\t\t`zcat | sed 1d` merge of eqtlbma_bf_parallel.bash; same files as a single run)" << endl
        << endl
        << "Limits of the device path: at most 2048 samples in the union over the subgroups, 64 subgroups\n"
-       << "(20 with --bfs all, 16 with --error mvlr; --inss: 10 with --bfs all); not built: --error hybrid, --lik other than\n"
+       << "(20 with --bfs all, 16 with --error mvlr|hybrid; --inss: 10 with --bfs all); --error hybrid: at most 6 covariates,\n"
+       << "covariate files in the order of the sorted sample names; not built: --lik other than\n"
        << "normal, tabix-indexed --scoord." << endl;
 }
 
@@ -522,8 +523,7 @@ void parse_cmdline(int argc, char **argv, Options &o)
   if (o.analys == "join" && (o.bfs == "sin" || o.bfs == "all") && o.gridS.empty())
     die_usage(argc, argv, "--gridS is required with --analys join and --bfs " + o.bfs);
   if (o.bfs != "gen" && o.bfs != "sin" && o.bfs != "all") die_usage(argc, argv, "--bfs " + o.bfs + " is not valid");
-  if (o.error == "hybrid") die_usage(argc, argv, "--error hybrid is not supported by the B200 front-end (out of scope)");
-  if (o.error != "uvlr" && o.error != "mvlr") die_usage(argc, argv, "--error " + o.error + " is not valid");
+  if (o.error != "uvlr" && o.error != "mvlr" && o.error != "hybrid") die_usage(argc, argv, "--error " + o.error + " is not valid");
   if (o.analys == "join" && o.error == "mvlr")
     cerr << "WARNING: summary statistics per subgroup won't be saved with --error mvlr" << endl;
   if (o.trick != 0 && o.trick != 1 && o.trick != 2) die_usage(argc, argv, "--trick is not valid");
@@ -1535,7 +1535,7 @@ int main(int argc, char **argv)
   cfg.n_snps = M;
   cfg.n_genes = G;
   cfg.bfs = o.bfs == "gen" ? EQB_BFS_GEN : (o.bfs == "sin" ? EQB_BFS_SIN : EQB_BFS_ALL);
-  cfg.error_model = o.error == "mvlr" ? EQB_ERROR_MVLR : EQB_ERROR_UVLR;
+  cfg.error_model = o.error == "mvlr" ? EQB_ERROR_MVLR : (o.error == "hybrid" ? EQB_ERROR_HYBRID : EQB_ERROR_UVLR);
   cfg.qnorm = o.qnorm ? 1 : 0;
   cfg.device = o.device;
   cfg.fiterr = o.fiterr;
