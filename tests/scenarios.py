@@ -72,6 +72,11 @@ SCENARIOS = {
     "hybrid_fit05_cov": dict(data=dict(BASE, seed=74, n_inds=100, n_genes=6, n_cov=2, ragged=True, ragged_min_frac=0.6,
                                        pad_names=True, n_subgroups=4), analysis="join", bfs="sin", wrtsize=3,
                              error="hybrid", fiterr=0.5, perm=dict(nperm=20, pbf="gen-sin", seed=9)),
+    # hybrid with --qnorm (diagonals only: the off-diagonal blocks read the raw expression levels), genes absent from
+    # some subgroups (skipped: eqtlbma_bf.cpp:747-762), 2 subgroups, --maxbf permutations on the general ABF
+    "hybrid_qnorm_maxbf": dict(data=dict(BASE, seed=75, n_subgroups=2, n_inds=80, n_genes=8, snps_per_gene=3, ragged=True,
+                                         ragged_min_frac=0.7, absent_gene_frac=0.2), analysis="join", bfs="gen", wrtsize=4,
+                               qnorm=True, error="hybrid", fiterr=0.3, perm=dict(nperm=30, pbf="gen", seed=11, maxbf=True)),
     # degenerate inputs: monomorphic SNPs (rank-deficient designs)
     "monomorphic": dict(data=dict(BASE, seed=81, monomorphic_frac=0.3, snps_per_gene=4), analysis="join",
                         bfs="all", wrtsize=3),
@@ -151,8 +156,10 @@ def ref_flags(sc):
 
 
 def engine_kwargs(sc):
+    # the reference holds --fiterr in a float (eqtlbma_bf.cpp:245,398): 0.3 on the command line is 0.300000011920929 in
+    # every formula; the engines take the double the front-end hands them (eqtlbma_bf_main.cpp keeps a float as well)
     return dict(analysis=sc["analysis"], bfs=sc["bfs"], error=sc.get("error", "uvlr"),
-                fiterr=sc.get("fiterr", 0.5), qnorm=bool(sc.get("qnorm")))
+                fiterr=float(np.float32(sc.get("fiterr", 0.5))), qnorm=bool(sc.get("qnorm")))
 
 
 def perm_kwargs(sc):

@@ -73,6 +73,44 @@ def test_cuda_matches_oracle(cuda_lib, oracle_lib, name):
     ora.close()
 
 
+# --error hybrid beyond the golden shapes, against the restatement (itself pinned to the reference dumps): 6 subgroups x
+# 2000 individuals (the per-subgroup bases no longer fit in shared memory: global workspace, bounded grid) and a
+# covariate design with unequal subgroups; true pass and a few permutations
+HYBRID_EXTRA = {
+    "wide_workspace": dict(data=dict(seed=801, n_subgroups=6, n_inds=2000, n_genes=3, snps_per_gene=2, ragged=True,
+                                     ragged_min_frac=0.7, nan_frac=0.01), bfs="sin", fiterr=0.5,
+                           perm=dict(nperm=3, seed=5, pbf="gen-sin", wrtsize=2)),
+    "cov3_all": dict(data=dict(seed=802, n_subgroups=4, n_inds=300, n_genes=5, snps_per_gene=3, ragged=True, n_cov=3,
+                               pad_names=True, dosage=True), bfs="all", fiterr=0.25,
+                     perm=dict(nperm=6, seed=6, pbf="all", wrtsize=3)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(HYBRID_EXTRA))
+def test_hybrid_extra_shapes_match_oracle(cuda_lib, oracle_lib, name):
+    import eqtlbma_b200
+    from eqtlbma_b200.synth import make_dataset
+    sc = HYBRID_EXTRA[name]
+    ds = make_dataset(**sc["data"])
+    kw = dict(analysis="join", bfs=sc["bfs"], error="hybrid", fiterr=sc["fiterr"])
+    eng = eqtlbma_b200.Engine(ds, **kw)
+    ora = AnyEngine(oracle_lib, "eqo_", ds, **kw)
+    a, b = eng.run(), ora.run()
+    assert np.array_equal(a.n, b.n)
+    assert np.isfinite(b.abf_w[:, 0]).all()
+    assert np.allclose(a.sstats[..., 0], b.sstats[..., 0], rtol=1e-9, atol=1e-12, equal_nan=True)
+    assert np.allclose(a.sstats[..., 1:], b.sstats[..., 1:], rtol=1e-9, atol=0, equal_nan=True)
+    for x, y in ((a.abf_gen, b.abf_gen), (a.abf_cfg, b.abf_cfg), (a.abf_w, b.abf_w)):
+        assert np.allclose(x, y, rtol=0, atol=1e-8, equal_nan=True)
+    pk = dict(trick=0, tricut=10, permsep=0, maxbf=False, **sc["perm"])
+    pa, pb = eng.run_permutations(**pk), ora.run_permutations(**pk)
+    assert np.array_equal(pa.count, pb.count)
+    assert np.allclose(pa.true_stat, pb.true_stat, rtol=0, atol=1e-8, equal_nan=True)
+    assert np.allclose(pa.perm_stats, pb.perm_stats, rtol=0, atol=1e-8, equal_nan=True)
+    eng.close()
+    ora.close()
+
+
 def test_cis_windows_match_linear_scan(cuda_lib, oracle_lib):
     """a1: the device binary search reproduces Gene::SetCisSnps / Snp::IsInCis bit-exactly,
     including the start < radius underflow guard and both anchors."""
