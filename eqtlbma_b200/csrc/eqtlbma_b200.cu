@@ -388,7 +388,7 @@ struct eqb_ctx {
   // work buffers (grow-only)
   DevBuf<int> d_genes, d_slots, d_out_n;
   DevBuf<long long> d_pair_off, d_count, d_done, d_total, d_consumed;
-  DevBuf<double> d_ss, d_gen, d_cfg, d_w, d_stat, d_stat2, d_true, d_basis_ws, d_table_ws;
+  DevBuf<double> d_ss, d_gen, d_cfg, d_w, d_stat, d_stat2, d_true, d_basis_ws, d_table_ws, d_hy_off;
   DevBuf<unsigned short> d_perm;
   // fast path (gene-independent masks): K1 outputs
   FastParams hfp;
@@ -611,7 +611,13 @@ int run_hybrid_kernel(eqb_ctx *ctx, const LaunchArgs &la, int ppg)
   const bool basis_smem = hybrid_smem_bytes(S, ctx->Qmax, ctx->ldn, ctx->cfg.qnorm, true) <= 200 * 1024;
   const size_t smem = hybrid_smem_bytes(S, ctx->Qmax, ctx->ldn, ctx->cfg.qnorm, basis_smem);
   const int npl_need = (ctx->ldn + 31) / 32;
-  const long long cap = basis_smem ? (1LL << 30) : std::max<long long>(1, (148 * 8) / std::max(1, ppg));
+  // off-diagonal cache: one slot of the largest cis window per gene of the launch, at most ~1 GB per launch
+  long long max_win = 1;
+  for (size_t g = 0; g < ctx->cb.size(); ++g) max_win = std::max<long long>(max_win, ctx->ce[g] - ctx->cb[g]);
+  const long long npsub = std::max(1, S * (S - 1) / 2);
+  const long long cap_off = std::max<long long>(1, (1LL << 27) / (max_win * npsub));
+  const long long cap =
+      std::min(cap_off, basis_smem ? (1LL << 30) : std::max<long long>(1, (148 * 8) / std::max(1, ppg)));
   for (long long g0 = 0; g0 < la.n_genes; g0 += cap) {
     const long long g1 = std::min<long long>(la.n_genes, g0 + cap);
     LaunchArgs l2 = la;
@@ -624,6 +630,15 @@ int run_hybrid_kernel(eqb_ctx *ctx, const LaunchArgs &la, int ppg)
     if (!basis_smem) {
       if (ctx->d_basis_ws.ensure((size_t)grid * nb) != cudaSuccess) return fail(ctx, "workspace alloc failed");
       l2.basis_ws = ctx->d_basis_ws.p;
+    }
+    if (ctx->d_hy_off.ensure((size_t)(g1 - g0) * max_win * npsub) != cudaSuccess) return fail(ctx, "workspace alloc failed");
+    l2.hy_off = ctx->d_hy_off.p;
+    l2.hy_stride = (int)max_win;
+    if (S > 1) {
+      const dim3 og((unsigned)(g1 - g0), (unsigned)std::min<long long>(64, (max_win + WARPS - 1) / WARPS));
+      hybrid_offdiag_kernel<<<og, THREADS, 0, ctx->stream>>>(ctx->d_prm, l2);
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) return fail(ctx, "hybrid_offdiag_kernel launch failed");
     }
     cudaError_t e;
     if (npl_need <= 4) e = launch_hybrid<4>(ctx, l2, (int)grid, smem);
@@ -1365,6 +1380,7 @@ void eqb_destroy(eqb_ctx *ctx)
   ctx->d_true.release();
   ctx->d_basis_ws.release();
   ctx->d_table_ws.release();
+  ctx->d_hy_off.release();
   ctx->d_perm.release();
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);

@@ -38,10 +38,11 @@ struct HyPair {
   double bVg[MV_MAXS];  // b' Vg^-1
   double Vg[MV_MAXS * MV_MAXS];
   double Vinv[MV_MAXS * MV_MAXS];
+  double scr[64];       // raw values of the (configuration, grid point) items of one pass
 };
 
 // inverse of an n x n matrix (row-major, stride HY_MAXQ2) by Gauss-Jordan with partial pivoting
-__device__ inline bool hy_inverse(const double *A, int n, double *inv)
+static __device__ __noinline__ bool hy_inverse(const double *A, int n, double *inv)
 {
   double T[HY_MAXQ2 * HY_MAXQ2];
   double scale = 0.0;
@@ -102,6 +103,43 @@ __device__ inline double hy_quad(const double *a, const double *M, const double 
   return acc;
 }
 
+// One (configuration, grid point) of CalcLog10AbfMvlr (gene_snp_pair.cpp:1165-1255).  W is non-zero on the active
+// subgroups only, so with B = I + W_aa (Vg^-1)_aa on the active block
+//   ln det(I + Vg^-1 W) = ln det B   (Sylvester),   b'Vg^-1 W (I + Vg^-1 W)^-1 Vg^-1 b = c_a' B^-1 W_aa c_a,  c = Vg^-1 b
+// (same value up to rounding as the reference's S x S products).
+static __device__ __noinline__ double hybrid_value(const HyPair &H, int S, unsigned long long gamma, double p2, double o2)
+{
+  int idx[MV_MAXS], na = 0;
+  for (int i = 0; i < S; ++i)
+    if ((gamma >> i) & 1ull) idx[na++] = i;
+  if (na == 1) {
+    const int i = idx[0];
+    const double w = H.sd[i] * (p2 + o2) * H.sd[i], bb = 1.0 + w * H.Vinv[i * MV_MAXS + i], c = H.bVg[i];
+    return (-0.5 * log(fabs(bb)) + 0.5 * c * w * c / bb) / LN10;
+  }
+  double W[MV_MAXS * MV_MAXS], B[MV_MAXS * MV_MAXS], rhs[MV_MAXS], x[MV_MAXS];
+  for (int a = 0; a < na; ++a)
+    for (int c = 0; c < na; ++c) W[a * MV_MAXS + c] = H.sd[idx[a]] * ((a == c) ? p2 + o2 : o2) * H.sd[idx[c]];
+  for (int a = 0; a < na; ++a) {
+    double r = 0.0;
+    for (int c = 0; c < na; ++c) {
+      double sacc = 0.0;
+      for (int e = 0; e < na; ++e) sacc += W[a * MV_MAXS + e] * H.Vinv[idx[e] * MV_MAXS + idx[c]];
+      B[a * MV_MAXS + c] = sacc + ((a == c) ? 1.0 : 0.0);
+      r += W[a * MV_MAXS + c] * H.bVg[idx[c]];
+    }
+    rhs[a] = r;
+  }
+  int piv[MV_MAXS];
+  mv_lu(B, na, piv);
+  double lndet = 0.0;
+  for (int a = 0; a < na; ++a) lndet += log(fabs(B[a * MV_MAXS + a]));
+  mv_lu_solve(B, piv, na, rhs, x);
+  double quad = 0.0;
+  for (int a = 0; a < na; ++a) quad += H.bVg[idx[a]] * x[a];
+  return (-0.5 * lndet + 0.5 * quad) / LN10;
+}
+
 // ABFs of one configuration over a grid (CalcLog10AbfMvlr, gene_snp_pair.cpp:1165-1255); writes the raw values
 // (optional) and returns the grid-averaged ABF
 static __device__ __noinline__ double hybrid_config(const HyPair &H, int S, unsigned long long gamma, const double *phi2,
@@ -142,6 +180,134 @@ static __device__ __noinline__ double hybrid_config(const HyPair &H, int S, unsi
     acc.add(v, 1.0 / (double)nk, g == 0);
   }
   return (nk > 0) ? acc.result() : nan("");
+}
+
+// Vg_12 of one pair of subgroups for one (gene, SNP) (CalcOffDiagCovarsFromPairsOfSubgroups, gene_snp_pair.cpp:1059-1132):
+// the warp accumulates the Gram matrices of z = [1, g, covariates of s1] over the individuals common to / unique to the
+// two subgroups and z'y1, z'y2, y1'y2 over the common ones; lane 0 does the (2 + Q)-sized algebra.  NaN = degenerate.
+static __device__ __noinline__ double hy_offdiag(const DevParams &prm, int g, long long m, int s1, int s2, double fit, int lane,
+                                                 int *err_flag)
+{
+  const int N = prm.N, ldn = prm.ldn;
+  bool degenerate = false;
+  double vg12 = nan("");
+  const SubDev &sa = prm.sub[s1], &sc = prm.sub[s2];
+  const int Q = sa.Q, Q2 = Q + 2, NT = Q2 * (Q2 + 1) / 2;
+  const double *Y1 = sa.Yall + (size_t)g * ldn, *Y2 = sc.Yall + (size_t)g * ldn;
+  const double *Xm = sa.X + (size_t)m * ldn;
+  double acc[3 * HY_NT + 2 * HY_MAXQ2 + 1];
+  for (int e = 0; e < 3 * NT + 2 * Q2 + 1; ++e) acc[e] = 0.0;
+  int n12 = 0, bad = 0;
+  for (int i = lane; i < N; i += 32) {
+    const double y1 = Y1[i], y2 = Y2[i];
+    const bool p1 = sa.gmask[i] && !isnan(y1);
+    const bool p2 = sc.gmask[i] && !isnan(y2);
+    if (!p1 && !p2) continue;
+    if (!sa.gmask[i] || (Q > 0 && !sa.cmask[i])) { // the reference reads past its vectors here
+      bad = 1;
+      continue;
+    }
+    double z[HY_MAXQ2];
+    z[0] = 1.0;
+    z[1] = Xm[i];
+    for (int k = 0; k < Q; ++k) z[2 + k] = sa.Call[(size_t)k * ldn + i];
+    double *G = acc + ((p1 && p2) ? 0 : (p1 ? 1 : 2)) * NT;
+    int t = 0;
+    for (int a = 0; a < Q2; ++a)
+      for (int b = 0; b <= a; ++b) G[t++] += z[a] * z[b];
+    if (p1 && p2) {
+      double *h = acc + 3 * NT;
+      for (int a = 0; a < Q2; ++a) {
+        h[a] += z[a] * y1;
+        h[Q2 + a] += z[a] * y2;
+      }
+      h[2 * Q2] += y1 * y2;
+      ++n12;
+    }
+  }
+  for (int e = 0; e < 3 * NT + 2 * Q2 + 1; ++e) acc[e] = warp_sum(acc[e]);
+  n12 = warp_sum_int(n12);
+  if (__any_sync(0xffffffffu, bad)) {
+    if (lane == 0) atomicExch(err_flag + 4, 1);
+    degenerate = true;
+  }
+  if (n12 == 0) { // "have no individuals in common": fatal in the reference (gene_snp_pair.cpp:897-901)
+    if (lane == 0) atomicExch(err_flag + 5, 1);
+    degenerate = true;
+  }
+  bool ok = true;
+  if (lane == 0 && !degenerate) {
+    double G12[HY_MAXQ2 * HY_MAXQ2], G1[HY_MAXQ2 * HY_MAXQ2], G2[HY_MAXQ2 * HY_MAXQ2];
+    int t = 0;
+    for (int a = 0; a < Q2; ++a)
+      for (int b = 0; b <= a; ++b, ++t) {
+        G12[a * HY_MAXQ2 + b] = G12[b * HY_MAXQ2 + a] = acc[t];
+        G1[a * HY_MAXQ2 + b] = G1[b * HY_MAXQ2 + a] = acc[t] + acc[NT + t];
+        G2[a * HY_MAXQ2 + b] = G2[b * HY_MAXQ2 + a] = acc[t] + acc[2 * NT + t];
+      }
+    const double *h1 = acc + 3 * NT, *h2 = h1 + Q2;
+    const double y12 = acc[3 * NT + 2 * Q2];
+    double I12[HY_MAXQ2 * HY_MAXQ2], I1[HY_MAXQ2 * HY_MAXQ2], I2[HY_MAXQ2 * HY_MAXQ2];
+    // (three separate calls of the out-of-line routine: inlined into one short-circuit chain the second and third
+    // inverses came back as the identity in the sm_100a build of nvcc 12.9)
+    const bool ok12 = hy_inverse(G12, Q2, I12);
+    const bool ok1 = hy_inverse(G1, Q2, I1);
+    const bool ok2 = hy_inverse(G2, Q2, I2);
+    ok = ok12 && ok1 && ok2;
+    if (ok) {
+      const double s_full = (y12 - hy_quad(h1, I12, h2, Q2)) / (double)n12;
+      // null model: the same without the genotype column
+      double Gc[HY_MAXQ2 * HY_MAXQ2], Ic[HY_MAXQ2 * HY_MAXQ2], c1[HY_MAXQ2], c2[HY_MAXQ2];
+      for (int a = 0, ra = 0; a < Q2; ++a) {
+        if (a == 1) continue;
+        c1[ra] = h1[a];
+        c2[ra] = h2[a];
+        for (int b = 0, rb = 0; b < Q2; ++b) {
+          if (b == 1) continue;
+          Gc[ra * HY_MAXQ2 + rb] = G12[a * HY_MAXQ2 + b];
+          ++rb;
+        }
+        ++ra;
+      }
+      ok = hy_inverse(Gc, Q2 - 1, Ic);
+      if (ok) {
+        const double s_null = (y12 - hy_quad(c1, Ic, c2, Q2 - 1)) / (double)n12;
+        const double sig12 = fit * s_full + (1.0 - fit) * s_null;
+        double cov11 = 0.0; // [(G12 + Gu1)^-1 G12 (G12 + Gu2)^-1][1][1]
+        for (int a = 0; a < Q2; ++a) {
+          double sacc = 0.0;
+          for (int b = 0; b < Q2; ++b) sacc += G12[a * HY_MAXQ2 + b] * I2[b * HY_MAXQ2 + 1];
+          cov11 += I1[1 * HY_MAXQ2 + a] * sacc;
+        }
+        vg12 = sig12 * cov11;
+      }
+    }
+  }
+  ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+  vg12 = __shfl_sync(0xffffffffu, vg12, 0);
+  return (ok && !degenerate) ? vg12 : nan("");
+}
+
+// off-diagonal cache of one launch: [gene of the work list][SNP of its window][pair of subgroups]
+__global__ void __launch_bounds__(THREADS) hybrid_offdiag_kernel(const DevParams *__restrict__ prm_, const LaunchArgs la)
+{
+  const DevParams &prm = *prm_;
+  const int S = prm.S, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gi = blockIdx.x, g = la.genes[gi];
+  const long long mbeg = prm.cis_begin[g], mend = prm.cis_end[g];
+  const int npsub = S * (S - 1) / 2;
+  for (long long m = mbeg + (long long)blockIdx.y * WARPS + warp; m < mend; m += (long long)WARPS * gridDim.y) {
+    bool all_geno = true;
+    for (int s = 0; s < S; ++s) all_geno = all_geno && prm.sub[s].snp_has[m];
+    if (!all_geno) continue; // pair skipped by the reference (gene.cpp:315-321)
+    double *off = la.hy_off + ((size_t)gi * la.hy_stride + (size_t)(m - mbeg)) * npsub;
+    int t = 0;
+    for (int s1 = 0; s1 + 1 < S; ++s1)
+      for (int s2 = s1 + 1; s2 < S; ++s2, ++t) {
+        const double v = hy_offdiag(prm, g, m, s1, s2, prm.fiterr, lane, la.err_flag);
+        if (lane == 0) off[t] = v;
+      }
+  }
 }
 
 __host__ __device__ inline size_t hybrid_smem_bytes(int S, int Qmax, int ldn, int qnorm, bool basis_in_smem)
@@ -387,8 +553,10 @@ __global__ void __launch_bounds__(THREADS) hybrid_kernel(const DevParams *__rest
             pve = 1.0 - rss / s_tss[s];
             sigmahat = sqrt(rss / (double)(n - rank));
             se = sigmahat * sqrt(1.0 / xx);
-            if (lane == 0) pval = 2.0 * tdist_Q(fabs(betahat / se), (double)(n - rank));
-            pval = __shfl_sync(0xffffffffu, pval, 0);
+            if (la.want_outputs) { // the p-value is only printed (no permutation statistic of the join analysis uses it)
+              if (lane == 0) pval = 2.0 * tdist_Q(fabs(betahat / se), (double)(n - rank));
+              pval = __shfl_sync(0xffffffffu, pval, 0);
+            }
             sig_ss = fit * (rss / (double)n) + (1.0 - fit) * (s_yy[s] / (double)n);
             vg_ss = sig_ss * (1.0 / xx);
           } else
@@ -413,99 +581,20 @@ __global__ void __launch_bounds__(THREADS) hybrid_kernel(const DevParams *__rest
         }
       }
       __syncwarp();
-      // -------- off-diagonals: Gram matrices over the individuals common to / unique to each pair of subgroups
-      for (int s1 = 0; s1 + 1 < S; ++s1)
-        for (int s2 = s1 + 1; s2 < S; ++s2) {
-          const SubDev &sa = prm.sub[s1], &sc = prm.sub[s2];
-          const int Q = sa.Q, Q2 = Q + 2, NT = Q2 * (Q2 + 1) / 2;
-          const double *Y1 = sa.Yall + (size_t)g * ldn, *Y2 = sc.Yall + (size_t)g * ldn;
-          const double *Xm = sa.X + (size_t)m * ldn;
-          double acc[3 * HY_NT + 2 * HY_MAXQ2 + 1];
-          for (int e = 0; e < 3 * NT + 2 * Q2 + 1; ++e) acc[e] = 0.0;
-          int n12 = 0, bad = 0;
-          for (int i = lane; i < N; i += 32) {
-            const double y1 = Y1[i], y2 = Y2[i];
-            const bool p1 = sa.gmask[i] && !isnan(y1);
-            const bool p2 = sc.gmask[i] && !isnan(y2);
-            if (!p1 && !p2) continue;
-            if (!sa.gmask[i] || (Q > 0 && !sa.cmask[i])) { // the reference reads past its vectors here
-              bad = 1;
-              continue;
-            }
-            double z[HY_MAXQ2];
-            z[0] = 1.0;
-            z[1] = Xm[i];
-            for (int k = 0; k < Q; ++k) z[2 + k] = sa.Call[(size_t)k * ldn + i];
-            double *G = acc + ((p1 && p2) ? 0 : (p1 ? 1 : 2)) * NT;
-            int t = 0;
-            for (int a = 0; a < Q2; ++a)
-              for (int b = 0; b <= a; ++b) G[t++] += z[a] * z[b];
-            if (p1 && p2) {
-              double *h = acc + 3 * NT;
-              for (int a = 0; a < Q2; ++a) {
-                h[a] += z[a] * y1;
-                h[Q2 + a] += z[a] * y2;
-              }
-              h[2 * Q2] += y1 * y2;
-              ++n12;
-            }
+      // -------- off-diagonals: Vg_12 of every pair of subgroups from the per-launch cache (hybrid_offdiag_kernel; they
+      // do not depend on the permutation)
+      {
+        const int npsub = S * (S - 1) / 2;
+        const double *off = la.hy_off + ((size_t)gi * la.hy_stride + (size_t)(m - mbeg)) * npsub;
+        int t = 0, bad = 0;
+        for (int s1 = 0; s1 + 1 < S; ++s1)
+          for (int s2 = s1 + 1; s2 < S; ++s2, ++t) {
+            const double v = off[t];
+            if (isnan(v)) bad = 1;
+            if (lane == 0) H.Vg[s1 * MV_MAXS + s2] = H.Vg[s2 * MV_MAXS + s1] = v;
           }
-          for (int e = 0; e < 3 * NT + 2 * Q2 + 1; ++e) acc[e] = warp_sum(acc[e]);
-          n12 = warp_sum_int(n12);
-          if (__any_sync(0xffffffffu, bad)) {
-            if (lane == 0) atomicExch(la.err_flag + 4, 1);
-            degenerate = true;
-          }
-          if (n12 == 0) { // "have no individuals in common": fatal in the reference (gene_snp_pair.cpp:897-901)
-            if (lane == 0) atomicExch(la.err_flag + 5, 1);
-            degenerate = true;
-          }
-          bool ok = true;
-          if (lane == 0 && !degenerate) {
-            double G12[HY_MAXQ2 * HY_MAXQ2], G1[HY_MAXQ2 * HY_MAXQ2], G2[HY_MAXQ2 * HY_MAXQ2];
-            int t = 0;
-            for (int a = 0; a < Q2; ++a)
-              for (int b = 0; b <= a; ++b, ++t) {
-                G12[a * HY_MAXQ2 + b] = G12[b * HY_MAXQ2 + a] = acc[t];
-                G1[a * HY_MAXQ2 + b] = G1[b * HY_MAXQ2 + a] = acc[t] + acc[NT + t];
-                G2[a * HY_MAXQ2 + b] = G2[b * HY_MAXQ2 + a] = acc[t] + acc[2 * NT + t];
-              }
-            const double *h1 = acc + 3 * NT, *h2 = h1 + Q2;
-            const double y12 = acc[3 * NT + 2 * Q2];
-            double I12[HY_MAXQ2 * HY_MAXQ2], I1[HY_MAXQ2 * HY_MAXQ2], I2[HY_MAXQ2 * HY_MAXQ2];
-            ok = hy_inverse(G12, Q2, I12) && hy_inverse(G1, Q2, I1) && hy_inverse(G2, Q2, I2);
-            if (ok) {
-              const double s_full = (y12 - hy_quad(h1, I12, h2, Q2)) / (double)n12;
-              // null model: the same without the genotype column
-              double Gc[HY_MAXQ2 * HY_MAXQ2], Ic[HY_MAXQ2 * HY_MAXQ2], c1[HY_MAXQ2], c2[HY_MAXQ2];
-              for (int a = 0, ra = 0; a < Q2; ++a) {
-                if (a == 1) continue;
-                c1[ra] = h1[a];
-                c2[ra] = h2[a];
-                for (int b = 0, rb = 0; b < Q2; ++b) {
-                  if (b == 1) continue;
-                  Gc[ra * HY_MAXQ2 + rb] = G12[a * HY_MAXQ2 + b];
-                  ++rb;
-                }
-                ++ra;
-              }
-              ok = hy_inverse(Gc, Q2 - 1, Ic);
-              if (ok) {
-                const double s_null = (y12 - hy_quad(c1, Ic, c2, Q2 - 1)) / (double)n12;
-                const double sig12 = fit * s_full + (1.0 - fit) * s_null;
-                double cov11 = 0.0; // [(G12 + Gu1)^-1 G12 (G12 + Gu2)^-1][1][1]
-                for (int a = 0; a < Q2; ++a) {
-                  double sacc = 0.0;
-                  for (int b = 0; b < Q2; ++b) sacc += G12[a * HY_MAXQ2 + b] * I2[b * HY_MAXQ2 + 1];
-                  cov11 += I1[1 * HY_MAXQ2 + a] * sacc;
-                }
-                H.Vg[s1 * MV_MAXS + s2] = H.Vg[s2 * MV_MAXS + s1] = sig12 * cov11;
-              }
-            }
-          }
-          ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
-          if (!ok) degenerate = true;
-        }
+        if (bad) degenerate = true;
+      }
       __syncwarp();
       if (degenerate) {
         if (lane == 0) atomicOr(la.err_flag + 1, 1); // documented unsupported degenerate design
@@ -523,28 +612,72 @@ __global__ void __launch_bounds__(THREADS) hybrid_kernel(const DevParams *__rest
       __syncwarp();
       const unsigned long long ones = (S >= 64) ? ~0ull : ((1ull << S) - 1ull);
       if (!degenerate) {
+        // lanes take (configuration, grid point) items: floor(32 / nk) configurations per pass (one configuration over
+        // two half-passes when 32 < nk <= 64); the owner lane of a configuration then averages its nk values in grid
+        // order (utils::log10_weighted_sum).  Larger grids: one lane per configuration (hybrid_config).
+        auto eval_set = [&](long long nconf, bool gen_set, const double *phi2, const double *oma2, int nk, double *raw,
+                            auto &&own) {
+          if (nk > 64 || nk < 1) {
+            for (long long c = lane; c < nconf; c += 32) {
+              const unsigned long long cm = gen_set ? ones : ((la.which == 2) ? (1ull << c) : prm.cfg_mask[c]);
+              own(c, hybrid_config(H, S, cm, phi2, oma2, nk, gen_set ? (int)c : 0, raw ? raw + c * nk : nullptr));
+            }
+            return;
+          }
+          const int npack = (nk <= 32) ? 32 / nk : 1, span = (nk <= 32) ? nk : 32;
+          for (long long c0 = 0; c0 < nconf; c0 += npack) {
+            for (int half = 0; half * 32 < nk; ++half) {
+              const int slot = lane / span, gp = (nk <= 32) ? lane % span : lane + 32 * half;
+              const long long c = c0 + slot;
+              if (slot < npack && c < nconf && gp < nk) {
+                const unsigned long long cm = gen_set ? ones : ((la.which == 2) ? (1ull << c) : prm.cfg_mask[c]);
+                const int variant = gen_set ? (int)c : 0;
+                const double ph = phi2[gp], om = oma2[gp];
+                const double p2 = (variant == 0) ? ph : ((variant == 1) ? 0.0 : ph + om);
+                const double o2 = (variant == 0) ? om : ((variant == 1) ? ph + om : 0.0);
+                const double v = hybrid_value(H, S, cm, p2, o2);
+                if (raw) raw[c * nk + gp] = v;
+                H.scr[slot * span + gp] = v;
+              }
+            }
+            __syncwarp();
+            if (lane < npack && c0 + lane < nconf) {
+              Lse a;
+              a.init();
+              const double *vals = H.scr + lane * span;
+              for (int g2 = 0; g2 < nk; ++g2) a.add(vals[g2], 1.0 / (double)nk, g2 == 0);
+              own(c0 + lane, a.result());
+            }
+            __syncwarp();
+          }
+        };
         // consistent configuration: gen, gen-fix, gen-maxh (gene_snp_pair.cpp:1257-1308)
         const int nvar = (p >= 0) ? 1 : 3;
-        if (lane < nvar) {
-          double *raw = (la.want_outputs && la.out_gen) ? la.out_gen + (pair * 3 + lane) * L : nullptr;
-          w_gen[0] = hybrid_config(H, S, ones, prm.phi2L, prm.oma2L, L, lane, raw);
+        double w_own[3] = {nan(""), nan(""), nan("")};
+        unsigned int has = 0u; // variants whose average this lane owns
+        eval_set(nvar, true, prm.phi2L, prm.oma2L, L, (la.want_outputs && la.out_gen) ? la.out_gen + pair * 3 * L : nullptr,
+                 [&](long long c, double w) {
+                   if (c == 0) w_own[0] = w;
+                   else if (c == 1) w_own[1] = w;
+                   else w_own[2] = w;
+                   has |= 1u << (int)c;
+                 });
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const unsigned int who = __ballot_sync(0xffffffffu, (has >> j) & 1u);
+          const double v = __shfl_sync(0xffffffffu, w_own[j], who ? __ffs(who) - 1 : 0);
+          w_gen[j] = who ? v : nan("");
         }
-        w_gen[1] = __shfl_sync(0xffffffffu, w_gen[0], 1);
-        w_gen[2] = __shfl_sync(0xffffffffu, w_gen[0], 2);
-        w_gen[0] = __shfl_sync(0xffffffffu, w_gen[0], 0);
-        if (p >= 0) w_gen[1] = w_gen[2] = nan("");
         if (la.which >= 2) { // singletons / every configuration on gridS (:1310-1382), BMAlite, BMA
           Lse lite, bma;
           lite.init();
           bma.init();
-          for (long long c = lane; c < C; c += 32) {
-            const unsigned long long cm = (la.which == 2) ? (1ull << c) : prm.cfg_mask[c];
-            double *raw = (la.want_outputs && la.out_cfg) ? la.out_cfg + (pair * C + c) * K : nullptr;
-            const double wc = hybrid_config(H, S, cm, prm.phi2S, prm.oma2S, K, 0, raw);
-            if (la.want_outputs && la.out_w) la.out_w[pair * (5 + C) + 5 + c] = wc;
-            if (c < S) lite.add(wc, 0.5 / (double)S, c == 0);
-            if (la.which == 3) bma.add(wc, prm.cfg_weight[c], c == 0);
-          }
+          eval_set(C, false, prm.phi2S, prm.oma2S, K, (la.want_outputs && la.out_cfg) ? la.out_cfg + pair * C * K : nullptr,
+                   [&](long long c, double wc) {
+                     if (la.want_outputs && la.out_w) la.out_w[pair * (5 + C) + 5 + c] = wc;
+                     if (c < S) lite.add(wc, 0.5 / (double)S, c == 0);
+                     if (la.which == 3) bma.add(wc, prm.cfg_weight[c], c == 0);
+                   });
           lite = warp_merge(lite);
           lite.add(w_gen[0], 0.5, false);
           w_gensin = lite.result();

@@ -74,6 +74,8 @@ struct LaunchArgs {
   double *basis_ws; // global workspace (nullptr -> dynamic shared memory)
   double *table_ws;
   int *err_flag;
+  double *hy_off; // --error hybrid: Vg_12 cache of the launch [gene][hy_stride][S (S - 1) / 2] (hybrid_offdiag_kernel)
+  int hy_stride;  // SNPs per gene slot of hy_off (largest cis window of the launch)
 };
 
 // sizes (in doubles) of the two workspaces
