@@ -41,7 +41,10 @@ enum { EQB_ANALYSIS_SEP = 0, EQB_ANALYSIS_JOIN = 1 };
 enum { EQB_BFS_GEN = 0, EQB_BFS_SIN = 1, EQB_BFS_ALL = 2 };
 /* --pbf (eqtlbma_bf.cpp:652-657) */
 enum { EQB_PBF_NONE = 0, EQB_PBF_GEN = 1, EQB_PBF_GEN_SIN = 2, EQB_PBF_ALL = 3 };
-/* --error (eqtlbma_bf.cpp:1596) */
+/* --error (eqtlbma_bf.cpp:1596).  MVLR: gene_snp_pair.cpp:624-758 + MVLR.cpp (same individuals in every subgroup,
+ * at most 16 subgroups).  HYBRID: gene_snp_pair.cpp:760-1423 (individuals common to / unique to each pair of subgroups;
+ * at most 16 subgroups and 6 covariates; with covariates their files must be in the order of the sorted sample names,
+ * because the reference indexes them by the all-sample index, :931-933 -- checked by eqb_finalize). */
 enum { EQB_ERROR_UVLR = 0, EQB_ERROR_MVLR = 1, EQB_ERROR_HYBRID = 2 };
 /* --anchor (snp.cpp:274-297) */
 enum { EQB_ANCHOR_TSS = 0, EQB_ANCHOR_TSS_TES = 1 };
