@@ -354,6 +354,36 @@ def run_hm_block(eqtlbma_b200, local_rank, hbm_gbs, with_cpu, n_genes=10000, snp
     return out
 
 
+def run_hybrid_block(eqtlbma_b200, local_rank, with_cpu, n_genes=200, ref_genes=6):
+    """--error hybrid on a slice of 3 ragged subgroups of up to 450 individuals, ~50 cis SNPs
+    per gene: device-timed true pass (--bfs sin) and permutation pass (--pbf gen-sin), inputs resident in HBM; the unmodified
+    reference binary on the first genes of the same workload beside it (one core: its true pass is single-threaded)."""
+    from eqtlbma_b200.synth import make_dataset
+    ds = make_dataset(seed=11, n_subgroups=3, n_inds=450, n_genes=n_genes, snps_per_gene=50, ragged=True, ragged_min_frac=0.6,
+                      radius=1000, gene_spacing=2001, far_snp=False, n_chr=2)
+    eng = eqtlbma_b200.Engine(ds, analysis="join", bfs="sin", error="hybrid", fiterr=0.5, device=local_rank)
+    pairs = int(eng.pair_offsets()[-1])
+    l0 = eng.launch_count()
+    ms = min(eng.run_device_only(raw=True) for _ in range(5))
+    launches = (eng.launch_count() - l0) // 5
+    nperm = 100
+    pms = min(eng.run_permutations_device_only(nperm, 7, pbf="gen-sin", wrtsize=n_genes) for _ in range(2))
+    eng.close()
+    out = {"workload": f"--error hybrid --bfs sin: 3 ragged subgroups of <= 450 individuals, {n_genes} genes x ~50 cis SNPs "
+                       f"({pairs} pairs); permutations: {nperm} per gene, --pbf gen-sin",
+           "value": pairs / ms * 1e3, "unit": "pairs/s", "ms_per_pass": ms, "gpu_launches_per_pass": int(launches),
+           "kernels": "hybrid_offdiag_kernel + hybrid_kernel", "timing": "device-timed, inputs resident in HBM, best of 5",
+           "perm": {"value": pairs * nperm / pms * 1e3, "unit": "pair-permutations/s", "ms": pms}}
+    if with_cpu:
+        sub = subset_dataset(ds, ref_genes)
+        r = time_reference_binary(sub, ["--analys", "join", "--bfs", "sin", "--error", "hybrid", "--fiterr", "0.5", "--outss", "--outw"])
+        if r and r.get("pairs"):
+            out["cpu_baseline"] = {"value": r["pairs"] / r["seconds"], "unit": "pairs/s", "cores": 1, "kind": "reference",
+                                   "sample": f"first {ref_genes} genes ({r['pairs']} pairs) through oracle/_ref/eqtlbma_bf_ref, "
+                                             f"association loop {r['seconds']:.2f} s"}
+    return out
+
+
 def cpu_baseline_hm(ds, sample_genes=1000):
     import re
     import shutil
@@ -609,6 +639,13 @@ def run_ours(args, rank, world, local_rank):
         except Exception as exc:  # the headline line must not depend on the widening block
             hm_info = {"error": repr(exc)[:300]}
 
+    hybrid_info = None
+    if rank == 0 and not args.no_hybrid:
+        try:
+            hybrid_info = run_hybrid_block(eqtlbma_b200, local_rank, with_cpu=(world == 1 and not args.no_cpu))
+        except Exception as exc:  # the headline line must not depend on the widening block
+            hybrid_info = {"error": repr(exc)[:300]}
+
     # ---- max over ranks, whole-job aggregate
     tot_pairs = pairs
     digests = [digest]
@@ -691,6 +728,8 @@ def run_ours(args, rank, world, local_rank):
         out["perm"] = perm_info
     if hm_info:
         out["hm"] = hm_info
+    if hybrid_info:
+        out["hybrid"] = hybrid_info
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_reference(ds, sample_genes=args.cpu_genes)
         par = parity_vs_reference(ds, eng, full, args.cpu_genes)
@@ -1003,6 +1042,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-perm", action="store_true")
     ap.add_argument("--no-hm", action="store_true", help="skip the hierarchical-model (eqtlbma_hm) block")
+    ap.add_argument("--no-hybrid", action="store_true", help="skip the --error hybrid block")
     ap.add_argument("--perm-genes", type=int, default=0, help="genes per GPU of the c3/c4-shape block (default 8)")
     ap.add_argument("--perm-nperm", type=int, default=0, help="permutations of the c4-shape block (default 2047)")
     ap.add_argument("--no-check", action="store_true", help="skip the sharding-invariance check")
