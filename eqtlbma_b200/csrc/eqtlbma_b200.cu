@@ -592,7 +592,7 @@ int run_mvlr_kernel(eqb_ctx *ctx, const LaunchArgs &la, int ppg)
 }
 
 template <int NPL>
-cudaError_t launch_hybrid(eqb_ctx *ctx, const LaunchArgs &la, int grid, size_t smem)
+cudaError_t launch_hybrid(eqb_ctx *ctx, const LaunchArgs &la, dim3 grid, size_t smem)
 {
   cudaError_t e = cudaFuncSetAttribute(hybrid_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -626,9 +626,15 @@ int run_hybrid_kernel(eqb_ctx *ctx, const LaunchArgs &la, int ppg)
     l2.pair_off = la.pair_off ? la.pair_off + g0 : nullptr;
     l2.n_genes = (int)(g1 - g0);
     if (la.out_stat) l2.out_stat = la.out_stat + (size_t)g0 * (la.perms_per_gene > 0 ? (size_t)la.P_total : 1);
-    const long long grid = (g1 - g0) * std::max(1, ppg);
+    const long long grid_x = (g1 - g0) * std::max(1, ppg);
+    // output-only launches (the true pass) cut the SNPs of a gene into slices until the device is filled twice over
+    long long nsplit = 1;
+    if (la.stat_kind == STAT_NONE && la.perms_per_gene == 0)
+      nsplit = std::max<long long>(1, std::min<long long>((max_win + WARPS - 1) / WARPS, (2LL * 2 * ctx->n_sm + grid_x - 1) / grid_x));
+    if (!basis_smem) nsplit = std::min<long long>(nsplit, std::max<long long>(1, (148 * 8) / grid_x));
+    const dim3 grid((unsigned)grid_x, (unsigned)nsplit);
     if (!basis_smem) {
-      if (ctx->d_basis_ws.ensure((size_t)grid * nb) != cudaSuccess) return fail(ctx, "workspace alloc failed");
+      if (ctx->d_basis_ws.ensure((size_t)grid_x * nsplit * nb) != cudaSuccess) return fail(ctx, "workspace alloc failed");
       l2.basis_ws = ctx->d_basis_ws.p;
     }
     if (ctx->d_hy_off.ensure((size_t)(g1 - g0) * max_win * npsub) != cudaSuccess) return fail(ctx, "workspace alloc failed");
@@ -641,11 +647,11 @@ int run_hybrid_kernel(eqb_ctx *ctx, const LaunchArgs &la, int ppg)
       if (cudaGetLastError() != cudaSuccess) return fail(ctx, "hybrid_offdiag_kernel launch failed");
     }
     cudaError_t e;
-    if (npl_need <= 4) e = launch_hybrid<4>(ctx, l2, (int)grid, smem);
-    else if (npl_need <= 8) e = launch_hybrid<8>(ctx, l2, (int)grid, smem);
-    else if (npl_need <= 16) e = launch_hybrid<16>(ctx, l2, (int)grid, smem);
-    else if (npl_need <= 32) e = launch_hybrid<32>(ctx, l2, (int)grid, smem);
-    else if (npl_need <= 64) e = launch_hybrid<64>(ctx, l2, (int)grid, smem);
+    if (npl_need <= 4) e = launch_hybrid<4>(ctx, l2, grid, smem);
+    else if (npl_need <= 8) e = launch_hybrid<8>(ctx, l2, grid, smem);
+    else if (npl_need <= 16) e = launch_hybrid<16>(ctx, l2, grid, smem);
+    else if (npl_need <= 32) e = launch_hybrid<32>(ctx, l2, grid, smem);
+    else if (npl_need <= 64) e = launch_hybrid<64>(ctx, l2, grid, smem);
     else return fail(ctx, "more than 2048 samples are not supported yet");
     if (e != cudaSuccess) return fail(ctx, std::string("hybrid_kernel launch: ") + cudaGetErrorString(e));
   }

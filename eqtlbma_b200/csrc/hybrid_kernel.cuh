@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(THREADS) hybrid_kernel(const DevParams *__rest
   const size_t nb = basis_doubles(S, Qmax, ldn, prm.qnorm);
   HyPair *hy_all = (HyPair *)dyn_smem;
   HyPair &H = hy_all[warp];
-  double *basis = la.basis_ws ? la.basis_ws + (size_t)blockIdx.x * nb : (double *)(hy_all + WARPS);
+  double *basis = la.basis_ws ? la.basis_ws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * nb : (double *)(hy_all + WARPS);
 
   // ------------------------------------------------------------------ phase 1: per-subgroup bases and residual
   // phenotypes on the (permuted) kept rows -- the uvlr setup (pair_kernel phase 1)
@@ -477,7 +477,9 @@ __global__ void __launch_bounds__(THREADS) hybrid_kernel(const DevParams *__rest
   double max_stat = -INFINITY;
   bool first_nan = false;
   int cnt_nonnan = 0;
-  for (long long m = mbeg + warp; m < mend; m += WARPS) {
+  // (gridDim.y > 1 only in output-only launches: the SNPs of a gene are then cut into slices so that a true pass over few
+  // genes with long windows fills the device; a launch that reduces a statistic over the gene keeps one CTA per gene)
+  for (long long m = mbeg + (long long)blockIdx.y * WARPS + warp; m < mend; m += (long long)WARPS * gridDim.y) {
     const bool is_first = (m == mbeg);
     const long long pair = la.want_outputs ? la.pair_off[gi] + (m - mbeg) : 0;
     bool all_geno = true;

@@ -51,3 +51,16 @@ def test_inss_missing_column_is_reported(tmp_path):
 def test_missing_compulsory_options():
     r = _run(["--out", "x", "--analys", "join"])
     assert r.returncode != 0 and "missing compulsory option --geno" in r.stderr
+
+
+def test_error_model_validation(tmp_path):
+    """--error uvlr|mvlr|hybrid are the reference's three models (eqtlbma_bf.cpp:617-622); anything else is rejected, and
+    --inss stays restricted to uvlr."""
+    lst = tmp_path / "l.txt"
+    lst.write_text("s1\t%s\n" % os.path.join(GOLD, "sumstats_s1.txt.gz"))
+    grid = os.path.join(GOLD, "grid_phi2_oma2_general.txt.gz")
+    r = _run(["--inss", str(lst), "--out", str(tmp_path / "o"), "--analys", "join", "--error", "bogus", "--gridL", grid])
+    assert r.returncode != 0 and "--error bogus is not valid" in r.stderr
+    r = _run(["--inss", str(lst), "--out", str(tmp_path / "o"), "--analys", "join", "--error", "hybrid", "--gridL", grid])
+    assert r.returncode != 0 and "is not valid" not in r.stderr and "--inss requires --error uvlr" in r.stderr
+    assert "hybrid" in _run(["--help"]).stdout
