@@ -59,7 +59,8 @@ def test_error_model_validation(tmp_path):
     lst = tmp_path / "l.txt"
     lst.write_text("s1\t%s\n" % os.path.join(GOLD, "sumstats_s1.txt.gz"))
     grid = os.path.join(GOLD, "grid_phi2_oma2_general.txt.gz")
-    r = _run(["--inss", str(lst), "--out", str(tmp_path / "o"), "--analys", "join", "--error", "bogus", "--gridL", grid])
+    r = _run(["--geno", grid, "--scoord", grid, "--exp", grid, "--gcoord", grid, "--out", str(tmp_path / "o"), "--analys", "join",
+              "--bfs", "gen", "--gridL", grid, "--error", "bogus"])
     assert r.returncode != 0 and "--error bogus is not valid" in r.stderr
     r = _run(["--inss", str(lst), "--out", str(tmp_path / "o"), "--analys", "join", "--error", "hybrid", "--gridL", grid])
     assert r.returncode != 0 and "is not valid" not in r.stderr and "--inss requires --error uvlr" in r.stderr
