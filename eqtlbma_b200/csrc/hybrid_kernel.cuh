@@ -18,10 +18,16 @@
 //   the model's own ABF (CalcLog10AbfMvlr :1165-1255):
 //                W = D (gamma gamma' o [phi2 I + oma2 11']) D,  D = diag(sqrt(Sigma_ss))
 //                log10 ABF = [ b'Vg^-1 W (I + Vg^-1 W)^-1 Vg^-1 b / 2 - ln det(I + Vg^-1 W) / 2 ] / ln 10.
-// One CTA = one (gene, permutation); warps take SNPs; per SNP the warp accumulates the dot products, lane 0 does the
-// (2 + Q)-sized algebra, lanes take configurations.  The reference's pseudo-inverses are plain inverses here: a
-// rank-deficient Gram matrix (monomorphic genotype on a set) is reported through the degenerate-design flag and the
-// pair's Bayes factors are NaN (same documented tie as the uvlr path).
+// Two kernels per launch:
+//   hybrid_offdiag_kernel  grid = genes x SNP slices, warp per SNP: the off-diagonal blocks do not depend on the permutation,
+//                          so they are computed once per (gene, SNP) -- the warp accumulates the dot products, lane 0 does
+//                          the (2 + Q)-sized algebra -- into a cache [gene][largest window][S (S - 1) / 2];
+//   hybrid_kernel<NPL>     CTA = (gene, permutation) (x SNP slices in output-only launches), warp per SNP: phase 1 = the
+//                          uvlr setup, per SNP the diagonals, Vg assembled and inverted once, then lanes take
+//                          (configuration, grid point) items with the ABF evaluated on the active block.
+// The reference's pseudo-inverses are plain inverses here: a rank-deficient Gram matrix (monomorphic genotype on a set)
+// is reported through the degenerate-design flag and the pair's Bayes factors are NaN (same documented tie as the uvlr
+// path).
 #pragma once
 
 #include "mvlr_kernel.cuh"
@@ -91,7 +97,7 @@ static __device__ __noinline__ bool hy_inverse(const double *A, int n, double *i
   return true;
 }
 
-// a' M b for n-vectors and an n x n matrix of stride HY_MAXQ2; `skip` drops one row / column (-1: none)
+// a' M b for n-vectors and an n x n matrix of stride HY_MAXQ2
 __device__ inline double hy_quad(const double *a, const double *M, const double *b, int n)
 {
   double acc = 0.0;
