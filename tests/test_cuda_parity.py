@@ -111,6 +111,30 @@ def test_hybrid_extra_shapes_match_oracle(cuda_lib, oracle_lib, name):
     ora.close()
 
 
+def test_hybrid_reference_failure_modes_are_reported(cuda_lib, oracle_lib):
+    """Inputs on which the reference stops or reads past its vectors: two subgroups without a common individual
+    (gene_snp_pair.cpp:897-901, fatal) and covariate files that are not in the order of the sorted sample names (the
+    off-diagonal designs index them by the all-sample index, :931-933).  Both are errors of the ABI, never silent values."""
+    import eqtlbma_b200
+    from eqtlbma_b200.synth import make_dataset
+    kw = dict(analysis="join", bfs="gen", error="hybrid", fiterr=0.5)
+    ds = make_dataset(seed=5, n_subgroups=2, n_inds=60, n_genes=3, snps_per_gene=2)
+    half = len(ds.samples) // 2
+    ds.subgroups[0].all2exp[half:] = -1
+    ds.subgroups[1].all2exp[:half] = -1
+    eng = eqtlbma_b200.Engine(ds, **kw)
+    with pytest.raises(RuntimeError, match="no individuals in common"):
+        eng.run()
+    eng.close()
+    ora = AnyEngine(oracle_lib, "eqo_", ds, **kw)
+    with pytest.raises(RuntimeError, match="no individuals in common"):
+        ora.run()
+    ora.close()
+    ds = make_dataset(seed=6, n_subgroups=2, n_inds=60, n_genes=3, snps_per_gene=2, n_cov=1)  # ind1, ind10, ind11, ...: not identity
+    with pytest.raises(RuntimeError, match="order of the sorted sample names"):
+        eqtlbma_b200.Engine(ds, **kw)
+
+
 def test_cis_windows_match_linear_scan(cuda_lib, oracle_lib):
     """a1: the device binary search reproduces Gene::SetCisSnps / Snp::IsInCis bit-exactly,
     including the start < radius underflow guard and both anchors."""
