@@ -6,7 +6,8 @@ check the primitives the hot path reaches -- gsl_cdf_tdist_P/Q (gene_snp_pair.cp
 gsl_cdf_ugaussian_Pinv (gene_snp_pair.cpp:274, utils_math.cpp:92), gsl_cdf_fdist_Q / gsl_cdf_chisq_Qinv (MVLR.cpp:404-405),
 gsl_multifit_linear + _rank (utils_math.cpp:189-190), gsl_rng_mt19937 / gsl_rng_uniform_int / gsl_ran_shuffle
 (gene.cpp:394,523,639), gsl_sort_index (utils_math.cpp:87), gsl_combination_next (gene_snp_pair.cpp:476-548),
-gsl_sf_choose (gene_snp_pair.cpp:591) -- against mpmath (50 digits), scipy.stats, numpy.linalg and numpy's own MT19937.
+gsl_sf_choose (gene_snp_pair.cpp:591), gsl_linalg_SV_decomp / gsl_linalg_LU_* (the hybrid error model: utils_math.cpp:249-301,
+gene_snp_pair.cpp:793-812,1196-1224) -- against mpmath (50 digits), scipy.stats, numpy.linalg and numpy's own MT19937.
 Residual risk that remains: real GSL's large-nu Cornish-Fisher shortcut inside gsl_cdf_tdist_P is deliberately not
 emulated, so the shim is, if anything, closer to the exact distribution than GSL."""
 import ctypes as C
@@ -273,3 +274,59 @@ def test_sort_index_and_combinations(shim):
             got.append(tuple(c.contents.data[i] for i in range(k)))
         assert got == list(itertools.combinations(range(n), k))  # lexicographic order (configuration names / order)
         shim.gsl_combination_free(c)
+
+
+class GslPermutation(C.Structure):
+    _fields_ = [("size", C.c_size_t), ("data", C.POINTER(C.c_size_t))]
+
+
+def _to_gsl(lib, A):
+    lib.gsl_matrix_alloc.restype = C.POINTER(GslMatrix)
+    m = lib.gsl_matrix_alloc(C.c_size_t(A.shape[0]), C.c_size_t(A.shape[1]))
+    for i in range(A.shape[0]):
+        for j in range(A.shape[1]):
+            m.contents.data[i * m.contents.tda + j] = A[i, j]
+    return m
+
+
+def _from_gsl(m):
+    c = m.contents
+    return np.array([[c.data[i * c.tda + j] for j in range(c.size2)] for i in range(c.size1)])
+
+
+def test_svd_and_lu_against_numpy(shim):
+    """gsl_linalg_SV_decomp and gsl_linalg_LU_decomp / _invert / _lndet: what the hybrid error model reaches through
+    mygsl_linalg_pseudoinverse, mygsl_linalg_invert and CalcLog10AbfMvlr (utils_math.cpp:249-301, gene_snp_pair.cpp:793-812,
+    1196-1224).  Singular values, the pseudo-inverse V D^-1 U' and the LU inverse / log-determinant against numpy.linalg."""
+    lib = shim
+    lib.gsl_vector_alloc.restype = C.POINTER(GslVector)
+    lib.gsl_permutation_alloc.restype = C.POINTER(GslPermutation)
+    lib.gsl_linalg_LU_lndet.restype = C.c_double
+    rng = np.random.default_rng(11)
+    for n, p in ((70, 2), (120, 4), (6, 6), (3, 3)):
+        A = rng.normal(size=(n, p))
+        A[:, 0] = 1.0  # an intercept column, like every design matrix of the path
+        U, V = _to_gsl(lib, A), _to_gsl(lib, np.zeros((p, p)))
+        S, work = lib.gsl_vector_alloc(C.c_size_t(p)), lib.gsl_vector_alloc(C.c_size_t(p))
+        assert lib.gsl_linalg_SV_decomp(U, V, S, work) == 0
+        sv = np.array([S.contents.data[j] for j in range(p)])
+        Um, Vm = _from_gsl(U), _from_gsl(V)
+        assert np.allclose(np.sort(sv)[::-1], np.linalg.svd(A, compute_uv=False), rtol=1e-12, atol=0)
+        assert np.allclose((Um * sv) @ Vm.T, A, rtol=0, atol=1e-12 * np.abs(A).max() * n)
+        assert np.allclose((Vm / sv) @ Um.T, np.linalg.pinv(A), rtol=1e-10, atol=1e-13)
+        for m in (U, V):
+            lib.gsl_matrix_free(m)
+        for v in (S, work):
+            lib.gsl_vector_free(v)
+    for n in (2, 3, 5, 9):
+        B = rng.normal(size=(n, n)) + n * np.eye(n)
+        LU, inv = _to_gsl(lib, B), _to_gsl(lib, np.zeros((n, n)))
+        perm = lib.gsl_permutation_alloc(C.c_size_t(n))
+        sign = C.c_int(0)
+        assert lib.gsl_linalg_LU_decomp(LU, perm, C.byref(sign)) == 0
+        assert abs(lib.gsl_linalg_LU_lndet(LU) - np.linalg.slogdet(B)[1]) < 1e-12
+        assert lib.gsl_linalg_LU_invert(LU, perm, inv) == 0
+        assert np.allclose(_from_gsl(inv), np.linalg.inv(B), rtol=1e-11, atol=1e-14)
+        lib.gsl_permutation_free(perm)
+        for m in (LU, inv):
+            lib.gsl_matrix_free(m)
